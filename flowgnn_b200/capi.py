@@ -1,0 +1,212 @@
+"""ctypes binding of ``libflowgnn_b200.so`` (the C ABI declared in ``include/flowgnn_b200.h``).
+
+This is the only way Python reaches the CUDA kernels; there is no CPU fallback.  If the shared
+library has not been built (``make -C flowgnn_b200/csrc`` or ``__graft_entry__.build()``), importing
+works but every call raises :class:`FlowGNNError`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from .dataset import Batch
+from .models import ModelSpec, get_model
+from .weights import Weights, check_weights
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflowgnn_b200.so")
+
+MODEL_IDS = {"gin": 0, "ginvn": 0, "gcn": 1, "gat": 2, "pna": 3, "dgn": 4}
+
+#: every symbol include/flowgnn_b200.h declares
+EXPORTED_SYMBOLS = (
+    "GIN_compute_graphs", "GCN_compute_graphs", "GAT_compute_graphs", "PNA_compute_graphs", "DGN_compute_graphs",
+    "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
+    "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_compute", "flowgnn_b200_download",
+    "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
+)
+
+
+class FlowGNNError(RuntimeError):
+    pass
+
+
+_lib: Optional[ctypes.CDLL] = None
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+def load_library() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise FlowGNNError(f"{LIB_PATH} not built: run `make -C flowgnn_b200/csrc` (needs nvcc, targets sm_100a)")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.flowgnn_b200_last_error.restype = ctypes.c_char_p
+        lib.flowgnn_b200_stream.restype = ctypes.c_void_p
+        lib.flowgnn_b200_stream.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+        lib.flowgnn_b200_destroy.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        lib.flowgnn_b200_load_weights.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_f32p), ctypes.c_int]
+        lib.flowgnn_b200_upload_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_void_p]
+        lib.flowgnn_b200_compute.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p]
+        lib.flowgnn_b200_download.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.flowgnn_b200_last_launch_count.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_synchronize.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_last_layer_ms.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().flowgnn_b200_last_error().decode(errors="replace")
+        raise FlowGNNError(f"{what} failed with code {rc}: {msg}")
+
+
+def _addr(a) -> Optional[int]:
+    """Address of a numpy array, a torch tensor (e.g. pinned host memory) or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise FlowGNNError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return int(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Context:
+    """One GPU's context (extended interface, Part 2 of the header)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        _check(self._lib.flowgnn_b200_create(ctypes.byref(self._h), device), "flowgnn_b200_create")
+        self.device = device
+        self._num_graphs = 0
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.flowgnn_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, name: str, value: int) -> None:
+        _check(self._lib.flowgnn_b200_set_option(self._h, name.encode(), int(value)), f"set_option({name})")
+
+    def load_weights(self, model: str, weights: Weights) -> None:
+        spec = get_model(model)
+        w = check_weights(spec, weights)
+        arrs = [w[n] for n in spec.weight_names]
+        ptrs = (_f32p * len(arrs))(*[a.ctypes.data_as(_f32p) for a in arrs])
+        _check(self._lib.flowgnn_b200_load_weights(self._h, MODEL_IDS[spec.name], ptrs, len(arrs)), "load_weights")
+
+    def upload(self, batch: Batch) -> None:
+        self.upload_arrays(batch.num_graphs, batch.total_nodes, batch.total_edges, batch.nums_of_nodes, batch.nums_of_edges,
+                           batch.node_feature, batch.edge_list, batch.edge_attr, batch.node_eigen)
+
+    def upload_arrays(self, num_graphs, total_nodes, total_edges, nums_of_nodes, nums_of_edges, node_feature, edge_list,
+                      edge_attr=None, node_eigen=None) -> None:
+        _check(self._lib.flowgnn_b200_upload_batch(self._h, int(num_graphs), int(total_nodes), int(total_edges),
+                                                   _addr(nums_of_nodes), _addr(nums_of_edges), _addr(node_feature),
+                                                   _addr(edge_list), _addr(edge_attr), _addr(node_eigen)), "upload_batch")
+        self._num_graphs = int(num_graphs)
+
+    def compute(self, model: str, timed: bool = True) -> float:
+        ms = ctypes.c_float(0.0)
+        _check(self._lib.flowgnn_b200_compute(self._h, MODEL_IDS[get_model(model).name], ctypes.byref(ms) if timed else None),
+               "compute")
+        return float(ms.value)
+
+    def download(self, out=None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self._num_graphs, dtype=np.float32)
+        _check(self._lib.flowgnn_b200_download(self._h, _addr(out), self._num_graphs), "download")
+        return out
+
+    def synchronize(self) -> None:
+        _check(self._lib.flowgnn_b200_synchronize(self._h), "synchronize")
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.flowgnn_b200_last_launch_count(self._h))
+
+    def last_layer_ms(self):
+        """Device time of each per-layer launch of the last compute (needs set_option("time_layers", 1))."""
+        buf = (ctypes.c_float * 16)()
+        n = self._lib.flowgnn_b200_last_layer_ms(self._h, buf, 16)
+        return [float(buf[i]) for i in range(n)]
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.flowgnn_b200_stream(self._h) or 0)
+
+    def run(self, model: str, batch: Batch, weights: Optional[Weights] = None) -> np.ndarray:
+        """load (optional) + upload + compute + download."""
+        if weights is not None:
+            self.load_weights(model, weights)
+        if get_model(model).virtual_node:
+            batch = batch.with_virtual_node()
+        self.upload(batch)
+        self.compute(model, timed=False)
+        return self.download()
+
+
+def compute_graphs(model: str, batch: Batch, weights: Weights, reload_weights: Optional[np.ndarray] = None,
+                   weight_sets: Optional[Sequence[Weights]] = None) -> np.ndarray:
+    """Call the reference-compatible entry point ``<MODEL>_compute_graphs`` (Part 1 of the header)
+    with host arrays, exactly as the reference's host would (GIN/src/host.cc:184-209).
+
+    ``weight_sets`` (optional) stacks several weight sets along the leading dimension; ``reload_weights``
+    then marks the graphs at which the kernel advances to the next set (GIN/src/GIN_compute.cc:49-63).
+    GIN-VN: the caller passes the virtual-node-augmented batch (as the reference's host does)."""
+    lib = load_library()
+    spec: ModelSpec = get_model(model)
+    sets = list(weight_sets) if weight_sets is not None else [weights]
+    sets = [check_weights(spec, w) for w in sets]
+    stacked: Dict[str, np.ndarray] = {n: np.ascontiguousarray(np.stack([w[n] for w in sets])) for n in spec.weight_names}
+    G = batch.num_graphs
+    if reload_weights is None:
+        reload_weights = np.zeros(G, dtype=np.int32)
+        if G:
+            reload_weights[0] = 1
+    reload_weights = np.ascontiguousarray(reload_weights, dtype=np.int32)
+    out = np.zeros(G, dtype=np.float32)
+    nn = np.ascontiguousarray(batch.nums_of_nodes, dtype=np.int32)
+    ne = np.ascontiguousarray(batch.nums_of_edges, dtype=np.int32)
+    args = [ctypes.c_int(G), nn.ctypes.data_as(_i32p), ne.ctypes.data_as(_i32p), reload_weights.ctypes.data_as(_i32p),
+            out.ctypes.data_as(_f32p), batch.node_feature.ctypes.data_as(_i32p)]
+    if spec.uses_eigen:
+        if batch.node_eigen is None:
+            raise FlowGNNError("DGN needs node_eigen")
+        args.append(batch.node_eigen.ctypes.data_as(_f32p))
+    args.append(batch.edge_list.ctypes.data_as(_i32p))
+    if spec.uses_edge_attr:
+        if batch.edge_attr is None:
+            raise FlowGNNError(f"{spec.name} needs edge_attr")
+        args.append(batch.edge_attr.ctypes.data_as(_i32p))
+    for n in spec.weight_names:
+        args.append(stacked[n].ctypes.data_as(_f32p))
+    fn = getattr(lib, spec.symbol)
+    fn.restype = ctypes.c_int
+    _check(fn(*args), spec.symbol)
+    return out

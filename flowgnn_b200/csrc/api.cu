@@ -1,0 +1,644 @@
+// C ABI (include/flowgnn_b200.h): contexts, load_weights, batch upload, and the reference-compatible
+// <MODEL>_compute_graphs entry points.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/flowgnn_b200.h"
+#include "internal.cuh"
+
+namespace fg {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int DevBuf::reserve(size_t bytes)
+{
+    if (bytes <= cap && ptr) return 0;
+    if (bytes == 0) bytes = 16;
+    if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+    bytes = (bytes + 255) & ~size_t(255);
+    FG_CUDA(cudaMalloc(&ptr, bytes));
+    cap = bytes;
+    return 0;
+}
+void DevBuf::release()
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+}
+
+void DeviceBatch::release()
+{
+    DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
+                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &sort_tmp, &status,
+                     &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
+    for (DevBuf* b : all) b->release();
+}
+
+int LayerTimer::mark(cudaStream_t s)
+{
+    if (marks >= MAX_MARKS) return 0;
+    if (marks >= created)
+    {
+        FG_CUDA(cudaEventCreate(&ev[created]));
+        created++;
+    }
+    FG_CUDA(cudaEventRecord(ev[marks], s));
+    marks++;
+    return 0;
+}
+
+static int upload(DevBuf& dst, const std::vector<float>& v, cudaStream_t s)
+{
+    FG_TRY(dst.reserve(v.size() * sizeof(float)));
+    FG_CUDA(cudaMemcpyAsync(dst.ptr, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    FG_CUDA(cudaStreamSynchronize(s));       // `v` is a temporary
+    return 0;
+}
+static int upload(DevBuf& dst, const float* p, size_t n, cudaStream_t s)
+{
+    return upload(dst, std::vector<float>(p, p + n), s);
+}
+
+// edge-embedding rows for the 60 distinct bond-attribute triples, summed exactly as the reference
+// does per edge: ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]   (GIN/src/message_passing.cc:136-142)
+static std::vector<float> combine_edge_embedding(const float* ee, int layers, int dim)
+{
+    std::vector<float> out((size_t)layers * ED_COMBOS * dim);
+    for (int l = 0; l < layers; l++)
+        for (int a0 = 0; a0 < 5; a0++)
+            for (int a1 = 0; a1 < 6; a1++)
+                for (int a2 = 0; a2 < 2; a2++)
+                {
+                    const int c = a0 * 12 + a1 * 2 + a2;
+                    const float* t = ee + (size_t)l * ED_FEATURE_PER_LAYER * dim;
+                    for (int d = 0; d < dim; d++)
+                    {
+                        float s = 0.0f;
+                        s += t[(0 + a0) * dim + d];
+                        s += t[(5 + a1) * dim + d];
+                        s += t[(11 + a2) * dim + d];
+                        out[((size_t)l * ED_COMBOS + c) * dim + d] = s;
+                    }
+                }
+    return out;
+}
+
+// [layers][n][k] (reference "[out][in]") -> k-major [layers][k][np] with zero-padded columns
+static std::vector<float> transpose_pad(const float* w, int layers, int n, int k, int np)
+{
+    std::vector<float> out((size_t)layers * k * np, 0.0f);
+    for (int l = 0; l < layers; l++)
+        for (int o = 0; o < n; o++)
+            for (int i = 0; i < k; i++) out[((size_t)l * k + i) * np + o] = w[((size_t)l * n + o) * k + i];
+    return out;
+}
+static std::vector<float> pad_rows(const float* b, int layers, int n, int np)
+{
+    std::vector<float> out((size_t)layers * np, 0.0f);
+    for (int l = 0; l < layers; l++)
+        for (int o = 0; o < n; o++) out[(size_t)l * np + o] = b[(size_t)l * n + o];
+    return out;
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+struct flowgnn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DeviceBatch batch;
+    bool batch_ready = false;
+    GinWeights gin; GcnWeights gcn; GatWeights gat; PnaWeights pna; DgnWeights dgn;
+    bool loaded[NUM_MODELS] = {false, false, false, false, false};
+    uint64_t weight_hash[NUM_MODELS] = {0, 0, 0, 0, 0};
+    RunOptions opt;
+    LayerTimer timer;
+    int time_layers = 0;
+    int last_launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+const int kNumWeights[NUM_MODELS] = {8, 11, 6, 10, 9};
+
+int load_gin(flowgnn_ctx* c, const float* const* w)
+{
+    cudaStream_t s = c->stream;
+    GinWeights& g = c->gin;
+    FG_TRY(upload(g.ne_table, w[0], (size_t)ND_FEATURE_TOTAL * 100, s));
+    FG_TRY(upload(g.ee_comb, combine_edge_embedding(w[1], 5, 100), s));
+    FG_TRY(upload(g.w1t, transpose_pad(w[2], 5, 200, 100, 208), s));
+    FG_TRY(upload(g.b1, pad_rows(w[3], 5, 200, 208), s));
+    FG_TRY(upload(g.w2t, transpose_pad(w[4], 5, 100, 200, 104), s));
+    FG_TRY(upload(g.b2, pad_rows(w[5], 5, 100, 104), s));
+    FG_TRY(upload(g.pred_w, w[6], 100, s));
+    FG_TRY(upload(g.pred_b, w[7], 1, s));
+    return 0;
+}
+
+int load_gcn(flowgnn_ctx* c, const float* const* w)
+{
+    cudaStream_t s = c->stream;
+    GcnWeights& g = c->gcn;
+    FG_TRY(upload(g.ne_table, w[0], (size_t)ND_FEATURE_TOTAL * 100, s));
+    FG_TRY(upload(g.ee_comb, combine_edge_embedding(w[1], 5, 100), s));
+    FG_TRY(upload(g.wt, transpose_pad(w[2], 5, 100, 100, 104), s));
+    FG_TRY(upload(g.b, pad_rows(w[3], 5, 100, 104), s));
+    FG_TRY(upload(g.root, w[4], 500, s));
+    FG_TRY(upload(g.bn_weight, w[5], 500, s));
+    FG_TRY(upload(g.bn_bias, w[6], 500, s));
+    FG_TRY(upload(g.bn_mean, w[7], 500, s));
+    std::vector<float> sv(500);
+    // bn_sqrt_var = sqrt(var + ap_fixed_epsilon) with epsilon = 2^-10 for <16,6> (GCN/src/load_inputs.cc:32)
+    for (int i = 0; i < 500; i++) sv[i] = std::sqrt(w[8][i] + (float)(1.0 / (1 << 10)));
+    FG_TRY(upload(g.bn_sqrt_var, sv, s));
+    FG_TRY(upload(g.pred_w, w[9], 100, s));
+    FG_TRY(upload(g.pred_b, w[10], 1, s));
+    return 0;
+}
+
+int load_gat(flowgnn_ctx* c, const float* const* w)
+{
+    cudaStream_t s = c->stream;
+    GatWeights& g = c->gat;
+    // reference layouts: scoring [l][h][d]; proj/skip [l][ho][do][hi][di]; activations are [v][d][h]
+    std::vector<float> a_tgt(5 * 64), a_src(5 * 64), projt(5 * 64 * 64), skipt(5 * 64 * 64), proj0(9 * 64);
+    for (int l = 0; l < 5; l++)
+        for (int h = 0; h < 4; h++)
+            for (int d = 0; d < 16; d++)
+            {
+                a_tgt[l * 64 + d * 4 + h] = w[0][(l * 4 + h) * 16 + d];
+                a_src[l * 64 + d * 4 + h] = w[1][(l * 4 + h) * 16 + d];
+            }
+    for (int l = 0; l < 5; l++)
+        for (int ho = 0; ho < 4; ho++)
+            for (int dd = 0; dd < 16; dd++)
+                for (int hi = 0; hi < 4; hi++)
+                    for (int di = 0; di < 16; di++)
+                    {
+                        const size_t srci = ((((size_t)l * 4 + ho) * 16 + dd) * 4 + hi) * 16 + di;
+                        const size_t dsti = ((size_t)l * 64 + (di * 4 + hi)) * 64 + (dd * 4 + ho);
+                        projt[dsti] = w[2][srci];
+                        skipt[dsti] = w[3][srci];
+                    }
+    // layer-0 projection sees the raw features at head_in 0, dim_in f < 9 (GAT/src/load_inputs.cc:203-215)
+    for (int f = 0; f < 9; f++)
+        for (int ho = 0; ho < 4; ho++)
+            for (int dd = 0; dd < 16; dd++) proj0[f * 64 + dd * 4 + ho] = w[2][((((size_t)0 * 4 + ho) * 16 + dd) * 4 + 0) * 16 + f];
+    FG_TRY(upload(g.a_tgt, a_tgt, s));
+    FG_TRY(upload(g.a_src, a_src, s));
+    FG_TRY(upload(g.projt, projt, s));
+    FG_TRY(upload(g.skipt, skipt, s));
+    FG_TRY(upload(g.proj0, proj0, s));
+    FG_TRY(upload(g.pred_w, w[4], 16, s));
+    FG_TRY(upload(g.pred_b, w[5], 1, s));
+    return 0;
+}
+
+int load_pna(flowgnn_ctx* c, const float* const* w)
+{
+    cudaStream_t s = c->stream;
+    PnaWeights& g = c->pna;
+    FG_TRY(upload(g.ne_table, w[0], (size_t)ND_FEATURE_TOTAL * 80, s));
+    // reference [l][out][scaler][aggr][in] -> wcat[l][aggr*80 + in][scaler*80 + out]
+    std::vector<float> wcat((size_t)4 * 320 * 240);
+    for (int l = 0; l < 4; l++)
+        for (int o = 0; o < 80; o++)
+            for (int sc = 0; sc < 3; sc++)
+                for (int a = 0; a < 4; a++)
+                    for (int i = 0; i < 80; i++)
+                        wcat[((size_t)l * 320 + a * 80 + i) * 240 + sc * 80 + o] = w[1][((((size_t)l * 80 + o) * 3 + sc) * 4 + a) * 80 + i];
+    FG_TRY(upload(g.wcat, wcat, s));
+    FG_TRY(upload(g.w_ref, w[1], (size_t)4 * 80 * 12 * 80, s));
+    FG_TRY(upload(g.b, w[2], 320, s));
+    FG_TRY(upload(g.m1w, w[3], 40 * 80, s));
+    FG_TRY(upload(g.m1b, w[4], 40, s));
+    FG_TRY(upload(g.m2w, w[5], 20 * 40, s));
+    FG_TRY(upload(g.m2b, w[6], 20, s));
+    FG_TRY(upload(g.m3w, w[7], 20, s));
+    FG_TRY(upload(g.m3b, w[8], 1, s));
+    g.avg_deg = w[9][0];
+    return 0;
+}
+
+int load_dgn(flowgnn_ctx* c, const float* const* w)
+{
+    cudaStream_t s = c->stream;
+    DgnWeights& g = c->dgn;
+    FG_TRY(upload(g.emb, w[0], (size_t)9 * 119 * 100, s));
+    FG_TRY(upload(g.wt, transpose_pad(w[1], 4, 100, 200, 104), s));
+    FG_TRY(upload(g.w_ref, w[1], (size_t)4 * 100 * 200, s));
+    FG_TRY(upload(g.b, pad_rows(w[2], 4, 100, 104), s));
+    FG_TRY(upload(g.m0w, w[3], 50 * 100, s));
+    FG_TRY(upload(g.m0b, w[4], 50, s));
+    FG_TRY(upload(g.m1w, w[5], 25 * 50, s));
+    FG_TRY(upload(g.m1b, w[6], 25, s));
+    FG_TRY(upload(g.m2w, w[7], 25, s));
+    FG_TRY(upload(g.m2b, w[8], 1, s));
+    return 0;
+}
+
+int check_ctx(flowgnn_ctx* ctx)
+{
+    if (!ctx) { set_last_error("null context"); return FG_ERR_INVALID; }
+    return 0;
+}
+
+int copy_in(DevBuf& dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    FG_TRY(dst.reserve(bytes));
+    if (bytes) FG_CUDA(cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+int check_status(flowgnn_ctx* ctx)
+{
+    int st = 0;
+    FG_CUDA(cudaMemcpyAsync(&st, ctx->batch.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (st & 1) { set_last_error("a graph has more than 1024 nodes (reference cap: MAX_NODE = 500)"); return FG_ERR_LIMIT; }
+    if (st & 2) { set_last_error("edge_list holds a node id outside [0, num_of_nodes)"); return FG_ERR_INVALID; }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* flowgnn_b200_last_error(void) { return g_last_error.c_str(); }
+
+int flowgnn_b200_create(flowgnn_ctx** out, int device)
+{
+    if (!out) { set_last_error("null out pointer"); return FG_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    FG_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { set_last_error("no such CUDA device"); return FG_ERR_INVALID; }
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    FG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+    {
+        set_last_error(std::string("flowgnn_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
+        return FG_ERR_INVALID;
+    }
+    std::unique_ptr<flowgnn_ctx> c(new flowgnn_ctx);
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    FG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FG_CUDA(cudaEventCreate(&c->ev0));
+    FG_CUDA(cudaEventCreate(&c->ev1));
+    *out = c.release();
+    return 0;
+}
+
+int flowgnn_b200_destroy(flowgnn_ctx* ctx)
+{
+    if (!ctx) return 0;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->batch.release();
+    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.pred_w, &ctx->gin.pred_b,
+                   &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
+                   &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
+                   &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
+                   &ctx->pna.m3w, &ctx->pna.m3b,
+                   &ctx->dgn.emb, &ctx->dgn.wt, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
+                   &ctx->dgn.m2w, &ctx->dgn.m2b,
+                   &ctx->gat.proj0, &ctx->gat.projt, &ctx->gat.skipt, &ctx->gat.a_src, &ctx->gat.a_tgt, &ctx->gat.pred_w, &ctx->gat.pred_b};
+    for (DevBuf* b : w) b->release();
+    for (int i = 0; i < ctx->timer.created; i++) cudaEventDestroy(ctx->timer.ev[i]);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
+{
+    FG_TRY(check_ctx(ctx));
+    if (!name) { set_last_error("null option name"); return FG_ERR_INVALID; }
+    if (!std::strcmp(name, "mp_only")) ctx->opt.mp_only = value;
+    else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
+    else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;
+    else { set_last_error(std::string("unknown option ") + name); return FG_ERR_INVALID; }
+    return 0;
+}
+
+int flowgnn_b200_load_weights(flowgnn_ctx* ctx, int model, const float* const* weights, int num_weights)
+{
+    FG_TRY(check_ctx(ctx));
+    if (model < 0 || model >= NUM_MODELS) { set_last_error("unknown model id"); return FG_ERR_INVALID; }
+    if (!weights || num_weights != kNumWeights[model])
+    {
+        set_last_error("load_weights: expected " + std::to_string(kNumWeights[model]) + " weight arrays");
+        return FG_ERR_INVALID;
+    }
+    for (int i = 0; i < num_weights; i++)
+        if (!weights[i]) { set_last_error("load_weights: null weight array " + std::to_string(i)); return FG_ERR_INVALID; }
+    DeviceGuard guard(ctx->device);
+    ctx->loaded[model] = false;
+    switch (model)
+    {
+    case MODEL_GIN: FG_TRY(load_gin(ctx, weights)); break;
+    case MODEL_GCN: FG_TRY(load_gcn(ctx, weights)); break;
+    case MODEL_GAT: FG_TRY(load_gat(ctx, weights)); break;
+    case MODEL_PNA: FG_TRY(load_pna(ctx, weights)); break;
+    case MODEL_DGN: FG_TRY(load_dgn(ctx, weights)); break;
+    }
+    ctx->loaded[model] = true;
+    ctx->weight_hash[model] = 0;
+    return 0;
+}
+
+int flowgnn_b200_upload_batch(flowgnn_ctx* ctx, int num_graphs, int64_t total_nodes, int64_t total_edges,
+                              const int32_t* nums_of_nodes, const int32_t* nums_of_edges, const int32_t* node_feature,
+                              const int32_t* edge_list, const int32_t* edge_attr, const float* node_eigen)
+{
+    FG_TRY(check_ctx(ctx));
+    if (num_graphs < 0 || total_nodes < 0 || total_edges < 0) { set_last_error("negative size"); return FG_ERR_INVALID; }
+    if (total_nodes >= (int64_t(1) << 31) / 100 * 4 || total_edges >= (int64_t(1) << 31) - 64)
+    {
+        set_last_error("batch too large for 32-bit node/edge positions; split it");
+        return FG_ERR_LIMIT;
+    }
+    if (num_graphs > 0 && (!nums_of_nodes || !nums_of_edges || (total_nodes && !node_feature) || (total_edges && !edge_list)))
+    {
+        set_last_error("null batch array");
+        return FG_ERR_INVALID;
+    }
+    DeviceGuard guard(ctx->device);
+    DeviceBatch& b = ctx->batch;
+    ctx->batch_ready = false;
+    b.num_graphs = num_graphs; b.total_nodes = total_nodes; b.total_edges = total_edges;
+    b.has_attr = edge_attr != nullptr; b.has_eigen = node_eigen != nullptr;
+    cudaStream_t s = ctx->stream;
+    FG_TRY(copy_in(b.nums_of_nodes, nums_of_nodes, sizeof(int) * (size_t)num_graphs, s));
+    FG_TRY(copy_in(b.nums_of_edges, nums_of_edges, sizeof(int) * (size_t)num_graphs, s));
+    FG_TRY(copy_in(b.node_feature, node_feature, sizeof(int) * ND_FEATURE * (size_t)total_nodes, s));
+    FG_TRY(copy_in(b.edge_list, edge_list, sizeof(int) * 2 * (size_t)total_edges, s));
+    if (edge_attr) FG_TRY(copy_in(b.edge_attr, edge_attr, sizeof(int) * 3 * (size_t)total_edges, s));
+    if (node_eigen) FG_TRY(copy_in(b.node_eigen, node_eigen, sizeof(float) * 4 * (size_t)total_nodes, s));
+    FG_TRY(b.out.reserve(sizeof(float) * (size_t)(num_graphs + 1)));
+    ctx->batch_ready = true;
+    return 0;
+}
+
+int flowgnn_b200_compute(flowgnn_ctx* ctx, int model, float* elapsed_ms)
+{
+    FG_TRY(check_ctx(ctx));
+    if (model < 0 || model >= NUM_MODELS) { set_last_error("unknown model id"); return FG_ERR_INVALID; }
+    if (!ctx->loaded[model]) { set_last_error("compute: load_weights has not been called for this model"); return FG_ERR_STATE; }
+    if (!ctx->batch_ready) { set_last_error("compute: no batch uploaded"); return FG_ERR_STATE; }
+    DeviceGuard guard(ctx->device);
+    DeviceBatch& b = ctx->batch;
+    cudaStream_t s = ctx->stream;
+    ctx->last_launches = 0;
+    if (elapsed_ms) *elapsed_ms = 0.f;
+    if (b.num_graphs == 0) return 0;
+    if (model == MODEL_DGN && !b.has_eigen) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
+    if ((model == MODEL_GIN || model == MODEL_GCN) && !b.has_attr) { set_last_error("GIN/GCN need edge_attr"); return FG_ERR_INVALID; }
+
+    if (elapsed_ms) FG_CUDA(cudaEventRecord(ctx->ev0, s));
+    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : 0;
+    const bool keep_attr = b.has_attr;
+    if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
+    int rc = prep_batch(b, flags, s);
+    b.has_attr = keep_attr;
+    FG_TRY(rc);
+    ctx->last_launches += 2;
+    ctx->timer.marks = 0;
+    ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
+    switch (model)
+    {
+    case MODEL_GIN: FG_TRY(gin_forward(b, ctx->gin, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
+    case MODEL_GCN: FG_TRY(gcn_forward(b, ctx->gcn, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
+    case MODEL_GAT: FG_TRY(gat_forward(b, ctx->gat, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
+    case MODEL_PNA: FG_TRY(pna_forward(b, ctx->pna, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
+    case MODEL_DGN: FG_TRY(dgn_forward(b, ctx->dgn, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
+    }
+    if (elapsed_ms)
+    {
+        FG_CUDA(cudaEventRecord(ctx->ev1, s));
+        FG_CUDA(cudaEventSynchronize(ctx->ev1));
+        FG_CUDA(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+        FG_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int flowgnn_b200_download(flowgnn_ctx* ctx, float* out, int num_graphs)
+{
+    FG_TRY(check_ctx(ctx));
+    if (num_graphs < 0 || num_graphs > ctx->batch.num_graphs || (num_graphs && !out)) { set_last_error("download: bad size"); return FG_ERR_INVALID; }
+    DeviceGuard guard(ctx->device);
+    if (num_graphs) FG_CUDA(cudaMemcpyAsync(out, ctx->batch.out.ptr, sizeof(float) * (size_t)num_graphs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->batch.status.ptr) FG_TRY(check_status(ctx));
+    else FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int flowgnn_b200_last_launch_count(flowgnn_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int flowgnn_b200_last_layer_ms(flowgnn_ctx* ctx, float* out, int max_layers)
+{
+    if (!ctx || !out || max_layers <= 0) return 0;
+    DeviceGuard guard(ctx->device);
+    const int n = ctx->timer.marks - 1;
+    if (n <= 0) return 0;
+    if (cudaEventSynchronize(ctx->timer.ev[n]) != cudaSuccess) return 0;
+    int k = 0;
+    for (; k < n && k < max_layers; k++)
+        if (cudaEventElapsedTime(&out[k], ctx->timer.ev[k], ctx->timer.ev[k + 1]) != cudaSuccess) break;
+    return k;
+}
+void* flowgnn_b200_stream(flowgnn_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int flowgnn_b200_synchronize(flowgnn_ctx* ctx)
+{
+    FG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    FG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- Part 1: the reference's kernel entry points ---------------------------------------------------
+
+namespace {
+
+struct DefaultCtx {
+    flowgnn_ctx* ctx = nullptr;
+    ~DefaultCtx() { if (ctx) flowgnn_b200_destroy(ctx); }
+};
+
+int default_ctx(flowgnn_ctx** out)
+{
+    static thread_local DefaultCtx holder;
+    int dev = 0;
+    FG_CUDA(cudaGetDevice(&dev));
+    if (holder.ctx && holder.ctx->device != dev) { flowgnn_b200_destroy(holder.ctx); holder.ctx = nullptr; }
+    if (!holder.ctx) FG_TRY(flowgnn_b200_create(&holder.ctx, dev));
+    *out = holder.ctx;
+    return 0;
+}
+
+// FNV-1a over the weight bytes, 8 bytes at a time: re-upload only when the contents change
+uint64_t hash_weights(const float* const* w, const size_t* counts, int n, size_t set)
+{
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < n; i++)
+    {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(w[i] + set * counts[i]);
+        const size_t bytes = counts[i] * sizeof(float);
+        size_t k = 0;
+        for (; k + 8 <= bytes; k += 8) { uint64_t v; std::memcpy(&v, p + k, 8); h = (h ^ v) * 1099511628211ull; }
+        for (; k < bytes; k++) h = (h ^ p[k]) * 1099511628211ull;
+    }
+    return h ? h : 1;
+}
+
+// Walk the batch as runs of graphs that share a weight set (reload_weights[g] != 0 starts the next
+// set; GIN/src/GIN_compute.cc:49-63) and run each through the extended interface.
+int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne, const int* reload, float* out,
+                        const int32_t* feat, const int32_t* edges, const int32_t* attr, const float* eig,
+                        const float* const* weights, const size_t* counts)
+{
+    if (num_graphs < 0) { set_last_error("num_graphs < 0"); return FG_ERR_INVALID; }
+    if (num_graphs == 0) return 0;
+    if (!nn || !ne || !reload || !out || !feat || !edges) { set_last_error("null argument"); return FG_ERR_INVALID; }
+    flowgnn_ctx* ctx = nullptr;
+    FG_TRY(default_ctx(&ctx));
+    const int nw = kNumWeights[model];
+    long set = -1;
+    int64_t node_base = 0, edge_base = 0;
+    int g = 0;
+    while (g < num_graphs)
+    {
+        if (reload[g]) set++;
+        if (set < 0) { set_last_error("reload_weights[0] must be non-zero (the reference would index weight set -1)"); return FG_ERR_INVALID; }
+        int g1 = g + 1;
+        int64_t n_run = nn[g], e_run = ne[g];
+        while (g1 < num_graphs && !reload[g1]) { n_run += nn[g1]; e_run += ne[g1]; g1++; }
+
+        const uint64_t h = hash_weights(weights, counts, nw, (size_t)set);
+        if (!ctx->loaded[model] || ctx->weight_hash[model] != h)
+        {
+            std::vector<const float*> ptrs(nw);
+            for (int i = 0; i < nw; i++) ptrs[i] = weights[i] + (size_t)set * counts[i];
+            FG_TRY(flowgnn_b200_load_weights(ctx, model, ptrs.data(), nw));
+            ctx->weight_hash[model] = h;
+        }
+        // the reference's GAT reads node features from the START of the batch buffer for every graph
+        const bool gat_bug = (model == MODEL_GAT) && ctx->opt.gat_node_offset_bug;
+        const int32_t* feat_run = gat_bug ? feat : feat + ND_FEATURE * node_base;
+        FG_TRY(flowgnn_b200_upload_batch(ctx, g1 - g, n_run, e_run, nn + g, ne + g, feat_run, edges + 2 * edge_base,
+                                         attr ? attr + 3 * edge_base : nullptr, eig ? eig + 4 * node_base : nullptr));
+        FG_TRY(flowgnn_b200_compute(ctx, model, nullptr));
+        FG_TRY(flowgnn_b200_download(ctx, out + g, g1 - g));
+        node_base += n_run; edge_base += e_run;
+        g = g1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int GIN_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, float* out,
+                       const int32_t* node_feature_in, const int32_t* edge_list_in, const int32_t* edge_attr_in,
+                       const float* node_embedding_weight_in, const float* edge_embedding_weight_in,
+                       const float* node_mlp_1_weights, const float* node_mlp_1_bias, const float* node_mlp_2_weights,
+                       const float* node_mlp_2_bias, const float* graph_pred_weights_in, const float* graph_pred_bias_in)
+{
+    const float* w[] = {node_embedding_weight_in, edge_embedding_weight_in, node_mlp_1_weights, node_mlp_1_bias,
+                        node_mlp_2_weights, node_mlp_2_bias, graph_pred_weights_in, graph_pred_bias_in};
+    const size_t counts[] = {173 * 100, 5 * 13 * 100, 5 * 200 * 100, 5 * 200, 5 * 100 * 200, 5 * 100, 100, 1};
+    for (const float* p : w) if (!p) { set_last_error("null weight argument"); return FG_ERR_INVALID; }
+    if (!edge_attr_in && num_graphs > 0) { set_last_error("GIN needs edge_attr_in"); return FG_ERR_INVALID; }
+    return run_reference_entry(MODEL_GIN, num_graphs, nums_of_nodes, nums_of_edges, reload_weights, out, node_feature_in, edge_list_in,
+                               edge_attr_in, nullptr, w, counts);
+}
+
+int GCN_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, float* out,
+                       const int32_t* node_feature_in, const int32_t* edge_list_in, const int32_t* edge_attr_in,
+                       const float* node_embedding_weight_in, const float* edge_embedding_weight_in, const float* convs_weight_in,
+                       const float* convs_bias_in, const float* convs_root_emb_weight_in, const float* bn_weight_in,
+                       const float* bn_bias_in, const float* bn_mean_in, const float* bn_var_in, const float* graph_pred_weights_in,
+                       const float* graph_pred_bias_in)
+{
+    const float* w[] = {node_embedding_weight_in, edge_embedding_weight_in, convs_weight_in, convs_bias_in, convs_root_emb_weight_in,
+                        bn_weight_in, bn_bias_in, bn_mean_in, bn_var_in, graph_pred_weights_in, graph_pred_bias_in};
+    const size_t counts[] = {173 * 100, 5 * 13 * 100, 5 * 100 * 100, 500, 500, 500, 500, 500, 500, 100, 1};
+    for (const float* p : w) if (!p) { set_last_error("null weight argument"); return FG_ERR_INVALID; }
+    if (!edge_attr_in && num_graphs > 0) { set_last_error("GCN needs edge_attr_in"); return FG_ERR_INVALID; }
+    return run_reference_entry(MODEL_GCN, num_graphs, nums_of_nodes, nums_of_edges, reload_weights, out, node_feature_in, edge_list_in,
+                               edge_attr_in, nullptr, w, counts);
+}
+
+int GAT_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, float* out,
+                       const int32_t* node_feature_in, const int32_t* edge_list_in, const float* scoring_fn_target_in,
+                       const float* scoring_fn_source_in, const float* linear_proj_weights_in, const float* skip_proj_weights_in,
+                       const float* graph_pred_weights_in, const float* graph_pred_bias_in)
+{
+    const float* w[] = {scoring_fn_target_in, scoring_fn_source_in, linear_proj_weights_in, skip_proj_weights_in,
+                        graph_pred_weights_in, graph_pred_bias_in};
+    const size_t counts[] = {5 * 64, 5 * 64, 5 * 4096, 5 * 4096, 16, 1};
+    for (const float* p : w) if (!p) { set_last_error("null weight argument"); return FG_ERR_INVALID; }
+    return run_reference_entry(MODEL_GAT, num_graphs, nums_of_nodes, nums_of_edges, reload_weights, out, node_feature_in, edge_list_in,
+                               nullptr, nullptr, w, counts);
+}
+
+int PNA_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, float* out,
+                       const int32_t* node_feature_in, const int32_t* edge_list_in, const float* node_embedding_weight_in,
+                       const float* node_conv_weights_in, const float* node_conv_bias_in, const float* graph_mlp_1_weights_in,
+                       const float* graph_mlp_1_bias_in, const float* graph_mlp_2_weights_in, const float* graph_mlp_2_bias_in,
+                       const float* graph_mlp_3_weights_in, const float* graph_mlp_3_bias_in, const float* avg_deg_in)
+{
+    const float* w[] = {node_embedding_weight_in, node_conv_weights_in, node_conv_bias_in, graph_mlp_1_weights_in, graph_mlp_1_bias_in,
+                        graph_mlp_2_weights_in, graph_mlp_2_bias_in, graph_mlp_3_weights_in, graph_mlp_3_bias_in, avg_deg_in};
+    const size_t counts[] = {173 * 80, 4 * 80 * 12 * 80, 320, 40 * 80, 40, 20 * 40, 20, 20, 1, 1};
+    for (const float* p : w) if (!p) { set_last_error("null weight argument"); return FG_ERR_INVALID; }
+    return run_reference_entry(MODEL_PNA, num_graphs, nums_of_nodes, nums_of_edges, reload_weights, out, node_feature_in, edge_list_in,
+                               nullptr, nullptr, w, counts);
+}
+
+int DGN_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, float* out,
+                       const int32_t* node_feature_in, const float* node_eigen_in, const int32_t* edge_list_in,
+                       const float* embedding_h_atom_embedding_list_weights_in,
+                       const float* layers_posttrans_fully_connected_0_linear_weight_in,
+                       const float* layers_posttrans_fully_connected_0_linear_bias_in, const float* MLP_layer_FC_layers_0_weight_in,
+                       const float* MLP_layer_FC_layers_0_bias_in, const float* MLP_layer_FC_layers_1_weight_in,
+                       const float* MLP_layer_FC_layers_1_bias_in, const float* MLP_layer_FC_layers_2_weight_in,
+                       const float* MLP_layer_FC_layers_2_bias_in)
+{
+    const float* w[] = {embedding_h_atom_embedding_list_weights_in, layers_posttrans_fully_connected_0_linear_weight_in,
+                        layers_posttrans_fully_connected_0_linear_bias_in, MLP_layer_FC_layers_0_weight_in, MLP_layer_FC_layers_0_bias_in,
+                        MLP_layer_FC_layers_1_weight_in, MLP_layer_FC_layers_1_bias_in, MLP_layer_FC_layers_2_weight_in,
+                        MLP_layer_FC_layers_2_bias_in};
+    const size_t counts[] = {9 * 119 * 100, 4 * 100 * 200, 400, 5000, 50, 1250, 25, 25, 1};
+    for (const float* p : w) if (!p) { set_last_error("null weight argument"); return FG_ERR_INVALID; }
+    if (!node_eigen_in && num_graphs > 0) { set_last_error("DGN needs node_eigen_in"); return FG_ERR_INVALID; }
+    return run_reference_entry(MODEL_DGN, num_graphs, nums_of_nodes, nums_of_edges, reload_weights, out, node_feature_in, edge_list_in,
+                               nullptr, node_eigen_in, w, counts);
+}
+
+}  // extern "C"

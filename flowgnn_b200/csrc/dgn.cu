@@ -1,0 +1,204 @@
+// DGN forward on B200.
+//
+// Reference pipeline, DGN/src/DGN_compute.cc:36-103 (same stage structure as GIN/PNA).  One launch per layer:
+//   message passing: m0_v = sum h_u,  m1_v = sum h_u * eig_w_uv,  eig_w_uv = phi_u - phi_v, phi = eig[:,1]
+//                    (DGN/src/message_passing.cc:121-153; load_inputs.cc:91-111)
+//   node transform : a1 = m0/outdeg(v);  a2 = |(m1 - B_v h_v)/A_v|, A_v = sum|eig_w| (0 -> 2^-13), B_v = sum eig_w;
+//                    acc = b + W[:,0,:] a1 + W[:,1,:] a2;  h <- h + relu(acc)      (DGN/src/node_embedding.cc:106-183)
+// The transform is one [rows x 200] x [200 x 100] GEMM on [a1 | a2].  A node with out-degree 0 gives
+// a1 = m0/0 (NaN or inf); those flow through the GEMM as the same products the reference forms, so
+// the result is non-finite exactly where the reference's is.
+#include "internal.cuh"
+#include "layers.cuh"
+
+#include <algorithm>
+
+namespace fg {
+
+namespace {
+
+constexpr int D = 100;
+constexpr int DP = 104;
+constexpr int Q = D / 4;
+constexpr int KA = 2 * D;
+constexpr int LDA = KA + 4;
+constexpr int NT = 224;
+
+using Gemm = TileGemm<KA, DP, 4, NT>;
+
+struct DgnLayerParams {
+    const float* h_in; float* h_out;
+    const int* in_ptr; const int* src; const float* eig_w; const int* out_deg;
+    const float* abssum; const float* wsum;
+    const float* wt; const float* b;
+    int num_nodes; int num_tiles;
+};
+
+struct DgnSmem {
+    static constexpr int BAR = 0;
+    static constexpr int PTR = 16;
+    static constexpr int SRC = PTR + 4 * 80;
+    static constexpr int EW = SRC + 4 * EDGE_CAP;
+    static constexpr int HS = EW + 4 * EDGE_CAP;
+    static constexpr int A = HS + 2 * 4 * TILE_M * D;
+    static constexpr int WBUF = A + 4 * TILE_M * LDA;
+    static constexpr int BYTES = WBUF + 4 * Gemm::WBUF_FLOATS;
+};
+
+__global__ void __launch_bounds__(NT, 1) dgn_layer_kernel(DgnLayerParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    using S = DgnSmem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
+    TileCsr csr;
+    csr.ptr = reinterpret_cast<int*>(smem + S::PTR);
+    csr.src = reinterpret_cast<int*>(smem + S::SRC);
+    csr.code = nullptr;
+    csr.w = reinterpret_cast<float*>(smem + S::EW);
+    float* hs = reinterpret_cast<float*>(smem + S::HS);
+    float* As = reinterpret_cast<float*>(smem + S::A);
+    float* wbuf = reinterpret_cast<float*>(smem + S::WBUF);
+
+    const int tid = threadIdx.x;
+    if (tid == 0)
+    {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles && tid == 0)
+    {
+        const int rows0 = min(TILE_M, p.num_nodes - tile * TILE_M);
+        mbar_arrive_expect_tx(&bar[0], rows0 * D * 4);
+        tma_load_1d(hs, p.h_in + (size_t)tile * TILE_M * D, rows0 * D * 4, &bar[0]);
+    }
+
+    for (int it = 0; tile < p.num_tiles; tile += gridDim.x, it++)
+    {
+        const int buf = it & 1;
+        const int n0 = tile * TILE_M;
+        const int rows = min(TILE_M, p.num_nodes - n0);
+        float* hcur = hs + buf * TILE_M * D;
+        const int next = tile + gridDim.x;
+        if (next < p.num_tiles && tid == 0)
+        {
+            const int rows_n = min(TILE_M, p.num_nodes - next * TILE_M);
+            mbar_arrive_expect_tx(&bar[buf ^ 1], rows_n * D * 4);
+            tma_load_1d(hs + (buf ^ 1) * TILE_M * D, p.h_in + (size_t)next * TILE_M * D, rows_n * D * 4, &bar[buf ^ 1]);
+        }
+        stage_tile_csr<NT, false, true>(csr, p.in_ptr, p.src, nullptr, p.eig_w, n0, rows);
+        mbar_wait(&bar[buf], (it >> 1) & 1);
+        __syncthreads();
+
+        for (int item = tid; item < rows * Q; item += NT)
+        {
+            const int v = item / Q, q = item - v * Q;
+            const int eb = csr.ptr[v] - csr.e0, ee = csr.ptr[v + 1] - csr.e0;
+            float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
+            for (int e = eb; e < ee; e++)
+            {
+                int u; float w;
+                if (csr.staged) { u = csr.src[e]; w = csr.w[e]; }
+                else { u = __ldg(p.src + csr.e0 + e); w = __ldg(p.eig_w + csr.e0 + e); }
+                const int ul = u - n0;
+                const float4 hu = ((unsigned)ul < (unsigned)rows) ? ld_f4(hcur + ul * D + 4 * q) : ldg_f4(p.h_in + (size_t)u * D + 4 * q);
+                m0.x += hu.x; m0.y += hu.y; m0.z += hu.z; m0.w += hu.w;
+                m1.x += hu.x * w; m1.y += hu.y * w; m1.z += hu.z * w; m1.w += hu.w * w;
+            }
+            const float deg = (float)__ldg(p.out_deg + n0 + v);
+            float abssum = __ldg(p.abssum + n0 + v);
+            if (abssum == 0.0f) abssum = 0.0001220703125f;           // ap_fixed_epsilon of <16,3> = 2^-13
+            const float wsum = __ldg(p.wsum + n0 + v);
+            const float4 hv = ld_f4(hcur + v * D + 4 * q);
+            float* a = As + v * LDA + 4 * q;
+            st_f4(a, make_float4(m0.x / deg, m0.y / deg, m0.z / deg, m0.w / deg));
+            st_f4(a + D, make_float4(fabsf((m1.x - wsum * hv.x) / abssum), fabsf((m1.y - wsum * hv.y) / abssum),
+                                     fabsf((m1.z - wsum * hv.z) / abssum), fabsf((m1.w - wsum * hv.w) / abssum)));
+        }
+        __syncthreads();
+
+        const int tx = tid % Gemm::CT, ty = tid / Gemm::CT;
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int n = 0; n < 4; n++) acc[i][n] = 0.f;
+        Gemm::run(As, LDA, p.wt, wbuf, acc);
+        if (ty < Gemm::RT && tx * 4 < D)
+        {
+            const float4 bb = ldg_f4(p.b + tx * 4);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+            {
+                const int r = ty + Gemm::RT * i;
+                if (r < rows)
+                {
+                    const float4 hv = ld_f4(hcur + r * D + tx * 4);
+                    stg_f4_stream(p.h_out + (size_t)(n0 + r) * D + tx * 4,
+                                  make_float4(hv.x + relu_f(acc[i][0] + bb.x), hv.y + relu_f(acc[i][1] + bb.y),
+                                              hv.z + relu_f(acc[i][2] + bb.z), hv.w + relu_f(acc[i][3] + bb.w)));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches)
+{
+    const long N = b.total_nodes;
+    if (b.num_graphs == 0) return 0;
+    FG_TRY(b.act[0].reserve(sizeof(float) * (size_t)N * D));
+    FG_TRY(b.act[1].reserve(sizeof(float) * (size_t)N * D));
+    float* h[2] = {b.act[0].as<float>(), b.act[1].as<float>()};
+    int nl = 0;
+    {
+        EmbedOffsets eo;
+        for (int f = 0; f < ND_FEATURE; f++) eo.off[f] = f * 119;      // nine separate [119][100] tables
+        const long items = N * Q;
+        const int blocks = (int)std::min<long>(ceil_div<long>(items, 256), (long)sm_count * 16);
+        embed_table_kernel<D><<<blocks, 256, 0, s>>>(b.node_feature.as<int>(), w.emb.as<float>(), eo, h[0], N);
+        FG_CUDA(cudaGetLastError());
+        nl++;
+    }
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        FG_CUDA(cudaFuncSetAttribute(dgn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DgnSmem::BYTES));
+        attr_set = true;
+    }
+    const int num_tiles = (int)ceil_div<long>(N, TILE_M);
+    const int grid = min(num_tiles, sm_count);
+    for (int l = 0; l < 4; l++)
+    {
+        if (opt.timer) FG_TRY(opt.timer->mark(s));
+        DgnLayerParams p{};
+        p.h_in = h[l & 1]; p.h_out = h[(l + 1) & 1];
+        p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.eig_w = b.edge_w.as<float>(); p.out_deg = b.out_deg.as<int>();
+        p.abssum = b.node_w0.as<float>(); p.wsum = b.node_w1.as<float>();
+        p.wt = w.wt.as<float>() + (size_t)l * KA * DP; p.b = w.b.as<float>() + (size_t)l * DP;
+        p.num_nodes = (int)N; p.num_tiles = num_tiles;
+        dgn_layer_kernel<<<grid, NT, DgnSmem::BYTES, s>>>(p);
+        FG_CUDA(cudaGetLastError());
+        nl++;
+    }
+    if (opt.timer) FG_TRY(opt.timer->mark(s));
+    HeadParams hp{};
+    hp.x = h[0]; hp.dim = D; hp.node_off = b.node_off.as<int>(); hp.nn = b.nums_of_nodes.as<int>(); hp.num_graphs = b.num_graphs;
+    hp.w[0] = w.m0w.as<float>(); hp.b[0] = w.m0b.as<float>();
+    hp.w[1] = w.m1w.as<float>(); hp.b[1] = w.m1b.as<float>();
+    hp.w[2] = w.m2w.as<float>(); hp.b[2] = w.m2b.as<float>();
+    hp.dims[0] = D; hp.dims[1] = 50; hp.dims[2] = 25; hp.dims[3] = 1; hp.num_layers = 3;
+    hp.out = b.out.as<float>();
+    FG_TRY(launch_pool_head(hp, s));
+    nl++;
+    if (launches) *launches += nl;
+    return 0;
+}
+
+}  // namespace fg

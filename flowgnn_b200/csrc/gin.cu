@@ -1,0 +1,251 @@
+// GIN / GIN-VN forward on B200.
+//
+// Replaces the reference's per-graph pipeline GIN/src/GIN_compute.cc:44-98:
+//   stage 0      load_input_node_embeddings        (load_inputs.cc:174-220)      -> embed_table_kernel
+//   stages 1..5  message_passing_pe scatter        (message_passing.cc:77-150)  \_ gin_layer_kernel
+//                node_embedding_multi_pe MLP       (node_embedding.cc:23-201)   /  (one launch per layer)
+//   stage 5      finalize: mean pool + Linear      (finalize.cc:14-115)          -> pool_head_kernel
+// GIN-VN is the same kernel on host-augmented graphs.
+//
+// Math per layer l:  m_v = sum_{(u,v)} relu(h_u + EE_l[attr_uv]);
+// z = W1_l (m_v + h_v) + b1_l;  h_v <- W2_l relu(z) + b2_l  (+ relu unless l == 4).
+// eps is never loaded by the reference kernel, so (1 + eps) == 1.
+#include "internal.cuh"
+#include "layers.cuh"
+
+#include <algorithm>
+
+namespace fg {
+
+namespace {
+
+constexpr int D = 100;               // EMB_DIM
+constexpr int H = 200;               // MLP_1_OUT
+constexpr int HP = 208;              // H padded to the 8-wide thread tile
+constexpr int DP = 104;              // D padded to the 4-wide thread tile
+constexpr int Q = D / 4;             // float4 chunks per row
+constexpr int NT = 224;              // threads per CTA: 26 column-threads x 8 row-threads (+16 copy helpers)
+constexpr int LDZ = 204;             // leading dimension of the hidden tile (bank spread, multiple of 4)
+
+using Gemm1 = TileGemm<D, HP, 8, NT>;
+using Gemm2 = TileGemm<H, DP, 4, NT>;
+
+struct GinLayerParams {
+    const float* h_in; float* h_out;
+    const int* in_ptr; const int* src; const uint8_t* code;
+    const float* ee_comb;            // [60][100] this layer
+    const float* w1t; const float* b1; const float* w2t; const float* b2;
+    int num_nodes; int num_tiles; int relu_out;
+};
+
+template <bool MP_ONLY>
+struct GinSmem {
+    // byte offsets into dynamic shared memory (all multiples of 16)
+    static constexpr int BAR = 0;                                   // 2 mbarriers
+    static constexpr int PTR = 16;                                  // (TILE_M + 1) ints, padded
+    static constexpr int SRC = PTR + 4 * 80;
+    static constexpr int CODE = SRC + 4 * EDGE_CAP;
+    static constexpr int TAB = CODE + EDGE_CAP;
+    static constexpr int HS = TAB + 4 * ED_COMBOS * D;              // 2 x [TILE_M][D]
+    static constexpr int A = HS + 2 * 4 * TILE_M * D;
+    static constexpr int Z = A + 4 * TILE_M * D;
+    static constexpr int WBUF = Z + 4 * TILE_M * LDZ;
+    static constexpr int END_FULL = WBUF + 4 * (Gemm1::WBUF_FLOATS > Gemm2::WBUF_FLOATS ? Gemm1::WBUF_FLOATS : Gemm2::WBUF_FLOATS);
+    static constexpr int BYTES = MP_ONLY ? A : END_FULL;
+};
+
+template <bool MP_ONLY>
+__global__ void __launch_bounds__(NT, 1) gin_layer_kernel(GinLayerParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    using S = GinSmem<MP_ONLY>;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
+    TileCsr csr;
+    csr.ptr = reinterpret_cast<int*>(smem + S::PTR);
+    csr.src = reinterpret_cast<int*>(smem + S::SRC);
+    csr.code = reinterpret_cast<uint8_t*>(smem + S::CODE);
+    csr.w = nullptr;
+    float* tab = reinterpret_cast<float*>(smem + S::TAB);
+    float* hs = reinterpret_cast<float*>(smem + S::HS);
+    float* As = reinterpret_cast<float*>(smem + S::A);
+    float* Zs = reinterpret_cast<float*>(smem + S::Z);
+    float* wbuf = reinterpret_cast<float*>(smem + S::WBUF);
+
+    const int tid = threadIdx.x;
+    if (tid == 0)
+    {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < ED_COMBOS * Q; i += NT) st_f4(tab + 4 * i, ldg_f4(p.ee_comb + 4 * i));
+    __syncthreads();
+
+    int tile = blockIdx.x;
+    if (tile < p.num_tiles && tid == 0)
+    {
+        const int rows0 = min(TILE_M, p.num_nodes - tile * TILE_M);
+        mbar_arrive_expect_tx(&bar[0], rows0 * D * 4);
+        tma_load_1d(hs, p.h_in + (size_t)tile * TILE_M * D, rows0 * D * 4, &bar[0]);
+    }
+
+    for (int it = 0; tile < p.num_tiles; tile += gridDim.x, it++)
+    {
+        const int buf = it & 1;
+        const int n0 = tile * TILE_M;
+        const int rows = min(TILE_M, p.num_nodes - n0);
+        float* hcur = hs + buf * TILE_M * D;
+
+        // stream the next tile's rows in while this one computes
+        const int next = tile + gridDim.x;
+        if (next < p.num_tiles && tid == 0)
+        {
+            const int rows_n = min(TILE_M, p.num_nodes - next * TILE_M);
+            mbar_arrive_expect_tx(&bar[buf ^ 1], rows_n * D * 4);
+            tma_load_1d(hs + (buf ^ 1) * TILE_M * D, p.h_in + (size_t)next * TILE_M * D, rows_n * D * 4, &bar[buf ^ 1]);
+        }
+
+        stage_tile_csr<NT, true, false>(csr, p.in_ptr, p.src, p.code, nullptr, n0, rows);
+        mbar_wait(&bar[buf], (it >> 1) & 1);
+        __syncthreads();
+
+        // ---- message passing: gather + edge embedding + relu + segmented sum, CSR order ----
+        for (int item = tid; item < rows * Q; item += NT)
+        {
+            const int v = item / Q, q = item - v * Q;
+            const int eb = csr.ptr[v] - csr.e0, ee = csr.ptr[v + 1] - csr.e0;
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = eb; e < ee; e++)
+            {
+                int u, c;
+                if (csr.staged) { u = csr.src[e]; c = csr.code[e]; }
+                else { u = __ldg(p.src + csr.e0 + e); c = __ldg(p.code + csr.e0 + e); }
+                const int ul = u - n0;
+                const float4 hu = ((unsigned)ul < (unsigned)rows) ? ld_f4(hcur + ul * D + 4 * q) : ldg_f4(p.h_in + (size_t)u * D + 4 * q);
+                const float4 t = ld_f4(tab + c * D + 4 * q);
+                m.x += relu_f(t.x + hu.x); m.y += relu_f(t.y + hu.y); m.z += relu_f(t.z + hu.z); m.w += relu_f(t.w + hu.w);
+            }
+            const float4 hv = ld_f4(hcur + v * D + 4 * q);
+            const float4 a = make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w);
+            if (MP_ONLY) stg_f4_stream(p.h_out + (size_t)(n0 + v) * D + 4 * q, a);
+            else st_f4(As + v * D + 4 * q, a);
+        }
+        __syncthreads();
+
+        if (!MP_ONLY)
+        {
+            const int tx = tid % 26, ty = tid / 26;
+            // ---- z = relu(W1 a + b1) ----
+            {
+                float acc[8][8];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int n = 0; n < 8; n++) acc[i][n] = 0.f;
+                Gemm1::run(As, D, p.w1t, wbuf, acc);
+                if (ty < Gemm1::RT && tx * 8 < H)
+                {
+                    const float4 ba = ldg_f4(p.b1 + tx * 8), bb = ldg_f4(p.b1 + tx * 8 + 4);
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                    {
+                        float* z = Zs + (ty + Gemm1::RT * i) * LDZ + tx * 8;
+                        st_f4(z, make_float4(relu_f(acc[i][0] + ba.x), relu_f(acc[i][1] + ba.y), relu_f(acc[i][2] + ba.z), relu_f(acc[i][3] + ba.w)));
+                        st_f4(z + 4, make_float4(relu_f(acc[i][4] + bb.x), relu_f(acc[i][5] + bb.y), relu_f(acc[i][6] + bb.z), relu_f(acc[i][7] + bb.w)));
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- h' = W2 z + b2 (relu unless last layer) ----
+            {
+                float acc[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int n = 0; n < 4; n++) acc[i][n] = 0.f;
+                Gemm2::run(Zs, LDZ, p.w2t, wbuf, acc);
+                if (ty < Gemm2::RT && tx * 4 < D)
+                {
+                    const float4 bb = ldg_f4(p.b2 + tx * 4);
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                    {
+                        const int r = ty + Gemm2::RT * i;
+                        if (r < rows)
+                        {
+                            float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+                            if (p.relu_out) o = make_float4(relu_f(o.x), relu_f(o.y), relu_f(o.z), relu_f(o.w));
+                            stg_f4_stream(p.h_out + (size_t)(n0 + r) * D + tx * 4, o);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches)
+{
+    const long N = b.total_nodes;
+    if (b.num_graphs == 0) return 0;
+    if (!b.has_attr) { set_last_error("GIN needs edge_attr"); return FG_ERR_INVALID; }
+    FG_TRY(b.act[0].reserve(sizeof(float) * (size_t)N * D));
+    FG_TRY(b.act[1].reserve(sizeof(float) * (size_t)N * D));
+    float* h[2] = {b.act[0].as<float>(), b.act[1].as<float>()};
+    int nl = 0;
+
+    {
+        const long items = N * Q;
+        const int blocks = (int)std::min<long>(ceil_div<long>(items, 256), (long)sm_count * 16);
+        embed_table_kernel<D><<<blocks, 256, 0, s>>>(b.node_feature.as<int>(), w.ne_table.as<float>(), concat_table_offsets(), h[0], N);
+        FG_CUDA(cudaGetLastError());
+        nl++;
+    }
+
+    const int num_tiles = (int)ceil_div<long>(N, TILE_M);
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        FG_CUDA(cudaFuncSetAttribute(gin_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GinSmem<false>::BYTES));
+        FG_CUDA(cudaFuncSetAttribute(gin_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GinSmem<true>::BYTES));
+        attr_set = true;
+    }
+    for (int l = 0; l < 5; l++)
+    {
+        if (opt.timer) FG_TRY(opt.timer->mark(s));
+        GinLayerParams p;
+        p.h_in = h[l & 1]; p.h_out = h[(l + 1) & 1];
+        p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
+        p.ee_comb = w.ee_comb.as<float>() + (size_t)l * ED_COMBOS * D;
+        p.w1t = w.w1t.as<float>() + (size_t)l * D * HP; p.b1 = w.b1.as<float>() + (size_t)l * HP;
+        p.w2t = w.w2t.as<float>() + (size_t)l * H * DP; p.b2 = w.b2.as<float>() + (size_t)l * DP;
+        p.num_nodes = (int)N; p.num_tiles = num_tiles; p.relu_out = (l != 4);
+        if (opt.mp_only)
+        {
+            const int grid = min(num_tiles, sm_count * 2);
+            gin_layer_kernel<true><<<grid, NT, GinSmem<true>::BYTES, s>>>(p);
+        }
+        else
+        {
+            const int grid = min(num_tiles, sm_count);
+            gin_layer_kernel<false><<<grid, NT, GinSmem<false>::BYTES, s>>>(p);
+        }
+        FG_CUDA(cudaGetLastError());
+        nl++;
+    }
+
+    if (opt.timer) FG_TRY(opt.timer->mark(s));
+    HeadParams hp{};
+    hp.x = h[1]; hp.dim = D; hp.node_off = b.node_off.as<int>(); hp.nn = b.nums_of_nodes.as<int>(); hp.num_graphs = b.num_graphs;
+    hp.w[0] = w.pred_w.as<float>(); hp.b[0] = w.pred_b.as<float>(); hp.dims[0] = D; hp.dims[1] = 1; hp.num_layers = 1;
+    hp.out = b.out.as<float>();
+    FG_TRY(launch_pool_head(hp, s));
+    nl++;
+    if (launches) *launches += nl;
+    return 0;
+}
+
+}  // namespace fg

@@ -1,0 +1,122 @@
+// Internal structures shared by the C-ABI (api.cu), the graph preprocessing (prep.cu) and the
+// per-model layer kernels.  Nothing here is part of the public interface (include/flowgnn_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace fg {
+
+enum ModelId { MODEL_GIN = 0, MODEL_GCN = 1, MODEL_GAT = 2, MODEL_PNA = 3, MODEL_DGN = 4, NUM_MODELS = 5 };
+
+// One growable device allocation.
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);      // grows (never shrinks); contents are NOT preserved
+    void release();
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+// The batch as the reference's host hands it to the kernel (GIN/src/host.cc:141-182), resident in HBM,
+// plus everything `load_graph` derives from it (GIN/src/load_inputs.cc:87-172 and per-model variants).
+struct DeviceBatch {
+    int num_graphs = 0;
+    long total_nodes = 0;
+    long total_edges = 0;
+    bool has_attr = false;
+    bool has_eigen = false;
+
+    // inputs (caller layout)
+    DevBuf nums_of_nodes, nums_of_edges;   // int32 [G]
+    DevBuf node_feature;                   // int32 [N][9]
+    DevBuf edge_list;                      // int32 [E][2], graph-local ids
+    DevBuf edge_attr;                      // int32 [E][3]
+    DevBuf node_eigen;                     // float [N][4]
+
+    // load_graph outputs: CSR by DESTINATION over global node ids, in-edges ordered (source, list order)
+    DevBuf node_off, edge_off;             // int32 [G+1] exclusive prefix sums
+    DevBuf in_ptr;                         // int32 [N+1]
+    DevBuf src;                            // int32 [E] global source node id
+    DevBuf code;                           // uint8 [E] bond-attribute triple a0*12 + a1*2 + a2
+    DevBuf edge_w;                         // float [E]  GCN: norm = dis[u]*dis[v]; DGN: eig_w = phi_u - phi_v
+    DevBuf out_deg;                        // int32 [N]
+    DevBuf node_w0, node_w1;               // float [N]  DGN: sum|eig_w|, sum eig_w over in-edges
+    DevBuf sort_tmp;                       // int32 [E] scratch for the two-pass stable sort
+    DevBuf status;                         // int32 [1] device-side limit violations
+
+    // activations
+    DevBuf act[4];                         // float [N][<=100] ping/pong (+2 extra for GAT)
+    DevBuf score[4];                       // float [N][4] GAT source/target scores ping/pong
+    DevBuf out;                            // float [G]
+
+    void release();
+};
+
+enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2 };
+
+// graph preprocessing: offsets scan + per-graph CSR build (prep.cu)
+int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream);
+
+// ---- per-model device weights, repacked once by load_weights (api.cu) ----------------------------
+struct GinWeights {
+    DevBuf ne_table;     // [173][100]
+    DevBuf ee_comb;      // [5][60][100]  ((0+T[a0])+T[5+a1])+T[11+a2]
+    DevBuf w1t, b1;      // [5][100][208], [5][208]   k-major, N padded with zeros
+    DevBuf w2t, b2;      // [5][200][104], [5][104]
+    DevBuf pred_w, pred_b;
+};
+struct GcnWeights {
+    DevBuf ne_table, ee_comb;   // as GIN
+    DevBuf wt, b;               // [5][100][104], [5][104]
+    DevBuf root;                // [5][100]
+    DevBuf bn_mean, bn_sqrt_var, bn_weight, bn_bias;   // [5][100]; sqrt_var = sqrt(var + 2^-10)
+    DevBuf pred_w, pred_b;
+};
+struct PnaWeights {
+    DevBuf ne_table;            // [173][80]
+    DevBuf wcat;                // [4][320][240]  k = aggr*80+in, n = scaler*80+out
+    DevBuf w_ref;               // [4][80][3][4][80] reference layout (exact path for out-degree-0 nodes)
+    DevBuf b;                   // [4][80]
+    DevBuf m1w, m1b, m2w, m2b, m3w, m3b;
+    float avg_deg = 0.f;
+};
+struct DgnWeights {
+    DevBuf emb;                 // [9][119][100]
+    DevBuf wt;                  // [4][200][104]  k = part*100+in
+    DevBuf w_ref;               // [4][100][200] reference layout (exact path for out-degree-0 nodes)
+    DevBuf b;                   // [4][104]
+    DevBuf m0w, m0b, m1w, m1b, m2w, m2b;
+};
+struct GatWeights {
+    DevBuf proj0;               // [9][64]  layer-0 projection of the raw features: [f][d*4+h]
+    DevBuf projt;               // [5][64][64]  k = di*4+hi, n = do*4+ho  (layer 0 unused)
+    DevBuf skipt;               // [5][64][64]
+    DevBuf a_src, a_tgt;        // [5][64]  index d*4+h
+    DevBuf pred_w, pred_b;      // [16], [1]
+};
+
+// Optional per-layer device timing: one event before each layer launch and one after the last.
+struct LayerTimer {
+    static constexpr int MAX_MARKS = 16;
+    cudaEvent_t ev[MAX_MARKS] = {};
+    int created = 0;
+    int marks = 0;
+    int mark(cudaStream_t s);
+};
+
+struct RunOptions {
+    int mp_only = 0;                 // GIN: node transform = identity (roofline variant)
+    int gat_node_offset_bug = 1;
+    LayerTimer* timer = nullptr;     // set while option "time_layers" is on
+};
+
+int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
+int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
+int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
+int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
+int gat_forward(DeviceBatch& b, const GatWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
+
+}  // namespace fg

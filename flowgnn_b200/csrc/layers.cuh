@@ -1,0 +1,190 @@
+// Building blocks shared by the per-model fused layer kernels.
+//
+// Every layer kernel is a persistent CTA that walks tiles of TILE_M consecutive nodes of the packed
+// batch (graph boundaries do not matter: the gather follows the CSR, the node transform is
+// row-wise).  Per tile:
+//   1. the tile's own feature rows are a contiguous [rows x D] block of HBM -> one bulk TMA copy
+//      (cp.async.bulk + mbarrier) into shared memory, double-buffered so tile t+1 streams in while
+//      tile t computes;
+//   2. the tile's slice of the destination-CSR (row pointers, source ids, edge codes/weights) is
+//      staged with coalesced loads;
+//   3. message passing gathers source rows from shared memory (same tile) or L2/HBM (halo) and
+//      reduces them per destination in CSR order -- deterministic, no atomics;
+//   4. the node transform is an fp32 register-tiled GEMM against k-major weights streamed from L2
+//      through a cp.async double buffer.
+#pragma once
+
+#include "common.cuh"
+
+namespace fg {
+
+constexpr int TILE_M = 64;           // nodes per tile
+constexpr int EDGE_CAP = 3072;       // in-edges of one tile staged in shared memory (else read from global)
+
+// ---- CSR slice of one tile ------------------------------------------------------------------------
+struct TileCsr {
+    int* ptr;          // [TILE_M + 1] absolute edge positions
+    int* src;          // [EDGE_CAP]
+    uint8_t* code;     // [EDGE_CAP]   (GIN/GCN)
+    float* w;          // [EDGE_CAP]   (GCN/DGN)
+    int e0;            // first edge of the tile
+    bool staged;       // slice fits in shared memory
+};
+
+template <int NT, bool HAS_CODE, bool HAS_W>
+__device__ __forceinline__ void stage_tile_csr(TileCsr& t, const int* __restrict__ in_ptr, const int* __restrict__ src,
+                                               const uint8_t* __restrict__ code, const float* __restrict__ w, int n0, int rows)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i <= rows; i += NT) t.ptr[i] = __ldg(in_ptr + n0 + i);
+    __syncthreads();
+    t.e0 = t.ptr[0];
+    const int ne = t.ptr[rows] - t.e0;
+    t.staged = ne <= EDGE_CAP;
+    if (t.staged)
+    {
+        for (int i = tid; i < ne; i += NT)
+        {
+            t.src[i] = __ldg(src + t.e0 + i);
+            if (HAS_CODE) t.code[i] = __ldg(code + t.e0 + i);
+            if (HAS_W) t.w[i] = __ldg(w + t.e0 + i);
+        }
+    }
+}
+
+// ---- register-tiled fp32 GEMM: C[TILE_M x NP] = A[TILE_M x K] * Wt[K x NP] -----------------------------
+// A: shared memory, row-major, leading dimension lda (multiple of 4).
+// Wt: global (L2-resident), k-major, row length NP (zero-padded N), streamed in chunks of GEMM_KC rows
+//     through wbuf[2][GEMM_KC * NP] (GEMM_KC = k-rows per cp.async stage).
+// Thread (tx, ty) = (tid % CT, tid / CT) with CT = NP / TN owns rows ty + RT*i (i < 8, RT = TILE_M/8)
+// and columns tx*TN .. tx*TN+TN-1; threads with ty >= RT only help with the copies.
+template <int K, int NP, int TN, int NT, int GEMM_KC = 20>
+struct TileGemm {
+    static constexpr int CT = NP / TN;
+    static constexpr int RT = TILE_M / 8;
+    static constexpr int NCHUNK = K / GEMM_KC;
+    static_assert(NP % TN == 0 && TN % 4 == 0, "column tiling");
+    static_assert(K % GEMM_KC == 0 && GEMM_KC % 4 == 0, "k tiling");
+    static_assert(CT * RT <= NT, "not enough threads for the output tile");
+    static constexpr int WBUF_FLOATS = 2 * GEMM_KC * NP;
+
+    __device__ static __forceinline__ void load_chunk(float* dst, const float* __restrict__ wt, int chunk)
+    {
+        const float4* g = reinterpret_cast<const float4*>(wt + (size_t)chunk * GEMM_KC * NP);
+        float4* s = reinterpret_cast<float4*>(dst);
+        constexpr int N4 = GEMM_KC * NP / 4;
+        for (int i = threadIdx.x; i < N4; i += NT) cp_async16(s + i, g + i);
+    }
+
+    // acc[i][n] += sum_k A[row_i][k] * Wt[k][col_n]; caller zero-initialises acc.  Ends with a
+    // __syncthreads(), so A and wbuf may be reused immediately afterwards.
+    __device__ static __forceinline__ void run(const float* __restrict__ As, int lda, const float* __restrict__ wt, float* wbuf,
+                                               float (&acc)[8][TN])
+    {
+        const int tid = threadIdx.x;
+        const int tx = tid % CT, ty = tid / CT;
+        const bool active = ty < RT;
+        load_chunk(wbuf, wt, 0);
+        cp_async_commit();
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; c++)
+        {
+            if (c + 1 < NCHUNK)
+            {
+                load_chunk(wbuf + ((c + 1) & 1) * GEMM_KC * NP, wt, c + 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+            }
+            else
+                cp_async_wait<0>();
+            __syncthreads();
+            if (active)
+            {
+                const float* wb = wbuf + (c & 1) * GEMM_KC * NP + tx * TN;
+                const float* ab = As + ty * lda + c * GEMM_KC;
+#pragma unroll
+                for (int kk = 0; kk < GEMM_KC; kk += 4)
+                {
+                    float4 a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) a[i] = ld_f4(ab + i * RT * lda + kk);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        float w[TN];
+#pragma unroll
+                        for (int n = 0; n < TN; n += 4)
+                        {
+                            const float4 w4 = ld_f4(wb + (kk + j) * NP + n);
+                            w[n] = w4.x; w[n + 1] = w4.y; w[n + 2] = w4.z; w[n + 3] = w4.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                        {
+                            const float av = (j == 0) ? a[i].x : (j == 1) ? a[i].y : (j == 2) ? a[i].z : a[i].w;
+#pragma unroll
+                            for (int n = 0; n < TN; n++) acc[i][n] = fmaf(av, w[n], acc[i][n]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+};
+
+// ---- load_input_node_embeddings: h0_v = sum_f Table[off_f + x_vf], f ascending from 0 ----------------
+// (GIN/src/load_inputs.cc:174-220; GCN :168-215; PNA :133-179; DGN :114-168 with nine separate
+// [119][D] tables, i.e. offsets f*119).
+struct EmbedOffsets { int off[ND_FEATURE]; };
+
+template <int DIM>
+__device__ __forceinline__ float4 embed_chunk(const int* __restrict__ feat_row, const float* __restrict__ table, const EmbedOffsets& o, int q)
+{
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < ND_FEATURE; f++)
+    {
+        const int row = o.off[f] + __ldg(feat_row + f);
+        const float4 t = ldg_f4(table + (size_t)row * DIM + 4 * q);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    return s;
+}
+
+template <int DIM>
+__global__ void embed_table_kernel(const int* __restrict__ feat, const float* __restrict__ table, EmbedOffsets o, float* __restrict__ h,
+                                   long num_nodes)
+{
+    constexpr int Q = DIM / 4;
+    const long total = num_nodes * Q;
+    for (long item = blockIdx.x * (long)blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x)
+    {
+        const long v = item / Q;
+        const int q = (int)(item - v * Q);
+        stg_f4_stream(h + v * DIM + 4 * q, embed_chunk<DIM>(feat + v * ND_FEATURE, table, o, q));
+    }
+}
+
+__host__ __device__ inline EmbedOffsets concat_table_offsets()
+{
+    EmbedOffsets o;
+    const int v[ND_FEATURE] = {0, 119, 123, 135, 147, 157, 163, 169, 171};
+    for (int i = 0; i < ND_FEATURE; i++) o.off[i] = v[i];
+    return o;
+}
+
+// ---- mean pool + prediction head (finalize) ---------------------------------------------------------
+// One warp per graph: mean over the graph's rows of x[N][D] (GIN/src/finalize.cc:36-115), then up to
+// three small dense layers (*/src/linear.cc).  Head shapes: GIN/GCN D->1; GAT 16->1;
+// PNA 80->40->20->1; DGN 100->50->25->1 (relu between, none on the last).
+struct HeadParams {
+    const float* x; int dim;
+    const int* node_off; const int* nn; int num_graphs;
+    const float* w[3]; const float* b[3]; int dims[4]; int num_layers;
+    float* out;
+};
+
+int launch_pool_head(const HeadParams& p, cudaStream_t stream);
+
+}  // namespace fg

@@ -1,0 +1,277 @@
+// On-device `load_graph`: COO edge list -> per-batch CSR by destination.
+//
+// Reference: GIN/src/load_inputs.cc:87-172 (and GCN :77-166, PNA :48-131, DGN :28-112, GAT :87-166).
+// The FPGA builds, per graph, four banked neighbour tables ordered by source node; a destination's
+// messages therefore arrive in (source ascending, edge-list order).  Here the whole batch gets ONE
+// CSR keyed by GLOBAL destination node id whose rows keep exactly that order, so the gather in the
+// layer kernels adds a node's in-edges in the reference's order and is deterministic (no float
+// atomics anywhere).  Derived per-edge / per-node tables follow the per-model variants:
+//   GCN  norm = dis[u]*dis[v], dis = 1/sqrt(outdeg+1) for nodes that appear as a source, else 0
+//        (GCN/src/load_inputs.cc:100-122,163)
+//   DGN  eig_w = phi_u - phi_v with phi = eig[:,1]; per destination sum|eig_w| and sum eig_w
+//        (DGN/src/load_inputs.cc:91-111)
+//   all  out-degree per node (degree_table)
+#include "internal.cuh"
+
+namespace fg {
+
+namespace {
+
+constexpr int SCAN_THREADS = 1024;
+
+// Exclusive prefix sums of nums_of_nodes / nums_of_edges (the reference carries them as running
+// offsets in its serial graph loop, GIN/src/GIN_compute.cc:44,96-97).
+__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const int* __restrict__ nn, const int* __restrict__ ne,
+                                                                    int* __restrict__ node_off, int* __restrict__ edge_off,
+                                                                    int num_graphs)
+{
+    __shared__ int2 warp_tot[SCAN_THREADS / 32];
+    __shared__ int2 carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = make_int2(0, 0);
+    __syncthreads();
+    for (int base = 0; base < num_graphs; base += SCAN_THREADS)
+    {
+        const int i = base + tid;
+        int2 x = make_int2(0, 0);
+        if (i < num_graphs) x = make_int2(nn[i], ne[i]);
+        int2 incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            int a = __shfl_up_sync(0xffffffffu, incl.x, d);
+            int b = __shfl_up_sync(0xffffffffu, incl.y, d);
+            if (lane >= d) { incl.x += a; incl.y += b; }
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0)
+        {
+            int2 t = warp_tot[lane];
+            int2 ti = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                int a = __shfl_up_sync(0xffffffffu, ti.x, d);
+                int b = __shfl_up_sync(0xffffffffu, ti.y, d);
+                if (lane >= d) { ti.x += a; ti.y += b; }
+            }
+            warp_tot[lane] = make_int2(ti.x - t.x, ti.y - t.y);   // exclusive over warps
+        }
+        __syncthreads();
+        const int2 c = carry_s;
+        const int2 w = warp_tot[wid];
+        if (i < num_graphs)
+        {
+            node_off[i] = c.x + w.x + incl.x - x.x;
+            edge_off[i] = c.y + w.y + incl.y - x.y;
+        }
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) carry_s = make_int2(c.x + w.x + incl.x, c.y + w.y + incl.y);
+        __syncthreads();
+    }
+    if (tid == 0)
+    {
+        node_off[num_graphs] = carry_s.x;
+        edge_off[num_graphs] = carry_s.y;
+    }
+}
+
+constexpr int CSR_WARPS = 4;
+constexpr int CSR_NCAP = 1024;     // nodes per graph supported by the warp-local tables (reference cap: 500)
+
+struct CsrParams {
+    const int* nn; const int* ne; const int* node_off; const int* edge_off;
+    const int* edge_list; const int* edge_attr; const float* node_eigen;
+    int* in_ptr; int* src; uint8_t* code; float* edge_w; int* out_deg; float* node_w0; float* node_w1;
+    int* sort_tmp; int* status;
+    int num_graphs; int flags; int has_attr;
+};
+
+// One warp per graph.  Two stable counting-sort passes (by source, then by destination) give the
+// (destination, source, list-order) ordering; ranks inside a 32-edge chunk come from
+// __match_any_sync, chunks are consumed in order, so the sort is stable and deterministic.
+__global__ void __launch_bounds__(CSR_WARPS * 32) build_csr_kernel(CsrParams p)
+{
+    __shared__ int s_deg[CSR_WARPS][CSR_NCAP];     // out-degree
+    __shared__ int s_pu[CSR_WARPS][CSR_NCAP];      // running slot by source
+    __shared__ int s_pv[CSR_WARPS][CSR_NCAP];      // running slot by destination
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * CSR_WARPS + wid;
+    if (g >= p.num_graphs) return;
+    const int n = p.nn[g], e = p.ne[g];
+    const int nb = p.node_off[g], eb = p.edge_off[g];
+    if (g == p.num_graphs - 1 && lane == 0) p.in_ptr[nb + n] = eb + e;
+    if (n > CSR_NCAP || n < 0 || e < 0)
+    {
+        if (lane == 0) atomicOr(p.status, 1);
+        // keep downstream kernels in bounds: empty rows
+        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; }
+        return;
+    }
+    int* deg = s_deg[wid];
+    int* pu = s_pu[wid];
+    int* pv = s_pv[wid];
+    const int2* edges = reinterpret_cast<const int2*>(p.edge_list) + eb;
+    const unsigned full = 0xffffffffu;
+
+    for (int i = lane; i < n; i += 32) { pu[i] = 0; pv[i] = 0; }
+    __syncwarp();
+    bool bad = false;
+    for (int i = lane; i < e; i += 32)
+    {
+        const int2 uv = __ldg(edges + i);
+        if ((unsigned)uv.x >= (unsigned)n || (unsigned)uv.y >= (unsigned)n) { bad = true; continue; }
+        atomicAdd(&pu[uv.x], 1);
+        atomicAdd(&pv[uv.y], 1);
+    }
+    if (__any_sync(full, bad))
+    {
+        if (lane == 0) atomicOr(p.status, 2);
+        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; }
+        return;
+    }
+    __syncwarp();
+    // exclusive scans of both histograms, 32 nodes at a time
+    int carry_u = 0, carry_v = 0;
+    for (int base = 0; base < n; base += 32)
+    {
+        const int i = base + lane;
+        const int cu = (i < n) ? pu[i] : 0, cv = (i < n) ? pv[i] : 0;
+        int su = cu, sv = cv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            int a = __shfl_up_sync(full, su, d), b = __shfl_up_sync(full, sv, d);
+            if (lane >= d) { su += a; sv += b; }
+        }
+        if (i < n)
+        {
+            deg[i] = cu;
+            pu[i] = carry_u + su - cu;
+            pv[i] = carry_v + sv - cv;
+            p.out_deg[nb + i] = cu;
+            p.in_ptr[nb + i] = eb + carry_v + sv - cv;
+        }
+        carry_u += __shfl_sync(full, su, 31);
+        carry_v += __shfl_sync(full, sv, 31);
+    }
+    __syncwarp();
+
+    int* tmp = p.sort_tmp + eb;
+    // pass 1: stable by source
+    for (int base = 0; base < e; base += 32)
+    {
+        const int i = base + lane;
+        const bool act = i < e;
+        const unsigned mask = __ballot_sync(full, act);
+        if (act)
+        {
+            const int u = __ldg(edges + i).x;
+            const unsigned peers = __match_any_sync(mask, u);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            tmp[pu[u] + rank] = i;
+            __syncwarp(mask);
+            if (rank == __popc(peers) - 1) pu[u] += rank + 1;
+        }
+        __syncwarp();
+    }
+    // pass 2: stable by destination, emit the CSR payload
+    for (int base = 0; base < e; base += 32)
+    {
+        const int k = base + lane;
+        const bool act = k < e;
+        const unsigned mask = __ballot_sync(full, act);
+        if (act)
+        {
+            const int i = tmp[k];
+            const int2 uv = __ldg(edges + i);
+            const unsigned peers = __match_any_sync(mask, uv.y);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int pos = eb + pv[uv.y] + rank;
+            p.src[pos] = nb + uv.x;
+            if (p.has_attr)
+            {
+                const int* a = p.edge_attr + 3 * (size_t)(eb + i);
+                p.code[pos] = (uint8_t)(__ldg(a) * 12 + __ldg(a + 1) * 2 + __ldg(a + 2));
+            }
+            if (p.flags & PREP_GCN_NORM)
+            {
+                // recip(sqrt(deg+1)); a node that never appears as a source keeps dis = 0
+                const float du = (deg[uv.x] > 0) ? __frcp_rn(__fsqrt_rn((float)(deg[uv.x] + 1))) : 0.0f;
+                const float dv = (deg[uv.y] > 0) ? __frcp_rn(__fsqrt_rn((float)(deg[uv.y] + 1))) : 0.0f;
+                p.edge_w[pos] = __fmul_rn(du, dv);
+            }
+            else if (p.flags & PREP_DGN_EIG)
+            {
+                const float* eig = p.node_eigen + 4 * (size_t)nb;
+                p.edge_w[pos] = __fsub_rn(__ldg(eig + 4 * uv.x + 1), __ldg(eig + 4 * uv.y + 1));
+            }
+            __syncwarp(mask);
+            if (rank == __popc(peers) - 1) pv[uv.y] += rank + 1;
+        }
+        __syncwarp();
+    }
+    if (p.flags & PREP_DGN_EIG)
+    {
+        // per-destination sums over the (now sorted) in-edges; pv[v] ends at the end of row v
+        __threadfence_block();
+        __syncwarp();
+        for (int v = lane; v < n; v += 32)
+        {
+            const int end = eb + pv[v];
+            const int beg = (v == 0) ? eb : eb + pv[v - 1];
+            float sa = 0.0f, sw = 0.0f;
+            for (int k = beg; k < end; k++)
+            {
+                const float w = p.edge_w[k];
+                sa = __fadd_rn(sa, fabsf(w));
+                sw = __fadd_rn(sw, w);
+            }
+            p.node_w0[nb + v] = sa;
+            p.node_w1[nb + v] = sw;
+        }
+    }
+}
+
+}  // namespace
+
+int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
+{
+    const int G = b.num_graphs;
+    if (G <= 0) return 0;
+    FG_TRY(b.node_off.reserve(sizeof(int) * (size_t)(G + 1)));
+    FG_TRY(b.edge_off.reserve(sizeof(int) * (size_t)(G + 1)));
+    FG_TRY(b.in_ptr.reserve(sizeof(int) * (size_t)(b.total_nodes + 1)));
+    FG_TRY(b.src.reserve(sizeof(int) * (size_t)(b.total_edges + 1)));
+    FG_TRY(b.code.reserve((size_t)(b.total_edges + 16)));
+    FG_TRY(b.out_deg.reserve(sizeof(int) * (size_t)(b.total_nodes + 1)));
+    FG_TRY(b.sort_tmp.reserve(sizeof(int) * (size_t)(b.total_edges + 1)));
+    FG_TRY(b.status.reserve(sizeof(int)));
+    if (flags & (PREP_GCN_NORM | PREP_DGN_EIG)) FG_TRY(b.edge_w.reserve(sizeof(float) * (size_t)(b.total_edges + 1)));
+    if (flags & PREP_DGN_EIG)
+    {
+        FG_TRY(b.node_w0.reserve(sizeof(float) * (size_t)(b.total_nodes + 1)));
+        FG_TRY(b.node_w1.reserve(sizeof(float) * (size_t)(b.total_nodes + 1)));
+    }
+    FG_CUDA(cudaMemsetAsync(b.status.ptr, 0, sizeof(int), stream));
+
+    scan_offsets_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.nums_of_edges.as<int>(), b.node_off.as<int>(),
+                                                         b.edge_off.as<int>(), G);
+    FG_CUDA(cudaGetLastError());
+
+    CsrParams p;
+    p.nn = b.nums_of_nodes.as<int>(); p.ne = b.nums_of_edges.as<int>();
+    p.node_off = b.node_off.as<int>(); p.edge_off = b.edge_off.as<int>();
+    p.edge_list = b.edge_list.as<int>(); p.edge_attr = b.edge_attr.as<int>(); p.node_eigen = b.node_eigen.as<float>();
+    p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>(); p.edge_w = b.edge_w.as<float>();
+    p.out_deg = b.out_deg.as<int>(); p.node_w0 = b.node_w0.as<float>(); p.node_w1 = b.node_w1.as<float>();
+    p.sort_tmp = b.sort_tmp.as<int>(); p.status = b.status.as<int>();
+    p.num_graphs = G; p.flags = flags; p.has_attr = b.has_attr ? 1 : 0;
+    build_csr_kernel<<<ceil_div(G, CSR_WARPS), CSR_WARPS * 32, 0, stream>>>(p);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fg

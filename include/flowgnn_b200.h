@@ -1,0 +1,166 @@
+/*
+ * flowgnn_b200 -- C ABI of the B200 (sm_100a) replacement for FlowGNN's kernel path.
+ *
+ * PART 1 is the drop-in boundary: one `extern "C"` symbol per model with exactly the argument list,
+ * order and buffer layouts of the reference's HLS kernel tops, which its host binds by name
+ * (`cl::Kernel(program, "GIN_compute_graphs")`, GIN/src/host.cc:48) and feeds with `setArg` in
+ * declaration order (GIN/src/host.cc:184-200).  Differences, all forced by the platform:
+ *   - FM_TYPE / WT_TYPE are fp32 (reference: ap_fixed<16,6>, DGN ap_fixed<16,3>);
+ *   - the functions return int (0 = ok, otherwise a CUDA error code or FLOWGNN_ERR_*); the
+ *     reference returns void and cannot fail;
+ *   - all pointers are HOST pointers owned by the caller; the library copies to the GPU, runs, and
+ *     copies `out` back before returning (the reference does the same through XRT buffers).
+ * Batch layout (GIN/src/host.cc:110-182): graphs are concatenated; `edge_list_in` holds (u, v) pairs
+ * with GRAPH-LOCAL node ids, u = source, v = destination; weight arrays carry a leading
+ * "weight set" dimension that advances each time `reload_weights[g]` is non-zero
+ * (GIN/src/GIN_compute.cc:49-63).
+ *
+ * PART 2 is the extended interface for callers that keep batches resident in HBM, want device
+ * timing, or shard across GPUs (one context per GPU).
+ *
+ * Threading: one context per GPU; a context is used by one host thread at a time (the reference
+ * kernel is single-instance and non-reentrant: its state lives in <MODEL>/src/globals.cc).
+ * Part-1 functions use a lazily created per-thread default context on the current CUDA device.
+ */
+#ifndef FLOWGNN_B200_H
+#define FLOWGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLOWGNN_ERR_INVALID 10001   /* bad argument */
+#define FLOWGNN_ERR_LIMIT   10002   /* a graph exceeds a documented limit (1024 nodes per graph) */
+#define FLOWGNN_ERR_STATE   10003   /* wrong call order (no weights / no batch) */
+
+/* ------------------------------------------------------------------------------------------------
+ * PART 1 -- reference-compatible entry points
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces GIN_compute_graphs, GIN/src/dcl.h:76-93 (also used for GIN-VN: the virtual node is a host-side
+ * graph augmentation, GIN-VN/src/host_load.cc:125-153). */
+int GIN_compute_graphs(
+    int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights,
+    float* out,                              /* [num_graphs][NUM_TASK = 1] */
+    const int32_t* node_feature_in,          /* [sum N][9] */
+    const int32_t* edge_list_in,             /* [sum E][2] */
+    const int32_t* edge_attr_in,             /* [sum E][3] */
+    const float* node_embedding_weight_in,   /* [][173][100] */
+    const float* edge_embedding_weight_in,   /* [][5][13][100] */
+    const float* node_mlp_1_weights,         /* [][5][200][100] */
+    const float* node_mlp_1_bias,            /* [][5][200] */
+    const float* node_mlp_2_weights,         /* [][5][100][200] */
+    const float* node_mlp_2_bias,            /* [][5][100] */
+    const float* graph_pred_weights_in,      /* [][1][100] */
+    const float* graph_pred_bias_in);        /* [][1] */
+
+/* Replaces GCN_compute_graphs, GCN/src/dcl.h:76-96. */
+int GCN_compute_graphs(
+    int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights,
+    float* out,
+    const int32_t* node_feature_in, const int32_t* edge_list_in, const int32_t* edge_attr_in,
+    const float* node_embedding_weight_in,   /* [][173][100] */
+    const float* edge_embedding_weight_in,   /* [][5][13][100] */
+    const float* convs_weight_in,            /* [][5][100][100] */
+    const float* convs_bias_in,              /* [][5][100] */
+    const float* convs_root_emb_weight_in,   /* [][5][100] */
+    const float* bn_weight_in, const float* bn_bias_in, const float* bn_mean_in, const float* bn_var_in, /* [][5][100] */
+    const float* graph_pred_weights_in, const float* graph_pred_bias_in);
+
+/* Replaces GAT_compute_graphs, GAT/src/dcl.h:79-93.  By default reproduces the reference's missing
+ * per-graph node-feature offset (GAT/src/GAT_compute.cc:72); see
+ * flowgnn_b200_set_option("gat_node_offset_bug"). */
+int GAT_compute_graphs(
+    int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights,
+    float* out,
+    const int32_t* node_feature_in, const int32_t* edge_list_in,
+    const float* scoring_fn_target_in,       /* [][5][4][16] */
+    const float* scoring_fn_source_in,       /* [][5][4][16] */
+    const float* linear_proj_weights_in,     /* [][5][4][16][4][16] */
+    const float* skip_proj_weights_in,       /* [][5][4][16][4][16] */
+    const float* graph_pred_weights_in,      /* [][1][16] */
+    const float* graph_pred_bias_in);
+
+/* Replaces PNA_compute_graphs, PNA/src/dcl.h:92-110. */
+int PNA_compute_graphs(
+    int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights,
+    float* out,
+    const int32_t* node_feature_in, const int32_t* edge_list_in,
+    const float* node_embedding_weight_in,   /* [][173][80] */
+    const float* node_conv_weights_in,       /* [][4][80][3 scalers][4 aggregators][80] */
+    const float* node_conv_bias_in,          /* [][4][80] */
+    const float* graph_mlp_1_weights_in, const float* graph_mlp_1_bias_in,   /* [][40][80], [][40] */
+    const float* graph_mlp_2_weights_in, const float* graph_mlp_2_bias_in,   /* [][20][40], [][20] */
+    const float* graph_mlp_3_weights_in, const float* graph_mlp_3_bias_in,   /* [][1][20],  [][1]  */
+    const float* avg_deg_in);                /* [] */
+
+/* Replaces DGN_compute_graphs, DGN/src/dcl.h:72-90. */
+int DGN_compute_graphs(
+    int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights,
+    float* out,
+    const int32_t* node_feature_in,
+    const float* node_eigen_in,              /* [sum N][4]; only column 1 is used (DGN/src/load_inputs.cc:105-106) */
+    const int32_t* edge_list_in,
+    const float* embedding_h_atom_embedding_list_weights_in,            /* [][9][119][100] */
+    const float* layers_posttrans_fully_connected_0_linear_weight_in,   /* [][4][100][200] */
+    const float* layers_posttrans_fully_connected_0_linear_bias_in,     /* [][4][100] */
+    const float* MLP_layer_FC_layers_0_weight_in, const float* MLP_layer_FC_layers_0_bias_in,   /* [][50][100], [][50] */
+    const float* MLP_layer_FC_layers_1_weight_in, const float* MLP_layer_FC_layers_1_bias_in,   /* [][25][50],  [][25] */
+    const float* MLP_layer_FC_layers_2_weight_in, const float* MLP_layer_FC_layers_2_bias_in);  /* [][1][25],   [][1]  */
+
+/* ------------------------------------------------------------------------------------------------
+ * PART 2 -- extended interface (not in the reference)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct flowgnn_ctx flowgnn_ctx;
+
+enum flowgnn_model { FLOWGNN_GIN = 0, FLOWGNN_GCN = 1, FLOWGNN_GAT = 2, FLOWGNN_PNA = 3, FLOWGNN_DGN = 4 };
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* flowgnn_b200_last_error(void);
+
+int flowgnn_b200_create(flowgnn_ctx** ctx, int device);
+int flowgnn_b200_destroy(flowgnn_ctx* ctx);
+
+/* Options: "mp_only" (GIN: node transform = identity; the edge gather-scatter roofline variant),
+ * "gat_node_offset_bug" (default 1), "time_layers" (see flowgnn_b200_last_layer_ms). */
+int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value);
+
+/* load_weights (GIN/src/load_inputs.cc:7-85 and per-model variants): upload ONE weight set and
+ * repack it for the kernels.  `weights` lists host pointers in the model's Part-1 argument order
+ * (GIN 8, GCN 11, GAT 6, PNA 10, DGN 9). */
+int flowgnn_b200_load_weights(flowgnn_ctx* ctx, int model, const float* const* weights, int num_weights);
+
+/* Copy a batch to the GPU (asynchronously on the context's stream; pinned host memory overlaps). */
+int flowgnn_b200_upload_batch(
+    flowgnn_ctx* ctx, int num_graphs, int64_t total_nodes, int64_t total_edges,
+    const int32_t* nums_of_nodes, const int32_t* nums_of_edges,
+    const int32_t* node_feature, const int32_t* edge_list,
+    const int32_t* edge_attr /* may be NULL */, const float* node_eigen /* may be NULL */);
+
+/* Run graph preprocessing (load_graph) + the full forward of `model` on the resident batch.
+ * `elapsed_ms` (may be NULL) receives the device time between CUDA events around exactly that work;
+ * passing it makes the call synchronous. */
+int flowgnn_b200_compute(flowgnn_ctx* ctx, int model, float* elapsed_ms);
+
+/* Copy the per-graph predictions of the last compute to host memory and synchronise. */
+int flowgnn_b200_download(flowgnn_ctx* ctx, float* out, int num_graphs);
+
+/* Kernels launched by the last flowgnn_b200_compute. */
+int flowgnn_b200_last_launch_count(flowgnn_ctx* ctx);
+
+/* With option "time_layers" = 1, flowgnn_b200_compute brackets every per-layer kernel launch with CUDA
+ * events; this returns the device time of each layer launch of the last compute (count written). */
+int flowgnn_b200_last_layer_ms(flowgnn_ctx* ctx, float* out, int max_layers);
+
+/* The context's cudaStream_t (as void*), for callers that want to order their own work. */
+void* flowgnn_b200_stream(flowgnn_ctx* ctx);
+
+int flowgnn_b200_synchronize(flowgnn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
