@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Headline benchmark: graphs/s of the GIN dim100 forward on synthetic molhiv-shaped batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A *step* is one pass of the hot path (on-device load_graph + embedding + 5 fused GIN layers + pool/head,
+i.e. what the reference's single kernel enqueue does, GIN/src/GIN_compute.cc:44-98) over one batch of
+41,127 synthetic molhiv-shaped graphs (BASELINE.json configs[1]).  Per-GPU work is fixed ("weak"
+scaling): under torchrun every rank owns its own batch of that size (graphs shard by index, no
+collective on the data path; NCCL only tallies graphs and the max time).
+
+Printed (rank 0, one JSON line):
+  value        graphs/s over all ranks, inputs resident in HBM, CUDA events on the context's stream
+  e2e          the same through the reference-compatible entry point GIN_compute_graphs(...) with
+               pinned HOST buffers: H2D of the batch, compute, D2H of the predictions, every step
+  roofline     dominant kernel (gin_layer_kernel): algorithmic bytes per launch / mean launch time
+  edge_gather  the mp_only variant of the same kernel (node transform = identity) -- the edge
+               gather-scatter figure of BASELINE.json's metric
+  cpu_baseline the reference's own kernel sources (oracle/_ref, fp32 flavour) on this box's host cores,
+               bounded sample of the same workload (rank 0, N = 1 only)
+
+--impl reference times that CPU build alone (one process per core; its state is in file-scope
+globals, */src/globals.cc, so it is not re-entrant) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+WEIGHT_DIRS = {"gin": "GIN", "ginvn": "GIN", "gcn": "GCN", "gat": "GAT", "pna": "PNA", "dgn": "DGN"}
+#: graphs per GPU per step and generator shape, per model (BASELINE.json configs)
+WORKLOADS = {
+    "gin": ("molhiv", 41127), "gcn": ("molhiv", 41127), "gat": ("molhiv", 41127), "dgn": ("molhiv", 41127),
+    "pna": ("molpcba", 437929), "ginvn": ("hep10k", 40000),
+}
+#: (D, L, attr words A, extra bytes per node X) of SURVEY.md 8(d): B_layer = 8*D*N + E*(8+4A) + X*N
+ALGO = {"gin": (100, 5, 3, 0), "ginvn": (100, 5, 3, 0), "gcn": (100, 5, 3, 0), "gat": (64, 5, 0, 64), "pna": (80, 4, 0, 0),
+        "dgn": (100, 4, 0, 0)}
+LAYER_KERNEL = {"gin": "gin_layer_kernel", "ginvn": "gin_layer_kernel", "gcn": "gcn_layer_kernel", "gat": "gat_layer_kernel",
+                "pna": "pna_layer_kernel", "dgn": "dgn_layer_kernel"}
+
+
+def layer_bytes(model: str, total_nodes: int, total_edges: int) -> int:
+    D, _, A, X = ALGO[model]
+    return 8 * D * total_nodes + total_edges * (8 + 4 * A) + X * total_nodes
+
+
+def graph_bytes(model: str, num_graphs: int, total_nodes: int, total_edges: int) -> int:
+    return 36 * total_nodes + ALGO[model][1] * layer_bytes(model, total_nodes, total_edges) + 4 * num_graphs
+
+
+def make_workload(model: str, num_graphs: int, seed_offset: int = 0, base_graphs: int = 0):
+    """Synthetic batch of the model's workload shape.  `base_graphs` > 0 generates
+    that many distinct graphs and tiles them (used where the Python generator would take minutes)."""
+    from flowgnn_b200.dataset import BASE_SEED, synthetic_hep, synthetic_molecules
+    shape, _ = WORKLOADS[model]
+    n_gen = min(num_graphs, base_graphs) if base_graphs else num_graphs
+    seed = BASE_SEED + seed_offset
+    if shape == "hep10k":
+        b = synthetic_hep(n_gen, seed=seed)
+    else:
+        b = synthetic_molecules(n_gen, shape, seed=seed, with_eigen=(model == "dgn"))
+    if n_gen < num_graphs:
+        b = b.tile(num_graphs)
+    if model == "ginvn":
+        b = b.with_virtual_node()
+    return b
+
+
+# ---- clocks during the timed region (B200_PROFILING.md "clocks line") ---------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_id: str):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", gpu_id, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for t, line in self.rows:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(self.REASONS, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the reference's CPU implementation, one process per core -----------------------------------------
+_cpu_state = {}
+
+
+def _cpu_init(model, kind, fast):
+    from flowgnn_b200.weights import load_weights
+    _cpu_state.update(model=model, kind=kind, fast=fast, w=load_weights(model, os.path.join(GOLDEN, "weights", WEIGHT_DIRS[model])))
+
+
+def _cpu_run(shard):
+    from oracle import refbind
+    st = _cpu_state
+    t0 = time.perf_counter()
+    if st["kind"] == "reference":
+        y = refbind.run_reference(st["model"], shard, st["w"], fast=st["fast"])
+    else:
+        y = refbind.run_port(st["model"], shard, st["w"], fast=st["fast"])
+    return time.perf_counter() - t0, int(np.isfinite(y).sum())
+
+
+class CpuReference:
+    """The reference's CPU build of the path on `cores` worker processes (contiguous graph shards)."""
+
+    def __init__(self, model: str, batch, cores: int):
+        import multiprocessing as mp
+        from flowgnn_b200.sharding import shard_of
+        from oracle import refbind
+        self.kind = "reference" if refbind.have_ref("ginvn" if model == "ginvn" else model) else "port"
+        self.cores = cores
+        self.shards = [shard_of(batch, r, cores)[0] for r in range(cores)]
+        self.num_graphs = batch.num_graphs
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(model, self.kind, True))
+
+    def step(self) -> float:
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_run, self.shards, chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = args.model
+    cores = host_cores()
+    per_core = args.cpu_graphs_per_core
+    sample = make_workload(model, per_core * cores, base_graphs=4096)
+    ref = CpuReference(model, sample, cores)
+    for _ in range(args.warmup):
+        ref.step()
+    t = [ref.step() for _ in range(args.steps)]
+    ref.close()
+    total = sum(t)
+    value = sample.num_graphs * args.steps / total
+    shape, full = WORKLOADS[model]
+    sample_txt = (f"first {sample.num_graphs} graphs ({per_core} per core) of the synthetic {shape}-shaped workload per step, "
+                  f"one process per core, timed around <MODEL>_compute_graphs only")
+    line = {
+        "impl": "reference", "metric": f"graphs/sec ({shape}-shaped, {model.upper()} forward)", "value": value, "unit": "graphs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{model.upper()} forward, {full} synthetic {shape}-shaped graphs per GPU per step",
+                   "reference_sample_graphs_per_step": sample.num_graphs},
+        "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": cores, "kind": ref.kind, "sample": sample_txt},
+        "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def pinned_copy(a):
+    import torch
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    return t, v
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from flowgnn_b200.capi import Context, compute_graphs
+    from flowgnn_b200.dataset import Batch
+    from flowgnn_b200.models import get_model
+    from flowgnn_b200.weights import load_weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU build)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    model = args.model
+    shape, default_graphs = WORKLOADS[model]
+    G = args.graphs or default_graphs
+    batch = make_workload(model, G, seed_offset=rank, base_graphs=args.base_graphs)
+    weights = load_weights(model, os.path.join(GOLDEN, "weights", WEIGHT_DIRS[model]))
+    N, E = batch.total_nodes, batch.total_edges
+
+    # pinned host copies of the batch: what a caller of the reference entry point owns (GIN/src/host.cc:141-182)
+    keep = []
+    arrays = {}
+    for name in ("nums_of_nodes", "nums_of_edges", "node_feature", "edge_list", "edge_attr", "node_eigen"):
+        a = getattr(batch, name)
+        if a is None:
+            arrays[name] = None
+            continue
+        t, v = pinned_copy(a)
+        keep.append(t)
+        arrays[name] = v
+    hbatch = Batch(arrays["nums_of_nodes"], arrays["nums_of_edges"], arrays["node_feature"], arrays["edge_list"], arrays["edge_attr"],
+                   arrays["node_eigen"], name=batch.name)                    # views of the pinned buffers, no copies
+    assert hbatch.node_feature.ctypes.data == arrays["node_feature"].ctypes.data
+    spec = get_model(model)
+    used = ["nums_of_nodes", "nums_of_edges", "node_feature", "edge_list"] + (["edge_attr"] if spec.uses_edge_attr else []) + \
+           (["node_eigen"] if spec.uses_eigen else [])
+    h2d = sum(arrays[k].nbytes for k in used)
+    d2h = 4 * G
+
+    ctx = Context(local)
+    ctx.load_weights(model, weights)
+    ctx.upload(hbatch)
+    ctx.set_option("time_layers", 1)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
+    if not gpu_id.startswith("GPU-"):
+        gpu_id = "GPU-" + gpu_id
+
+    # ---- device-resident arm ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.compute(model, timed=True)
+    sampler = ClockSampler(gpu_id) if rank == 0 else None
+    windows = []
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    ev0.record(stream)
+    layer_ms = []
+    for _ in range(args.steps):
+        ctx.compute(model, timed=True)
+        layer_ms.extend(ctx.last_layer_ms())
+    ev1.record(stream)
+    barrier()
+    windows.append((w0, time.perf_counter()))
+    launches = ctx.last_launch_count * args.steps
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    total_graphs = sum_over_ranks(float(G))
+    value = total_graphs * args.steps / (dev_ms * 1e-3)
+    y_dev = ctx.download()
+
+    # ---- end-to-end arm: the reference-compatible entry point with host buffers ---------------------
+    for _ in range(args.warmup):
+        y_e2e = compute_graphs(model, hbatch, weights)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        y_e2e = compute_graphs(model, hbatch, weights)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    windows.append((w0, time.perf_counter()))
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = total_graphs * args.steps / e2e_s
+    if not np.array_equal(y_dev.view(np.int32), y_e2e.view(np.int32)):
+        raise SystemExit("bench.py: device-resident and end-to-end predictions differ")
+    clocks = sampler.stop(windows) if sampler else None
+
+    # ---- roofline of the dominant kernel (per-layer CUDA events recorded inside the timed region) ---
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        with open(peaks_path) as f:
+            hbm_peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    lb = layer_bytes(model, N, E)
+    mean_layer_ms = float(np.mean(layer_ms)) if layer_ms else float("nan")
+    achieved = lb / (mean_layer_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(LAYER_KERNEL[model])
+    roofline = {"bound": "hbm", "kernel": LAYER_KERNEL[model], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": lb,
+                "mean_launch_ms": mean_layer_ms, "share_of_step": mean_layer_ms * ALGO[model][1] * args.steps / ev0.elapsed_time(ev1)}
+
+    edge_gather = None
+    if model in ("gin", "ginvn"):
+        ctx.set_option("mp_only", 1)
+        for _ in range(args.warmup):
+            ctx.compute(model, timed=True)
+        mp_ms = []
+        for _ in range(max(5, args.steps // 2)):
+            ctx.compute(model, timed=True)
+            mp_ms.extend(ctx.last_layer_ms())
+        ctx.set_option("mp_only", 0)
+        a = lb / (float(np.mean(mp_ms)) * 1e-3) / 1e9
+        edge_gather = {"kernel": "gin_layer_kernel<mp_only>", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                       "mean_launch_ms": float(np.mean(mp_ms)), "algorithmic_bytes_per_launch": lb}
+    ctx.close()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        per_core = args.cpu_graphs_per_core * 8
+        sample = batch.slice(0, min(G, per_core * cores))
+        ref = CpuReference(model, sample, cores)
+        ref.step() if sample.num_graphs <= 64 * cores else None
+        t = ref.step()
+        ref.close()
+        cpu_baseline = {"value": sample.num_graphs / t, "unit": "graphs/s", "cores": cores, "kind": ref.kind,
+                        "sample": f"first {sample.num_graphs} graphs of this run's batch, one process per core, one pass ({t:.1f} s), "
+                                  f"timed around <MODEL>_compute_graphs only"}
+
+    if rank == 0:
+        line = {
+            "metric": f"graphs/sec ({shape}-shaped, {model.upper()} forward, device-timed)", "value": value, "unit": "graphs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{model.upper()} forward, {G} synthetic {shape}-shaped graphs per GPU per step "
+                                   f"(sum N = {N}, sum E = {E} on rank 0); trained weights shipped with the reference",
+                       "l2": "inputs larger than L2 (activations 2 x %.0f MB per GPU)" % (N * ALGO[model][0] * 4 / 1e6),
+                       "parallelism": f"graphs sharded by index over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "host clock around the synchronous C-ABI calls"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "edge_gather": edge_gather,
+            "algorithmic_bytes_per_graph": graph_bytes(model, G, N, E) / G,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--model", choices=tuple(WORKLOADS), default="gin")
+    ap.add_argument("--graphs", type=int, default=0, help="graphs per GPU per step (default: the model's BASELINE config)")
+    ap.add_argument("--base-graphs", type=int, default=0, help="generate this many distinct graphs and tile them")
+    ap.add_argument("--cpu-graphs-per-core", type=int, default=256, help="reference arm: graphs per core per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.model == "pna" and not args.base_graphs:
+        args.base_graphs = 32768
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()
