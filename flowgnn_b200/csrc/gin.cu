@@ -223,6 +223,12 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         p.w1t = w.w1t.as<float>() + (size_t)l * D * HP; p.b1 = w.b1.as<float>() + (size_t)l * HP;
         p.w2t = w.w2t.as<float>() + (size_t)l * H * DP; p.b2 = w.b2.as<float>() + (size_t)l * DP;
         p.num_nodes = (int)N; p.num_tiles = num_tiles; p.relu_out = (l != 4);
+        if (!opt.mp_only && !opt.gin_ffma)
+        {
+            FG_TRY(gin_layer_tc_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
+            nl++;
+            continue;
+        }
         if (opt.mp_only)
         {
             const int grid = min(num_tiles, sm_count * 2);

@@ -66,6 +66,11 @@ struct GinWeights {
     DevBuf ee_comb;      // [5][60][100]  ((0+T[a0])+T[5+a1])+T[11+a2]
     DevBuf w1t, b1;      // [5][100][208], [5][208]   k-major, N padded with zeros
     DevBuf w2t, b2;      // [5][200][104], [5][104]
+    // tensor-core path (gin_tc.cu): per layer W1_hi | W1_lo | W2_hi | W2_lo as bf16 in the stationary
+    // shared-memory B layout (tc.cuh), 4 x 46,592 bytes; raw edge-embedding rows; b2 padded to 112
+    DevBuf wpack;        // [5][4][46592] bytes
+    DevBuf ee_raw;       // [5][13][100]
+    DevBuf b2p;          // [5][112]
     DevBuf pred_w, pred_b;
 };
 struct GcnWeights {
@@ -109,11 +114,13 @@ struct LayerTimer {
 
 struct RunOptions {
     int mp_only = 0;                 // GIN: node transform = identity (roofline variant)
+    int gin_ffma = 0;                // GIN: node MLP on the FP32 FFMA pipe (on-device fp32 reference) instead of tcgen05
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
 };
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
+int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);

@@ -125,7 +125,8 @@ int flowgnn_b200_create(flowgnn_ctx** ctx, int device);
 int flowgnn_b200_destroy(flowgnn_ctx* ctx);
 
 /* Options: "mp_only" (GIN: node transform = identity; the edge gather-scatter roofline variant),
- * "gat_node_offset_bug" (default 1), "time_layers" (see flowgnn_b200_last_layer_ms). */
+ * "gin_ffma" (GIN: run the node MLP on the FP32 FFMA pipe instead of the tcgen05 bf16x3 split path; the
+ * on-device fp32 reference), "gat_node_offset_bug" (default 1), "time_layers" (see flowgnn_b200_last_layer_ms). */
 int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value);
 
 /* load_weights (GIN/src/load_inputs.cc:7-85 and per-model variants): upload ONE weight set and

@@ -44,6 +44,21 @@ def test_other_datasets_match_reference(model, ds, ctx, weights, datasets, golde
     assert_parity(got, golden[ds][model], what=f"{model}/{ds}")
 
 
+@pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
+def test_gin_ffma_reference_path_agrees_with_tensor_core_path(ds, ctx, weights, datasets, golden):
+    """GIN's node MLP runs on tcgen05 (bf16 hi/lo split, 3 products); the FP32-FFMA kernel is kept as the
+    on-device fp32 reference.  Both must sit inside the 1e-4 contract and agree with each other."""
+    tc = ctx.run("gin", datasets[ds], weights["gin"])
+    ctx.set_option("gin_ffma", 1)
+    try:
+        ffma = ctx.run("gin", datasets[ds])
+    finally:
+        ctx.set_option("gin_ffma", 0)
+    assert_parity(ffma, golden[ds]["gin"], what=f"gin ffma/{ds}")
+    assert_parity(tc, golden[ds]["gin"], what=f"gin tcgen05/{ds}")
+    assert_parity(tc, ffma, tol=5e-5, what=f"gin tcgen05 vs ffma/{ds}")
+
+
 def test_gat_hep10k_is_the_prediction_bias(ctx, weights, datasets, golden):
     got = ctx.run("gat", datasets["hep10k"], weights["gat"])
     assert_parity(got, golden["hep10k"]["gat"], what="gat/hep10k")
