@@ -36,37 +36,41 @@ static_assert(N1 * K1 == N2 * K2, "weight blocks share a size");
 
 constexpr int EPI_WARPS = 4, GATHER_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS;
-constexpr int NT = (MMA_WARP + 1) * 32;       // 416 threads
+constexpr int LOAD_WARP = MMA_WARP + 1;
+constexpr int NT = (LOAD_WARP + 1) * 32;      // 448 threads
 
 // tensor-memory columns
 constexpr uint32_t TC_A1_HI = 0, TC_A1_LO = 56, TC_Z = 128, TC_H = 384;
 constexpr uint32_t TMEM_COLS = 512;
 
-// gather K-slices (float4 chunks): team T handles slices T and T + 2
-constexpr int SLICE_Q = 7;
-constexpr int STAGE_LO = 16;                  // per row: 14 hi words at 0, 14 lo words at 16 (16-byte aligned: the 8-word
-constexpr int STAGE_WORDS = 36;               // TMEM store operands then come from aligned LDS.128); stride = 4 x odd words
-constexpr int STAGE_BYTES = TM * STAGE_WORDS * 4;
+// per-tile slice of the destination CSR staged in shared memory by the loader warp (double buffered)
+constexpr int CSR_CAP = 1024;                 // in-edges of one tile; larger tiles read src/code from global
+struct CsrBuf {
+    int ptr[TM + 4];                          // absolute edge positions of the tile's rows (+1)
+    int src[CSR_CAP];
+    uint8_t code[CSR_CAP];
+    int e0; int staged; int pad[2];
+};
 
 struct Smem {
     static constexpr int W = 0;                                   // W1_hi | W1_lo | W2_hi | W2_lo
-    static constexpr int EE = W + 4 * WBLOCK;                     // [13][100] fp32
-    static constexpr int B1 = EE + ED_FEATURE_PER_LAYER * D * 4;  // [208]
+    static constexpr int EE = W + 4 * WBLOCK;                     // [60][100] fp32 combined edge-embedding rows
+    static constexpr int B1 = EE + ED_COMBOS * D * 4;             // [208]
     static constexpr int B2 = B1 + N1 * 4;                        // [112]
-    static constexpr int STAGE = B2 + N2 * 4;                     // 2 teams
-    static constexpr int BAR = STAGE + 2 * STAGE_BYTES;
-    static constexpr int TMEM_PTR = BAR + 8 * 8;
+    static constexpr int CSR = B2 + N2 * 4;                       // 2 x CsrBuf
+    static constexpr int BAR = CSR + 2 * (int)sizeof(CsrBuf);
+    static constexpr int TMEM_PTR = BAR + 16 * 8;
     static constexpr int BYTES = TMEM_PTR + 16;
 };
-static_assert(Smem::STAGE % 16 == 0 && Smem::BAR % 8 == 0, "alignment");
+static_assert(Smem::CSR % 16 == 0 && Smem::BAR % 8 == 0 && sizeof(CsrBuf) % 16 == 0, "alignment");
 static_assert(Smem::BYTES <= 232448, "shared memory budget");
 
-enum { BAR_W = 0, BAR_A1_FULL, BAR_G1_DONE, BAR_A2_FULL, BAR_G2_DONE };
+enum { BAR_W = 0, BAR_A1_FULL, BAR_G1_DONE, BAR_A2_FULL, BAR_G2_DONE, BAR_CSR_FULL /* 2 */, BAR_CSR_EMPTY = BAR_CSR_FULL + 2 /* 2 */ };
 
 struct GinTcParams {
     const float* h_in; float* h_out;
     const int* in_ptr; const int* src; const uint8_t* code;
-    const float* ee_raw;             // [13][100] this layer
+    const float* ee_comb;            // [60][100] this layer: ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]
     const unsigned char* wpack;      // 4 x WBLOCK this layer
     const float* b1; const float* b2;   // [208], [112] zero padded
     int num_nodes; int num_tiles; int relu_out;
@@ -76,7 +80,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
 
 // (x0, x1) -> packed bf16 pairs: hi = rn(x), lo = rn(x - hi); element 0 in the low half
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo)
@@ -87,80 +90,92 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
-__device__ __forceinline__ void st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+// 16 lanes x 256 bit TMEM store: thread t supplies columns 2(t%4), 2(t%4)+1 of lane t/4 (r0, r1) and of lane t/4 + 8 (r2, r3)
+// -- the layout of an m16n8 accumulator fragment (verified on hardware with tools/tc_probe2.cu)
+__device__ __forceinline__ void st_16x256(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
 {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st2(uint32_t taddr, uint32_t a, uint32_t b)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
-// One K-slice of the tile's A operand: NQ float4 chunks starting at chunk Q0 for all TM rows, computed by
-// the 128 threads of a team and written to the team's transposition buffer as packed bf16 (hi | lo) words.
-template <int NQ>
-__device__ __forceinline__ void gather_slice(const GinTcParams& p, const float* ee, uint32_t* stage, int tt, int n0, int rows, int q0)
+// The in-edges of one tile row, as far as they fit in registers (molecular graphs: in-degree <= 4 almost always);
+// longer lists continue from `tail` in the staged CSR / global memory.
+struct RowEdges {
+    int node;            // global id of the row (clamped to a valid node for dead rows)
+    int deg;             // in-degree (0 for dead rows)
+    int eb;              // absolute position of the first in-edge
+    int u[4]; int c[4];  // source node / bond-attribute code of the first four in-edges (own node / 0 where absent)
+};
+
+__device__ __forceinline__ RowEdges load_row_edges(const GinTcParams& p, const CsrBuf& cb, int n0, int rows, int r)
 {
-    for (int item = tt; item < TM * NQ; item += 128)
+    RowEdges re;
+    const bool live = r < rows;
+    re.node = n0 + (live ? r : rows - 1);
+    re.eb = live ? cb.ptr[r] : 0;
+    re.deg = live ? cb.ptr[r + 1] - re.eb : 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
     {
-        const int v = item / NQ, qq = item - v * NQ;
-        const int q = q0 + qq;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v < rows)
+        re.u[j] = re.node; re.c[j] = 0;
+        if (j < re.deg)
         {
-            const int node = n0 + v;
-            const int eb = __ldg(p.in_ptr + node), ee_end = __ldg(p.in_ptr + node + 1);
-            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int e = eb; e < ee_end; e++)
+            if (cb.staged) { re.u[j] = cb.src[re.eb + j - cb.e0]; re.c[j] = cb.code[re.eb + j - cb.e0]; }
+            else { re.u[j] = __ldg(p.src + re.eb + j); re.c[j] = __ldg(p.code + re.eb + j); }
+        }
+    }
+    return re;
+}
+
+// a_v[4q .. 4q+3] = sum over in-edges (CSR order) relu(h_u + EE[attr]) + h_v for two rows at once: all global
+// loads of the step are issued before the first use (no branches in between), the edge tail (in-degree > 4) follows.
+__device__ __forceinline__ void gather_pair(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& ra, const RowEdges& rb,
+                                            int q, float4& a, float4& b)
+{
+    const float* hq = p.h_in + 4 * q;
+    const float4 hva = ldg_f4(hq + (size_t)ra.node * D), hvb = ldg_f4(hq + (size_t)rb.node * D);
+    float4 hua[4], hub[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) hua[j] = ldg_f4(hq + (size_t)ra.u[j] * D);
+#pragma unroll
+    for (int j = 0; j < 4; j++) hub[j] = ldg_f4(hq + (size_t)rb.u[j] * D);
+    float4 ma = make_float4(0.f, 0.f, 0.f, 0.f), mb = ma;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const float4 t = ld_f4(ee + ra.c[j] * D + 4 * q);
+        const bool on = j < ra.deg;
+        ma.x += on ? relu_f(t.x + hua[j].x) : 0.f; ma.y += on ? relu_f(t.y + hua[j].y) : 0.f;
+        ma.z += on ? relu_f(t.z + hua[j].z) : 0.f; ma.w += on ? relu_f(t.w + hua[j].w) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const float4 t = ld_f4(ee + rb.c[j] * D + 4 * q);
+        const bool on = j < rb.deg;
+        mb.x += on ? relu_f(t.x + hub[j].x) : 0.f; mb.y += on ? relu_f(t.y + hub[j].y) : 0.f;
+        mb.z += on ? relu_f(t.z + hub[j].z) : 0.f; mb.w += on ? relu_f(t.w + hub[j].w) : 0.f;
+    }
+    if (ra.deg > 4 || rb.deg > 4)
+    {
+#pragma unroll 1
+        for (int side = 0; side < 2; side++)
+        {
+            const RowEdges& r = side ? rb : ra;
+            float4 m = side ? mb : ma;
+            for (int e = r.eb + 4; e < r.eb + r.deg; e++)
             {
-                const int u = __ldg(p.src + e);
-                const int c = __ldg(p.code + e);
-                const int a0 = c / 12, r = c - a0 * 12;
-                const float4 hu = ldg_f4(p.h_in + (size_t)u * D + 4 * q);
-                // ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]   (GIN/src/message_passing.cc:136-142)
-                const float4 t0 = ld_f4(ee + a0 * D + 4 * q);
-                const float4 t1 = ld_f4(ee + (5 + (r >> 1)) * D + 4 * q);
-                const float4 t2 = ld_f4(ee + (11 + (r & 1)) * D + 4 * q);
-                const float4 t = make_float4((t0.x + t1.x) + t2.x, (t0.y + t1.y) + t2.y, (t0.z + t1.z) + t2.z, (t0.w + t1.w) + t2.w);
+                int u, c;
+                if (cb.staged) { u = cb.src[e - cb.e0]; c = cb.code[e - cb.e0]; }
+                else { u = __ldg(p.src + e); c = __ldg(p.code + e); }
+                const float4 hu = ldg_f4(hq + (size_t)u * D);
+                const float4 t = ld_f4(ee + c * D + 4 * q);
                 m.x += relu_f(t.x + hu.x); m.y += relu_f(t.y + hu.y); m.z += relu_f(t.z + hu.z); m.w += relu_f(t.w + hu.w);
             }
-            const float4 hv = ldg_f4(p.h_in + (size_t)node * D + 4 * q);
-            a = make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w);
-        }
-        uint32_t h0, l0, h1, l1;
-        split2(a.x, a.y, h0, l0);
-        split2(a.z, a.w, h1, l1);
-        uint32_t* row = stage + v * STAGE_WORDS;
-        *reinterpret_cast<uint2*>(row + 2 * qq) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(row + STAGE_LO + 2 * qq) = make_uint2(l0, l1);
-    }
-}
-
-// row `lane` of the team's buffer -> TMEM columns [col0, col0 + NW) of A1_hi and A1_lo (NW = 14 or 8 words)
-template <int NW>
-__device__ __forceinline__ void stage_to_tmem(const uint32_t* stage, int row, uint32_t lane_base, uint32_t col0)
-{
-    const uint4* r4 = reinterpret_cast<const uint4*>(stage + row * STAGE_WORDS);
-    uint32_t w[STAGE_WORDS];
-#pragma unroll
-    for (int i = 0; i < STAGE_WORDS / 4; i++)
-    {
-        const uint4 x = r4[i];
-        w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
-    }
-#pragma unroll
-    for (int part = 0; part < 2; part++)
-    {
-        const uint32_t t = lane_base + (part ? TC_A1_LO : TC_A1_HI) + col0;
-        const uint32_t* s = w + part * STAGE_LO;
-        const uint32_t v8[8] = {s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7]};
-        tc::st8(t, v8);
-        if (NW == 14)
-        {
-            st4(t + 8, s[8], s[9], s[10], s[11]);
-            st2(t + 12, s[12], s[13]);
+            if (side) mb = m; else ma = m;
         }
     }
+    a = make_float4(ma.x + hva.x, ma.y + hva.y, ma.z + hva.z, ma.w + hva.w);
+    b = make_float4(mb.x + hvb.x, mb.y + hvb.y, mb.z + hvb.z, mb.w + hvb.w);
 }
 
 __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
@@ -181,6 +196,11 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
         mbar_init(&bar[BAR_G1_DONE], 1);
         mbar_init(&bar[BAR_A2_FULL], EPI_WARPS);
         mbar_init(&bar[BAR_G2_DONE], 1);
+        for (int i = 0; i < 2; i++)
+        {
+            mbar_init(&bar[BAR_CSR_FULL + i], 1);
+            mbar_init(&bar[BAR_CSR_EMPTY + i], GATHER_WARPS);
+        }
         fence_mbar_init();
     }
     if (warp == MMA_WARP)
@@ -188,7 +208,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
         tc::tmem_alloc(tmem_ptr, TMEM_COLS);
         tc::tmem_relinquish();
     }
-    for (int i = tid; i < ED_FEATURE_PER_LAYER * Q; i += NT) st_f4(ee + 4 * i, ldg_f4(p.ee_raw + 4 * i));
+    for (int i = tid; i < ED_COMBOS * Q; i += NT) st_f4(ee + 4 * i, ldg_f4(p.ee_comb + 4 * i));
     for (int i = tid; i < N1; i += NT) b1s[i] = __ldg(p.b1 + i);
     for (int i = tid; i < N2; i += NT) b2s[i] = __ldg(p.b2 + i);
     tc::fence_before_sync();
@@ -247,60 +267,94 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
             }
         }
     }
+    else if (warp == LOAD_WARP)
+    {
+        // ===== loader warp: stages the next tile's CSR slice in shared memory and prefetches feature rows into L2 =====
+        CsrBuf* csr = reinterpret_cast<CsrBuf*>(smem + Smem::CSR);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++)
+        {
+            CsrBuf& cb = csr[it & 1];
+            if (it >= 2) mbar_wait(&bar[BAR_CSR_EMPTY + (it & 1)], ((it >> 1) - 1) & 1);
+            const int n0 = tile * TM;
+            const int rows = min(TM, p.num_nodes - n0);
+            if (lane == 0)
+            {
+                const int ahead = tile + 2 * gridDim.x;
+                if (ahead < p.num_tiles)
+                {
+                    const int rn = min(TM, p.num_nodes - ahead * TM);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (size_t)ahead * TM * D), "r"(rn * D * 4) : "memory");
+                }
+            }
+            for (int i = lane; i <= rows; i += 32) cb.ptr[i] = __ldg(p.in_ptr + n0 + i);
+            __syncwarp();
+            const int e0 = cb.ptr[0], ne = cb.ptr[rows] - e0;
+            const bool staged = ne <= CSR_CAP;
+            if (staged)
+            {
+                for (int i = lane; i < ne; i += 32)
+                {
+                    cb.src[i] = __ldg(p.src + e0 + i);
+                    cb.code[i] = __ldg(p.code + e0 + i);
+                }
+            }
+            if (lane == 0) { cb.e0 = e0; cb.staged = staged ? 1 : 0; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[BAR_CSR_FULL + (it & 1)]);
+        }
+    }
     else if (warp >= EPI_WARPS)
     {
-        // ===== gather warps: build the A operand of GEMM1 in tensor memory =====
+        // ===== gather warps: build the A operand of GEMM1 directly in tensor memory =====
+        // warp -> TMEM lane quadrant (warp % 4) and 16-row half; thread t -> rows t/4 and t/4 + 8 of that half and,
+        // per k-step ks, the float4 chunk q = 4 ks + t % 4 (k = 16 ks + 4 (t%4) .. +3 = TMEM columns 2(t%4), 2(t%4)+1)
         const int gw = warp - EPI_WARPS;          // 0..7
-        const int team = gw >> 2;                 // 0 / 1
-        const int tt = tid - (EPI_WARPS + 4 * team) * 32;   // 0..127 within the team
-        const int quad = warp & 3;
-        const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
-        uint32_t* stage = reinterpret_cast<uint32_t*>(smem + Smem::STAGE + team * STAGE_BYTES);
-        const int row = quad * 32 + lane;
-        if (team == 0)
-        {
-            // K padding columns (k = 100..111) of A1 stay zero for the whole launch
-            const uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            tc::st8(lane_base + TC_A1_HI + 48, z8);
-            tc::st8(lane_base + TC_A1_LO + 48, z8);
-            tc::wait_st();
-        }
-        team_sync(team);
+        const int quad = warp & 3, half = gw >> 2;
+        const uint32_t taddr = tbase + ((uint32_t)(quad * 32 + half * 16) << 16);
+        const int r_a = quad * 32 + half * 16 + (lane >> 2), r_b = r_a + 8;
+        const int qsub = lane & 3;
+        const CsrBuf* csr = reinterpret_cast<const CsrBuf*>(smem + Smem::CSR);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++)
         {
             const int n0 = tile * TM;
             const int rows = min(TM, p.num_nodes - n0);
-            if (gw == 0 && lane == 0)
+            const CsrBuf& cb = csr[it & 1];
+            mbar_wait(&bar[BAR_CSR_FULL + (it & 1)], (it >> 1) & 1);
+            const RowEdges ra = load_row_edges(p, cb, n0, rows, r_a), rb = load_row_edges(p, cb, n0, rows, r_b);
+            const bool live_a = r_a < rows, live_b = r_b < rows;
+#pragma unroll 1
+            for (int ks = 0; ks < K1 / 16; ks++)
             {
-                const int next = tile + gridDim.x;
-                if (next < p.num_tiles)
-                {
-                    const int rn = min(TM, p.num_nodes - next * TM);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (size_t)next * TM * D), "r"(rn * D * 4) : "memory");
-                }
-            }
-#pragma unroll
-            for (int si = 0; si < 2; si++)
-            {
-                const int s = team + 2 * si;
-                if (s < 3) gather_slice<SLICE_Q>(p, ee, stage, tt, n0, rows, SLICE_Q * s);
-                else gather_slice<Q - 3 * SLICE_Q>(p, ee, stage, tt, n0, rows, SLICE_Q * s);
-                team_sync(team);
-                if (si == 0 && it > 0)
+                const int q = 4 * ks + qsub;
+                float4 a, b;
+                gather_pair(p, ee, cb, ra, rb, min(q, Q - 1), a, b);
+                if (q >= Q || !live_a) a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q >= Q || !live_b) b = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t ha0, la0, ha1, la1, hb0, lb0, hb1, lb1;
+                split2(a.x, a.y, ha0, la0);
+                split2(a.z, a.w, ha1, la1);
+                split2(b.x, b.y, hb0, lb0);
+                split2(b.z, b.w, hb1, lb1);
+                if (ks == 0 && it > 0)
                 {
                     // A1 of the previous tile has been consumed once GEMM1 of that tile completed
                     mbar_wait(&bar[BAR_G1_DONE], (it - 1) & 1);
                     tc::fence_after_sync();
                 }
-                if (s < 3) stage_to_tmem<14>(stage, row, lane_base, 14 * s);
-                else stage_to_tmem<8>(stage, row, lane_base, 14 * s);
-                team_sync(team);
+                __syncwarp();
+                st_16x256(taddr + TC_A1_HI + 8 * ks, ha0, ha1, hb0, hb1);
+                st_16x256(taddr + TC_A1_LO + 8 * ks, la0, la1, lb0, lb1);
             }
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar[BAR_A1_FULL]);
+            if (lane == 0)
+            {
+                mbar_arrive(&bar[BAR_A1_FULL]);
+                mbar_arrive(&bar[BAR_CSR_EMPTY + (it & 1)]);
+            }
         }
     }
     else
@@ -380,7 +434,7 @@ int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, co
     GinTcParams p;
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
-    p.ee_raw = w.ee_raw.as<float>() + (size_t)layer * ED_FEATURE_PER_LAYER * D;
+    p.ee_comb = w.ee_comb.as<float>() + (size_t)layer * ED_COMBOS * D;
     p.wpack = w.wpack.as<unsigned char>() + (size_t)layer * 4 * WBLOCK;
     p.b1 = w.b1.as<float>() + (size_t)layer * N1;
     p.b2 = w.b2p.as<float>() + (size_t)layer * N2;
