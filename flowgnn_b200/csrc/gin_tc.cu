@@ -55,7 +55,7 @@ struct CsrBuf {
 struct Smem {
     static constexpr int W = 0;                                   // W1_hi | W1_lo | W2_hi | W2_lo
     static constexpr int EE = W + 4 * WBLOCK;                     // [60][100] fp32 combined edge-embedding rows
-    static constexpr int B1 = EE + ED_COMBOS * D * 4;             // [208]
+    static constexpr int B1 = EE + (ED_COMBOS + 1) * D * 4;       // [208]   (EE row 60 = -3e38 sentinel for absent edge slots)
     static constexpr int B2 = B1 + N1 * 4;                        // [112]
     static constexpr int CSR = B2 + N2 * 4;                       // 2 x CsrBuf
     static constexpr int BAR = CSR + 2 * (int)sizeof(CsrBuf);
@@ -75,6 +75,14 @@ struct GinTcParams {
     const float* b1; const float* b2;   // [208], [112] zero padded
     int num_nodes; int num_tiles; int relu_out;
 };
+
+// relu that lets NaN through, like the reference's compare-select (GIN/src/util.h:20-25), in ONE instruction
+__device__ __forceinline__ float relu_nan(float x)
+{
+    float y;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(0.0f));
+    return y;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
@@ -98,65 +106,76 @@ __device__ __forceinline__ void st_16x256(uint32_t taddr, uint32_t r0, uint32_t 
 }
 
 // The in-edges of one tile row, as far as they fit in registers (molecular graphs: in-degree <= 4 almost always);
-// longer lists continue from `tail` in the staged CSR / global memory.
+// longer lists continue from edge 4 in the staged CSR / global memory.  Absent slots point at the row's own
+// features and at the sentinel table row (-3e38): relu(-3e38 + h) adds exactly 0 for finite h, and for a
+// non-finite h_v the row's result m_v + h_v is the same non-finite value either way.
 struct RowEdges {
-    int node;            // global id of the row (clamped to a valid node for dead rows)
-    int deg;             // in-degree (0 for dead rows)
-    int eb;              // absolute position of the first in-edge
-    int u[4]; int c[4];  // source node / bond-attribute code of the first four in-edges (own node / 0 where absent)
+    const float* hv;         // own feature row, offset by the thread's float4 sub-chunk
+    const float* hu[4];      // source rows of the first four in-edges (own row where absent)
+    uint32_t t[4];           // shared-memory byte address of their edge-embedding rows (sentinel where absent)
+    int deg; int eb;
 };
 
-__device__ __forceinline__ RowEdges load_row_edges(const GinTcParams& p, const CsrBuf& cb, int n0, int rows, int r)
+__device__ __forceinline__ RowEdges load_row_edges(const GinTcParams& p, const float* ee, const CsrBuf& cb, int n0, int rows, int r, int qsub)
 {
     RowEdges re;
     const bool live = r < rows;
-    re.node = n0 + (live ? r : rows - 1);
+    const int node = n0 + (live ? r : rows - 1);
     re.eb = live ? cb.ptr[r] : 0;
     re.deg = live ? cb.ptr[r + 1] - re.eb : 0;
+    re.hv = p.h_in + (size_t)node * D + 4 * qsub;
+    const uint32_t ee_addr = smem_u32(ee) + 16 * qsub;
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-        re.u[j] = re.node; re.c[j] = 0;
+        int u = node, c = ED_COMBOS;
         if (j < re.deg)
         {
-            if (cb.staged) { re.u[j] = cb.src[re.eb + j - cb.e0]; re.c[j] = cb.code[re.eb + j - cb.e0]; }
-            else { re.u[j] = __ldg(p.src + re.eb + j); re.c[j] = __ldg(p.code + re.eb + j); }
+            if (cb.staged) { u = cb.src[re.eb + j - cb.e0]; c = cb.code[re.eb + j - cb.e0]; }
+            else { u = __ldg(p.src + re.eb + j); c = __ldg(p.code + re.eb + j); }
         }
+        re.hu[j] = p.h_in + (size_t)u * D + 4 * qsub;
+        re.t[j] = ee_addr + c * (D * 4);
     }
     return re;
 }
 
-// a_v[4q .. 4q+3] = sum over in-edges (CSR order) relu(h_u + EE[attr]) + h_v for two rows at once: all global
-// loads of the step are issued before the first use (no branches in between), the edge tail (in-degree > 4) follows.
-__device__ __forceinline__ void gather_pair(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& ra, const RowEdges& rb,
-                                            int q, float4& a, float4& b)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
 {
-    const float* hq = p.h_in + 4 * q;
-    const float4 hva = ldg_f4(hq + (size_t)ra.node * D), hvb = ldg_f4(hq + (size_t)rb.node * D);
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// a_v[4q .. 4q+3] = sum over in-edges (CSR order) relu(h_u + EE[attr]) + h_v for two rows at once, q = 4 KS + qsub:
+// all global loads of the step are issued before the first use, addresses are pointer + immediate.
+template <int KS>
+__device__ __forceinline__ void gather_pair(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& ra, const RowEdges& rb,
+                                            int qsub, float4& a, float4& b)
+{
+    constexpr int OFF = 16 * KS;      // floats
+    const float4 hva = ldg_f4(ra.hv + OFF), hvb = ldg_f4(rb.hv + OFF);
     float4 hua[4], hub[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) hua[j] = ldg_f4(hq + (size_t)ra.u[j] * D);
+    for (int j = 0; j < 4; j++) hua[j] = ldg_f4(ra.hu[j] + OFF);
 #pragma unroll
-    for (int j = 0; j < 4; j++) hub[j] = ldg_f4(hq + (size_t)rb.u[j] * D);
+    for (int j = 0; j < 4; j++) hub[j] = ldg_f4(rb.hu[j] + OFF);
     float4 ma = make_float4(0.f, 0.f, 0.f, 0.f), mb = ma;
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-        const float4 t = ld_f4(ee + ra.c[j] * D + 4 * q);
-        const bool on = j < ra.deg;
-        ma.x += on ? relu_f(t.x + hua[j].x) : 0.f; ma.y += on ? relu_f(t.y + hua[j].y) : 0.f;
-        ma.z += on ? relu_f(t.z + hua[j].z) : 0.f; ma.w += on ? relu_f(t.w + hua[j].w) : 0.f;
+        const float4 t = lds_f4(ra.t[j] + 4 * OFF);
+        ma.x += relu_nan(t.x + hua[j].x); ma.y += relu_nan(t.y + hua[j].y); ma.z += relu_nan(t.z + hua[j].z); ma.w += relu_nan(t.w + hua[j].w);
     }
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-        const float4 t = ld_f4(ee + rb.c[j] * D + 4 * q);
-        const bool on = j < rb.deg;
-        mb.x += on ? relu_f(t.x + hub[j].x) : 0.f; mb.y += on ? relu_f(t.y + hub[j].y) : 0.f;
-        mb.z += on ? relu_f(t.z + hub[j].z) : 0.f; mb.w += on ? relu_f(t.w + hub[j].w) : 0.f;
+        const float4 t = lds_f4(rb.t[j] + 4 * OFF);
+        mb.x += relu_nan(t.x + hub[j].x); mb.y += relu_nan(t.y + hub[j].y); mb.z += relu_nan(t.z + hub[j].z); mb.w += relu_nan(t.w + hub[j].w);
     }
     if (ra.deg > 4 || rb.deg > 4)
     {
+        const int q = 4 * KS + qsub;
 #pragma unroll 1
         for (int side = 0; side < 2; side++)
         {
@@ -167,15 +186,41 @@ __device__ __forceinline__ void gather_pair(const GinTcParams& p, const float* e
                 int u, c;
                 if (cb.staged) { u = cb.src[e - cb.e0]; c = cb.code[e - cb.e0]; }
                 else { u = __ldg(p.src + e); c = __ldg(p.code + e); }
-                const float4 hu = ldg_f4(hq + (size_t)u * D);
+                const float4 hu = ldg_f4(p.h_in + (size_t)u * D + 4 * q);
                 const float4 t = ld_f4(ee + c * D + 4 * q);
-                m.x += relu_f(t.x + hu.x); m.y += relu_f(t.y + hu.y); m.z += relu_f(t.z + hu.z); m.w += relu_f(t.w + hu.w);
+                m.x += relu_nan(t.x + hu.x); m.y += relu_nan(t.y + hu.y); m.z += relu_nan(t.z + hu.z); m.w += relu_nan(t.w + hu.w);
             }
             if (side) mb = m; else ma = m;
         }
     }
     a = make_float4(ma.x + hva.x, ma.y + hva.y, ma.z + hva.z, ma.w + hva.w);
     b = make_float4(mb.x + hvb.x, mb.y + hvb.y, mb.z + hvb.z, mb.w + hvb.w);
+}
+
+// one k-step of the A operand: gather, split into bf16 hi/lo, store to TMEM (16 lanes x 256 bit)
+template <int KS>
+__device__ __forceinline__ void gather_step(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& ra, const RowEdges& rb,
+                                            int qsub, bool live_a, bool live_b, uint32_t taddr, uint64_t* g1_done, int it)
+{
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    // the last k-step holds chunk 24 (k = 96..99) in sub-chunk 0 and zero padding (k = 100..111) in the others
+    if (KS < 6 || qsub == 0) gather_pair<KS>(p, ee, cb, ra, rb, qsub, a, b);
+    if (!live_a) a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!live_b) b = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t ha0, la0, ha1, la1, hb0, lb0, hb1, lb1;
+    split2(a.x, a.y, ha0, la0);
+    split2(a.z, a.w, ha1, la1);
+    split2(b.x, b.y, hb0, lb0);
+    split2(b.z, b.w, hb1, lb1);
+    if (KS == 0 && it > 0)
+    {
+        // A1 of the previous tile has been consumed once GEMM1 of that tile completed
+        mbar_wait(g1_done, (it - 1) & 1);
+        tc::fence_after_sync();
+    }
+    __syncwarp();
+    st_16x256(taddr + TC_A1_HI + 8 * KS, ha0, ha1, hb0, hb1);
+    st_16x256(taddr + TC_A1_LO + 8 * KS, la0, la1, lb0, lb1);
 }
 
 __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
@@ -209,6 +254,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
         tc::tmem_relinquish();
     }
     for (int i = tid; i < ED_COMBOS * Q; i += NT) st_f4(ee + 4 * i, ldg_f4(p.ee_comb + 4 * i));
+    for (int i = tid; i < D; i += NT) ee[ED_COMBOS * D + i] = -3.0e38f;
     for (int i = tid; i < N1; i += NT) b1s[i] = __ldg(p.b1 + i);
     for (int i = tid; i < N2; i += NT) b2s[i] = __ldg(p.b2 + i);
     tc::fence_before_sync();
@@ -278,14 +324,13 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
             if (it >= 2) mbar_wait(&bar[BAR_CSR_EMPTY + (it & 1)], ((it >> 1) - 1) & 1);
             const int n0 = tile * TM;
             const int rows = min(TM, p.num_nodes - n0);
-            if (lane == 0)
             {
+                // feature rows of the tile after next -> L2, 4 rows (1,600 B) per lane
                 const int ahead = tile + 2 * gridDim.x;
-                if (ahead < p.num_tiles)
-                {
-                    const int rn = min(TM, p.num_nodes - ahead * TM);
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (size_t)ahead * TM * D), "r"(rn * D * 4) : "memory");
-                }
+                const int rn = ahead < p.num_tiles ? min(TM, p.num_nodes - ahead * TM) : 0;
+                const int r0 = 4 * lane, nr = min(4, rn - r0);
+                if (nr > 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + ((size_t)ahead * TM + r0) * D), "r"(nr * D * 4) : "memory");
             }
             for (int i = lane; i <= rows; i += 32) cb.ptr[i] = __ldg(p.in_ptr + n0 + i);
             __syncwarp();
@@ -322,31 +367,15 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
             const int rows = min(TM, p.num_nodes - n0);
             const CsrBuf& cb = csr[it & 1];
             mbar_wait(&bar[BAR_CSR_FULL + (it & 1)], (it >> 1) & 1);
-            const RowEdges ra = load_row_edges(p, cb, n0, rows, r_a), rb = load_row_edges(p, cb, n0, rows, r_b);
+            const RowEdges ra = load_row_edges(p, ee, cb, n0, rows, r_a, qsub), rb = load_row_edges(p, ee, cb, n0, rows, r_b, qsub);
             const bool live_a = r_a < rows, live_b = r_b < rows;
-#pragma unroll 1
-            for (int ks = 0; ks < K1 / 16; ks++)
-            {
-                const int q = 4 * ks + qsub;
-                float4 a, b;
-                gather_pair(p, ee, cb, ra, rb, min(q, Q - 1), a, b);
-                if (q >= Q || !live_a) a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q >= Q || !live_b) b = make_float4(0.f, 0.f, 0.f, 0.f);
-                uint32_t ha0, la0, ha1, la1, hb0, lb0, hb1, lb1;
-                split2(a.x, a.y, ha0, la0);
-                split2(a.z, a.w, ha1, la1);
-                split2(b.x, b.y, hb0, lb0);
-                split2(b.z, b.w, hb1, lb1);
-                if (ks == 0 && it > 0)
-                {
-                    // A1 of the previous tile has been consumed once GEMM1 of that tile completed
-                    mbar_wait(&bar[BAR_G1_DONE], (it - 1) & 1);
-                    tc::fence_after_sync();
-                }
-                __syncwarp();
-                st_16x256(taddr + TC_A1_HI + 8 * ks, ha0, ha1, hb0, hb1);
-                st_16x256(taddr + TC_A1_LO + 8 * ks, la0, la1, lb0, lb1);
-            }
+            gather_step<0>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
+            gather_step<1>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
+            gather_step<2>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
+            gather_step<3>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
+            gather_step<4>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
+            gather_step<5>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
+            gather_step<6>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
@@ -377,10 +406,11 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
                 tc::wait_ld();
                 uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++)
+                for (int j = 0; j < 4; j++)
                 {
-                    const float2 b = *reinterpret_cast<const float2*>(b1s + 16 * c + 2 * j);
-                    split2(relu_f(__uint_as_float(r[2 * j]) + b.x), relu_f(__uint_as_float(r[2 * j + 1]) + b.y), hi[j], lo[j]);
+                    const float4 b = ld_f4(b1s + 16 * c + 4 * j);
+                    split2(relu_nan(__uint_as_float(r[4 * j]) + b.x), relu_nan(__uint_as_float(r[4 * j + 1]) + b.y), hi[2 * j], lo[2 * j]);
+                    split2(relu_nan(__uint_as_float(r[4 * j + 2]) + b.z), relu_nan(__uint_as_float(r[4 * j + 3]) + b.w), hi[2 * j + 1], lo[2 * j + 1]);
                 }
                 tc::st8(lane_base + TC_Z + 16 * c, hi);
                 tc::st8(lane_base + TC_Z + 16 * c + 8, lo);
@@ -408,7 +438,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
                         const float4 b = ld_f4(b2s + 16 * c + 4 * j);
                         float4 o = make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
                                                __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
-                        if (p.relu_out) o = make_float4(relu_f(o.x), relu_f(o.y), relu_f(o.z), relu_f(o.w));
+                        if (p.relu_out) o = make_float4(relu_nan(o.x), relu_nan(o.y), relu_nan(o.z), relu_nan(o.w));
                         if (live) stg_f4_stream(out + 16 * c + 4 * j, o);
                     }
                 }
