@@ -106,9 +106,8 @@ __device__ __forceinline__ void st_16x256(uint32_t taddr, uint32_t r0, uint32_t 
 }
 
 // The in-edges of one tile row, as far as they fit in registers (molecular graphs: in-degree <= 4 almost always);
-// longer lists continue from edge 4 in the staged CSR / global memory.  Absent slots point at the row's own
-// features and at the sentinel table row (-3e38): relu(-3e38 + h) adds exactly 0 for finite h, and for a
-// non-finite h_v the row's result m_v + h_v is the same non-finite value either way.
+// longer lists continue from edge 4 in the staged CSR / global memory.  Absent slots are never loaded: they
+// read as h_u = 0, EE = -3e38, and relu(-3e38 + 0) adds exactly 0.
 struct RowEdges {
     const float* hv;         // own feature row, offset by the thread's float4 sub-chunk
     const float* hu[4];      // source rows of the first four in-edges (own row where absent)
@@ -140,10 +139,28 @@ __device__ __forceinline__ RowEdges load_row_edges(const GinTcParams& p, const f
     return re;
 }
 
-__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+// predicated 16-byte loads (no branch, no memory traffic when `on` is false): absent edge slots read as
+// h_u = 0 and EE = -3e38, so that relu(EE + h_u) contributes exactly 0
+__device__ __forceinline__ float4 ldg_f4_if(const float* ptr, bool on)
 {
     float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+        "@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
+        : "l"(ptr), "r"((int)on));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4_if(uint32_t addr, bool on)
+{
+    float4 v;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.f32 %0, 0fFF61B1E6;\n\tmov.f32 %1, 0fFF61B1E6;\n\tmov.f32 %2, 0fFF61B1E6;\n\tmov.f32 %3, 0fFF61B1E6;\n\t"
+        "@p ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
+        : "r"(addr), "r"((int)on));
     return v;
 }
 
@@ -157,20 +174,20 @@ __device__ __forceinline__ void gather_pair(const GinTcParams& p, const float* e
     const float4 hva = ldg_f4(ra.hv + OFF), hvb = ldg_f4(rb.hv + OFF);
     float4 hua[4], hub[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) hua[j] = ldg_f4(ra.hu[j] + OFF);
+    for (int j = 0; j < 4; j++) hua[j] = ldg_f4_if(ra.hu[j] + OFF, j < ra.deg);
 #pragma unroll
-    for (int j = 0; j < 4; j++) hub[j] = ldg_f4(rb.hu[j] + OFF);
+    for (int j = 0; j < 4; j++) hub[j] = ldg_f4_if(rb.hu[j] + OFF, j < rb.deg);
     float4 ma = make_float4(0.f, 0.f, 0.f, 0.f), mb = ma;
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-        const float4 t = lds_f4(ra.t[j] + 4 * OFF);
+        const float4 t = lds_f4_if(ra.t[j] + 4 * OFF, j < ra.deg);
         ma.x += relu_nan(t.x + hua[j].x); ma.y += relu_nan(t.y + hua[j].y); ma.z += relu_nan(t.z + hua[j].z); ma.w += relu_nan(t.w + hua[j].w);
     }
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-        const float4 t = lds_f4(rb.t[j] + 4 * OFF);
+        const float4 t = lds_f4_if(rb.t[j] + 4 * OFF, j < rb.deg);
         mb.x += relu_nan(t.x + hub[j].x); mb.y += relu_nan(t.y + hub[j].y); mb.z += relu_nan(t.z + hub[j].z); mb.w += relu_nan(t.w + hub[j].w);
     }
     if (ra.deg > 4 || rb.deg > 4)
@@ -394,7 +411,6 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++)
         {
             const uint32_t ph = it & 1;
-            const int node = tile * TM + warp * 32 + lane;
             mbar_wait(&bar[BAR_G1_DONE], ph);
             tc::fence_after_sync();
             // z = relu(acc + b1) -> bf16 hi/lo, in place: columns [16c, 16c+8) hi, [16c+8, 16c+16) lo of k-step c
@@ -422,24 +438,41 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
 
             mbar_wait(&bar[BAR_G2_DONE], ph);
             tc::fence_after_sync();
-            float* out = p.h_out + (size_t)node * D;
-            const bool live = node < p.num_nodes;
-#pragma unroll 1
-            for (int c = 0; c < N2 / 16; c++)
-            {
-                uint32_t r[16];
-                tc::ld16(lane_base + TC_H + 16 * c, r);
-                tc::wait_ld();
+            // h' = acc + b2 (+ relu): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
+            // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction
+            const int tile_row0 = tile * TM + warp * 32;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+            for (int half = 0; half < 2; half++)
+            {
+                const int row_a = tile_row0 + half * 16 + (lane >> 2), row_b = row_a + 8;
+                const uint32_t ta = lane_base + ((uint32_t)(half * 16) << 16) + TC_H;
+#pragma unroll
+                for (int g4 = 0; g4 < 13; g4 += 4)
                 {
-                    if (16 * c + 4 * j < D)
+                    uint32_t r[16];
+                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                                 : "r"(ta + 8 * g4)
+                                 : "memory");
+                    tc::wait_ld();
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
                     {
-                        const float4 b = ld_f4(b2s + 16 * c + 4 * j);
-                        float4 o = make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
-                                               __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
-                        if (p.relu_out) o = make_float4(relu_nan(o.x), relu_nan(o.y), relu_nan(o.z), relu_nan(o.w));
-                        if (live) stg_f4_stream(out + 16 * c + 4 * j, o);
+                        const int col = 8 * (g4 + g) + 2 * (lane & 3);
+                        if (8 * (g4 + g) < D && col < D)
+                        {
+                            const float2 bb = *reinterpret_cast<const float2*>(b2s + col);
+                            float2 oa = make_float2(__uint_as_float(r[4 * g]) + bb.x, __uint_as_float(r[4 * g + 1]) + bb.y);
+                            float2 ob = make_float2(__uint_as_float(r[4 * g + 2]) + bb.x, __uint_as_float(r[4 * g + 3]) + bb.y);
+                            if (p.relu_out)
+                            {
+                                oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
+                                ob = make_float2(relu_nan(ob.x), relu_nan(ob.y));
+                            }
+                            if (row_a < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_a * D + col) = oa;
+                            if (row_b < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
+                        }
                     }
                 }
             }
