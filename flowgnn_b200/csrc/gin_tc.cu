@@ -7,13 +7,18 @@
 // B200 mapping (one CTA per SM, tiles of 128 consecutive nodes, UMMA M = 128, cta_group::1):
 //   * W1 / W2 are STATIONARY in shared memory for the whole launch, each as a bf16 hi + bf16 lo pair
 //     (no-swizzle K-major canonical layout, 4 x 46,592 B, loaded once by bulk TMA);
-//   * activations flow through TENSOR MEMORY: 8 gather warps build a_v in fp32 (coalesced float4 gathers,
-//     CSR order -> deterministic), split it into bf16 hi/lo and hand it over through a small shared-memory
-//     transposition buffer into TMEM (tcgen05.st) as the A operand of GEMM1;
-//   * GEMM1 = 3 x 7 tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM, N = 208);
-//     4 epilogue warps read z from TMEM, add b1, relu, split to bf16 hi/lo and write it back IN PLACE: the
-//     16 fp32 columns of k-step j become its 8 hi + 8 lo operand columns for GEMM2 (3 x 13 MMAs, N = 112);
-//   * the second epilogue adds b2 (+ relu) and streams h' to HBM.
+//   * activations flow through TENSOR MEMORY.  8 gather warps build a_v in fp32 (16-byte gathers in CSR
+//     order -> deterministic, no atomics; the tile's CSR slice is staged in shared memory by a loader warp
+//     one tile ahead, feature rows are prefetched into L2 two tiles ahead), split it into bf16 hi/lo and
+//     store it straight into TMEM with 16-lane x 256-bit tcgen05.st (the m16n8 fragment layout) as the A
+//     operand of GEMM1;
+//   * GEMM1 = 3 products (hi*hi + lo*hi + hi*lo) x 7 k-steps, fp32 accumulate in TMEM, issued as two N halves
+//     (112 + 96) so that 8 epilogue warps convert the first half while the tensor core works on the second:
+//     z = relu(acc + b1) is split to bf16 hi/lo and written back IN PLACE -- the 16 fp32 columns of k-step j
+//     become its 8 hi + 8 lo operand columns for GEMM2 (3 x 13 MMAs, N = 112, started on the first half
+//     while the second is being converted);
+//   * the second epilogue adds b2 (+ relu) and streams h' to HBM, one full 32-byte sector per row and store;
+//   * registers are redistributed with setmaxnreg: gather warps grow, epilogue / MMA / loader warps shrink.
 // The 3-product bf16 split keeps the fp32 contract (|y - y_ref| <= 1e-4 * max(1,|y_ref|); measured 7e-6 on
 // molhiv, 1.7e-5 on GIN-VN, tools/split_precision_probe.py) at 2.25 PFLOP/s-class tensor throughput.
 #include "internal.cuh"
@@ -34,10 +39,13 @@ constexpr int K2 = 208, N2 = 112;             // GEMM2  [TM x K2] * [N2 x K2]^T
 constexpr int WBLOCK = N1 * K1 * 2;           // bytes of one bf16 weight block (N1*K1 == N2*K2)
 static_assert(N1 * K1 == N2 * K2, "weight blocks share a size");
 
-constexpr int EPI_WARPS = 4, GATHER_WARPS = 8;
+// warp roles (warpgroup aligned, for setmaxnreg): 0-7 epilogue, 8-15 gather, 16 MMA issuer, 17 loader, 18-19 idle
+constexpr int EPI_WARPS = 8, GATHER_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS;
 constexpr int LOAD_WARP = MMA_WARP + 1;
-constexpr int NT = (LOAD_WARP + 1) * 32;      // 448 threads
+constexpr int NT = (MMA_WARP + 4) * 32;       // 640 threads
+constexpr int REGS_EPI = 80, REGS_MISC = 72, REGS_GATHER = 120;   // launch allocation: 96 per thread
+constexpr int N1A = 112, N1B = N1 - N1A;      // GEMM1 N halves = GEMM2 K halves (7 + 6 k-steps)
 
 // tensor-memory columns
 constexpr uint32_t TC_A1_HI = 0, TC_A1_LO = 56, TC_Z = 128, TC_H = 384;
@@ -65,7 +73,7 @@ struct Smem {
 static_assert(Smem::CSR % 16 == 0 && Smem::BAR % 8 == 0 && sizeof(CsrBuf) % 16 == 0, "alignment");
 static_assert(Smem::BYTES <= 232448, "shared memory budget");
 
-enum { BAR_W = 0, BAR_A1_FULL, BAR_G1_DONE, BAR_A2_FULL, BAR_G2_DONE, BAR_CSR_FULL /* 2 */, BAR_CSR_EMPTY = BAR_CSR_FULL + 2 /* 2 */ };
+enum { BAR_W = 0, BAR_A1_FULL, BAR_G1A_DONE, BAR_G1B_DONE, BAR_A2A_FULL, BAR_A2B_FULL, BAR_G2_DONE, BAR_CSR_FULL /* 2 */, BAR_CSR_EMPTY = BAR_CSR_FULL + 2 /* 2 */ };
 
 struct GinTcParams {
     const float* h_in; float* h_out;
@@ -83,6 +91,9 @@ __device__ __forceinline__ float relu_nan(float x)
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(0.0f));
     return y;
 }
+
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
@@ -107,7 +118,7 @@ __device__ __forceinline__ void st_16x256(uint32_t taddr, uint32_t r0, uint32_t 
 
 // The in-edges of one tile row, as far as they fit in registers (molecular graphs: in-degree <= 4 almost always);
 // longer lists continue from edge 4 in the staged CSR / global memory.  Absent slots are never loaded: they
-// read as h_u = 0, EE = -3e38, and relu(-3e38 + 0) adds exactly 0.
+// read as h_u = 0 and point at the sentinel table row (-3e38): relu(-3e38 + 0) adds exactly 0.
 struct RowEdges {
     const float* hv;         // own feature row, offset by the thread's float4 sub-chunk
     const float* hu[4];      // source rows of the first four in-edges (own row where absent)
@@ -139,8 +150,7 @@ __device__ __forceinline__ RowEdges load_row_edges(const GinTcParams& p, const f
     return re;
 }
 
-// predicated 16-byte loads (no branch, no memory traffic when `on` is false): absent edge slots read as
-// h_u = 0 and EE = -3e38, so that relu(EE + h_u) contributes exactly 0
+// predicated 16-byte load (no branch, no memory traffic when `on` is false): absent edge slots read as h_u = 0
 __device__ __forceinline__ float4 ldg_f4_if(const float* ptr, bool on)
 {
     float4 v;
@@ -152,52 +162,46 @@ __device__ __forceinline__ float4 ldg_f4_if(const float* ptr, bool on)
         : "l"(ptr), "r"((int)on));
     return v;
 }
-__device__ __forceinline__ float4 lds_f4_if(uint32_t addr, bool on)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
 {
     float4 v;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-        "mov.f32 %0, 0fFF61B1E6;\n\tmov.f32 %1, 0fFF61B1E6;\n\tmov.f32 %2, 0fFF61B1E6;\n\tmov.f32 %3, 0fFF61B1E6;\n\t"
-        "@p ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
-        : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
-        : "r"(addr), "r"((int)on));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
 
-// a_v[4q .. 4q+3] = sum over in-edges (CSR order) relu(h_u + EE[attr]) + h_v for two rows at once, q = 4 KS + qsub:
-// all global loads of the step are issued before the first use, addresses are pointer + immediate.
+// Software-pipelined gather of one tile row: `row_loads<KS>` issues the 16-byte loads of chunk q = 4 KS + qsub
+// (own row + up to four source rows, addresses = pointer + immediate), `row_finish<KS>` consumes them:
+// a_v[4q .. 4q+3] = sum over in-edges (CSR order) relu(h_u + EE[attr]) + h_v.  The loads of the NEXT half-step
+// are always issued before the current one is consumed, so every thread keeps five loads in flight.
+struct RowLoads { float4 hv; float4 hu[4]; };
+
 template <int KS>
-__device__ __forceinline__ void gather_pair(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& ra, const RowEdges& rb,
-                                            int qsub, float4& a, float4& b)
+__device__ __forceinline__ void row_loads(const RowEdges& r, int qsub, RowLoads& L)
 {
     constexpr int OFF = 16 * KS;      // floats
-    const float4 hva = ldg_f4(ra.hv + OFF), hvb = ldg_f4(rb.hv + OFF);
-    float4 hua[4], hub[4];
+    const bool on = (KS < 6) || (qsub == 0);      // the last k-step only holds chunk 24 (sub-chunk 0); the rest is zero padding
+    L.hv = ldg_f4_if(r.hv + OFF, on);
 #pragma unroll
-    for (int j = 0; j < 4; j++) hua[j] = ldg_f4_if(ra.hu[j] + OFF, j < ra.deg);
-#pragma unroll
-    for (int j = 0; j < 4; j++) hub[j] = ldg_f4_if(rb.hu[j] + OFF, j < rb.deg);
-    float4 ma = make_float4(0.f, 0.f, 0.f, 0.f), mb = ma;
+    for (int j = 0; j < 4; j++) L.hu[j] = ldg_f4_if(r.hu[j] + OFF, on && j < r.deg);
+}
+
+template <int KS>
+__device__ __forceinline__ float4 row_finish(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& r, int qsub, bool live,
+                                             const RowLoads& L)
+{
+    constexpr int OFF = 16 * KS;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 4; j++)
     {
-        const float4 t = lds_f4_if(ra.t[j] + 4 * OFF, j < ra.deg);
-        ma.x += relu_nan(t.x + hua[j].x); ma.y += relu_nan(t.y + hua[j].y); ma.z += relu_nan(t.z + hua[j].z); ma.w += relu_nan(t.w + hua[j].w);
+        const float4 t = lds_f4(r.t[j] + 4 * OFF);
+        m.x += relu_nan(t.x + L.hu[j].x); m.y += relu_nan(t.y + L.hu[j].y); m.z += relu_nan(t.z + L.hu[j].z); m.w += relu_nan(t.w + L.hu[j].w);
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-    {
-        const float4 t = lds_f4_if(rb.t[j] + 4 * OFF, j < rb.deg);
-        mb.x += relu_nan(t.x + hub[j].x); mb.y += relu_nan(t.y + hub[j].y); mb.z += relu_nan(t.z + hub[j].z); mb.w += relu_nan(t.w + hub[j].w);
-    }
-    if (ra.deg > 4 || rb.deg > 4)
+    if (r.deg > 4)
     {
         const int q = 4 * KS + qsub;
-#pragma unroll 1
-        for (int side = 0; side < 2; side++)
+        if (q < Q)
         {
-            const RowEdges& r = side ? rb : ra;
-            float4 m = side ? mb : ma;
             for (int e = r.eb + 4; e < r.eb + r.deg; e++)
             {
                 int u, c;
@@ -207,23 +211,17 @@ __device__ __forceinline__ void gather_pair(const GinTcParams& p, const float* e
                 const float4 t = ld_f4(ee + c * D + 4 * q);
                 m.x += relu_nan(t.x + hu.x); m.y += relu_nan(t.y + hu.y); m.z += relu_nan(t.z + hu.z); m.w += relu_nan(t.w + hu.w);
             }
-            if (side) mb = m; else ma = m;
         }
     }
-    a = make_float4(ma.x + hva.x, ma.y + hva.y, ma.z + hva.z, ma.w + hva.w);
-    b = make_float4(mb.x + hvb.x, mb.y + hvb.y, mb.z + hvb.z, mb.w + hvb.w);
+    float4 a = make_float4(m.x + L.hv.x, m.y + L.hv.y, m.z + L.hv.z, m.w + L.hv.w);
+    if (!live || (KS == 6 && qsub != 0)) a = make_float4(0.f, 0.f, 0.f, 0.f);
+    return a;
 }
 
-// one k-step of the A operand: gather, split into bf16 hi/lo, store to TMEM (16 lanes x 256 bit)
+// split one k-step of both rows into bf16 hi/lo and store it to TMEM (16 lanes x 256 bit)
 template <int KS>
-__device__ __forceinline__ void gather_step(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& ra, const RowEdges& rb,
-                                            int qsub, bool live_a, bool live_b, uint32_t taddr, uint64_t* g1_done, int it)
+__device__ __forceinline__ void store_step(const float4& a, const float4& b, uint32_t taddr, uint64_t* a1_free, int it)
 {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    // the last k-step holds chunk 24 (k = 96..99) in sub-chunk 0 and zero padding (k = 100..111) in the others
-    if (KS < 6 || qsub == 0) gather_pair<KS>(p, ee, cb, ra, rb, qsub, a, b);
-    if (!live_a) a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!live_b) b = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t ha0, la0, ha1, la1, hb0, lb0, hb1, lb1;
     split2(a.x, a.y, ha0, la0);
     split2(a.z, a.w, ha1, la1);
@@ -232,12 +230,43 @@ __device__ __forceinline__ void gather_step(const GinTcParams& p, const float* e
     if (KS == 0 && it > 0)
     {
         // A1 of the previous tile has been consumed once GEMM1 of that tile completed
-        mbar_wait(g1_done, (it - 1) & 1);
+        mbar_wait(a1_free, (it - 1) & 1);
         tc::fence_after_sync();
     }
     __syncwarp();
     st_16x256(taddr + TC_A1_HI + 8 * KS, ha0, ha1, hb0, hb1);
     st_16x256(taddr + TC_A1_LO + 8 * KS, la0, la1, lb0, lb1);
+}
+
+template <int KS>
+__device__ __forceinline__ void gather_steps(const GinTcParams& p, const float* ee, const CsrBuf& cb, const RowEdges& ra, const RowEdges& rb, int qsub,
+                                             bool live_a, bool live_b, uint32_t taddr, uint64_t* a1_free, int it, RowLoads& La, RowLoads& Lb)
+{
+    // on entry the loads of (KS, row a) are in flight in La
+    row_loads<KS>(rb, qsub, Lb);
+    const float4 a = row_finish<KS>(p, ee, cb, ra, qsub, live_a, La);
+    if (KS < 6) row_loads<(KS < 6 ? KS + 1 : KS)>(ra, qsub, La);
+    const float4 b = row_finish<KS>(p, ee, cb, rb, qsub, live_b, Lb);
+    store_step<KS>(a, b, taddr, a1_free, it);
+    if constexpr (KS < 6) gather_steps<KS + 1>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, a1_free, it, La, Lb);
+}
+
+// z = relu(acc + b1) for 16 accumulator columns of this thread's row -> bf16 hi/lo, written back in place
+__device__ __forceinline__ void convert_chunk(uint32_t zaddr, const float* b1c)
+{
+    uint32_t r[16];
+    tc::ld16(zaddr, r);
+    tc::wait_ld();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const float4 b = ld_f4(b1c + 4 * j);
+        split2(relu_nan(__uint_as_float(r[4 * j]) + b.x), relu_nan(__uint_as_float(r[4 * j + 1]) + b.y), hi[2 * j], lo[2 * j]);
+        split2(relu_nan(__uint_as_float(r[4 * j + 2]) + b.z), relu_nan(__uint_as_float(r[4 * j + 3]) + b.w), hi[2 * j + 1], lo[2 * j + 1]);
+    }
+    tc::st8(zaddr, hi);
+    tc::st8(zaddr + 8, lo);
 }
 
 __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
@@ -255,8 +284,10 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
     {
         mbar_init(&bar[BAR_W], 1);
         mbar_init(&bar[BAR_A1_FULL], GATHER_WARPS);
-        mbar_init(&bar[BAR_G1_DONE], 1);
-        mbar_init(&bar[BAR_A2_FULL], EPI_WARPS);
+        mbar_init(&bar[BAR_G1A_DONE], 1);
+        mbar_init(&bar[BAR_G1B_DONE], 1);
+        mbar_init(&bar[BAR_A2A_FULL], EPI_WARPS);
+        mbar_init(&bar[BAR_A2B_FULL], EPI_WARPS);
         mbar_init(&bar[BAR_G2_DONE], 1);
         for (int i = 0; i < 2; i++)
         {
@@ -279,95 +310,110 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
     tc::fence_after_sync();
     const uint32_t tbase = *tmem_ptr;
 
-    if (warp == MMA_WARP)
+    if (warp >= MMA_WARP)
     {
-        // ===== weight loader + MMA issuer (one thread) =====
-        if (lane == 0)
+        reg_dec<REGS_MISC>();
+        if (warp == MMA_WARP)
         {
-            mbar_arrive_expect_tx(&bar[BAR_W], 4 * WBLOCK);
+            // ===== weight loader + MMA issuer (one thread) =====
+            if (lane == 0)
+            {
+                mbar_arrive_expect_tx(&bar[BAR_W], 4 * WBLOCK);
 #pragma unroll
-            for (int i = 0; i < 4; i++) tma_load_1d(smem + Smem::W + i * WBLOCK, p.wpack + (size_t)i * WBLOCK, WBLOCK, &bar[BAR_W]);
-            mbar_wait(&bar[BAR_W], 0);
-            const uint32_t w_addr = smem_u32(smem + Smem::W);
-            const uint32_t idesc1 = tc::idesc_bf16(TM, N1), idesc2 = tc::idesc_bf16(TM, N2);
+                for (int i = 0; i < 4; i++) tma_load_1d(smem + Smem::W + i * WBLOCK, p.wpack + (size_t)i * WBLOCK, WBLOCK, &bar[BAR_W]);
+                mbar_wait(&bar[BAR_W], 0);
+                const uint32_t w_addr = smem_u32(smem + Smem::W);
+                const uint32_t idesc1a = tc::idesc_bf16(TM, N1A), idesc1b = tc::idesc_bf16(TM, N1B), idesc2 = tc::idesc_bf16(TM, N2);
+                int it = 0;
+                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++)
+                {
+                    const uint32_t ph = it & 1;
+                    mbar_wait(&bar[BAR_A1_FULL], ph);
+                    tc::fence_after_sync();
+                    // GEMM1, N half a (z columns 0..111) then half b (112..207): B rows are 16 bytes apart inside a k-chunk
+#pragma unroll
+                    for (int nh = 0; nh < 2; nh++)
+                    {
+                        bool acc = false;
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++)
+                        {
+                            const uint32_t a_col = tbase + (prod == 1 ? TC_A1_LO : TC_A1_HI);
+                            const uint32_t b_addr = w_addr + (prod == 2 ? WBLOCK : 0) + (nh ? N1A * 16 : 0);
+#pragma unroll
+                            for (int j = 0; j < K1 / 16; j++)
+                            {
+                                tc::mma_ts(tbase + TC_Z + (nh ? N1A : 0), a_col + 8 * j, tc::smem_desc(b_addr + 2 * j * N1 * 16, N1 * 16, 128),
+                                           nh ? idesc1b : idesc1a, acc);
+                                acc = true;
+                            }
+                        }
+                        tc::commit(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
+                    }
+                    // GEMM2, K half a (k-steps 0..6, operand columns converted from z half a) then half b (7..12)
+                    bool acc = false;
+#pragma unroll
+                    for (int kh = 0; kh < 2; kh++)
+                    {
+                        mbar_wait(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
+                        tc::fence_after_sync();
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++)
+                        {
+                            const uint32_t a_col = tbase + TC_Z + (prod == 1 ? 8 : 0);
+                            const uint32_t b_addr = w_addr + 2 * WBLOCK + (prod == 2 ? WBLOCK : 0);
+#pragma unroll
+                            for (int j = (kh ? N1A / 16 : 0); j < (kh ? K2 / 16 : N1A / 16); j++)
+                            {
+                                tc::mma_ts(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * N2 * 16, N2 * 16, 128), idesc2, acc);
+                                acc = true;
+                            }
+                        }
+                    }
+                    tc::commit(&bar[BAR_G2_DONE]);
+                }
+            }
+        }
+        else if (warp == LOAD_WARP)
+        {
+            // ===== loader warp: stages the next tile's CSR slice in shared memory and prefetches feature rows into L2 =====
+            CsrBuf* csr = reinterpret_cast<CsrBuf*>(smem + Smem::CSR);
             int it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++)
             {
-                const uint32_t ph = it & 1;
-                mbar_wait(&bar[BAR_A1_FULL], ph);
-                tc::fence_after_sync();
-                bool acc = false;
-#pragma unroll
-                for (int prod = 0; prod < 3; prod++)
+                CsrBuf& cb = csr[it & 1];
+                if (it >= 2) mbar_wait(&bar[BAR_CSR_EMPTY + (it & 1)], ((it >> 1) - 1) & 1);
+                const int n0 = tile * TM;
+                const int rows = min(TM, p.num_nodes - n0);
                 {
-                    const uint32_t a_col = tbase + (prod == 1 ? TC_A1_LO : TC_A1_HI);
-                    const uint32_t b_addr = w_addr + (prod == 2 ? WBLOCK : 0);
-#pragma unroll
-                    for (int j = 0; j < K1 / 16; j++)
+                    // feature rows of the tile after next -> L2, 4 rows (1,600 B) per lane
+                    const int ahead = tile + 2 * gridDim.x;
+                    const int rn = ahead < p.num_tiles ? min(TM, p.num_nodes - ahead * TM) : 0;
+                    const int r0 = 4 * lane, nr = min(4, rn - r0);
+                    if (nr > 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + ((size_t)ahead * TM + r0) * D), "r"(nr * D * 4) : "memory");
+                }
+                for (int i = lane; i <= rows; i += 32) cb.ptr[i] = __ldg(p.in_ptr + n0 + i);
+                __syncwarp();
+                const int e0 = cb.ptr[0], ne = cb.ptr[rows] - e0;
+                const bool staged = ne <= CSR_CAP;
+                if (staged)
+                {
+                    for (int i = lane; i < ne; i += 32)
                     {
-                        tc::mma_ts(tbase + TC_Z, a_col + 8 * j, tc::smem_desc(b_addr + 2 * j * N1 * 16, N1 * 16, 128), idesc1, acc);
-                        acc = true;
+                        cb.src[i] = __ldg(p.src + e0 + i);
+                        cb.code[i] = __ldg(p.code + e0 + i);
                     }
                 }
-                tc::commit(&bar[BAR_G1_DONE]);
-
-                mbar_wait(&bar[BAR_A2_FULL], ph);
-                tc::fence_after_sync();
-                acc = false;
-#pragma unroll
-                for (int prod = 0; prod < 3; prod++)
-                {
-                    const uint32_t a_col = tbase + TC_Z + (prod == 1 ? 8 : 0);
-                    const uint32_t b_addr = w_addr + 2 * WBLOCK + (prod == 2 ? WBLOCK : 0);
-#pragma unroll
-                    for (int j = 0; j < K2 / 16; j++)
-                    {
-                        tc::mma_ts(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * N2 * 16, N2 * 16, 128), idesc2, acc);
-                        acc = true;
-                    }
-                }
-                tc::commit(&bar[BAR_G2_DONE]);
+                if (lane == 0) { cb.e0 = e0; cb.staged = staged ? 1 : 0; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[BAR_CSR_FULL + (it & 1)]);
             }
-        }
-    }
-    else if (warp == LOAD_WARP)
-    {
-        // ===== loader warp: stages the next tile's CSR slice in shared memory and prefetches feature rows into L2 =====
-        CsrBuf* csr = reinterpret_cast<CsrBuf*>(smem + Smem::CSR);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++)
-        {
-            CsrBuf& cb = csr[it & 1];
-            if (it >= 2) mbar_wait(&bar[BAR_CSR_EMPTY + (it & 1)], ((it >> 1) - 1) & 1);
-            const int n0 = tile * TM;
-            const int rows = min(TM, p.num_nodes - n0);
-            {
-                // feature rows of the tile after next -> L2, 4 rows (1,600 B) per lane
-                const int ahead = tile + 2 * gridDim.x;
-                const int rn = ahead < p.num_tiles ? min(TM, p.num_nodes - ahead * TM) : 0;
-                const int r0 = 4 * lane, nr = min(4, rn - r0);
-                if (nr > 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + ((size_t)ahead * TM + r0) * D), "r"(nr * D * 4) : "memory");
-            }
-            for (int i = lane; i <= rows; i += 32) cb.ptr[i] = __ldg(p.in_ptr + n0 + i);
-            __syncwarp();
-            const int e0 = cb.ptr[0], ne = cb.ptr[rows] - e0;
-            const bool staged = ne <= CSR_CAP;
-            if (staged)
-            {
-                for (int i = lane; i < ne; i += 32)
-                {
-                    cb.src[i] = __ldg(p.src + e0 + i);
-                    cb.code[i] = __ldg(p.code + e0 + i);
-                }
-            }
-            if (lane == 0) { cb.e0 = e0; cb.staged = staged ? 1 : 0; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar[BAR_CSR_FULL + (it & 1)]);
         }
     }
     else if (warp >= EPI_WARPS)
     {
+        reg_inc<REGS_GATHER>();
         // ===== gather warps: build the A operand of GEMM1 directly in tensor memory =====
         // warp -> TMEM lane quadrant (warp % 4) and 16-row half; thread t -> rows t/4 and t/4 + 8 of that half and,
         // per k-step ks, the float4 chunk q = 4 ks + t % 4 (k = 16 ks + 4 (t%4) .. +3 = TMEM columns 2(t%4), 2(t%4)+1)
@@ -386,13 +432,9 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
             mbar_wait(&bar[BAR_CSR_FULL + (it & 1)], (it >> 1) & 1);
             const RowEdges ra = load_row_edges(p, ee, cb, n0, rows, r_a, qsub), rb = load_row_edges(p, ee, cb, n0, rows, r_b, qsub);
             const bool live_a = r_a < rows, live_b = r_b < rows;
-            gather_step<0>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
-            gather_step<1>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
-            gather_step<2>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
-            gather_step<3>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
-            gather_step<4>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
-            gather_step<5>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
-            gather_step<6>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1_DONE], it);
+            RowLoads La, Lb;
+            row_loads<0>(ra, qsub, La);
+            gather_steps<0>(p, ee, cb, ra, rb, qsub, live_a, live_b, taddr, &bar[BAR_G1B_DONE], it, La, Lb);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
@@ -405,74 +447,67 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
     }
     else
     {
-        // ===== epilogue warps: thread = tile row (TMEM lane) =====
-        const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+        reg_dec<REGS_EPI>();
+        // ===== epilogue warps: two per TMEM lane quadrant =====
+        const int quad = warp & 3, pp = warp >> 2;
+        const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++)
         {
             const uint32_t ph = it & 1;
-            mbar_wait(&bar[BAR_G1_DONE], ph);
+            // z = relu(acc + b1) -> bf16 hi/lo, in place (thread = row): columns [16c, 16c+8) hi, [16c+8, 16c+16) lo of
+            // k-step c; the two warps of a quadrant take alternate chunks
+            mbar_wait(&bar[BAR_G1A_DONE], ph);
             tc::fence_after_sync();
-            // z = relu(acc + b1) -> bf16 hi/lo, in place: columns [16c, 16c+8) hi, [16c+8, 16c+16) lo of k-step c
 #pragma unroll 1
-            for (int c = 0; c < N1 / 16; c++)
-            {
-                uint32_t r[16];
-                tc::ld16(lane_base + TC_Z + 16 * c, r);
-                tc::wait_ld();
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                {
-                    const float4 b = ld_f4(b1s + 16 * c + 4 * j);
-                    split2(relu_nan(__uint_as_float(r[4 * j]) + b.x), relu_nan(__uint_as_float(r[4 * j + 1]) + b.y), hi[2 * j], lo[2 * j]);
-                    split2(relu_nan(__uint_as_float(r[4 * j + 2]) + b.z), relu_nan(__uint_as_float(r[4 * j + 3]) + b.w), hi[2 * j + 1], lo[2 * j + 1]);
-                }
-                tc::st8(lane_base + TC_Z + 16 * c, hi);
-                tc::st8(lane_base + TC_Z + 16 * c + 8, lo);
-            }
+            for (int c = pp; c < N1A / 16; c += 2) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar[BAR_A2_FULL]);
+            if (lane == 0) mbar_arrive(&bar[BAR_A2A_FULL]);
+
+            mbar_wait(&bar[BAR_G1B_DONE], ph);
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c = N1A / 16 + (pp ^ 1); c < N1 / 16; c += 2) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[BAR_A2B_FULL]);
 
             mbar_wait(&bar[BAR_G2_DONE], ph);
             tc::fence_after_sync();
             // h' = acc + b2 (+ relu): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
-            // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction
-            const int tile_row0 = tile * TM + warp * 32;
+            // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction; warp pp of the
+            // quadrant takes its 16-row half
+            const int row_a = tile * TM + quad * 32 + pp * 16 + (lane >> 2), row_b = row_a + 8;
+            const uint32_t ta = lane_base + ((uint32_t)(pp * 16) << 16) + TC_H;
 #pragma unroll
-            for (int half = 0; half < 2; half++)
+            for (int g4 = 0; g4 < 13; g4 += 4)
             {
-                const int row_a = tile_row0 + half * 16 + (lane >> 2), row_b = row_a + 8;
-                const uint32_t ta = lane_base + ((uint32_t)(half * 16) << 16) + TC_H;
+                uint32_t r[16];
+                asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(ta + 8 * g4)
+                             : "memory");
+                tc::wait_ld();
 #pragma unroll
-                for (int g4 = 0; g4 < 13; g4 += 4)
+                for (int g = 0; g < 4; g++)
                 {
-                    uint32_t r[16];
-                    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                                 : "r"(ta + 8 * g4)
-                                 : "memory");
-                    tc::wait_ld();
-#pragma unroll
-                    for (int g = 0; g < 4; g++)
+                    const int col = 8 * (g4 + g) + 2 * (lane & 3);
+                    if (8 * (g4 + g) < D && col < D)
                     {
-                        const int col = 8 * (g4 + g) + 2 * (lane & 3);
-                        if (8 * (g4 + g) < D && col < D)
+                        const float2 bb = *reinterpret_cast<const float2*>(b2s + col);
+                        float2 oa = make_float2(__uint_as_float(r[4 * g]) + bb.x, __uint_as_float(r[4 * g + 1]) + bb.y);
+                        float2 ob = make_float2(__uint_as_float(r[4 * g + 2]) + bb.x, __uint_as_float(r[4 * g + 3]) + bb.y);
+                        if (p.relu_out)
                         {
-                            const float2 bb = *reinterpret_cast<const float2*>(b2s + col);
-                            float2 oa = make_float2(__uint_as_float(r[4 * g]) + bb.x, __uint_as_float(r[4 * g + 1]) + bb.y);
-                            float2 ob = make_float2(__uint_as_float(r[4 * g + 2]) + bb.x, __uint_as_float(r[4 * g + 3]) + bb.y);
-                            if (p.relu_out)
-                            {
-                                oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
-                                ob = make_float2(relu_nan(ob.x), relu_nan(ob.y));
-                            }
-                            if (row_a < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_a * D + col) = oa;
-                            if (row_b < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
+                            oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
+                            ob = make_float2(relu_nan(ob.x), relu_nan(ob.y));
                         }
+                        if (row_a < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_a * D + col) = oa;
+                        if (row_b < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
                     }
                 }
             }

@@ -21,7 +21,7 @@ tot = sum(int(x[idx['# Samples']]) for x in data); toti = sum(int(x[idx['Instruc
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 print("total samples", tot, "warp instructions", toti)
 cum = 0; cumi = 0
-marks = ('LDTM', 'STTM', 'UTCBAR', 'UBLKPF', 'EXIT', 'STG')
+marks = ('UTCBAR', 'USETMAXREG', 'EXIT')
 for i, x in enumerate(data):
     n = int(x[idx['# Samples']]); cum += n; cumi += int(x[idx['Instructions Executed']])
     s = x[idx['Source']].strip()
