@@ -171,6 +171,51 @@ class Context:
         return self.download()
 
 
+class ReferenceCall:
+    """A prepared call of the reference-compatible entry point ``<MODEL>_compute_graphs`` (Part 1 of the header)
+    with HOST arrays, marshalled once: ``run()`` is then exactly the C call a host written in C++ would make
+    (GIN/src/host.cc:184-209), with no per-call Python work."""
+
+    def __init__(self, model: str, batch: Batch, weights: Weights, reload_weights: Optional[np.ndarray] = None,
+                 weight_sets: Optional[Sequence[Weights]] = None):
+        lib = load_library()
+        spec: ModelSpec = get_model(model)
+        sets = list(weight_sets) if weight_sets is not None else [weights]
+        sets = [check_weights(spec, w) for w in sets]
+        stacked: Dict[str, np.ndarray] = {n: np.ascontiguousarray(np.stack([w[n] for w in sets])) for n in spec.weight_names}
+        G = batch.num_graphs
+        if reload_weights is None:
+            reload_weights = np.zeros(G, dtype=np.int32)
+            if G:
+                reload_weights[0] = 1
+        reload_weights = np.ascontiguousarray(reload_weights, dtype=np.int32)
+        self.out = np.zeros(G, dtype=np.float32)
+        nn = np.ascontiguousarray(batch.nums_of_nodes, dtype=np.int32)
+        ne = np.ascontiguousarray(batch.nums_of_edges, dtype=np.int32)
+        args = [ctypes.c_int(G), nn.ctypes.data_as(_i32p), ne.ctypes.data_as(_i32p), reload_weights.ctypes.data_as(_i32p),
+                self.out.ctypes.data_as(_f32p), batch.node_feature.ctypes.data_as(_i32p)]
+        if spec.uses_eigen:
+            if batch.node_eigen is None:
+                raise FlowGNNError("DGN needs node_eigen")
+            args.append(batch.node_eigen.ctypes.data_as(_f32p))
+        args.append(batch.edge_list.ctypes.data_as(_i32p))
+        if spec.uses_edge_attr:
+            if batch.edge_attr is None:
+                raise FlowGNNError(f"{spec.name} needs edge_attr")
+            args.append(batch.edge_attr.ctypes.data_as(_i32p))
+        for n in spec.weight_names:
+            args.append(stacked[n].ctypes.data_as(_f32p))
+        self._keep = (nn, ne, reload_weights, stacked, batch)
+        self._args = args
+        self._symbol = spec.symbol
+        self._fn = getattr(lib, spec.symbol)
+        self._fn.restype = ctypes.c_int
+
+    def run(self) -> np.ndarray:
+        _check(self._fn(*self._args), self._symbol)
+        return self.out
+
+
 def compute_graphs(model: str, batch: Batch, weights: Weights, reload_weights: Optional[np.ndarray] = None,
                    weight_sets: Optional[Sequence[Weights]] = None) -> np.ndarray:
     """Call the reference-compatible entry point ``<MODEL>_compute_graphs`` (Part 1 of the header)
@@ -179,34 +224,4 @@ def compute_graphs(model: str, batch: Batch, weights: Weights, reload_weights: O
     ``weight_sets`` (optional) stacks several weight sets along the leading dimension; ``reload_weights``
     then marks the graphs at which the kernel advances to the next set (GIN/src/GIN_compute.cc:49-63).
     GIN-VN: the caller passes the virtual-node-augmented batch (as the reference's host does)."""
-    lib = load_library()
-    spec: ModelSpec = get_model(model)
-    sets = list(weight_sets) if weight_sets is not None else [weights]
-    sets = [check_weights(spec, w) for w in sets]
-    stacked: Dict[str, np.ndarray] = {n: np.ascontiguousarray(np.stack([w[n] for w in sets])) for n in spec.weight_names}
-    G = batch.num_graphs
-    if reload_weights is None:
-        reload_weights = np.zeros(G, dtype=np.int32)
-        if G:
-            reload_weights[0] = 1
-    reload_weights = np.ascontiguousarray(reload_weights, dtype=np.int32)
-    out = np.zeros(G, dtype=np.float32)
-    nn = np.ascontiguousarray(batch.nums_of_nodes, dtype=np.int32)
-    ne = np.ascontiguousarray(batch.nums_of_edges, dtype=np.int32)
-    args = [ctypes.c_int(G), nn.ctypes.data_as(_i32p), ne.ctypes.data_as(_i32p), reload_weights.ctypes.data_as(_i32p),
-            out.ctypes.data_as(_f32p), batch.node_feature.ctypes.data_as(_i32p)]
-    if spec.uses_eigen:
-        if batch.node_eigen is None:
-            raise FlowGNNError("DGN needs node_eigen")
-        args.append(batch.node_eigen.ctypes.data_as(_f32p))
-    args.append(batch.edge_list.ctypes.data_as(_i32p))
-    if spec.uses_edge_attr:
-        if batch.edge_attr is None:
-            raise FlowGNNError(f"{spec.name} needs edge_attr")
-        args.append(batch.edge_attr.ctypes.data_as(_i32p))
-    for n in spec.weight_names:
-        args.append(stacked[n].ctypes.data_as(_f32p))
-    fn = getattr(lib, spec.symbol)
-    fn.restype = ctypes.c_int
-    _check(fn(*args), spec.symbol)
-    return out
+    return ReferenceCall(model, batch, weights, reload_weights, weight_sets).run()

@@ -152,6 +152,13 @@ struct flowgnn_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DeviceBatch batch;
     bool batch_ready = false;
+    // host-pointer entry points: the batch is cut into chunks that alternate between two device batches, so that
+    // the H2D copy of chunk i+1 (copy_stream) overlaps the kernels of chunk i (stream)
+    DeviceBatch pipe[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t up_done[2] = {nullptr, nullptr}, buf_free[2] = {nullptr, nullptr};
+    float* h_out = nullptr; size_t h_out_cap = 0;      // pinned staging of the predictions
+    int* h_status = nullptr;                           // pinned, one word per chunk
     GinWeights gin; GcnWeights gcn; GatWeights gat; PnaWeights pna; DgnWeights dgn;
     bool loaded[NUM_MODELS] = {false, false, false, false, false};
     uint64_t weight_hash[NUM_MODELS] = {0, 0, 0, 0, 0};
@@ -350,6 +357,13 @@ int flowgnn_b200_create(flowgnn_ctx** out, int device)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     FG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++)
+    {
+        FG_CUDA(cudaEventCreateWithFlags(&c->up_done[i], cudaEventDisableTiming));
+        FG_CUDA(cudaEventCreateWithFlags(&c->buf_free[i], cudaEventDisableTiming));
+    }
+    FG_CUDA(cudaMallocHost(&c->h_status, sizeof(int) * 64));
     FG_CUDA(cudaEventCreate(&c->ev0));
     FG_CUDA(cudaEventCreate(&c->ev1));
     *out = c.release();
@@ -361,7 +375,17 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (!ctx) return 0;
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
     ctx->batch.release();
+    for (int i = 0; i < 2; i++)
+    {
+        ctx->pipe[i].release();
+        cudaEventDestroy(ctx->up_done[i]);
+        cudaEventDestroy(ctx->buf_free[i]);
+    }
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    cudaStreamDestroy(ctx->copy_stream);
     DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
@@ -417,11 +441,14 @@ int flowgnn_b200_load_weights(flowgnn_ctx* ctx, int model, const float* const* w
     return 0;
 }
 
-int flowgnn_b200_upload_batch(flowgnn_ctx* ctx, int num_graphs, int64_t total_nodes, int64_t total_edges,
-                              const int32_t* nums_of_nodes, const int32_t* nums_of_edges, const int32_t* node_feature,
-                              const int32_t* edge_list, const int32_t* edge_attr, const float* node_eigen)
+}  // extern "C"
+
+namespace {
+
+int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_nodes, int64_t total_edges, const int32_t* nums_of_nodes,
+                const int32_t* nums_of_edges, const int32_t* node_feature, const int32_t* edge_list, const int32_t* edge_attr,
+                const float* node_eigen)
 {
-    FG_TRY(check_ctx(ctx));
     if (num_graphs < 0 || total_nodes < 0 || total_edges < 0) { set_last_error("negative size"); return FG_ERR_INVALID; }
     if (total_nodes >= (int64_t(1) << 31) / 100 * 4 || total_edges >= (int64_t(1) << 31) - 64)
     {
@@ -433,12 +460,8 @@ int flowgnn_b200_upload_batch(flowgnn_ctx* ctx, int num_graphs, int64_t total_no
         set_last_error("null batch array");
         return FG_ERR_INVALID;
     }
-    DeviceGuard guard(ctx->device);
-    DeviceBatch& b = ctx->batch;
-    ctx->batch_ready = false;
     b.num_graphs = num_graphs; b.total_nodes = total_nodes; b.total_edges = total_edges;
     b.has_attr = edge_attr != nullptr; b.has_eigen = node_eigen != nullptr;
-    cudaStream_t s = ctx->stream;
     FG_TRY(copy_in(b.nums_of_nodes, nums_of_nodes, sizeof(int) * (size_t)num_graphs, s));
     FG_TRY(copy_in(b.nums_of_edges, nums_of_edges, sizeof(int) * (size_t)num_graphs, s));
     FG_TRY(copy_in(b.node_feature, node_feature, sizeof(int) * ND_FEATURE * (size_t)total_nodes, s));
@@ -446,26 +469,15 @@ int flowgnn_b200_upload_batch(flowgnn_ctx* ctx, int num_graphs, int64_t total_no
     if (edge_attr) FG_TRY(copy_in(b.edge_attr, edge_attr, sizeof(int) * 3 * (size_t)total_edges, s));
     if (node_eigen) FG_TRY(copy_in(b.node_eigen, node_eigen, sizeof(float) * 4 * (size_t)total_nodes, s));
     FG_TRY(b.out.reserve(sizeof(float) * (size_t)(num_graphs + 1)));
-    ctx->batch_ready = true;
     return 0;
 }
 
-int flowgnn_b200_compute(flowgnn_ctx* ctx, int model, float* elapsed_ms)
+// load_graph + the full forward of `model` on a resident batch, all on stream `s`
+int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
 {
-    FG_TRY(check_ctx(ctx));
-    if (model < 0 || model >= NUM_MODELS) { set_last_error("unknown model id"); return FG_ERR_INVALID; }
-    if (!ctx->loaded[model]) { set_last_error("compute: load_weights has not been called for this model"); return FG_ERR_STATE; }
-    if (!ctx->batch_ready) { set_last_error("compute: no batch uploaded"); return FG_ERR_STATE; }
-    DeviceGuard guard(ctx->device);
-    DeviceBatch& b = ctx->batch;
-    cudaStream_t s = ctx->stream;
-    ctx->last_launches = 0;
-    if (elapsed_ms) *elapsed_ms = 0.f;
     if (b.num_graphs == 0) return 0;
     if (model == MODEL_DGN && !b.has_eigen) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
     if ((model == MODEL_GIN || model == MODEL_GCN) && !b.has_attr) { set_last_error("GIN/GCN need edge_attr"); return FG_ERR_INVALID; }
-
-    if (elapsed_ms) FG_CUDA(cudaEventRecord(ctx->ev0, s));
     const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
@@ -483,6 +495,39 @@ int flowgnn_b200_compute(flowgnn_ctx* ctx, int model, float* elapsed_ms)
     case MODEL_PNA: FG_TRY(pna_forward(b, ctx->pna, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
     case MODEL_DGN: FG_TRY(dgn_forward(b, ctx->dgn, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
     }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flowgnn_b200_upload_batch(flowgnn_ctx* ctx, int num_graphs, int64_t total_nodes, int64_t total_edges,
+                              const int32_t* nums_of_nodes, const int32_t* nums_of_edges, const int32_t* node_feature,
+                              const int32_t* edge_list, const int32_t* edge_attr, const float* node_eigen)
+{
+    FG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    ctx->batch_ready = false;
+    FG_TRY(upload_into(ctx->batch, ctx->stream, num_graphs, total_nodes, total_edges, nums_of_nodes, nums_of_edges, node_feature, edge_list,
+                       edge_attr, node_eigen));
+    ctx->batch_ready = true;
+    return 0;
+}
+
+int flowgnn_b200_compute(flowgnn_ctx* ctx, int model, float* elapsed_ms)
+{
+    FG_TRY(check_ctx(ctx));
+    if (model < 0 || model >= NUM_MODELS) { set_last_error("unknown model id"); return FG_ERR_INVALID; }
+    if (!ctx->loaded[model]) { set_last_error("compute: load_weights has not been called for this model"); return FG_ERR_STATE; }
+    if (!ctx->batch_ready) { set_last_error("compute: no batch uploaded"); return FG_ERR_STATE; }
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ctx->last_launches = 0;
+    if (elapsed_ms) *elapsed_ms = 0.f;
+    if (ctx->batch.num_graphs == 0) return 0;
+    if (elapsed_ms) FG_CUDA(cudaEventRecord(ctx->ev0, s));
+    FG_TRY(compute_on(ctx, ctx->batch, s, model));
     if (elapsed_ms)
     {
         FG_CUDA(cudaEventRecord(ctx->ev1, s));
@@ -596,13 +641,54 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             FG_TRY(flowgnn_b200_load_weights(ctx, model, ptrs.data(), nw));
             ctx->weight_hash[model] = h;
         }
-        // the reference's GAT reads node features from the START of the batch buffer for every graph
+        // Cut the run into chunks and alternate between two device batches: the H2D copy of chunk i+1 (copy stream)
+        // overlaps the kernels of chunk i (compute stream).  Chunks are whole graphs, so results do not depend on the cut.
+        // the reference's GAT reads node features from the START of the batch buffer for every graph.
         const bool gat_bug = (model == MODEL_GAT) && ctx->opt.gat_node_offset_bug;
-        const int32_t* feat_run = gat_bug ? feat : feat + ND_FEATURE * node_base;
-        FG_TRY(flowgnn_b200_upload_batch(ctx, g1 - g, n_run, e_run, nn + g, ne + g, feat_run, edges + 2 * edge_base,
-                                         attr ? attr + 3 * edge_base : nullptr, eig ? eig + 4 * node_base : nullptr));
-        FG_TRY(flowgnn_b200_compute(ctx, model, nullptr));
-        FG_TRY(flowgnn_b200_download(ctx, out + g, g1 - g));
+        const int run_graphs = g1 - g;
+        int nchunks = run_graphs / 8192;
+        nchunks = nchunks < 1 ? 1 : (nchunks > 4 ? 4 : nchunks);
+        const int per_chunk = (run_graphs + nchunks - 1) / nchunks;
+        if ((size_t)run_graphs > ctx->h_out_cap)
+        {
+            if (ctx->h_out) cudaFreeHost(ctx->h_out);
+            ctx->h_out = nullptr; ctx->h_out_cap = 0;
+            FG_CUDA(cudaMallocHost(&ctx->h_out, sizeof(float) * (size_t)run_graphs));
+            ctx->h_out_cap = (size_t)run_graphs;
+        }
+        ctx->last_launches = 0;
+        ctx->timer.marks = 0;
+        int64_t nb = node_base, eb = edge_base;
+        int cg = g;
+        for (int ci = 0; ci < nchunks; ci++)
+        {
+            const int c1 = (cg + per_chunk < g1) ? cg + per_chunk : g1;
+            int64_t n_c = 0, e_c = 0;
+            for (int k = cg; k < c1; k++) { n_c += nn[k]; e_c += ne[k]; }
+            DeviceBatch& db = ctx->pipe[ci & 1];
+            if (ci >= 2) FG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->buf_free[ci & 1], 0));
+            FG_TRY(upload_into(db, ctx->copy_stream, c1 - cg, n_c, e_c, nn + cg, ne + cg, gat_bug ? feat : feat + ND_FEATURE * nb,
+                               edges + 2 * eb, attr ? attr + 3 * eb : nullptr, eig ? eig + 4 * nb : nullptr));
+            FG_CUDA(cudaEventRecord(ctx->up_done[ci & 1], ctx->copy_stream));
+            FG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->up_done[ci & 1], 0));
+            FG_TRY(compute_on(ctx, db, ctx->stream, model));
+            if (c1 > cg)
+            {
+                FG_CUDA(cudaMemcpyAsync(ctx->h_out + (cg - g), db.out.ptr, sizeof(float) * (size_t)(c1 - cg), cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(cudaMemcpyAsync(ctx->h_status + ci, db.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            else ctx->h_status[ci] = 0;
+            FG_CUDA(cudaEventRecord(ctx->buf_free[ci & 1], ctx->stream));
+            nb += n_c; eb += e_c;
+            cg = c1;
+        }
+        FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        FG_CUDA(cudaGetLastError());
+        int st = 0;
+        for (int ci = 0; ci < nchunks; ci++) st |= ctx->h_status[ci];
+        if (st & 1) { set_last_error("a graph has more than 1024 nodes (reference cap: MAX_NODE = 500)"); return FG_ERR_LIMIT; }
+        if (st & 2) { set_last_error("edge_list holds a node id outside [0, num_of_nodes)"); return FG_ERR_INVALID; }
+        std::memcpy(out + g, ctx->h_out, sizeof(float) * (size_t)run_graphs);
         node_base += n_run; edge_base += e_run;
         g = g1;
     }

@@ -40,11 +40,15 @@ constexpr int WBLOCK = N1 * K1 * 2;           // bytes of one bf16 weight block 
 static_assert(N1 * K1 == N2 * K2, "weight blocks share a size");
 
 // warp roles (warpgroup aligned, for setmaxnreg): 0-7 epilogue, 8-15 gather, 16 MMA issuer, 17 loader, 18-19 idle
-constexpr int EPI_WARPS = 8, GATHER_WARPS = 8;
+#ifndef FG_EPI_WARPS
+#define FG_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = FG_EPI_WARPS, GATHER_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS;
 constexpr int LOAD_WARP = MMA_WARP + 1;
-constexpr int NT = (MMA_WARP + 4) * 32;       // 640 threads
-constexpr int REGS_EPI = 80, REGS_MISC = 72, REGS_GATHER = 120;   // launch allocation: 96 per thread
+constexpr int NT = (MMA_WARP + 4) * 32;       // 512 / 640 threads
+constexpr bool REBALANCE_REGS = EPI_WARPS == 8;                   // 640 threads: launch allocation 96 per thread
+constexpr int REGS_EPI = 80, REGS_MISC = 72, REGS_GATHER = 120;
 constexpr int N1A = 112, N1B = N1 - N1A;      // GEMM1 N halves = GEMM2 K halves (7 + 6 k-steps)
 
 // tensor-memory columns
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
 
     if (warp >= MMA_WARP)
     {
-        reg_dec<REGS_MISC>();
+        if (REBALANCE_REGS) reg_dec<REGS_MISC>();
         if (warp == MMA_WARP)
         {
             // ===== weight loader + MMA issuer (one thread) =====
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
     }
     else if (warp >= EPI_WARPS)
     {
-        reg_inc<REGS_GATHER>();
+        if (REBALANCE_REGS) reg_inc<REGS_GATHER>();
         // ===== gather warps: build the A operand of GEMM1 directly in tensor memory =====
         // warp -> TMEM lane quadrant (warp % 4) and 16-row half; thread t -> rows t/4 and t/4 + 8 of that half and,
         // per k-step ks, the float4 chunk q = 4 ks + t % 4 (k = 16 ks + 4 (t%4) .. +3 = TMEM columns 2(t%4), 2(t%4)+1)
@@ -447,8 +451,9 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
     }
     else
     {
-        reg_dec<REGS_EPI>();
+        if (REBALANCE_REGS) reg_dec<REGS_EPI>();
         // ===== epilogue warps: two per TMEM lane quadrant =====
+        constexpr int PER_QUAD = EPI_WARPS / 4;      // warps per TMEM lane quadrant
         const int quad = warp & 3, pp = warp >> 2;
         const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
         int it = 0;
@@ -460,7 +465,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
             mbar_wait(&bar[BAR_G1A_DONE], ph);
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int c = pp; c < N1A / 16; c += 2) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
+            for (int c = pp; c < N1A / 16; c += PER_QUAD) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
             mbar_wait(&bar[BAR_G1B_DONE], ph);
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int c = N1A / 16 + (pp ^ 1); c < N1 / 16; c += 2) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
+            for (int c = N1A / 16 + (PER_QUAD == 2 ? (pp ^ 1) : 0); c < N1 / 16; c += PER_QUAD) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
@@ -480,8 +485,11 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
             // h' = acc + b2 (+ relu): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
             // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction; warp pp of the
             // quadrant takes its 16-row half
-            const int row_a = tile * TM + quad * 32 + pp * 16 + (lane >> 2), row_b = row_a + 8;
-            const uint32_t ta = lane_base + ((uint32_t)(pp * 16) << 16) + TC_H;
+#pragma unroll
+            for (int hh = pp; hh < 2; hh += PER_QUAD)
+            {
+            const int row_a = tile * TM + quad * 32 + hh * 16 + (lane >> 2), row_b = row_a + 8;
+            const uint32_t ta = lane_base + ((uint32_t)(hh * 16) << 16) + TC_H;
 #pragma unroll
             for (int g4 = 0; g4 < 13; g4 += 4)
             {
@@ -510,6 +518,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
                         if (row_b < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
                     }
                 }
+            }
             }
         }
     }

@@ -20,60 +20,55 @@ namespace {
 constexpr int SCAN_THREADS = 1024;
 
 // Exclusive prefix sums of nums_of_nodes / nums_of_edges (the reference carries them as running
-// offsets in its serial graph loop, GIN/src/GIN_compute.cc:44,96-97).
+// offsets in its serial graph loop, GIN/src/GIN_compute.cc:44,96-97).  One block; every thread owns a
+// contiguous run of graphs (serial sum, block scan of the run totals, serial write-out), so the cost is
+// two passes over 8 bytes per graph instead of one block-wide scan per 1024 graphs.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const int* __restrict__ nn, const int* __restrict__ ne,
                                                                     int* __restrict__ node_off, int* __restrict__ edge_off,
                                                                     int num_graphs)
 {
     __shared__ int2 warp_tot[SCAN_THREADS / 32];
-    __shared__ int2 carry_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = make_int2(0, 0);
-    __syncthreads();
-    for (int base = 0; base < num_graphs; base += SCAN_THREADS)
+    const int per = (num_graphs + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int g0 = min(tid * per, num_graphs), g1 = min(g0 + per, num_graphs);
+    int2 x = make_int2(0, 0);
+    for (int g = g0; g < g1; g++) { x.x += __ldg(nn + g); x.y += __ldg(ne + g); }
+    int2 incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
     {
-        const int i = base + tid;
-        int2 x = make_int2(0, 0);
-        if (i < num_graphs) x = make_int2(nn[i], ne[i]);
-        int2 incl = x;
+        int a = __shfl_up_sync(0xffffffffu, incl.x, d);
+        int b = __shfl_up_sync(0xffffffffu, incl.y, d);
+        if (lane >= d) { incl.x += a; incl.y += b; }
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0)
+    {
+        int2 t = warp_tot[lane];
+        int2 ti = t;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
         {
-            int a = __shfl_up_sync(0xffffffffu, incl.x, d);
-            int b = __shfl_up_sync(0xffffffffu, incl.y, d);
-            if (lane >= d) { incl.x += a; incl.y += b; }
+            int a = __shfl_up_sync(0xffffffffu, ti.x, d);
+            int b = __shfl_up_sync(0xffffffffu, ti.y, d);
+            if (lane >= d) { ti.x += a; ti.y += b; }
         }
-        if (lane == 31) warp_tot[wid] = incl;
-        __syncthreads();
-        if (wid == 0)
-        {
-            int2 t = warp_tot[lane];
-            int2 ti = t;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                int a = __shfl_up_sync(0xffffffffu, ti.x, d);
-                int b = __shfl_up_sync(0xffffffffu, ti.y, d);
-                if (lane >= d) { ti.x += a; ti.y += b; }
-            }
-            warp_tot[lane] = make_int2(ti.x - t.x, ti.y - t.y);   // exclusive over warps
-        }
-        __syncthreads();
-        const int2 c = carry_s;
-        const int2 w = warp_tot[wid];
-        if (i < num_graphs)
-        {
-            node_off[i] = c.x + w.x + incl.x - x.x;
-            edge_off[i] = c.y + w.y + incl.y - x.y;
-        }
-        __syncthreads();
-        if (tid == SCAN_THREADS - 1) carry_s = make_int2(c.x + w.x + incl.x, c.y + w.y + incl.y);
-        __syncthreads();
+        warp_tot[lane] = make_int2(ti.x - t.x, ti.y - t.y);   // exclusive over warps
     }
-    if (tid == 0)
+    __syncthreads();
+    const int2 w = warp_tot[wid];
+    int2 run = make_int2(w.x + incl.x - x.x, w.y + incl.y - x.y);
+    for (int g = g0; g < g1; g++)
     {
-        node_off[num_graphs] = carry_s.x;
-        edge_off[num_graphs] = carry_s.y;
+        node_off[g] = run.x;
+        edge_off[g] = run.y;
+        run.x += __ldg(nn + g); run.y += __ldg(ne + g);
+    }
+    if (tid == SCAN_THREADS - 1)
+    {
+        node_off[num_graphs] = run.x;
+        edge_off[num_graphs] = run.y;
     }
 }
 
