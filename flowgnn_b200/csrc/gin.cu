@@ -185,6 +185,39 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_kernel(GinLayerParams p)
     }
 }
 
+// ---- the edge gather-scatter on its own ("mp_only": node transform = identity, h <- m + h) --------------------
+// One warp per destination row: lanes 0..24 own one float4 chunk each, so every feature row (own and source rows)
+// is read as one coalesced 400-byte access, the 60 combined edge-embedding rows sit in shared memory, in-edges are
+// added in CSR order.  This is the HBM-roofline variant of BASELINE.json's metric.
+constexpr int GATHER_WARPS = 8;
+
+__global__ void __launch_bounds__(GATHER_WARPS * 32) gin_gather_kernel(const float* __restrict__ h_in, float* __restrict__ h_out,
+                                                                       const int* __restrict__ in_ptr, const int* __restrict__ src,
+                                                                       const uint8_t* __restrict__ code, const float* __restrict__ ee_comb,
+                                                                       int num_nodes)
+{
+    __shared__ __align__(16) float tab[ED_COMBOS * D];
+    for (int i = threadIdx.x; i < ED_COMBOS * Q; i += GATHER_WARPS * 32) st_f4(tab + 4 * i, ldg_f4(ee_comb + 4 * i));
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GATHER_WARPS;
+    if (lane >= Q) return;
+    for (int v = warp; v < num_nodes; v += nwarps)
+    {
+        const int eb = __ldg(in_ptr + v), ee = __ldg(in_ptr + v + 1);
+        const float4 hv = ldg_f4(h_in + (size_t)v * D + 4 * lane);
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = eb; e < ee; e++)
+        {
+            const int u = __ldg(src + e), c = __ldg(code + e);
+            const float4 hu = ldg_f4(h_in + (size_t)u * D + 4 * lane);
+            const float4 t = ld_f4(tab + c * D + 4 * lane);
+            m.x += relu_f(t.x + hu.x); m.y += relu_f(t.y + hu.y); m.z += relu_f(t.z + hu.z); m.w += relu_f(t.w + hu.w);
+        }
+        stg_f4_stream(h_out + (size_t)v * D + 4 * lane, make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w));
+    }
+}
+
 }  // namespace
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches)
@@ -231,8 +264,8 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         }
         if (opt.mp_only)
         {
-            const int grid = min(num_tiles, sm_count * 2);
-            gin_layer_kernel<true><<<grid, NT, GinSmem<true>::BYTES, s>>>(p);
+            const int grid = (int)std::min<long>(ceil_div<long>(N, GATHER_WARPS), (long)sm_count * 8);
+            gin_gather_kernel<<<grid, GATHER_WARPS * 32, 0, s>>>(p.h_in, p.h_out, p.in_ptr, p.src, p.code, p.ee_comb, (int)N);
         }
         else
         {
