@@ -165,6 +165,29 @@ class Batch:
             if self.node_eigen is not None:
                 f.write(self.node_eigen.tobytes())
 
+    def save_reference_layout(self, root: str, first: int = 1) -> None:
+        """Write the batch in the reference's per-graph file layout (what its host reads, GIN/src/host.cc:119-138 and
+        DGN/src/host_load.cc:201-215): graphs/graph_info/g%d_info.txt, graphs/graph_bin/g%d_{node_feature,edge_list,
+        edge_attr}.bin, DGN/eig/g%d.txt (a printed tensor) and common/includes/dataset/dataset_size.txt."""
+        for d in ("graphs/graph_info", "graphs/graph_bin", "DGN/eig", "common/includes/dataset"):
+            os.makedirs(os.path.join(root, d), exist_ok=True)
+        no, eo = self.node_offsets, self.edge_offsets
+        for i in range(self.num_graphs):
+            g = first + i
+            n0, n1, e0, e1 = int(no[i]), int(no[i + 1]), int(eo[i]), int(eo[i + 1])
+            with open(os.path.join(root, f"graphs/graph_info/g{g}_info.txt"), "w") as f:
+                f.write(f"{n1 - n0}\n{e1 - e0}")
+            self.node_feature[n0:n1].astype("<i4").tofile(os.path.join(root, f"graphs/graph_bin/g{g}_node_feature.bin"))
+            self.edge_list[e0:e1].astype("<i4").tofile(os.path.join(root, f"graphs/graph_bin/g{g}_edge_list.bin"))
+            attr = self.edge_attr[e0:e1] if self.edge_attr is not None else np.zeros((e1 - e0, EDGE_ATTR), np.int32)
+            attr.astype("<i4").tofile(os.path.join(root, f"graphs/graph_bin/g{g}_edge_attr.bin"))
+            if self.node_eigen is not None:
+                rows = ",\n        ".join("[" + ", ".join(repr(float(x)) for x in r) + "]" for r in self.node_eigen[n0:n1])
+                with open(os.path.join(root, f"DGN/eig/g{g}.txt"), "w") as f:
+                    f.write("tensor([" + rows + "])")
+        with open(os.path.join(root, "common/includes/dataset/dataset_size.txt"), "w") as f:
+            f.write(str(first + self.num_graphs - 1))
+
     def save_npz(self, path: str) -> None:
         arrays = dict(nums_of_nodes=self.nums_of_nodes, nums_of_edges=self.nums_of_edges,
                       node_feature=self.node_feature.astype(np.uint8) if self.node_feature.max(initial=0) < 256 else self.node_feature,

@@ -1,0 +1,305 @@
+// host_b200 -- C++ driver for the B200 kernels, the counterpart of the reference's `./host <xclbin>`
+// (<MODEL>/src/host.cc + host_load.cc).  Same flow, same files, same output format:
+//
+//   load_weights()   reads the reference's weight blobs (*.weights.all.bin, GAT: the eight split files)
+//                    GIN/src/host_load.cc:18-98, GCN :31-170, PNA :23-130, DGN :11-149, GAT :20-91
+//   graphs           graphs/graph_info/g%d_info.txt ("N\nE"), graphs/graph_bin/g%d_{node_feature,edge_list,edge_attr}.bin,
+//                    DGN: DGN/eig/g%d.txt                      GIN/src/host.cc:119-138, host_load.cc:100-143
+//   GIN-VN           virtual-node augmentation on the host     GIN-VN/src/host_load.cc:125-153, host.cc:133-134
+//   run              <MODEL>_compute_graphs(...) NUM_TRIALS times (the reference: enqueueTask + migrate + finish,
+//                    GIN/src/host.cc:203-210) -- here the C ABI of include/flowgnn_b200.h, host pointers in, predictions out
+//   output           "g%d: %.8f\n", 1-based graph ids           GIN/src/host.cc:213-222
+//
+// The OpenCL/XRT plumbing (xcl2, cl::Buffer, bitstream programming) has no counterpart: the library owns the GPU.
+//
+//   host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE]
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/flowgnn_b200.h"
+
+namespace {
+
+constexpr int ND_FEATURE = 9, EDGE_ATTR = 3;
+const int kNdTable[ND_FEATURE] = {119, 4, 12, 12, 10, 6, 6, 2, 2};
+
+[[noreturn]] void die(const std::string& msg)
+{
+    std::fprintf(stderr, "host_b200: %s\n", msg.c_str());
+    std::exit(1);
+}
+
+std::vector<float> read_floats(const std::string& path, size_t expect = 0)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) die("cannot open weight file " + path);
+    std::fseek(f, 0, SEEK_END);
+    const size_t n = (size_t)std::ftell(f) / sizeof(float);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<float> v(n);
+    if (std::fread(v.data(), sizeof(float), n, f) != n) die("short read on " + path);
+    std::fclose(f);
+    if (expect && n < expect) die(path + ": expected at least " + std::to_string(expect) + " floats, found " + std::to_string(n));
+    return v;
+}
+
+std::vector<float> take(const std::vector<float>& blob, size_t off, size_t n)
+{
+    if (off + n > blob.size()) die("weight blob too short");
+    return std::vector<float>(blob.begin() + off, blob.begin() + off + n);
+}
+void append(std::vector<float>& dst, const std::vector<float>& blob, size_t off, size_t n)
+{
+    if (off + n > blob.size()) die("weight blob too short");
+    dst.insert(dst.end(), blob.begin() + off, blob.begin() + off + n);
+}
+
+struct Weights { std::vector<std::vector<float>> arrays; };   // kernel argument order (include/flowgnn_b200.h)
+
+Weights load_weights(const std::string& model, const std::string& dir)
+{
+    Weights w;
+    if (model == "gin" || model == "ginvn")
+    {
+        // nd_embed @0; layer l @ 17300 + 41601 l: eps | W1 | b1 | W2 | b2 | ed_embed; pred_w @225305, pred_b @225405
+        const auto blob = read_floats(dir + "/gin_ep1_noBN_dim100.weights.all.bin", 225406);
+        std::vector<float> w1, b1, w2, b2, ee;
+        for (int l = 0; l < 5; l++)
+        {
+            const size_t base = 17300 + 41601 * (size_t)l;      // blob[base] is eps: never handed to the kernel
+            append(w1, blob, base + 1, 20000); append(b1, blob, base + 20001, 200);
+            append(w2, blob, base + 20201, 20000); append(b2, blob, base + 40201, 100);
+            append(ee, blob, base + 40301, 1300);
+        }
+        w.arrays = {take(blob, 0, 17300), ee, w1, b1, w2, b2, take(blob, 225305, 100), take(blob, 225405, 1)};
+    }
+    else if (model == "gcn")
+    {
+        const auto blob = read_floats(dir + "/gcn_ep1_dim100.weights.all.bin", 76906);
+        std::vector<float> cw, cb, cr, ee, bw, bb, bm, bv;
+        for (int l = 0; l < 5; l++)
+        {
+            const size_t base = 17300 + 11500 * (size_t)l;
+            append(cw, blob, base, 10000); append(cb, blob, base + 10000, 100); append(cr, blob, base + 10100, 100);
+            append(ee, blob, base + 10200, 1300);
+            const size_t bn = 74800 + 401 * (size_t)l;          // one scalar (num_batches_tracked) follows each layer's var
+            append(bw, blob, bn, 100); append(bb, blob, bn + 100, 100); append(bm, blob, bn + 200, 100); append(bv, blob, bn + 300, 100);
+        }
+        w.arrays = {take(blob, 0, 17300), ee, cw, cb, cr, bw, bb, bm, bv, take(blob, 76805, 100), take(blob, 76905, 1)};
+    }
+    else if (model == "pna")
+    {
+        const auto blob = read_floats(dir + "/pna_ep1_noBN_dim80.weights.all.bin", 325441);
+        std::vector<float> cw, cb;
+        for (int l = 0; l < 4; l++)
+        {
+            const size_t base = 13840 + 76880 * (size_t)l;
+            append(cw, blob, base, 76800); append(cb, blob, base + 76800, 80);
+        }
+        w.arrays = {take(blob, 0, 13840), cw, cb, take(blob, 321360, 3200), take(blob, 324560, 40), take(blob, 324600, 800),
+                    take(blob, 325400, 20), take(blob, 325420, 20), take(blob, 325440, 1),
+                    std::vector<float>{6.885701656341553f}};   // avg_deg, PNA/src/host_load.cc:127
+    }
+    else if (model == "dgn")
+    {
+        const auto blob = read_floats(dir + "/dgn_ep1_noBN_dim100.weights.all.bin", 104051);
+        std::vector<float> emb((size_t)9 * 119 * 100, 0.0f), lw, lb;
+        size_t off = 0;
+        for (int f = 0; f < ND_FEATURE; f++)
+        {
+            std::copy(blob.begin() + off, blob.begin() + off + (size_t)kNdTable[f] * 100, emb.begin() + (size_t)f * 11900);
+            off += (size_t)kNdTable[f] * 100;
+        }
+        for (int l = 0; l < 4; l++)
+        {
+            const size_t base = 17300 + 20100 * (size_t)l;
+            append(lw, blob, base, 20000); append(lb, blob, base + 20000, 100);
+        }
+        w.arrays = {emb, lw, lb, take(blob, 97700, 5000), take(blob, 102700, 50), take(blob, 102750, 1250), take(blob, 104000, 25),
+                    take(blob, 104025, 25), take(blob, 104050, 1)};
+    }
+    else if (model == "gat")
+    {
+        auto part = [&](const char* name, size_t n) { return read_floats(dir + "/gat_ep1_" + name + "_layer5.bin", n); };
+        std::vector<float> proj((size_t)5 * 4096, 0.0f), skip((size_t)5 * 4096, 0.0f);
+        for (int which = 0; which < 2; which++)
+        {
+            std::vector<float>& full = which ? skip : proj;
+            const auto l0 = part(which ? "skip_proj_weight_0" : "linear_proj_weight_0", 4 * 16 * 9);
+            const auto l14 = part(which ? "skip_proj_weight_1" : "linear_proj_weight_1", 4 * 4096);
+            // layer 0 only sees head_in 0, dim_in < 9 (GAT/src/host_load.cc:69-78)
+            for (int ho = 0; ho < 4; ho++)
+                for (int d = 0; d < 16; d++)
+                    for (int f = 0; f < 9; f++) full[(((size_t)ho * 16 + d) * 4 + 0) * 16 + f] = l0[((size_t)ho * 16 + d) * 9 + f];
+            std::copy(l14.begin(), l14.begin() + 4 * 4096, full.begin() + 4096);
+        }
+        w.arrays = {part("scoring_fn_target", 320), part("scoring_fn_source", 320), proj, skip, part("pred_weights", 16), part("pred_bias", 1)};
+    }
+    else
+        die("unknown model " + model);
+    return w;
+}
+
+struct Graphs {
+    std::vector<int> nn, ne, reload;
+    std::vector<int32_t> feat, edges, attr;
+    std::vector<float> eig;
+};
+
+std::vector<int32_t> read_ints(const std::string& path, size_t n)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) die("cannot open " + path);
+    std::vector<int32_t> v(n);
+    if (n && std::fread(v.data(), sizeof(int32_t), n, f) != n) die("short read on " + path);
+    std::fclose(f);
+    return v;
+}
+
+// DGN/eig/g%d.txt is a printed tensor, "tensor([[a, b, c, d],\n [..], ...])": take the numbers in order, 4 per node
+// (the reference walks it with fscanf, DGN/src/host_load.cc:201-215)
+void read_eigen(const std::string& path, int n, std::vector<float>& out)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) die("cannot open " + path);
+    std::string text;
+    char buf[4096];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+    std::fclose(f);
+    const char* p = text.c_str();
+    size_t count = 0;
+    while (*p && count < (size_t)4 * n)
+    {
+        if ((*p >= '0' && *p <= '9') || ((*p == '-' || *p == '+' || *p == '.') && p[1] >= '0' && p[1] <= '9') || !std::strncmp(p, "nan", 3) ||
+            !std::strncmp(p, "inf", 3) || !std::strncmp(p, "-inf", 4))
+        {
+            char* end = nullptr;
+            out.push_back(std::strtof(p, &end));
+            count++;
+            p = end;
+        }
+        else
+            p++;
+    }
+    if (count < (size_t)4 * n) die(path + ": too few numbers");
+}
+
+Graphs load_graphs(const std::string& root, int first, int count, bool with_eigen, bool virtual_node)
+{
+    Graphs g;
+    for (int id = first; id < first + count; id++)
+    {
+        const std::string info = root + "/graphs/graph_info/g" + std::to_string(id) + "_info.txt";
+        FILE* f = std::fopen(info.c_str(), "r");
+        if (!f) die("cannot open " + info);
+        int n = 0, e = 0;
+        if (std::fscanf(f, "%d %d", &n, &e) != 2) die("bad info file " + info);
+        std::fclose(f);
+        const std::string stem = root + "/graphs/graph_bin/g" + std::to_string(id);
+        const auto nf = read_ints(stem + "_node_feature.bin", (size_t)n * ND_FEATURE);
+        const auto el = read_ints(stem + "_edge_list.bin", (size_t)e * 2);
+        const auto ea = read_ints(stem + "_edge_attr.bin", (size_t)e * EDGE_ATTR);
+        g.feat.insert(g.feat.end(), nf.begin(), nf.end());
+        g.edges.insert(g.edges.end(), el.begin(), el.end());
+        g.attr.insert(g.attr.end(), ea.begin(), ea.end());
+        if (with_eigen) read_eigen(root + "/DGN/eig/g" + std::to_string(id) + ".txt", n, g.eig);
+        if (virtual_node)
+        {
+            // one extra all-zero node N; after the real edges the pairs (i, N), (N, i) with attr {0,0,0}
+            g.feat.insert(g.feat.end(), ND_FEATURE, 0);
+            for (int i = 0; i < n; i++)
+            {
+                const int32_t pair[4] = {i, n, n, i};
+                g.edges.insert(g.edges.end(), pair, pair + 4);
+                g.attr.insert(g.attr.end(), 2 * EDGE_ATTR, 0);
+            }
+            e += 2 * n;
+            n += 1;
+        }
+        g.nn.push_back(n);
+        g.ne.push_back(e);
+        g.reload.push_back(id == first ? 1 : 0);       // GIN/src/host.cc:135
+    }
+    return g;
+}
+
+int run_model(const std::string& model, Graphs& g, Weights& w, std::vector<float>& out)
+{
+    const int G = (int)g.nn.size();
+    std::vector<const float*> a;
+    for (auto& v : w.arrays) a.push_back(v.data());
+    if (model == "gin" || model == "ginvn")
+        return GIN_compute_graphs(G, g.nn.data(), g.ne.data(), g.reload.data(), out.data(), g.feat.data(), g.edges.data(), g.attr.data(), a[0],
+                                  a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+    if (model == "gcn")
+        return GCN_compute_graphs(G, g.nn.data(), g.ne.data(), g.reload.data(), out.data(), g.feat.data(), g.edges.data(), g.attr.data(), a[0],
+                                  a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+    if (model == "gat")
+        return GAT_compute_graphs(G, g.nn.data(), g.ne.data(), g.reload.data(), out.data(), g.feat.data(), g.edges.data(), a[0], a[1], a[2], a[3],
+                                  a[4], a[5]);
+    if (model == "pna")
+        return PNA_compute_graphs(G, g.nn.data(), g.ne.data(), g.reload.data(), out.data(), g.feat.data(), g.edges.data(), a[0], a[1], a[2], a[3],
+                                  a[4], a[5], a[6], a[7], a[8], a[9]);
+    return DGN_compute_graphs(G, g.nn.data(), g.ne.data(), g.reload.data(), out.data(), g.feat.data(), g.eig.data(), g.edges.data(), a[0], a[1],
+                              a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    if (argc < 4)
+        die("usage: host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE]");
+    const std::string model = argv[1], root = argv[2], wdir = argv[3];
+    int count = -1, first = 1, trials = 25;                      // NUM_TRIALS = 25, GIN/src/host.h:8
+    std::string out_path = "B200_output.txt";
+    for (int i = 4; i + 1 < argc; i += 2)
+    {
+        const std::string k = argv[i];
+        if (k == "--graphs") count = std::atoi(argv[i + 1]);
+        else if (k == "--first") first = std::atoi(argv[i + 1]);
+        else if (k == "--trials") trials = std::atoi(argv[i + 1]);
+        else if (k == "--out") out_path = argv[i + 1];
+        else die("unknown option " + k);
+    }
+    if (count < 0)
+    {
+        // NUM_GRAPHS comes from common/includes/dataset/dataset_size.txt in the reference (dataset.hpp:1-3)
+        FILE* f = std::fopen((root + "/common/includes/dataset/dataset_size.txt").c_str(), "r");
+        if (!f || std::fscanf(f, "%d", &count) != 1) die("pass --graphs N (no dataset_size.txt under " + root + ")");
+        std::fclose(f);
+        count -= first - 1;
+    }
+    Weights w = load_weights(model, wdir);
+    std::printf("******* Weights loading done *******\n");
+    Graphs g = load_graphs(root, first, count, model == "dgn", model == "ginvn");
+    std::printf("******* Graphs loading done: %d graphs *******\n", count);
+
+    std::vector<float> out((size_t)count, 0.0f);
+    double best_ms = 1e30, sum_ms = 0;
+    for (int t = 0; t < std::max(trials, 1); t++)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = run_model(model, g, w, out);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (rc != 0) die(std::string("kernel entry point failed (") + std::to_string(rc) + "): " + flowgnn_b200_last_error());
+        if (t > 0 || trials == 1) { best_ms = std::min(best_ms, ms); sum_ms += ms; }
+    }
+    const int timed = trials > 1 ? trials - 1 : 1;
+    std::printf("%s: %d graphs, %d trials: mean %.3f ms, best %.3f ms per batch (host buffers in, predictions out) = %.1f us/graph, %.0f graphs/s\n",
+                model.c_str(), count, trials, sum_ms / timed, best_ms, 1e3 * best_ms / count, count / (best_ms * 1e-3));
+
+    FILE* f = std::fopen(out_path.c_str(), "w");
+    if (!f) die("cannot write " + out_path);
+    for (int i = 0; i < count; i++) std::fprintf(f, "g%d: %.8f\n", first + i, out[i]);
+    std::fclose(f);
+    std::printf("******* %s written *******\n", out_path.c_str());
+    return 0;
+}
