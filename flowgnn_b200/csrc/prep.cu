@@ -20,55 +20,63 @@ namespace {
 constexpr int SCAN_THREADS = 1024;
 
 // Exclusive prefix sums of nums_of_nodes / nums_of_edges (the reference carries them as running
-// offsets in its serial graph loop, GIN/src/GIN_compute.cc:44,96-97).  One block; every thread owns a
-// contiguous run of graphs (serial sum, block scan of the run totals, serial write-out), so the cost is
-// two passes over 8 bytes per graph instead of one block-wide scan per 1024 graphs.
+// offsets in its serial graph loop, GIN/src/GIN_compute.cc:44,96-97).  One block of 32 warps; every warp owns
+// a contiguous segment of graphs: pass 1 sums it (coalesced, independent loads), the 32 segment totals are
+// scanned, pass 2 re-reads the segment and writes warp-scanned offsets with a running carry.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const int* __restrict__ nn, const int* __restrict__ ne,
                                                                     int* __restrict__ node_off, int* __restrict__ edge_off,
                                                                     int num_graphs)
 {
-    __shared__ int2 warp_tot[SCAN_THREADS / 32];
+    __shared__ int2 seg_tot[SCAN_THREADS / 32];
+    const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int per = (num_graphs + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int g0 = min(tid * per, num_graphs), g1 = min(g0 + per, num_graphs);
+    const int per = ((num_graphs + SCAN_THREADS - 1) / SCAN_THREADS) * 32;      // graphs per warp, multiple of 32
+    const int g0 = min(wid * per, num_graphs), g1 = min(g0 + per, num_graphs);
     int2 x = make_int2(0, 0);
-    for (int g = g0; g < g1; g++) { x.x += __ldg(nn + g); x.y += __ldg(ne + g); }
-    int2 incl = x;
+#pragma unroll 4
+    for (int g = g0 + lane; g < g1; g += 32) { x.x += __ldg(nn + g); x.y += __ldg(ne + g); }
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-    {
-        int a = __shfl_up_sync(0xffffffffu, incl.x, d);
-        int b = __shfl_up_sync(0xffffffffu, incl.y, d);
-        if (lane >= d) { incl.x += a; incl.y += b; }
-    }
-    if (lane == 31) warp_tot[wid] = incl;
+    for (int d = 16; d > 0; d >>= 1) { x.x += __shfl_xor_sync(full, x.x, d); x.y += __shfl_xor_sync(full, x.y, d); }
+    if (lane == 0) seg_tot[wid] = x;
     __syncthreads();
     if (wid == 0)
     {
-        int2 t = warp_tot[lane];
+        const int2 t = seg_tot[lane];
         int2 ti = t;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
         {
-            int a = __shfl_up_sync(0xffffffffu, ti.x, d);
-            int b = __shfl_up_sync(0xffffffffu, ti.y, d);
+            int a = __shfl_up_sync(full, ti.x, d), b = __shfl_up_sync(full, ti.y, d);
             if (lane >= d) { ti.x += a; ti.y += b; }
         }
-        warp_tot[lane] = make_int2(ti.x - t.x, ti.y - t.y);   // exclusive over warps
+        seg_tot[lane] = make_int2(ti.x - t.x, ti.y - t.y);      // exclusive over segments
     }
     __syncthreads();
-    const int2 w = warp_tot[wid];
-    int2 run = make_int2(w.x + incl.x - x.x, w.y + incl.y - x.y);
-    for (int g = g0; g < g1; g++)
+    int2 carry = seg_tot[wid];
+#pragma unroll 4
+    for (int base = g0; base < g1; base += 32)
     {
-        node_off[g] = run.x;
-        edge_off[g] = run.y;
-        run.x += __ldg(nn + g); run.y += __ldg(ne + g);
+        const int g = base + lane;
+        const int2 v = (g < g1) ? make_int2(__ldg(nn + g), __ldg(ne + g)) : make_int2(0, 0);
+        int2 incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            int a = __shfl_up_sync(full, incl.x, d), b = __shfl_up_sync(full, incl.y, d);
+            if (lane >= d) { incl.x += a; incl.y += b; }
+        }
+        if (g < g1)
+        {
+            node_off[g] = carry.x + incl.x - v.x;
+            edge_off[g] = carry.y + incl.y - v.y;
+        }
+        carry.x += __shfl_sync(full, incl.x, 31);
+        carry.y += __shfl_sync(full, incl.y, 31);
     }
-    if (tid == SCAN_THREADS - 1)
+    if (g1 == num_graphs && g0 < g1 && lane == 0)
     {
-        node_off[num_graphs] = run.x;
-        edge_off[num_graphs] = run.y;
+        node_off[num_graphs] = carry.x;
+        edge_off[num_graphs] = carry.y;
     }
 }
 
