@@ -203,17 +203,35 @@ __device__ __forceinline__ float4 row_finish(const GinTcParams& p, const float* 
     }
     if (r.deg > 4)
     {
+        // long in-edge lists (virtual nodes, kNN graphs): continue in rounds of four edges, loads first
         const int q = 4 * KS + qsub;
         if (q < Q)
         {
-            for (int e = r.eb + 4; e < r.eb + r.deg; e++)
+            const float* hq = p.h_in + 4 * q;
+            const int e_end = r.eb + r.deg;
+            for (int e = r.eb + 4; e < e_end; e += 4)
             {
-                int u, c;
-                if (cb.staged) { u = cb.src[e - cb.e0]; c = cb.code[e - cb.e0]; }
-                else { u = __ldg(p.src + e); c = __ldg(p.code + e); }
-                const float4 hu = ldg_f4(p.h_in + (size_t)u * D + 4 * q);
-                const float4 t = ld_f4(ee + c * D + 4 * q);
-                m.x += relu_nan(t.x + hu.x); m.y += relu_nan(t.y + hu.y); m.z += relu_nan(t.z + hu.z); m.w += relu_nan(t.w + hu.w);
+                float4 hu[4];
+                int c[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const bool on = e + j < e_end;
+                    int u = 0;
+                    c[j] = ED_COMBOS;
+                    if (on)
+                    {
+                        if (cb.staged) { u = cb.src[e + j - cb.e0]; c[j] = cb.code[e + j - cb.e0]; }
+                        else { u = __ldg(p.src + e + j); c[j] = __ldg(p.code + e + j); }
+                    }
+                    hu[j] = ldg_f4_if(hq + (size_t)u * D, on);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const float4 t = ld_f4(ee + c[j] * D + 4 * q);
+                    m.x += relu_nan(t.x + hu[j].x); m.y += relu_nan(t.y + hu[j].y); m.z += relu_nan(t.z + hu[j].z); m.w += relu_nan(t.w + hu[j].w);
+                }
             }
         }
     }

@@ -82,6 +82,26 @@ def test_reference_entry_point_with_host_pointers(model, weights, datasets, gold
     assert_parity(got, golden["molhiv"][model][:300], what=f"{model} entry point")
 
 
+@pytest.mark.parametrize("model", ["gin", "gat", "dgn"])
+def test_entry_point_chunked_pipeline_is_bit_identical_to_one_shot(model, ctx, weights, datasets):
+    """Host-pointer entry points cut large batches into chunks that alternate between two device batches (H2D of
+    chunk i+1 overlaps the kernels of chunk i).  Chunks are whole graphs, so every prediction must be bit-identical
+    to the device-resident one-shot path -- including GAT with the reference's node-offset quirk, which reads features
+    from the start of the caller's buffer."""
+    from flowgnn_b200.capi import ReferenceCall
+    b = datasets["molpcba"].tile(20000)
+    if model == "dgn":
+        from flowgnn_b200.dataset import synthetic_molecules
+        b = synthetic_molecules(2500, "molhiv", seed=3, with_eigen=True).tile(20000)
+    call = ReferenceCall(model, b, weights[model])
+    got = call.run().copy()
+    again = call.run()
+    ctx.set_option("gat_node_offset_bug", 1)
+    want = ctx.run(model, b, weights[model])
+    assert np.array_equal(got.view(np.int32), want.view(np.int32)), model
+    assert np.array_equal(got.view(np.int32), again.view(np.int32)), model
+
+
 def test_ginvn_entry_point_on_augmented_batch(weights, datasets, golden):
     from flowgnn_b200.capi import compute_graphs
     b = datasets["molhiv"].slice(0, 200).with_virtual_node()
