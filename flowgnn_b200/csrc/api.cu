@@ -633,22 +633,24 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         int64_t n_run = nn[g], e_run = ne[g];
         while (g1 < num_graphs && !reload[g1]) { n_run += nn[g1]; e_run += ne[g1]; g1++; }
 
-        const uint64_t h = hash_weights(weights, counts, nw, (size_t)set);
-        if (!ctx->loaded[model] || ctx->weight_hash[model] != h)
-        {
-            std::vector<const float*> ptrs(nw);
-            for (int i = 0; i < nw; i++) ptrs[i] = weights[i] + (size_t)set * counts[i];
-            FG_TRY(flowgnn_b200_load_weights(ctx, model, ptrs.data(), nw));
-            ctx->weight_hash[model] = h;
-        }
         // Cut the run into chunks and alternate between two device batches: the H2D copy of chunk i+1 (copy stream)
-        // overlaps the kernels of chunk i (compute stream).  Chunks are whole graphs, so results do not depend on the cut.
+        // overlaps the kernels of chunk i (compute stream).  Chunks are whole graphs, so results do not depend on the cut;
+        // the first chunk is small so that the kernels start early, and the weight hash runs while it is in flight.
         // the reference's GAT reads node features from the START of the batch buffer for every graph.
         const bool gat_bug = (model == MODEL_GAT) && ctx->opt.gat_node_offset_bug;
         const int run_graphs = g1 - g;
-        int nchunks = run_graphs / 8192;
-        nchunks = nchunks < 1 ? 1 : (nchunks > 4 ? 4 : nchunks);
-        const int per_chunk = (run_graphs + nchunks - 1) / nchunks;
+        int nchunks = 1;
+        int bounds[5] = {g, g1, g1, g1, g1};
+        if (run_graphs >= 16384)
+        {
+            nchunks = 4;
+            bounds[1] = g + run_graphs / 8; bounds[2] = g + (3 * run_graphs) / 8; bounds[3] = g + (11 * run_graphs) / 16; bounds[4] = g1;
+        }
+        else if (run_graphs >= 8192)
+        {
+            nchunks = 2;
+            bounds[1] = g + run_graphs / 3; bounds[2] = g1;
+        }
         if ((size_t)run_graphs > ctx->h_out_cap)
         {
             if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -659,28 +661,43 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         ctx->last_launches = 0;
         ctx->timer.marks = 0;
         int64_t nb = node_base, eb = edge_base;
-        int cg = g;
-        for (int ci = 0; ci < nchunks; ci++)
-        {
-            const int c1 = (cg + per_chunk < g1) ? cg + per_chunk : g1;
+        auto issue_upload = [&](int ci) -> int {
+            const int c0 = bounds[ci], c1 = bounds[ci + 1];
             int64_t n_c = 0, e_c = 0;
-            for (int k = cg; k < c1; k++) { n_c += nn[k]; e_c += ne[k]; }
+            for (int k = c0; k < c1; k++) { n_c += nn[k]; e_c += ne[k]; }
             DeviceBatch& db = ctx->pipe[ci & 1];
             if (ci >= 2) FG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->buf_free[ci & 1], 0));
-            FG_TRY(upload_into(db, ctx->copy_stream, c1 - cg, n_c, e_c, nn + cg, ne + cg, gat_bug ? feat : feat + ND_FEATURE * nb,
+            FG_TRY(upload_into(db, ctx->copy_stream, c1 - c0, n_c, e_c, nn + c0, ne + c0, gat_bug ? feat : feat + ND_FEATURE * nb,
                                edges + 2 * eb, attr ? attr + 3 * eb : nullptr, eig ? eig + 4 * nb : nullptr));
             FG_CUDA(cudaEventRecord(ctx->up_done[ci & 1], ctx->copy_stream));
+            nb += n_c; eb += e_c;
+            return 0;
+        };
+        FG_TRY(issue_upload(0));
+
+        const uint64_t h = hash_weights(weights, counts, nw, (size_t)set);
+        if (!ctx->loaded[model] || ctx->weight_hash[model] != h)
+        {
+            std::vector<const float*> ptrs(nw);
+            for (int i = 0; i < nw; i++) ptrs[i] = weights[i] + (size_t)set * counts[i];
+            FG_TRY(flowgnn_b200_load_weights(ctx, model, ptrs.data(), nw));
+            ctx->weight_hash[model] = h;
+        }
+        for (int ci = 0; ci < nchunks; ci++)
+        {
+            const int c0 = bounds[ci], c1 = bounds[ci + 1];
+            DeviceBatch& db = ctx->pipe[ci & 1];
             FG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->up_done[ci & 1], 0));
+            if (ci + 1 < nchunks && ci + 1 < 2) FG_TRY(issue_upload(ci + 1));       // chunk 1 goes to the other buffer right away
             FG_TRY(compute_on(ctx, db, ctx->stream, model));
-            if (c1 > cg)
+            if (c1 > c0)
             {
-                FG_CUDA(cudaMemcpyAsync(ctx->h_out + (cg - g), db.out.ptr, sizeof(float) * (size_t)(c1 - cg), cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(cudaMemcpyAsync(ctx->h_out + (c0 - g), db.out.ptr, sizeof(float) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, ctx->stream));
                 FG_CUDA(cudaMemcpyAsync(ctx->h_status + ci, db.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             }
             else ctx->h_status[ci] = 0;
             FG_CUDA(cudaEventRecord(ctx->buf_free[ci & 1], ctx->stream));
-            nb += n_c; eb += e_c;
-            cg = c1;
+            if (ci + 2 < nchunks) FG_TRY(issue_upload(ci + 2));                     // reuses this chunk's buffer once it is free
         }
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
         FG_CUDA(cudaGetLastError());
