@@ -36,7 +36,7 @@ void DevBuf::release()
 void DeviceBatch::release()
 {
     DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
-                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &sort_tmp, &status,
+                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &sort_tmp, &status,
                      &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
     for (DevBuf* b : all) b->release();
 }
@@ -200,6 +200,16 @@ int load_gin(flowgnn_ctx* c, const float* const* w)
         FG_CUDA(cudaMemcpyAsync(g.wpack.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
         FG_CUDA(cudaStreamSynchronize(s));
     }
+    {
+        const size_t per_layer = gin_tc2_pack_bytes();
+        std::vector<unsigned char> pack(5 * per_layer);
+        for (int l = 0; l < 5; l++)
+            gin_tc2_pack_layer(w[2] + (size_t)l * 200 * 100, w[4] + (size_t)l * 100 * 200, pack.data() + (size_t)l * per_layer, bf16_rn, bf16_to_float);
+        FG_TRY(g.wpack2.reserve(pack.size()));
+        FG_CUDA(cudaMemcpyAsync(g.wpack2.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
+        FG_CUDA(cudaStreamSynchronize(s));
+    }
+    FG_TRY(upload(g.b2p2, pad_rows(w[5], 5, 100, 128), s));
     FG_TRY(upload(g.ee_raw, w[1], (size_t)5 * ED_FEATURE_PER_LAYER * 100, s));
     FG_TRY(upload(g.b2p, pad_rows(w[5], 5, 100, 112), s));
     FG_TRY(upload(g.pred_w, w[6], 100, s));
@@ -386,7 +396,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaStreamDestroy(ctx->copy_stream);
-    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
+    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.b2p2, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
                    &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
@@ -409,6 +419,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     if (!name) { set_last_error("null option name"); return FG_ERR_INVALID; }
     if (!std::strcmp(name, "mp_only")) ctx->opt.mp_only = value;
     else if (!std::strcmp(name, "gin_ffma")) ctx->opt.gin_ffma = value;
+    else if (!std::strcmp(name, "gin_tc1")) ctx->opt.gin_tc1 = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;
     else { set_last_error(std::string("unknown option ") + name); return FG_ERR_INVALID; }
@@ -478,7 +489,7 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     if (b.num_graphs == 0) return 0;
     if (model == MODEL_DGN && !b.has_eigen) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
     if ((model == MODEL_GIN || model == MODEL_GCN) && !b.has_attr) { set_last_error("GIN/GCN need edge_attr"); return FG_ERR_INVALID; }
-    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : 0;
+    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN) ? PREP_ROW_DESC : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
     int rc = prep_batch(b, flags, s);

@@ -1,0 +1,716 @@
+// GIN / GIN-VN layer on the B200 tensor cores, CTA-PAIR version: one persistent cluster of two CTAs per TPC
+// (tcgen05 cta_group::2, UMMA M = 256 = 2 x 128 consecutive nodes), warp specialised.
+//
+// Reference work per layer (GIN/src/message_passing.cc:77-150, node_embedding.cc:23-201):
+//   m_v = sum_{(u,v)} relu(h_u + EE_l[attr_uv]);  a_v = m_v + h_v  (eps is never loaded: SURVEY.md F4)
+//   z = relu(W1 a + b1);  h'_v = W2 z + b2  (+ relu unless last layer)
+//
+// Why a pair: with cta_group::2 each CTA holds only HALF of every weight matrix (the N rows of the B operand are
+// split over the pair), 94 KB instead of 186 KB.  The shared memory this frees holds a double-buffered bf16 hi/lo
+// tile of a_v in the UMMA canonical K-major layout, so the edge gather is no longer tied to the tensor-memory
+// fragment layout (4 lanes per feature row, 64-byte pieces, ~11 L1 wavefronts per load instruction): it uses 8 lanes
+// per row (128-byte pieces, 4 rows per instruction) and twice as many gather warps.
+//
+// Per CTA (896 threads):
+//   warps 0-7   epilogue: z = relu(acc + b1) -> bf16 hi/lo written back to tensor memory IN PLACE (A operand of GEMM2);
+//               h' = acc + b2 (+ relu) streamed to HBM, one full 32-byte sector per row and store
+//   warps 8-23  gather: 8 rows each, as two passes of 4 rows; thread (g = lane / 8, j = lane % 8) owns row 4 pass + g
+//               and, per step ks < 4, the float4 chunk 8 ks + j of that row: own row + up to four source rows are
+//               loaded with addresses = pointer + immediate, the loads of step ks + 1 are issued before step ks is
+//               reduced (CSR order, deterministic), split to bf16 hi/lo and stored to the A tile.  The CSR slice of
+//               the NEXT tile (row pointers, packed source/code) is prefetched into registers one tile ahead and
+//               handed to the threads with warp shuffles.
+//   warp 24     (leader CTA only) MMA issuer: GEMM1 = 3 products (hi*hi + lo*hi + hi*lo) x 7 k-steps from shared
+//               memory (SS), as two N halves (112 + 96) so that the conversion of the first half overlaps the second;
+//               GEMM2 = 3 x 13 k-steps with A = z from tensor memory (TS), N = 128 (TS needs N % 32 == 0 for pairs)
+//   warp 25     L2 prefetch of the feature rows two tiles ahead
+// Barriers that the MMA issuer waits on live in the leader CTA and are arrived on remotely by the peer's warps;
+// tcgen05.commit multicasts completion to both CTAs.
+#include "internal.cuh"
+#include "layers.cuh"
+#include "tc.cuh"
+
+#include <algorithm>
+#include <type_traits>
+
+namespace fg {
+
+namespace {
+
+constexpr int D = 100;
+constexpr int Q = D / 4;
+constexpr int TM = 128;                       // nodes per CTA tile (pair tile = 256)
+constexpr int N1A = 112, N1B = 96, N1 = N1A + N1B;   // GEMM1 N halves (z columns), whole pair
+constexpr int N2 = 128;                       // GEMM2 N (100 used)
+constexpr int K1_STEPS = 7, K2_STEPS = 13;    // K = 16 per step
+constexpr int K1_CHUNKS = 13;                 // stored 8-element K chunks of A and W1 (k < 104; chunk 13 reads as zero)
+constexpr int K2_CHUNKS = 25;                 // stored K chunks of W2 (k < 200; z columns 200..207 are exactly zero)
+
+// per-CTA weight image (bytes): half of the N rows of every block
+constexpr int LBO_W1A = (N1A / 2) * 16, LBO_W1B = (N1B / 2) * 16, LBO_W2 = (N2 / 2) * 16;
+constexpr int W1A_BYTES = LBO_W1A * K1_CHUNKS, W1B_BYTES = LBO_W1B * K1_CHUNKS, W2_BYTES = LBO_W2 * K2_CHUNKS;
+constexpr int OFF_W1A_HI = 0, OFF_W1A_LO = OFF_W1A_HI + W1A_BYTES, OFF_W1B_HI = OFF_W1A_LO + W1A_BYTES, OFF_W1B_LO = OFF_W1B_HI + W1B_BYTES,
+              OFF_W2_HI = OFF_W1B_LO + W1B_BYTES, OFF_W2_LO = OFF_W2_HI + W2_BYTES;
+constexpr int W_BYTES = OFF_W2_LO + W2_BYTES;           // 94,464
+
+// A operand tile in shared memory: canonical no-swizzle K-major, byte(r, k) = (k / 8) * LBO_A + r * 16 + (k % 8) * 2;
+// the 32-byte pad per chunk makes the 8-byte stores of a warp (4 rows x 8 lanes) hit every bank group exactly twice
+constexpr int LBO_A = TM * 16 + 32;
+constexpr int A_BYTES = K1_CHUNKS * LBO_A;              // one hi or lo buffer: 26,832
+constexpr int ZERO_BYTES = TM * 16;                     // K chunk 13 of every A buffer (and the tail of W2_lo) reads from here
+
+// warp roles (warpgroup aligned, for setmaxnreg): 0-7 epilogue, 8-23 gather, 24 MMA issuer, 25 L2 prefetch, 26-27 idle
+constexpr int EPI_WARPS = 8, GATHER_WARPS = 16;
+constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, LOAD_WARP = MMA_WARP + 1;
+constexpr int NT = (MMA_WARP + 4) * 32;       // 896
+constexpr int REGS_LAUNCH = 72;               // 65,536 / 896 rounded down to a multiple of 8
+constexpr int REGS_EPI = 64, REGS_MISC = 24, REGS_GATHER = 88;
+// setmaxnreg moves registers inside the CTA's launch allocation: the new sizes must fit it or the increase never returns
+static_assert(32 * (EPI_WARPS * REGS_EPI + GATHER_WARPS * REGS_GATHER + 4 * REGS_MISC) <= NT * REGS_LAUNCH, "setmaxnreg pool");
+constexpr int ROWS_PER_WARP = TM / GATHER_WARPS;   // 8
+constexpr int LPR = 8;                             // lanes per row
+constexpr int GSTEPS = 4;                          // steps per row: chunk 8 ks + j (the last step only holds chunk 24)
+
+// tensor-memory columns
+constexpr uint32_t TC_Z = 0, TC_H = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Smem {
+    static constexpr int W = 0;
+    static constexpr int ZEROW = W + W_BYTES;                       // K chunk 25 of W2_lo (the last block of W) reads these zeros
+    static constexpr int A = ZEROW + LBO_W2;                        // [2 stages][hi, lo][A_BYTES]
+    static constexpr int ZERO = A + 4 * A_BYTES;                    // K chunk 13 of every A buffer (must lie above them: LBO >= 0)
+    static constexpr int EE = ZERO + ZERO_BYTES;                    // [61][100] fp32 combined edge-embedding rows; row 60 = sentinel
+    static constexpr int B1 = EE + (ED_COMBOS + 1) * D * 4;         // [208]
+    static constexpr int B2 = B1 + N1 * 4;                          // [128]
+    static constexpr int BAR = B2 + N2 * 4;
+    static constexpr int TMEM_PTR = BAR + 16 * 8;
+    static constexpr int BYTES = TMEM_PTR + 16;
+};
+static_assert(Smem::ZEROW % 16 == 0 && Smem::ZERO % 16 == 0 && Smem::A % 16 == 0 && Smem::EE % 16 == 0 && Smem::BAR % 8 == 0, "alignment");
+static_assert(Smem::BYTES <= 232448, "shared memory budget");
+
+enum { BAR_W = 0, BAR_A_FULL /* 2 */, BAR_A_FREE = BAR_A_FULL + 2 /* 2 */, BAR_G1A_DONE = BAR_A_FREE + 2, BAR_G1B_DONE, BAR_A2A_FULL, BAR_A2B_FULL, BAR_G2_DONE };
+
+struct GinTc2Params {
+    const float* h_in; float* h_out;
+    const int* in_ptr; const int* src; const uint8_t* code;
+    const int4* row_desc;            // [N] first four in-edges of every node, packed (prep.cu)
+    const float* ee_comb;            // [60][100] this layer: ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]
+    const unsigned char* wpack;      // [2 ranks][W_BYTES] this layer
+    const float* b1; const float* b2;   // [208], [128] zero padded
+    int num_nodes; int num_pair_tiles; int relu_out;
+};
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// ---- cluster / pair primitives ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    // default semantics (release, CTA scope) as in CUTLASS' ClusterBarrier::arrive(cta_id): what the waiter consumes was
+    // either written through the async proxy after fence.proxy.async or lives in tensor memory behind tcgen05 fences;
+    // .release.cluster would add a GPU-scope MEMBAR to every arrival
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire: the arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in both CTAs once all MMAs issued so far have completed
+__device__ __forceinline__ void commit2(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// D[tmem, 256 x N over the pair] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T, one K = 16 step
+__device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// relu that lets NaN through, like the reference's compare-select (GIN/src/util.h:20-25), in ONE instruction
+__device__ __forceinline__ float relu_nan(float x)
+{
+    float y;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(0.0f));
+    return y;
+}
+
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// (x0, x1) -> packed bf16 pairs: hi = rn(x), lo = rn(x - hi); element 0 in the low half
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo)
+{
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi << 16);
+    const float r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b)
+{
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// 16-byte load that is not issued when `on` is false (reads as zero).  Plain C++ on purpose: ptxas turns this into
+// "zero the quad, @p LDG into the same quad"; an inline-asm version made it load into a scratch quad and copy, i.e.
+// wait for every load right after issuing it.
+__device__ __forceinline__ float4 ldg_f4_if(const float* ptr, bool on)
+{
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) v = __ldg(reinterpret_cast<const float4*>(ptr));
+    return v;
+}
+
+__device__ __forceinline__ void acc_edge(float4& m, const float4& t, const float4& h)
+{
+    m.x += relu_nan(t.x + h.x); m.y += relu_nan(t.y + h.y); m.z += relu_nan(t.z + h.z); m.w += relu_nan(t.w + h.w);
+}
+
+// ---- one destination row as seen by one of its 8 threads ----------------------------------------------------------
+// Pointers to this thread's 16-byte chunk (step 0) of the row itself and of the source rows of its first four
+// in-edges, the shared-memory addresses of their edge-embedding rows, the in-degree.  Everything comes from the
+// node's 16-byte row descriptor (prep.cu): no in_ptr -> src/code pointer chase.  Absent slots are never loaded (they
+// read as 0) and point at the sentinel table row; in-edges beyond the fourth are read from the CSR arrays.
+struct RowEdges {
+    const float* hv;
+    const float* hu[4];
+    uint32_t t[4];
+    int deg;
+};
+
+// predicated 16-byte load (no branch, no memory traffic when `on` is false): absent edge slots read as h_u = 0.
+// The pointers stay live across the steps, which keeps ptxas from loading over the address registers.
+__device__ __forceinline__ float4 ldg_f4_pred(const float* ptr, bool on)
+{
+    float4 v;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+        "@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
+        : "l"(ptr), "r"((int)on));
+    return v;
+}
+
+struct RowLoads { float4 hv; float4 hu[4]; };
+
+template <int KS>
+__device__ __forceinline__ void row_loads(const float* hv, const float* const (&hu)[4], int deg, int j, RowLoads& L)
+{
+    constexpr int OFF = 4 * LPR * KS;                        // floats
+    const bool on = (KS < GSTEPS - 1) || (j == 0);           // the last step only holds chunk 24
+    L.hv = ldg_f4_pred(hv + OFF, on);
+#pragma unroll
+    for (int s = 0; s < 4; s++) L.hu[s] = ldg_f4_pred(hu[s] + OFF, on && s < deg);
+}
+
+// reduce one step of one row (CSR order), split to bf16 hi / lo and store this thread's 4 columns to the A tile
+template <int KS>
+__device__ __forceinline__ void row_finish(const GinTc2Params& p, const RowLoads& L, const uint32_t (&t)[4], int deg, int maxdeg, int node, bool live, int j,
+                                           const float* h_thr, uint32_t ee_thr, uint32_t a_dst)
+{
+    constexpr int OFF = 4 * LPR * KS;
+    const bool on = (KS < GSTEPS - 1) || (j == 0);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; q++) acc_edge(m, lds_f4(t[q] + 4 * OFF), L.hu[q]);
+    if (maxdeg > 4)
+    {
+        // long in-edge lists (virtual nodes, kNN graphs): rounds of four edges from the CSR arrays, loads first
+        const int eb = __ldg(p.in_ptr + min(node, p.num_nodes - 1));
+        for (int e4 = 4; e4 < maxdeg; e4 += 4)
+        {
+            float4 hx[4];
+            uint32_t tx[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const bool ok = on && e4 + q < deg;
+                int u = 0, c = ED_COMBOS;
+                if (ok) { u = __ldg(p.src + eb + e4 + q); c = __ldg(p.code + eb + e4 + q); }
+                hx[q] = ldg_f4_pred(h_thr + (size_t)u * D + OFF, ok);
+                tx[q] = ee_thr + c * (D * 4) + 4 * OFF;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc_edge(m, lds_f4(tx[q]), hx[q]);
+        }
+    }
+    if (on)
+    {
+        uint32_t h0, l0, h1, l1;
+        split2(live ? m.x + L.hv.x : 0.f, live ? m.y + L.hv.y : 0.f, h0, l0);
+        split2(live ? m.z + L.hv.z : 0.f, live ? m.w + L.hv.w : 0.f, h1, l1);
+        sts_v2(a_dst + KS * (4 * LBO_A), h0, h1);
+        sts_v2(a_dst + KS * (4 * LBO_A) + A_BYTES, l0, l1);
+    }
+}
+
+// a register copy the compiler cannot fold: the consumer of a prefetched value waits for its load HERE, once, and
+// later uses of the copy carry no scoreboard dependency that would serialise them behind the feature-row loads
+__device__ __forceinline__ int reg_copy(int x)
+{
+    int y;
+    asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+
+
+// z = relu(acc + b1) for 16 accumulator columns of this thread's row -> bf16 hi/lo, written back in place
+__device__ __forceinline__ void convert_chunk(uint32_t zaddr, const float* b1c)
+{
+    uint32_t r[16];
+    tc::ld16(zaddr, r);
+    tc::wait_ld();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+        const float4 b = ld_f4(b1c + 4 * j);
+        split2(relu_nan(__uint_as_float(r[4 * j]) + b.x), relu_nan(__uint_as_float(r[4 * j + 1]) + b.y), hi[2 * j], lo[2 * j]);
+        split2(relu_nan(__uint_as_float(r[4 * j + 2]) + b.z), relu_nan(__uint_as_float(r[4 * j + 3]) + b.w), hi[2 * j + 1], lo[2 * j + 1]);
+    }
+    tc::st8(zaddr, hi);
+    tc::st8(zaddr + 8, lo);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2_kernel(GinTc2Params p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* ee = reinterpret_cast<float*>(smem + Smem::EE);
+    float* b1s = reinterpret_cast<float*>(smem + Smem::B1);
+    float* b2s = reinterpret_cast<float*>(smem + Smem::B2);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::BAR);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (tid == 0)
+    {
+        mbar_init(&bar[BAR_W], 1);
+        for (int i = 0; i < 2; i++)
+        {
+            mbar_init(&bar[BAR_A_FULL + i], 2 * GATHER_WARPS);
+            mbar_init(&bar[BAR_A_FREE + i], 1);
+        }
+        mbar_init(&bar[BAR_G1A_DONE], 1);
+        mbar_init(&bar[BAR_G1B_DONE], 1);
+        mbar_init(&bar[BAR_A2A_FULL], 2 * EPI_WARPS);
+        mbar_init(&bar[BAR_A2B_FULL], 2 * EPI_WARPS);
+        mbar_init(&bar[BAR_G2_DONE], 1);
+        fence_mbar_init();
+        // this CTA's half of the weights: one bulk copy, waited for by the first gather warp before it reports tile 0
+        mbar_arrive_expect_tx(&bar[BAR_W], W_BYTES);
+        tma_load_1d(smem + Smem::W, p.wpack + (size_t)rank * W_BYTES, W_BYTES, &bar[BAR_W]);
+    }
+    __syncthreads();
+    cluster_sync();          // both CTAs are running and their barriers are initialised
+    if (warp == MMA_WARP)
+    {
+        tmem_alloc2(tmem_ptr, TMEM_COLS);
+        tmem_relinquish2();
+    }
+    for (int i = tid; i < ED_COMBOS * Q; i += NT) st_f4(ee + 4 * i, ldg_f4(p.ee_comb + 4 * i));
+    for (int i = tid; i < D; i += NT) ee[ED_COMBOS * D + i] = -3.0e38f;       // absent edge slots: relu(-3e38 + 0) adds exactly 0
+    for (int i = tid; i < N1; i += NT) b1s[i] = __ldg(p.b1 + i);
+    for (int i = tid; i < N2; i += NT) b2s[i] = __ldg(p.b2 + i);
+    // zero blocks + A buffers (k = 100..103 of every row stays zero for the whole launch)
+    for (int i = tid; i < (Smem::EE - Smem::ZEROW) / 16; i += NT) st_f4(reinterpret_cast<float*>(smem + Smem::ZEROW) + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+    fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    cluster_sync();
+    tc::fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+    const uint32_t a_base = smem_u32(smem + Smem::A);
+
+    if (warp >= MMA_WARP)
+    {
+        reg_dec<REGS_MISC>();
+        if (warp == MMA_WARP)
+        {
+            // ===== MMA issuer: one thread of the leader CTA =====
+            if (rank == 0 && lane == 0)
+            {
+                const uint32_t w_addr = smem_u32(smem + Smem::W);
+                const uint32_t zero_addr = smem_u32(smem + Smem::ZERO);
+                const uint32_t idesc1a = tc::idesc_bf16(2 * TM, N1A), idesc1b = tc::idesc_bf16(2 * TM, N1B), idesc2 = tc::idesc_bf16(2 * TM, N2);
+                int it = 0;
+                for (int t = pair; t < p.num_pair_tiles; t += npairs, it++)
+                {
+                    const uint32_t ph = it & 1, s = it & 1;
+                    mbar_wait(&bar[BAR_A_FULL + s], (it >> 1) & 1);
+                    tc::fence_after_sync();
+                    // GEMM1, N half a (z columns 0..111) then half b (112..207)
+#pragma unroll
+                    for (int nh = 0; nh < 2; nh++)
+                    {
+                        bool acc = false;
+                        const uint32_t lbo_b = nh ? LBO_W1B : LBO_W1A;
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++)
+                        {
+                            const uint32_t a_addr = a_base + (2 * s + (prod == 1 ? 1 : 0)) * A_BYTES;
+                            const uint32_t b_addr = w_addr + (nh ? (prod == 2 ? OFF_W1B_LO : OFF_W1B_HI) : (prod == 2 ? OFF_W1A_LO : OFF_W1A_HI));
+#pragma unroll
+                            for (int j = 0; j < K1_STEPS; j++)
+                            {
+                                const uint32_t a_start = a_addr + 2 * j * LBO_A;
+                                // the last k-step pairs chunk 12 with the shared zero block (k = 104..111 does not exist)
+                                const uint32_t a_lbo = (j < K1_STEPS - 1) ? (uint32_t)LBO_A : zero_addr - a_start;
+                                mma_ss2(tbase + TC_Z + (nh ? N1A : 0), tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128),
+                                        nh ? idesc1b : idesc1a, acc);
+                                acc = true;
+                            }
+                        }
+                        commit2(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
+                    }
+                    commit2(&bar[BAR_A_FREE + s]);
+                    // GEMM2, K half a (k-steps 0..6, operand columns converted from z half a) then half b (7..12)
+                    bool acc = false;
+#pragma unroll
+                    for (int kh = 0; kh < 2; kh++)
+                    {
+                        mbar_wait(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
+                        tc::fence_after_sync();
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++)
+                        {
+                            const uint32_t a_col = tbase + TC_Z + (prod == 1 ? 8 : 0);
+                            const uint32_t b_addr = w_addr + (prod == 2 ? OFF_W2_LO : OFF_W2_HI);
+#pragma unroll
+                            for (int j = (kh ? N1A / 16 : 0); j < (kh ? K2_STEPS : N1A / 16); j++)
+                            {
+                                mma_ts2(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * LBO_W2, LBO_W2, 128), idesc2, acc);
+                                acc = true;
+                            }
+                        }
+                    }
+                    commit2(&bar[BAR_G2_DONE]);
+                }
+            }
+        }
+        else if (warp == LOAD_WARP)
+        {
+            // ===== L2 prefetch of the feature rows of the tile after next: 4 rows (1,600 B) per lane =====
+            for (int t = pair + 2 * npairs; t < p.num_pair_tiles; t += npairs)
+            {
+                const long n0 = ((long)t * 2 + rank) * TM;
+                const int rn = (int)min((long)TM, (long)p.num_nodes - n0);
+                const int r0 = 4 * lane, nr = min(4, rn - r0);
+                if (nr > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (n0 + r0) * D), "r"(nr * D * 4) : "memory");
+                // ... and its CSR slice (row pointers, sources, codes), so that the gather warps' dependent loads hit L2
+                if (rn > 0)
+                {
+                    const int e_lo = __ldg(p.in_ptr + n0), e_hi = __ldg(p.in_ptr + n0 + rn);
+                    const int eb = e_lo + 32 * lane;                       // 32 edges per lane: 128 B of sources, 32 B of codes
+                    if (eb < e_hi)
+                    {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src + eb) : "memory");
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.code + eb) : "memory");
+                    }
+                    if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in_ptr + n0 + 32 * lane) : "memory");
+                }
+                // pace the prefetch: do not run more than two tiles ahead of the tensor pipe
+                mbar_wait(&bar[BAR_G1A_DONE], ((t - pair) / npairs - 2) & 1);
+            }
+        }
+    }
+    else if (warp >= EPI_WARPS)
+    {
+        reg_inc<REGS_GATHER>();
+        // ===== gather warps: a_v for 8 rows each, written as bf16 hi/lo into the shared-memory A tile =====
+        // Software pipeline over (tile, pass, step): the loads of the next step -- of the next pass, of the next tile --
+        // are always in flight while the current one is reduced; the row descriptor is prefetched one pass ahead.
+        const int gw = warp - EPI_WARPS;
+        const int g = lane >> 3, j = lane & 7;
+        const uint32_t ee_thr = smem_u32(ee) + 16 * j;
+        const float* h_thr = p.h_in + 4 * j;
+        const uint32_t bar_full0 = mapa(smem_u32(&bar[BAR_A_FULL]), 0);
+        // this thread's 8-byte slot in row (8 gw + g) of the A tile, step 0: chunk j -> K chunk pair j / 2, half j % 2
+        const uint32_t a_thr = a_base + (j >> 1) * LBO_A + (j & 1) * 8 + (gw * ROWS_PER_WARP + g) * 16;
+        const int tile_rows = 2 * npairs * TM;                                    // row distance between this CTA's tiles
+        const int last = p.num_nodes - 1;
+
+        // decode a row descriptor into pointers / table addresses
+        auto decode_ptrs = [&](const int4& d, int node, const float*& hv, const float* (&hu)[4]) {
+            const int nc = min(node, last);
+            hv = h_thr + (size_t)nc * D;
+            hu[0] = h_thr + (size_t)(nc + (d.x & 0xFFFF) - 32768) * D;
+            hu[1] = h_thr + (size_t)(nc + (d.y & 0xFFFF) - 32768) * D;
+            hu[2] = h_thr + (size_t)(nc + (d.z & 0xFFFF) - 32768) * D;
+            hu[3] = h_thr + (size_t)(nc + (d.w & 0xFFFF) - 32768) * D;
+        };
+        auto decode_tabs = [&](const int4& d, int node, uint32_t (&t)[4], int& deg, int& maxdeg) {
+            t[0] = ee_thr + ((d.x >> 16) & 0x3F) * (D * 4);
+            t[1] = ee_thr + ((d.y >> 16) & 0x3F) * (D * 4);
+            t[2] = ee_thr + ((d.z >> 16) & 0x3F) * (D * 4);
+            t[3] = ee_thr + ((d.w >> 16) & 0x3F) * (D * 4);
+            deg = node <= last ? (int)((unsigned)d.x >> 24) : 0;
+            if (deg == 255) deg = __ldg(p.in_ptr + min(node, last) + 1) - __ldg(p.in_ptr + min(node, last));
+            // longest in-edge list of the four rows of this pass (warp-uniform trip count of the tail rounds)
+            maxdeg = max(deg, __shfl_xor_sync(FULL, deg, 8));
+            maxdeg = max(maxdeg, __shfl_xor_sync(FULL, maxdeg, 16));
+        };
+
+        int node = (pair * 2 + (int)rank) * TM + gw * ROWS_PER_WARP + g;         // this thread's row in pass 0 of its first tile
+        const float* hv;
+        const float* hu[4];
+        uint32_t tab[4];
+        int deg, maxdeg;
+        RowLoads La, Lb;
+        int4 dn;                                                                  // descriptor of the NEXT pass's row
+        {
+            const int4 d0 = __ldg(p.row_desc + min(node, last));
+            decode_ptrs(d0, node, hv, hu);
+            decode_tabs(d0, node, tab, deg, maxdeg);
+            row_loads<0>(hv, hu, deg, j, La);
+            dn = __ldg(p.row_desc + min(node + 4, last));
+        }
+        int it = 0;
+        for (int t = pair; t < p.num_pair_tiles; t += npairs, it++)
+        {
+            const int s = it & 1;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++)
+            {
+                const bool live = node <= last;
+                const uint32_t a_dst = a_thr + 2 * s * A_BYTES + pass * (4 * 16);
+                const int node_next = pass == 0 ? node + 4 : node - 4 + tile_rows;
+                row_loads<1>(hv, hu, deg, j, Lb);
+                if (pass == 0 && it >= 2) mbar_wait(&bar[BAR_A_FREE + s], ((it >> 1) - 1) & 1);
+                row_finish<0>(p, La, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
+                row_loads<2>(hv, hu, deg, j, La);
+                row_finish<1>(p, Lb, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
+                row_loads<3>(hv, hu, deg, j, Lb);
+                row_finish<2>(p, La, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
+                // the pointers of this row are no longer needed: switch them to the next pass's row and start its loads
+                const int deg_next = node_next <= last ? (int)((unsigned)dn.x >> 24) : 0;
+                decode_ptrs(dn, node_next, hv, hu);
+                row_loads<0>(hv, hu, deg_next, j, La);
+                row_finish<3>(p, Lb, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
+                decode_tabs(dn, node_next, tab, deg, maxdeg);
+                node = node_next;
+                dn = __ldg(p.row_desc + min(pass == 0 ? node - 4 + tile_rows : node + 4, last));
+            }
+            // make the tile visible to the tensor core (async proxy) and report it to the leader CTA
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0)
+            {
+                if (it == 0 && gw == 0) mbar_wait(&bar[BAR_W], 0);      // this CTA's weights have landed
+                mbar_arrive_cluster(bar_full0 + 8 * s);
+            }
+        }
+    }
+    else
+    {
+        reg_dec<REGS_EPI>();
+        // ===== epilogue warps: two per TMEM lane quadrant =====
+        constexpr int PER_QUAD = EPI_WARPS / 4;
+        const int quad = warp & 3, pp = warp >> 2;
+        const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
+        const uint32_t bar_a2a0 = mapa(smem_u32(&bar[BAR_A2A_FULL]), 0), bar_a2b0 = mapa(smem_u32(&bar[BAR_A2B_FULL]), 0);
+        int it = 0;
+        for (int t = pair; t < p.num_pair_tiles; t += npairs, it++)
+        {
+            const uint32_t ph = it & 1;
+            // z = relu(acc + b1) -> bf16 hi/lo, in place (thread = row): columns [16c, 16c+8) hi, [16c+8, 16c+16) lo of
+            // k-step c; the two warps of a quadrant take alternate chunks
+            mbar_wait(&bar[BAR_G1A_DONE], ph);
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c = pp; c < N1A / 16; c += PER_QUAD) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_a2a0);
+
+            mbar_wait(&bar[BAR_G1B_DONE], ph);
+            tc::fence_after_sync();
+#pragma unroll 1
+            for (int c = N1A / 16 + (pp ^ 1); c < N1 / 16; c += PER_QUAD) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_a2b0);
+
+            mbar_wait(&bar[BAR_G2_DONE], ph);
+            tc::fence_after_sync();
+            // h' = acc + b2 (+ relu): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
+            // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction; warp pp of the
+            // quadrant takes its 16-row half
+            const long row_a = ((long)t * 2 + rank) * TM + quad * 32 + pp * 16 + (lane >> 2), row_b = row_a + 8;
+            const uint32_t ta = lane_base + ((uint32_t)(pp * 16) << 16) + TC_H;
+#pragma unroll
+            for (int g4 = 0; g4 < 13; g4 += 4)
+            {
+                uint32_t r[16];
+                asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(ta + 8 * g4)
+                             : "memory");
+                tc::wait_ld();
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                {
+                    const int col = 8 * (g4 + g) + 2 * (lane & 3);
+                    if (8 * (g4 + g) < D && col < D)
+                    {
+                        const float2 bb = *reinterpret_cast<const float2*>(b2s + col);
+                        float2 oa = make_float2(__uint_as_float(r[4 * g]) + bb.x, __uint_as_float(r[4 * g + 1]) + bb.y);
+                        float2 ob = make_float2(__uint_as_float(r[4 * g + 2]) + bb.x, __uint_as_float(r[4 * g + 3]) + bb.y);
+                        if (p.relu_out)
+                        {
+                            oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
+                            ob = make_float2(relu_nan(ob.x), relu_nan(ob.y));
+                        }
+                        if (row_a < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_a * D + col) = oa;
+                        if (row_b < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
+                    }
+                }
+            }
+        }
+    }
+
+    // both CTAs must be done with tensor memory, shared memory and each other's barriers before either leaves
+    tc::fence_before_sync();
+    __syncthreads();
+    __syncwarp();
+    cluster_sync();
+    if (warp == MMA_WARP) tmem_dealloc2(tbase, TMEM_COLS);
+}
+
+}  // namespace
+
+// bytes of one layer's weight image (both ranks) -- api.cu packs with gin_tc2_pack_layer
+size_t gin_tc2_pack_bytes() { return 2 * (size_t)W_BYTES; }
+
+// W1 [200][100], W2 [100][200] (reference "[out][in]") -> per-rank bf16 hi/lo blocks in the stationary B layout.
+// Rank r holds z columns 56r..56r+55 (block 1A) and 112+48r..112+48r+47 (block 1B) of W1 and output columns
+// 64r..64r+63 of W2; rows beyond the real matrix and k beyond the real K are zero.
+void gin_tc2_pack_layer(const float* w1, const float* w2, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t))
+{
+    std::fill(dst, dst + 2 * (size_t)W_BYTES, (unsigned char)0);
+    auto put = [&](unsigned char* hi_blk, unsigned char* lo_blk, int rows, int n_local, int k, float x) {
+        const size_t off = (size_t)(k / 8) * rows * 16 + (size_t)n_local * 16 + (size_t)(k % 8) * 2;
+        const uint16_t hi = bf16_rn(x);
+        const uint16_t lo = bf16_rn(x - bf16_to_float(hi));
+        hi_blk[off] = (unsigned char)(hi & 0xFF); hi_blk[off + 1] = (unsigned char)(hi >> 8);
+        lo_blk[off] = (unsigned char)(lo & 0xFF); lo_blk[off + 1] = (unsigned char)(lo >> 8);
+    };
+    for (int r = 0; r < 2; r++)
+    {
+        unsigned char* img = dst + (size_t)r * W_BYTES;
+        for (int n = 0; n < N1A / 2; n++)
+        {
+            const int z = (N1A / 2) * r + n;
+            for (int k = 0; k < D; k++) put(img + OFF_W1A_HI, img + OFF_W1A_LO, N1A / 2, n, k, w1[(size_t)z * D + k]);
+        }
+        for (int n = 0; n < N1B / 2; n++)
+        {
+            const int z = N1A + (N1B / 2) * r + n;
+            if (z >= 200) continue;
+            for (int k = 0; k < D; k++) put(img + OFF_W1B_HI, img + OFF_W1B_LO, N1B / 2, n, k, w1[(size_t)z * D + k]);
+        }
+        for (int n = 0; n < N2 / 2; n++)
+        {
+            const int o = (N2 / 2) * r + n;
+            if (o >= D) continue;
+            for (int k = 0; k < 200; k++) put(img + OFF_W2_HI, img + OFF_W2_LO, N2 / 2, n, k, w2[(size_t)o * 200 + k]);
+        }
+    }
+}
+
+int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
+{
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        FG_CUDA(cudaFuncSetAttribute(gin_layer_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::BYTES));
+        attr_set = true;
+    }
+    GinTc2Params p;
+    p.h_in = h_in; p.h_out = h_out;
+    p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
+    p.row_desc = b.row_desc.as<int4>();
+    p.ee_comb = w.ee_comb.as<float>() + (size_t)layer * ED_COMBOS * D;
+    p.wpack = w.wpack2.as<unsigned char>() + (size_t)layer * 2 * W_BYTES;
+    p.b1 = w.b1.as<float>() + (size_t)layer * N1;
+    p.b2 = w.b2p2.as<float>() + (size_t)layer * N2;
+    p.num_nodes = (int)b.total_nodes;
+    p.num_pair_tiles = (int)ceil_div<long>(b.total_nodes, 2 * TM);
+    p.relu_out = (layer != 4);
+    const int pairs = std::max(1, std::min(p.num_pair_tiles, sm_count / 2));
+    gin_layer_tc2_kernel<<<2 * pairs, NT, Smem::BYTES, s>>>(p);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fg

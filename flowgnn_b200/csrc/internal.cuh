@@ -44,6 +44,7 @@ struct DeviceBatch {
     DevBuf edge_w;                         // float [E]  GCN: norm = dis[u]*dis[v]; DGN: eig_w = phi_u - phi_v
     DevBuf out_deg;                        // int32 [N]
     DevBuf node_w0, node_w1;               // float [N]  DGN: sum|eig_w|, sum eig_w over in-edges
+    DevBuf row_desc;                       // int4 [N]  GIN: first four in-edges of every node, packed (prep.cu)
     DevBuf sort_tmp;                       // int32 [E] scratch for the two-pass stable sort
     DevBuf status;                         // int32 [1] device-side limit violations
 
@@ -55,7 +56,7 @@ struct DeviceBatch {
     void release();
 };
 
-enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2 };
+enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2, PREP_ROW_DESC = 4 };
 
 // graph preprocessing: offsets scan + per-graph CSR build (prep.cu)
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream);
@@ -71,6 +72,9 @@ struct GinWeights {
     DevBuf wpack;        // [5][4][46592] bytes
     DevBuf ee_raw;       // [5][13][100]
     DevBuf b2p;          // [5][112]
+    // CTA-pair tensor-core path (gin_tc2.cu): per layer and cluster rank, half of every weight block
+    DevBuf wpack2;       // [5][2][gin_tc2_pack_bytes() / 2] bytes
+    DevBuf b2p2;         // [5][128]
     DevBuf pred_w, pred_b;
 };
 struct GcnWeights {
@@ -115,12 +119,16 @@ struct LayerTimer {
 struct RunOptions {
     int mp_only = 0;                 // GIN: node transform = identity (roofline variant)
     int gin_ffma = 0;                // GIN: node MLP on the FP32 FFMA pipe (on-device fp32 reference) instead of tcgen05
+    int gin_tc1 = 0;                 // GIN: single-CTA tcgen05 kernel (gin_tc.cu) instead of the CTA-pair kernel (gin_tc2.cu)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
 };
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+size_t gin_tc2_pack_bytes();
+void gin_tc2_pack_layer(const float* w1, const float* w2, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
 int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);

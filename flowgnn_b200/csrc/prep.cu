@@ -80,13 +80,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const int* _
     }
 }
 
+// Row descriptor of a node for the GIN tensor-core kernel (gin_tc2.cu): its first four in-edges, each packed as
+// (source - node + 32768) | code << 16 (absent slots: the node itself, sentinel code 60), in-degree (capped at 255)
+// in bits 24..31 of .x.  One 16-byte load replaces the in_ptr -> src/code pointer chase of the gather.
+__device__ __forceinline__ int4 empty_row_desc()
+{
+    const int e = 32768 | (ED_COMBOS << 16);
+    return make_int4(e, e, e, e);
+}
+
 constexpr int CSR_WARPS = 4;
 constexpr int CSR_NCAP = 1024;     // nodes per graph supported by the warp-local tables (reference cap: 500)
 
 struct CsrParams {
     const int* nn; const int* ne; const int* node_off; const int* edge_off;
     const int* edge_list; const int* edge_attr; const float* node_eigen;
-    int* in_ptr; int* src; uint8_t* code; float* edge_w; int* out_deg; float* node_w0; float* node_w1;
+    int* in_ptr; int* src; uint8_t* code; float* edge_w; int* out_deg; float* node_w0; float* node_w1; int4* row_desc;
     int* sort_tmp; int* status;
     int num_graphs; int flags; int has_attr;
 };
@@ -110,7 +119,7 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) build_csr_kernel(CsrParams p)
     {
         if (lane == 0) atomicOr(p.status, 1);
         // keep downstream kernels in bounds: empty rows
-        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; }
+        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; if (p.row_desc) p.row_desc[nb + i] = empty_row_desc(); }
         return;
     }
     int* deg = s_deg[wid];
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) build_csr_kernel(CsrParams p)
     if (__any_sync(full, bad))
     {
         if (lane == 0) atomicOr(p.status, 2);
-        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; }
+        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; if (p.row_desc) p.row_desc[nb + i] = empty_row_desc(); }
         return;
     }
     __syncwarp();
@@ -216,6 +225,22 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) build_csr_kernel(CsrParams p)
         }
         __syncwarp();
     }
+    if (p.row_desc)
+    {
+        __threadfence_block();
+        __syncwarp();
+        for (int v = lane; v < n; v += 32)
+        {
+            const int end = eb + pv[v];
+            const int beg = (v == 0) ? eb : eb + pv[v - 1];
+            int4 d = empty_row_desc();
+            int* dq = reinterpret_cast<int*>(&d);
+            for (int q = 0; q < 4 && beg + q < end; q++)
+                dq[q] = ((p.src[beg + q] - (nb + v) + 32768) & 0xFFFF) | ((p.has_attr ? (int)p.code[beg + q] : 0) << 16);
+            d.x |= min(end - beg, 255) << 24;
+            p.row_desc[nb + v] = d;
+        }
+    }
     if (p.flags & PREP_DGN_EIG)
     {
         // per-destination sums over the (now sorted) in-edges; pv[v] ends at the end of row v
@@ -252,6 +277,7 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
     FG_TRY(b.out_deg.reserve(sizeof(int) * (size_t)(b.total_nodes + 1)));
     FG_TRY(b.sort_tmp.reserve(sizeof(int) * (size_t)(b.total_edges + 1)));
     FG_TRY(b.status.reserve(sizeof(int)));
+    if (flags & PREP_ROW_DESC) FG_TRY(b.row_desc.reserve(sizeof(int4) * (size_t)(b.total_nodes + 1)));
     if (flags & (PREP_GCN_NORM | PREP_DGN_EIG)) FG_TRY(b.edge_w.reserve(sizeof(float) * (size_t)(b.total_edges + 1)));
     if (flags & PREP_DGN_EIG)
     {
@@ -271,6 +297,7 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>(); p.edge_w = b.edge_w.as<float>();
     p.out_deg = b.out_deg.as<int>(); p.node_w0 = b.node_w0.as<float>(); p.node_w1 = b.node_w1.as<float>();
     p.sort_tmp = b.sort_tmp.as<int>(); p.status = b.status.as<int>();
+    p.row_desc = (flags & PREP_ROW_DESC) ? b.row_desc.as<int4>() : nullptr;
     p.num_graphs = G; p.flags = flags; p.has_attr = b.has_attr ? 1 : 0;
     build_csr_kernel<<<ceil_div(G, CSR_WARPS), CSR_WARPS * 32, 0, stream>>>(p);
     FG_CUDA(cudaGetLastError());
