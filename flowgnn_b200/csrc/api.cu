@@ -204,12 +204,12 @@ int load_gin(flowgnn_ctx* c, const float* const* w)
         const size_t per_layer = gin_tc2_pack_bytes();
         std::vector<unsigned char> pack(5 * per_layer);
         for (int l = 0; l < 5; l++)
-            gin_tc2_pack_layer(w[2] + (size_t)l * 200 * 100, w[4] + (size_t)l * 100 * 200, pack.data() + (size_t)l * per_layer, bf16_rn, bf16_to_float);
+            gin_tc2_pack_layer(w[2] + (size_t)l * 200 * 100, w[3] + (size_t)l * 200, w[4] + (size_t)l * 100 * 200, w[5] + (size_t)l * 100,
+                               pack.data() + (size_t)l * per_layer, bf16_rn, bf16_to_float);
         FG_TRY(g.wpack2.reserve(pack.size()));
         FG_CUDA(cudaMemcpyAsync(g.wpack2.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
         FG_CUDA(cudaStreamSynchronize(s));
     }
-    FG_TRY(upload(g.b2p2, pad_rows(w[5], 5, 100, 128), s));
     FG_TRY(upload(g.ee_raw, w[1], (size_t)5 * ED_FEATURE_PER_LAYER * 100, s));
     FG_TRY(upload(g.b2p, pad_rows(w[5], 5, 100, 112), s));
     FG_TRY(upload(g.pred_w, w[6], 100, s));
@@ -396,7 +396,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaStreamDestroy(ctx->copy_stream);
-    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.b2p2, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
+    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
                    &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,

@@ -44,7 +44,7 @@ constexpr int N1A = 112, N1B = 96, N1 = N1A + N1B;   // GEMM1 N halves (z column
 constexpr int N2 = 128;                       // GEMM2 N (100 used)
 constexpr int K1_STEPS = 7, K2_STEPS = 13;    // K = 16 per step
 constexpr int K1_CHUNKS = 13;                 // stored 8-element K chunks of A and W1 (k < 104; chunk 13 reads as zero)
-constexpr int K2_CHUNKS = 25;                 // stored K chunks of W2 (k < 200; z columns 200..207 are exactly zero)
+constexpr int K2_CHUNKS = 26;                 // stored K chunks of W2: k < 200 plus the bias column k = 200 (z column 200 == 1)
 
 // per-CTA weight image (bytes): half of the N rows of every block
 constexpr int LBO_W1A = (N1A / 2) * 16, LBO_W1B = (N1B / 2) * 16, LBO_W2 = (N2 / 2) * 16;
@@ -64,12 +64,12 @@ constexpr int EPI_WARPS = 8, GATHER_WARPS = 16;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, LOAD_WARP = MMA_WARP + 1;
 constexpr int NT = (MMA_WARP + 4) * 32;       // 896
 constexpr int REGS_LAUNCH = 72;               // 65,536 / 896 rounded down to a multiple of 8
-constexpr int REGS_EPI = 64, REGS_MISC = 24, REGS_GATHER = 88;
+constexpr int REGS_EPI = 80, REGS_MISC = 24, REGS_GATHER = 80;
 // setmaxnreg moves registers inside the CTA's launch allocation: the new sizes must fit it or the increase never returns
 static_assert(32 * (EPI_WARPS * REGS_EPI + GATHER_WARPS * REGS_GATHER + 4 * REGS_MISC) <= NT * REGS_LAUNCH, "setmaxnreg pool");
 constexpr int ROWS_PER_WARP = TM / GATHER_WARPS;   // 8
 constexpr int LPR = 8;                             // lanes per row
-constexpr int GSTEPS = 4;                          // steps per row: chunk 8 ks + j (the last step only holds chunk 24)
+constexpr int GSTEPS = 3;                          // steps per row: chunk 8 ks + j; chunk 24 is gathered once per tile with one lane per row
 
 // tensor-memory columns
 constexpr uint32_t TC_Z = 0, TC_H = 256;
@@ -77,17 +77,14 @@ constexpr uint32_t TMEM_COLS = 512;
 
 struct Smem {
     static constexpr int W = 0;
-    static constexpr int ZEROW = W + W_BYTES;                       // K chunk 25 of W2_lo (the last block of W) reads these zeros
-    static constexpr int A = ZEROW + LBO_W2;                        // [2 stages][hi, lo][A_BYTES]
+    static constexpr int A = W + W_BYTES;                           // [2 stages][hi, lo][A_BYTES]
     static constexpr int ZERO = A + 4 * A_BYTES;                    // K chunk 13 of every A buffer (must lie above them: LBO >= 0)
     static constexpr int EE = ZERO + ZERO_BYTES;                    // [61][100] fp32 combined edge-embedding rows; row 60 = sentinel
-    static constexpr int B1 = EE + (ED_COMBOS + 1) * D * 4;         // [208]
-    static constexpr int B2 = B1 + N1 * 4;                          // [128]
-    static constexpr int BAR = B2 + N2 * 4;
+    static constexpr int BAR = EE + (ED_COMBOS + 1) * D * 4;
     static constexpr int TMEM_PTR = BAR + 16 * 8;
     static constexpr int BYTES = TMEM_PTR + 16;
 };
-static_assert(Smem::ZEROW % 16 == 0 && Smem::ZERO % 16 == 0 && Smem::A % 16 == 0 && Smem::EE % 16 == 0 && Smem::BAR % 8 == 0, "alignment");
+static_assert(Smem::ZERO % 16 == 0 && Smem::A % 16 == 0 && Smem::EE % 16 == 0 && Smem::BAR % 8 == 0, "alignment");
 static_assert(Smem::BYTES <= 232448, "shared memory budget");
 
 enum { BAR_W = 0, BAR_A_FULL /* 2 */, BAR_A_FREE = BAR_A_FULL + 2 /* 2 */, BAR_G1A_DONE = BAR_A_FREE + 2, BAR_G1B_DONE, BAR_A2A_FULL, BAR_A2B_FULL, BAR_G2_DONE };
@@ -98,7 +95,6 @@ struct GinTc2Params {
     const int4* row_desc;            // [N] first four in-edges of every node, packed (prep.cu)
     const float* ee_comb;            // [60][100] this layer: ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]
     const unsigned char* wpack;      // [2 ranks][W_BYTES] this layer
-    const float* b1; const float* b2;   // [208], [128] zero padded
     int num_nodes; int num_pair_tiles; int relu_out;
 };
 
@@ -262,7 +258,7 @@ template <int KS>
 __device__ __forceinline__ void row_loads(const float* hv, const float* const (&hu)[4], int deg, int j, RowLoads& L)
 {
     constexpr int OFF = 4 * LPR * KS;                        // floats
-    const bool on = (KS < GSTEPS - 1) || (j == 0);           // the last step only holds chunk 24
+    const bool on = true;
     L.hv = ldg_f4_pred(hv + OFF, on);
 #pragma unroll
     for (int s = 0; s < 4; s++) L.hu[s] = ldg_f4_pred(hu[s] + OFF, on && s < deg);
@@ -274,7 +270,7 @@ __device__ __forceinline__ void row_finish(const GinTc2Params& p, const RowLoads
                                            const float* h_thr, uint32_t ee_thr, uint32_t a_dst)
 {
     constexpr int OFF = 4 * LPR * KS;
-    const bool on = (KS < GSTEPS - 1) || (j == 0);
+    const bool on = true;
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < 4; q++) acc_edge(m, lds_f4(t[q] + 4 * OFF), L.hu[q]);
@@ -319,30 +315,41 @@ __device__ __forceinline__ int reg_copy(int x)
 }
 
 
-// z = relu(acc + b1) for 16 accumulator columns of this thread's row -> bf16 hi/lo, written back in place
-__device__ __forceinline__ void convert_chunk(uint32_t zaddr, const float* b1c)
+// z = relu(acc) for 16 accumulator columns of this thread's row (b1 is already in acc: the A tile carries a constant-1
+// column k = 100 and W1 the bias in that column) -> bf16 hi/lo, written back in place
+__device__ __forceinline__ void convert_regs(uint32_t zaddr, const uint32_t (&r)[16])
 {
-    uint32_t r[16];
-    tc::ld16(zaddr, r);
-    tc::wait_ld();
     uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-    {
-        const float4 b = ld_f4(b1c + 4 * j);
-        split2(relu_nan(__uint_as_float(r[4 * j]) + b.x), relu_nan(__uint_as_float(r[4 * j + 1]) + b.y), hi[2 * j], lo[2 * j]);
-        split2(relu_nan(__uint_as_float(r[4 * j + 2]) + b.z), relu_nan(__uint_as_float(r[4 * j + 3]) + b.w), hi[2 * j + 1], lo[2 * j + 1]);
-    }
+    for (int j = 0; j < 8; j++) split2(relu_nan(__uint_as_float(r[2 * j])), relu_nan(__uint_as_float(r[2 * j + 1])), hi[j], lo[j]);
     tc::st8(zaddr, hi);
     tc::st8(zaddr + 8, lo);
+}
+// chunks c, c + 2, ... < c_end of 16 columns each; the TMEM load of the next chunk is in flight while one is converted
+__device__ __forceinline__ void convert_range(uint32_t zbase, int c, int c_end)
+{
+    uint32_t r0[16], r1[16];
+    if (c >= c_end) return;
+    tc::ld16(zbase + 16 * c, r0);
+    while (true)
+    {
+        tc::wait_ld();
+        if (c + 2 < c_end) tc::ld16(zbase + 16 * (c + 2), r1);
+        convert_regs(zbase + 16 * c, r0);
+        c += 2;
+        if (c >= c_end) break;
+        tc::wait_ld();
+        if (c + 2 < c_end) tc::ld16(zbase + 16 * (c + 2), r0);
+        convert_regs(zbase + 16 * c, r1);
+        c += 2;
+        if (c >= c_end) break;
+    }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2_kernel(GinTc2Params p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float* ee = reinterpret_cast<float*>(smem + Smem::EE);
-    float* b1s = reinterpret_cast<float*>(smem + Smem::B1);
-    float* b2s = reinterpret_cast<float*>(smem + Smem::B2);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::BAR);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
 
@@ -377,10 +384,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
     }
     for (int i = tid; i < ED_COMBOS * Q; i += NT) st_f4(ee + 4 * i, ldg_f4(p.ee_comb + 4 * i));
     for (int i = tid; i < D; i += NT) ee[ED_COMBOS * D + i] = -3.0e38f;       // absent edge slots: relu(-3e38 + 0) adds exactly 0
-    for (int i = tid; i < N1; i += NT) b1s[i] = __ldg(p.b1 + i);
-    for (int i = tid; i < N2; i += NT) b2s[i] = __ldg(p.b2 + i);
-    // zero blocks + A buffers (k = 100..103 of every row stays zero for the whole launch)
-    for (int i = tid; i < (Smem::EE - Smem::ZEROW) / 16; i += NT) st_f4(reinterpret_cast<float*>(smem + Smem::ZEROW) + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+    // A buffers + zero block (k = 101..103 of every row stays zero for the whole launch)
+    for (int i = tid; i < (Smem::EE - Smem::A) / 16; i += NT) st_f4(reinterpret_cast<float*>(smem + Smem::A) + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+    __syncthreads();
+    // bias column: a_hi[row][k = 100] = 1 in both stages, never overwritten (the gather writes k < 100 only)
+    for (int i = tid; i < 2 * TM; i += NT)
+        *reinterpret_cast<uint16_t*>(smem + Smem::A + (i / TM) * 2 * A_BYTES + (D / 8) * LBO_A + (i % TM) * 16 + (D % 8) * 2) = 0x3F80;
     fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -483,7 +492,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
     }
     else if (warp >= EPI_WARPS)
     {
-        reg_inc<REGS_GATHER>();
+        if constexpr (REGS_GATHER > REGS_LAUNCH) reg_inc<REGS_GATHER>(); else reg_dec<REGS_GATHER>();
         // ===== gather warps: a_v for 8 rows each, written as bf16 hi/lo into the shared-memory A tile =====
         // Software pipeline over (tile, pass, step): the loads of the next step -- of the next pass, of the next tile --
         // are always in flight while the current one is reduced; the row descriptor is prefetched one pass ahead.
@@ -536,27 +545,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
         for (int t = pair; t < p.num_pair_tiles; t += npairs, it++)
         {
             const int s = it & 1;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; pass++)
-            {
+            // one pass = 3 steps on 2 load buffers, so the buffers swap roles from pass to pass: X holds steps 0 and 2,
+            // Y step 1 and then step 0 of the NEXT pass
+            auto do_pass = [&](int pass, RowLoads& X, RowLoads& Y) {
                 const bool live = node <= last;
                 const uint32_t a_dst = a_thr + 2 * s * A_BYTES + pass * (4 * 16);
                 const int node_next = pass == 0 ? node + 4 : node - 4 + tile_rows;
-                row_loads<1>(hv, hu, deg, j, Lb);
+                row_loads<1>(hv, hu, deg, j, Y);
                 if (pass == 0 && it >= 2) mbar_wait(&bar[BAR_A_FREE + s], ((it >> 1) - 1) & 1);
-                row_finish<0>(p, La, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
-                row_loads<2>(hv, hu, deg, j, La);
-                row_finish<1>(p, Lb, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
-                row_loads<3>(hv, hu, deg, j, Lb);
-                row_finish<2>(p, La, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
+                row_finish<0>(p, X, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
+                // the next row's descriptor was requested together with X's loads: it is here by now.  Copying it out at this
+                // point (and not where it is decoded) keeps its scoreboard from serialising behind the loads issued below.
+                const int4 dc = make_int4(reg_copy(dn.x), reg_copy(dn.y), reg_copy(dn.z), reg_copy(dn.w));
+                row_loads<2>(hv, hu, deg, j, X);
+                row_finish<1>(p, Y, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
                 // the pointers of this row are no longer needed: switch them to the next pass's row and start its loads
-                const int deg_next = node_next <= last ? (int)((unsigned)dn.x >> 24) : 0;
-                decode_ptrs(dn, node_next, hv, hu);
-                row_loads<0>(hv, hu, deg_next, j, La);
-                row_finish<3>(p, Lb, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
-                decode_tabs(dn, node_next, tab, deg, maxdeg);
+                const int deg_next = node_next <= last ? (int)((unsigned)dc.x >> 24) : 0;
+                decode_ptrs(dc, node_next, hv, hu);
+                row_loads<0>(hv, hu, deg_next, j, Y);
+                dn = __ldg(p.row_desc + min(node + tile_rows, last));       // row of the pass after next
+                row_finish<2>(p, X, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
+                decode_tabs(dc, node_next, tab, deg, maxdeg);
                 node = node_next;
-                dn = __ldg(p.row_desc + min(pass == 0 ? node - 4 + tile_rows : node + 4, last));
+            };
+            do_pass(0, La, Lb);
+            do_pass(1, Lb, La);
+            // The last float4 of every row (columns 96..99, chunk 24) does not fit 8 lanes x 3 steps: lanes 0..7 gather it
+            // for the warp's 8 rows, one lane per row (the gather warps have the slack for the exposed latency).
+            {
+                const int R = gw * ROWS_PER_WARP + (lane & 7);
+                const int nodeT = (t * 2 + (int)rank) * TM + R, nc = min(nodeT, last);
+                const bool mine = lane < 8, liveT = nodeT <= last;
+                const float* h24 = p.h_in + 4 * (Q - 1);
+                const int4 d = __ldg(p.row_desc + nc);
+                int dgT = mine && liveT ? (int)((unsigned)d.x >> 24) : 0;
+                if (dgT == 255) dgT = __ldg(p.in_ptr + nc + 1) - __ldg(p.in_ptr + nc);
+                const float4 hvT = ldg_f4_pred(h24 + (size_t)nc * D, mine);
+                const float4 x0 = ldg_f4_pred(h24 + (size_t)(nc + (d.x & 0xFFFF) - 32768) * D, 0 < dgT);
+                const float4 x1 = ldg_f4_pred(h24 + (size_t)(nc + (d.y & 0xFFFF) - 32768) * D, 1 < dgT);
+                const float4 x2 = ldg_f4_pred(h24 + (size_t)(nc + (d.z & 0xFFFF) - 32768) * D, 2 < dgT);
+                const float4 x3 = ldg_f4_pred(h24 + (size_t)(nc + (d.w & 0xFFFF) - 32768) * D, 3 < dgT);
+                float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc_edge(m, ld_f4(ee + ((d.x >> 16) & 0x3F) * D + 4 * (Q - 1)), x0);
+                acc_edge(m, ld_f4(ee + ((d.y >> 16) & 0x3F) * D + 4 * (Q - 1)), x1);
+                acc_edge(m, ld_f4(ee + ((d.z >> 16) & 0x3F) * D + 4 * (Q - 1)), x2);
+                acc_edge(m, ld_f4(ee + ((d.w >> 16) & 0x3F) * D + 4 * (Q - 1)), x3);
+                if (dgT > 4)
+                {
+                    const int eb = __ldg(p.in_ptr + nc);
+                    for (int e = eb + 4; e < eb + dgT; e++)
+                        acc_edge(m, ld_f4(ee + (int)__ldg(p.code + e) * D + 4 * (Q - 1)), __ldg(reinterpret_cast<const float4*>(h24 + (size_t)__ldg(p.src + e) * D)));
+                }
+                if (mine)
+                {
+                    uint32_t h0, l0, h1, l1;
+                    split2(liveT ? m.x + hvT.x : 0.f, liveT ? m.y + hvT.y : 0.f, h0, l0);
+                    split2(liveT ? m.z + hvT.z : 0.f, liveT ? m.w + hvT.w : 0.f, h1, l1);
+                    const uint32_t dst = a_base + 2 * s * A_BYTES + ((Q - 1) >> 1) * LBO_A + R * 16;
+                    sts_v2(dst, h0, h1);
+                    sts_v2(dst + A_BYTES, l0, l1);
+                }
             }
             // make the tile visible to the tensor core (async proxy) and report it to the leader CTA
             fence_proxy_async();
@@ -570,7 +618,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
     }
     else
     {
-        reg_dec<REGS_EPI>();
+        if constexpr (REGS_EPI > REGS_LAUNCH) reg_inc<REGS_EPI>(); else reg_dec<REGS_EPI>();
         // ===== epilogue warps: two per TMEM lane quadrant =====
         constexpr int PER_QUAD = EPI_WARPS / 4;
         const int quad = warp & 3, pp = warp >> 2;
@@ -584,8 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             // k-step c; the two warps of a quadrant take alternate chunks
             mbar_wait(&bar[BAR_G1A_DONE], ph);
             tc::fence_after_sync();
-#pragma unroll 1
-            for (int c = pp; c < N1A / 16; c += PER_QUAD) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
+            convert_range(lane_base + TC_Z, pp, N1A / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
@@ -593,8 +640,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
 
             mbar_wait(&bar[BAR_G1B_DONE], ph);
             tc::fence_after_sync();
-#pragma unroll 1
-            for (int c = N1A / 16 + (pp ^ 1); c < N1 / 16; c += PER_QUAD) convert_chunk(lane_base + TC_Z + 16 * c, b1s + 16 * c);
+            convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
@@ -602,30 +648,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
 
             mbar_wait(&bar[BAR_G2_DONE], ph);
             tc::fence_after_sync();
-            // h' = acc + b2 (+ relu): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
+            // h' = acc (+ relu; b2 is already in acc through the bias column k = 200 of W2): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
             // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction; warp pp of the
             // quadrant takes its 16-row half
             const long row_a = ((long)t * 2 + rank) * TM + quad * 32 + pp * 16 + (lane >> 2), row_b = row_a + 8;
             const uint32_t ta = lane_base + ((uint32_t)(pp * 16) << 16) + TC_H;
-#pragma unroll
-            for (int g4 = 0; g4 < 13; g4 += 4)
-            {
-                uint32_t r[16];
+            auto ld_h = [&](int g4, uint32_t (&r)[16]) {
                 asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
                                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                              : "r"(ta + 8 * g4)
                              : "memory");
-                tc::wait_ld();
+            };
+            auto st_h = [&](int g4, const uint32_t (&r)[16]) {
 #pragma unroll
                 for (int g = 0; g < 4; g++)
                 {
                     const int col = 8 * (g4 + g) + 2 * (lane & 3);
                     if (8 * (g4 + g) < D && col < D)
                     {
-                        const float2 bb = *reinterpret_cast<const float2*>(b2s + col);
-                        float2 oa = make_float2(__uint_as_float(r[4 * g]) + bb.x, __uint_as_float(r[4 * g + 1]) + bb.y);
-                        float2 ob = make_float2(__uint_as_float(r[4 * g + 2]) + bb.x, __uint_as_float(r[4 * g + 3]) + bb.y);
+                        float2 oa = make_float2(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]));
+                        float2 ob = make_float2(__uint_as_float(r[4 * g + 2]), __uint_as_float(r[4 * g + 3]));
                         if (p.relu_out)
                         {
                             oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
@@ -635,6 +678,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                         if (row_b < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
                     }
                 }
+            };
+            {
+                uint32_t r0[16], r1[16];
+                ld_h(0, r0);
+                tc::wait_ld(); ld_h(4, r1); st_h(0, r0);
+                tc::wait_ld(); ld_h(8, r0); st_h(4, r1);
+                tc::wait_ld(); ld_h(12, r1); st_h(8, r0);
+                tc::wait_ld(); st_h(12, r1);
             }
         }
     }
@@ -655,7 +706,10 @@ size_t gin_tc2_pack_bytes() { return 2 * (size_t)W_BYTES; }
 // W1 [200][100], W2 [100][200] (reference "[out][in]") -> per-rank bf16 hi/lo blocks in the stationary B layout.
 // Rank r holds z columns 56r..56r+55 (block 1A) and 112+48r..112+48r+47 (block 1B) of W1 and output columns
 // 64r..64r+63 of W2; rows beyond the real matrix and k beyond the real K are zero.
-void gin_tc2_pack_layer(const float* w1, const float* w2, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t))
+// The biases ride along as one more K column: the A tile has a constant 1 at k = 100, so W1[z][100] = b1[z]; the extra
+// row z = 200 of W1 is (0, ..., 0, 1) so that z column 200 == relu(1) == 1, and W2[o][200] = b2[o].
+void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
+                        float (*bf16_to_float)(uint16_t))
 {
     std::fill(dst, dst + 2 * (size_t)W_BYTES, (unsigned char)0);
     auto put = [&](unsigned char* hi_blk, unsigned char* lo_blk, int rows, int n_local, int k, float x) {
@@ -665,25 +719,25 @@ void gin_tc2_pack_layer(const float* w1, const float* w2, unsigned char* dst, ui
         hi_blk[off] = (unsigned char)(hi & 0xFF); hi_blk[off + 1] = (unsigned char)(hi >> 8);
         lo_blk[off] = (unsigned char)(lo & 0xFF); lo_blk[off + 1] = (unsigned char)(lo >> 8);
     };
+    auto w1_row = [&](unsigned char* hi_blk, unsigned char* lo_blk, int rows, int n, int z) {
+        if (z < 200)
+        {
+            for (int k = 0; k < D; k++) put(hi_blk, lo_blk, rows, n, k, w1[(size_t)z * D + k]);
+            put(hi_blk, lo_blk, rows, n, D, b1[z]);
+        }
+        else if (z == 200) put(hi_blk, lo_blk, rows, n, D, 1.0f);
+    };
     for (int r = 0; r < 2; r++)
     {
         unsigned char* img = dst + (size_t)r * W_BYTES;
-        for (int n = 0; n < N1A / 2; n++)
-        {
-            const int z = (N1A / 2) * r + n;
-            for (int k = 0; k < D; k++) put(img + OFF_W1A_HI, img + OFF_W1A_LO, N1A / 2, n, k, w1[(size_t)z * D + k]);
-        }
-        for (int n = 0; n < N1B / 2; n++)
-        {
-            const int z = N1A + (N1B / 2) * r + n;
-            if (z >= 200) continue;
-            for (int k = 0; k < D; k++) put(img + OFF_W1B_HI, img + OFF_W1B_LO, N1B / 2, n, k, w1[(size_t)z * D + k]);
-        }
+        for (int n = 0; n < N1A / 2; n++) w1_row(img + OFF_W1A_HI, img + OFF_W1A_LO, N1A / 2, n, (N1A / 2) * r + n);
+        for (int n = 0; n < N1B / 2; n++) w1_row(img + OFF_W1B_HI, img + OFF_W1B_LO, N1B / 2, n, N1A + (N1B / 2) * r + n);
         for (int n = 0; n < N2 / 2; n++)
         {
             const int o = (N2 / 2) * r + n;
             if (o >= D) continue;
             for (int k = 0; k < 200; k++) put(img + OFF_W2_HI, img + OFF_W2_LO, N2 / 2, n, k, w2[(size_t)o * 200 + k]);
+            put(img + OFF_W2_HI, img + OFF_W2_LO, N2 / 2, n, 200, b2[o]);
         }
     }
 }
@@ -702,8 +756,6 @@ int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, c
     p.row_desc = b.row_desc.as<int4>();
     p.ee_comb = w.ee_comb.as<float>() + (size_t)layer * ED_COMBOS * D;
     p.wpack = w.wpack2.as<unsigned char>() + (size_t)layer * 2 * W_BYTES;
-    p.b1 = w.b1.as<float>() + (size_t)layer * N1;
-    p.b2 = w.b2p2.as<float>() + (size_t)layer * N2;
     p.num_nodes = (int)b.total_nodes;
     p.num_pair_tiles = (int)ceil_div<long>(b.total_nodes, 2 * TM);
     p.relu_out = (layer != 4);

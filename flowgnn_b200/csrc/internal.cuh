@@ -73,8 +73,7 @@ struct GinWeights {
     DevBuf ee_raw;       // [5][13][100]
     DevBuf b2p;          // [5][112]
     // CTA-pair tensor-core path (gin_tc2.cu): per layer and cluster rank, half of every weight block
-    DevBuf wpack2;       // [5][2][gin_tc2_pack_bytes() / 2] bytes
-    DevBuf b2p2;         // [5][128]
+    DevBuf wpack2;       // [5][2][gin_tc2_pack_bytes() / 2] bytes (weights and biases)
     DevBuf pred_w, pred_b;
 };
 struct GcnWeights {
@@ -128,7 +127,8 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
 int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t gin_tc2_pack_bytes();
-void gin_tc2_pack_layer(const float* w1, const float* w2, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
+void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
+                        float (*bf16_to_float)(uint16_t));
 int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
