@@ -49,7 +49,7 @@ WORKLOADS = {
 #: (D, L, attr words A, extra bytes per node X) of SURVEY.md 8(d): B_layer = 8*D*N + E*(8+4A) + X*N
 ALGO = {"gin": (100, 5, 3, 0), "ginvn": (100, 5, 3, 0), "gcn": (100, 5, 3, 0), "gat": (64, 5, 0, 64), "pna": (80, 4, 0, 0),
         "dgn": (100, 4, 0, 0)}
-LAYER_KERNEL = {"gin": "gin_layer_tc_kernel", "ginvn": "gin_layer_tc_kernel", "gcn": "gcn_layer_kernel", "gat": "gat_layer_kernel",
+LAYER_KERNEL = {"gin": "gin_layer_tc2_kernel", "ginvn": "gin_layer_tc2_kernel", "gcn": "gcn_layer_kernel", "gat": "gat_layer_kernel",
                 "pna": "pna_layer_kernel", "dgn": "dgn_layer_kernel"}
 
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -154,9 +155,10 @@ struct flowgnn_ctx {
     bool batch_ready = false;
     // host-pointer entry points: the batch is cut into chunks that alternate between two device batches, so that
     // the H2D copy of chunk i+1 (copy_stream) overlaps the kernels of chunk i (stream)
-    DeviceBatch pipe[2];
+    static constexpr int PIPE = 2;      // measured: a third buffer lets the uploads run ahead but slows the kernels more than it saves
+    DeviceBatch pipe[PIPE];
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t up_done[2] = {nullptr, nullptr}, buf_free[2] = {nullptr, nullptr};
+    cudaEvent_t up_done[PIPE] = {}, buf_free[PIPE] = {};
     float* h_out = nullptr; size_t h_out_cap = 0;      // pinned staging of the predictions
     int* h_status = nullptr;                           // pinned, one word per chunk
     GinWeights gin; GcnWeights gcn; GatWeights gat; PnaWeights pna; DgnWeights dgn;
@@ -368,7 +370,7 @@ int flowgnn_b200_create(flowgnn_ctx** out, int device)
     c->sm_count = prop.multiProcessorCount;
     FG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < flowgnn_ctx::PIPE; i++)
     {
         FG_CUDA(cudaEventCreateWithFlags(&c->up_done[i], cudaEventDisableTiming));
         FG_CUDA(cudaEventCreateWithFlags(&c->buf_free[i], cudaEventDisableTiming));
@@ -387,7 +389,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
     ctx->batch.release();
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < flowgnn_ctx::PIPE; i++)
     {
         ctx->pipe[i].release();
         cudaEventDestroy(ctx->up_done[i]);
@@ -651,16 +653,24 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         const bool gat_bug = (model == MODEL_GAT) && ctx->opt.gat_node_offset_bug;
         const int run_graphs = g1 - g;
         int nchunks = 1;
-        int bounds[5] = {g, g1, g1, g1, g1};
-        if (run_graphs >= 16384)
+        int bounds[17];
+        for (int i = 0; i <= 16; i++) bounds[i] = g1;
+        bounds[0] = g;
         {
-            nchunks = 4;
-            bounds[1] = g + run_graphs / 8; bounds[2] = g + (3 * run_graphs) / 8; bounds[3] = g + (11 * run_graphs) / 16; bounds[4] = g1;
-        }
-        else if (run_graphs >= 8192)
-        {
-            nchunks = 2;
-            bounds[1] = g + run_graphs / 3; bounds[2] = g1;
+            // graded schedule: chunk i gets weight min(i + 1, 3) (a small first chunk starts the kernels early)
+            int want = run_graphs >= 16384 ? 3 : run_graphs >= 8192 ? 2 : 1;     // measured on B200: 3.87 / 3.18 / 3.11 / 3.19 / 3.54 ms for 1 / 2 / 3 / 4 / 6 chunks of the 41k-graph batch
+            if (const char* e = std::getenv("FLOWGNN_B200_CHUNKS")) want = std::max(1, std::min(16, std::atoi(e)));
+            if (run_graphs < 2 * want) want = 1;
+            nchunks = want;
+            int total_w = 0;
+            for (int i = 0; i < want; i++) total_w += std::min(i + 1, 3);
+            int acc_w = 0;
+            for (int i = 0; i < want - 1; i++)
+            {
+                acc_w += std::min(i + 1, 3);
+                bounds[i + 1] = g + (int)((int64_t)run_graphs * acc_w / total_w);
+            }
+            bounds[want] = g1;
         }
         if ((size_t)run_graphs > ctx->h_out_cap)
         {
@@ -676,11 +686,12 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             const int c0 = bounds[ci], c1 = bounds[ci + 1];
             int64_t n_c = 0, e_c = 0;
             for (int k = c0; k < c1; k++) { n_c += nn[k]; e_c += ne[k]; }
-            DeviceBatch& db = ctx->pipe[ci & 1];
-            if (ci >= 2) FG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->buf_free[ci & 1], 0));
+            constexpr int P = flowgnn_ctx::PIPE;
+            DeviceBatch& db = ctx->pipe[ci % P];
+            if (ci >= P) FG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->buf_free[ci % P], 0));
             FG_TRY(upload_into(db, ctx->copy_stream, c1 - c0, n_c, e_c, nn + c0, ne + c0, gat_bug ? feat : feat + ND_FEATURE * nb,
                                edges + 2 * eb, attr ? attr + 3 * eb : nullptr, eig ? eig + 4 * nb : nullptr));
-            FG_CUDA(cudaEventRecord(ctx->up_done[ci & 1], ctx->copy_stream));
+            FG_CUDA(cudaEventRecord(ctx->up_done[ci % P], ctx->copy_stream));
             nb += n_c; eb += e_c;
             return 0;
         };
@@ -697,9 +708,10 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         for (int ci = 0; ci < nchunks; ci++)
         {
             const int c0 = bounds[ci], c1 = bounds[ci + 1];
-            DeviceBatch& db = ctx->pipe[ci & 1];
-            FG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->up_done[ci & 1], 0));
-            if (ci + 1 < nchunks && ci + 1 < 2) FG_TRY(issue_upload(ci + 1));       // chunk 1 goes to the other buffer right away
+            constexpr int P = flowgnn_ctx::PIPE;
+            DeviceBatch& db = ctx->pipe[ci % P];
+            if (ci == 0) for (int k = 1; k < P && k < nchunks; k++) FG_TRY(issue_upload(k));   // the other buffers fill right away
+            FG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->up_done[ci % P], 0));
             FG_TRY(compute_on(ctx, db, ctx->stream, model));
             if (c1 > c0)
             {
@@ -707,8 +719,8 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
                 FG_CUDA(cudaMemcpyAsync(ctx->h_status + ci, db.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             }
             else ctx->h_status[ci] = 0;
-            FG_CUDA(cudaEventRecord(ctx->buf_free[ci & 1], ctx->stream));
-            if (ci + 2 < nchunks) FG_TRY(issue_upload(ci + 2));                     // reuses this chunk's buffer once it is free
+            FG_CUDA(cudaEventRecord(ctx->buf_free[ci % P], ctx->stream));
+            if (ci + P < nchunks) FG_TRY(issue_upload(ci + P));                     // reuses this chunk's buffer once it is free
         }
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
         FG_CUDA(cudaGetLastError());

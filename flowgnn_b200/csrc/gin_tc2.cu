@@ -125,6 +125,24 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
     // .release.cluster would add a GPU-scope MEMBAR to every arrival
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// mbarrier wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or the hint
+// expires) instead of re-issuing try_wait in a tight loop -- the spinning warps of the other roles otherwise take a
+// fifth of all issue slots (and of the power budget the kernel runs into)
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!done);
+}
 // wait with cluster-scope acquire: the arrivals may come from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
 {
@@ -413,7 +431,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                 for (int t = pair; t < p.num_pair_tiles; t += npairs, it++)
                 {
                     const uint32_t ph = it & 1, s = it & 1;
-                    mbar_wait(&bar[BAR_A_FULL + s], (it >> 1) & 1);
+                    mbar_wait_park(&bar[BAR_A_FULL + s], (it >> 1) & 1);
                     tc::fence_after_sync();
                     // GEMM1, N half a (z columns 0..111) then half b (112..207)
 #pragma unroll
@@ -445,7 +463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
 #pragma unroll
                     for (int kh = 0; kh < 2; kh++)
                     {
-                        mbar_wait(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
+                        mbar_wait_park(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
                         tc::fence_after_sync();
 #pragma unroll
                         for (int prod = 0; prod < 3; prod++)
@@ -486,7 +504,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                     if (lane < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in_ptr + n0 + 32 * lane) : "memory");
                 }
                 // pace the prefetch: do not run more than two tiles ahead of the tensor pipe
-                mbar_wait(&bar[BAR_G1A_DONE], ((t - pair) / npairs - 2) & 1);
+                mbar_wait_park(&bar[BAR_G1A_DONE], ((t - pair) / npairs - 2) & 1);
             }
         }
     }
@@ -552,7 +570,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                 const uint32_t a_dst = a_thr + 2 * s * A_BYTES + pass * (4 * 16);
                 const int node_next = pass == 0 ? node + 4 : node - 4 + tile_rows;
                 row_loads<1>(hv, hu, deg, j, Y);
-                if (pass == 0 && it >= 2) mbar_wait(&bar[BAR_A_FREE + s], ((it >> 1) - 1) & 1);
+                if (pass == 0 && it >= 2) mbar_wait_park(&bar[BAR_A_FREE + s], ((it >> 1) - 1) & 1);
                 row_finish<0>(p, X, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
                 // the next row's descriptor was requested together with X's loads: it is here by now.  Copying it out at this
                 // point (and not where it is decoded) keeps its scoreboard from serialising behind the loads issued below.
@@ -611,7 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             __syncwarp();
             if (lane == 0)
             {
-                if (it == 0 && gw == 0) mbar_wait(&bar[BAR_W], 0);      // this CTA's weights have landed
+                if (it == 0 && gw == 0) mbar_wait_park(&bar[BAR_W], 0);      // this CTA's weights have landed
                 mbar_arrive_cluster(bar_full0 + 8 * s);
             }
         }
@@ -630,7 +648,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             const uint32_t ph = it & 1;
             // z = relu(acc + b1) -> bf16 hi/lo, in place (thread = row): columns [16c, 16c+8) hi, [16c+8, 16c+16) lo of
             // k-step c; the two warps of a quadrant take alternate chunks
-            mbar_wait(&bar[BAR_G1A_DONE], ph);
+            mbar_wait_park(&bar[BAR_G1A_DONE], ph);
             tc::fence_after_sync();
             convert_range(lane_base + TC_Z, pp, N1A / 16);
             tc::wait_st();
@@ -638,7 +656,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_a2a0);
 
-            mbar_wait(&bar[BAR_G1B_DONE], ph);
+            mbar_wait_park(&bar[BAR_G1B_DONE], ph);
             tc::fence_after_sync();
             convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
             tc::wait_st();
@@ -646,7 +664,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_a2b0);
 
-            mbar_wait(&bar[BAR_G2_DONE], ph);
+            mbar_wait_park(&bar[BAR_G2_DONE], ph);
             tc::fence_after_sync();
             // h' = acc (+ relu; b2 is already in acc through the bias column k = 200 of W2): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
             // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction; warp pp of the

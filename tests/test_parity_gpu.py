@@ -45,6 +45,30 @@ def test_other_datasets_match_reference(model, ds, ctx, weights, datasets, golde
 
 
 @pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
+def test_gin_single_cta_kernel_agrees_with_cta_pair_kernel(ds, ctx, weights, datasets, golden):
+    """The default GIN layer kernel runs on CTA pairs (tcgen05 cta_group::2, gin_tc2.cu: A tile in shared memory, row
+    descriptors, biases folded into the GEMMs); the single-CTA kernel (gin_tc.cu, option gin_tc1) is kept as a
+    second implementation.  Both must sit inside the 1e-4 contract and agree with each other."""
+    pair = ctx.run("gin", datasets[ds], weights["gin"])
+    ctx.set_option("gin_tc1", 1)
+    try:
+        single = ctx.run("gin", datasets[ds])
+    finally:
+        ctx.set_option("gin_tc1", 0)
+    assert_parity(pair, golden[ds]["gin"], what=f"gin cta pair/{ds}")
+    assert_parity(single, golden[ds]["gin"], what=f"gin single cta/{ds}")
+    assert_parity(pair, single, tol=5e-5, what=f"gin cta pair vs single cta/{ds}")
+
+
+@pytest.mark.parametrize("n_graphs", [1, 3, 10, 11, 21, 100])
+def test_gin_tile_boundaries(n_graphs, ctx, weights, datasets, golden):
+    """Batches whose node count falls on either side of the 128-row CTA tile and the 256-row pair tile (a lone first
+    CTA, an empty second CTA, partially filled tiles)."""
+    b = datasets["molhiv"].slice(0, n_graphs)
+    assert_parity(ctx.run("gin", b, weights["gin"]), golden["molhiv"]["gin"][:n_graphs], what=f"gin first {n_graphs} graphs ({b.total_nodes} nodes)")
+
+
+@pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
 def test_gin_ffma_reference_path_agrees_with_tensor_core_path(ds, ctx, weights, datasets, golden):
     """GIN's node MLP runs on tcgen05 (bf16 hi/lo split, 3 products); the FP32-FFMA kernel is kept as the
     on-device fp32 reference.  Both must sit inside the 1e-4 contract and agree with each other."""

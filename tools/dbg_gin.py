@@ -41,3 +41,16 @@ with Context(0) as c:
             c.compute("gin")
         ms = [c.compute("gin") for _ in range(10)]
         print(f"bench tc1={tc1} step ms {np.mean(ms):.3f} layers {np.round(c.last_layer_ms(), 4)}", flush=True)
+    # sustained (bench-like) comparison: 200 back-to-back forwards, host clock around the lot
+    import time
+    c.set_option("time_layers", 0)
+    for tc1 in (1, 0, 1, 0):
+        c.set_option("gin_tc1", tc1)
+        for _ in range(5):
+            c.compute("gin", timed=False)
+        c.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            c.compute("gin", timed=False)
+        c.synchronize()
+        print(f"sustained tc1={tc1} ms/step {(time.perf_counter() - t0) * 5:.3f}", flush=True)
