@@ -91,6 +91,33 @@ static std::vector<float> combine_edge_embedding(const float* ee, int layers, in
     return out;
 }
 
+// combined node-embedding tables of embed4_kernel (layers.cuh): A = T0; B = T1 + T2; C = T3 + T4; E = ((T5 + T6) + T7) + T8
+static std::vector<float> combine_node_embedding(const float* t, int dim)
+{
+    static const int off[9] = {0, 119, 123, 135, 147, 157, 163, 169, 171};
+    std::vector<float> out((size_t)431 * dim);
+    auto row = [&](int f, int x) { return t + (size_t)(off[f] + x) * dim; };
+    for (int d = 0; d < dim; d++)
+    {
+        for (int x0 = 0; x0 < 119; x0++) out[(size_t)x0 * dim + d] = row(0, x0)[d];
+        for (int x1 = 0; x1 < 4; x1++)
+            for (int x2 = 0; x2 < 12; x2++) out[(size_t)(119 + x1 * 12 + x2) * dim + d] = row(1, x1)[d] + row(2, x2)[d];
+        for (int x3 = 0; x3 < 12; x3++)
+            for (int x4 = 0; x4 < 10; x4++) out[(size_t)(167 + x3 * 10 + x4) * dim + d] = row(3, x3)[d] + row(4, x4)[d];
+        for (int x5 = 0; x5 < 6; x5++)
+            for (int x6 = 0; x6 < 6; x6++)
+                for (int x7 = 0; x7 < 2; x7++)
+                    for (int x8 = 0; x8 < 2; x8++)
+                    {
+                        float s = row(5, x5)[d] + row(6, x6)[d];
+                        s += row(7, x7)[d];
+                        s += row(8, x8)[d];
+                        out[(size_t)(287 + ((x5 * 6 + x6) * 2 + x7) * 2 + x8) * dim + d] = s;
+                    }
+    }
+    return out;
+}
+
 // [layers][n][k] (reference "[out][in]") -> k-major [layers][k][np] with zero-padded columns
 static std::vector<float> transpose_pad(const float* w, int layers, int n, int k, int np)
 {
@@ -185,6 +212,7 @@ int load_gin(flowgnn_ctx* c, const float* const* w)
     cudaStream_t s = c->stream;
     GinWeights& g = c->gin;
     FG_TRY(upload(g.ne_table, w[0], (size_t)ND_FEATURE_TOTAL * 100, s));
+    FG_TRY(upload(g.ne_table4, combine_node_embedding(w[0], 100), s));
     FG_TRY(upload(g.ee_comb, combine_edge_embedding(w[1], 5, 100), s));
     FG_TRY(upload(g.w1t, transpose_pad(w[2], 5, 200, 100, 208), s));
     FG_TRY(upload(g.b1, pad_rows(w[3], 5, 200, 208), s));
@@ -283,6 +311,7 @@ int load_pna(flowgnn_ctx* c, const float* const* w)
     cudaStream_t s = c->stream;
     PnaWeights& g = c->pna;
     FG_TRY(upload(g.ne_table, w[0], (size_t)ND_FEATURE_TOTAL * 80, s));
+    FG_TRY(upload(g.ne_table4, combine_node_embedding(w[0], 80), s));
     // reference [l][out][scaler][aggr][in] -> wcat[l][aggr*80 + in][scaler*80 + out]
     std::vector<float> wcat((size_t)4 * 320 * 240);
     for (int l = 0; l < 4; l++)
@@ -398,7 +427,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaStreamDestroy(ctx->copy_stream);
-    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
+    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
                    &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,

@@ -31,6 +31,7 @@
 #include "tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace fg {

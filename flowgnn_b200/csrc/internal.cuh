@@ -64,6 +64,7 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream);
 // ---- per-model device weights, repacked once by load_weights (api.cu) ----------------------------
 struct GinWeights {
     DevBuf ne_table;     // [173][100]
+    DevBuf ne_table4;    // [431][100] combined tables of embed4_kernel (layers.cuh)
     DevBuf ee_comb;      // [5][60][100]  ((0+T[a0])+T[5+a1])+T[11+a2]
     DevBuf w1t, b1;      // [5][100][208], [5][208]   k-major, N padded with zeros
     DevBuf w2t, b2;      // [5][200][104], [5][104]
@@ -85,6 +86,7 @@ struct GcnWeights {
 };
 struct PnaWeights {
     DevBuf ne_table;            // [173][80]
+    DevBuf ne_table4;           // [431][80] combined tables of embed4_kernel (layers.cuh)
     DevBuf wcat;                // [4][320][240]  k = aggr*80+in, n = scaler*80+out
     DevBuf w_ref;               // [4][80][3][4][80] reference layout (exact path for out-degree-0 nodes)
     DevBuf b;                   // [4][80]

@@ -137,6 +137,7 @@ struct TileGemm {
 // (GIN/src/load_inputs.cc:174-220; GCN :168-215; PNA :133-179; DGN :114-168 with nine separate
 // [119][D] tables, i.e. offsets f*119).
 struct EmbedOffsets { int off[ND_FEATURE]; };
+__host__ __device__ inline EmbedOffsets concat_table_offsets();
 
 template <int DIM>
 __device__ __forceinline__ float4 embed_chunk(const int* __restrict__ feat_row, const float* __restrict__ table, const EmbedOffsets& o, int q)
@@ -163,6 +164,71 @@ __global__ void embed_table_kernel(const int* __restrict__ feat, const float* __
         const long v = item / Q;
         const int q = (int)(item - v * Q);
         stg_f4_stream(h + v * DIM + 4 * q, embed_chunk<DIM>(feat + v * ND_FEATURE, table, o, q));
+    }
+}
+
+// ---- the same embedding with fewer table reads (GIN, PNA: the nine tables are concatenated) ------------------------
+// The kernel above is bound by L1 wavefronts (nine 16-byte lookups per output chunk, 2-3 nodes per warp).  Here a warp
+// owns a node: lanes 0..8 read its nine categorical features once, and the nine lookups shrink to four through
+// combined tables built at load_weights time:
+//     A[x0] = T0[x0];  B[x1][x2] = T1 + T2;  C[x3][x4] = T3 + T4;  E[x5][x6][x7][x8] = ((T5 + T6) + T7) + T8
+//     h0 = ((A + B) + C) + E
+// (431 rows instead of 173).  This changes the ASSOCIATION of the reference's left-to-right sum (load_inputs.cc:
+// 174-220), i.e. the last bit of h0, not its value; the parity bar is 1e-4.  A node with a feature outside its
+// vocabulary takes the nine-lookup path, which reads what the reference would read.
+constexpr int EMB4_ROWS = 119 + 4 * 12 + 12 * 10 + 6 * 6 * 2 * 2;      // 431
+constexpr int EMB4_B = 119, EMB4_C = EMB4_B + 48, EMB4_E = EMB4_C + 120;
+
+template <int DIM>
+__global__ void __launch_bounds__(256) embed4_kernel(const int* __restrict__ feat, const float* __restrict__ table9, const float* __restrict__ table4,
+                                                     float* __restrict__ h, long num_nodes)
+{
+    constexpr int Q = DIM / 4;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    // Two nodes per step: lanes 0..8 read the features of node v, lanes 16..24 those of node v + 1 (one load instruction,
+    // the two 36-byte rows are adjacent); a warp walks a contiguous range of nodes and requests the next pair's
+    // features before it works on the current one.
+    const int fl = lane & 15;                                                   // feature index held by this lane
+    const int vocab = fl == 0 ? 119 : fl == 1 ? 4 : fl == 2 ? 12 : fl == 3 ? 12 : fl == 4 ? 10 : fl == 5 ? 6 : fl == 6 ? 6 : 2;
+    long per = (num_nodes + nwarps - 1) / nwarps;
+    per += per & 1;
+    const long v_end = min(num_nodes, (warp + 1) * per);
+    long v = warp * per;
+    auto load_feat = [&](long vv) { const long node = vv + (lane >> 4); return (fl < ND_FEATURE && node < v_end) ? __ldg(feat + node * ND_FEATURE + fl) : 0; };
+    int f_next = v < v_end ? load_feat(v) : 0;
+    for (; v < v_end; v += 2)
+    {
+        const int f = f_next;
+        if (v + 2 < v_end) f_next = load_feat(v + 2);
+        const bool in_vocab = __all_sync(full, fl >= ND_FEATURE || (unsigned)f < (unsigned)vocab);
+        float4 s[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int b = 16 * i;
+            const int x0 = __shfl_sync(full, f, b), x1 = __shfl_sync(full, f, b + 1), x2 = __shfl_sync(full, f, b + 2), x3 = __shfl_sync(full, f, b + 3),
+                      x4 = __shfl_sync(full, f, b + 4), x5 = __shfl_sync(full, f, b + 5), x6 = __shfl_sync(full, f, b + 6), x7 = __shfl_sync(full, f, b + 7),
+                      x8 = __shfl_sync(full, f, b + 8);
+            if (lane < Q && v + i < v_end)
+            {
+                if (in_vocab)
+                {
+                    const float4 a = ldg_f4(table4 + (size_t)x0 * DIM + 4 * lane);
+                    const float4 bb = ldg_f4(table4 + (size_t)(EMB4_B + x1 * 12 + x2) * DIM + 4 * lane);
+                    const float4 c = ldg_f4(table4 + (size_t)(EMB4_C + x3 * 10 + x4) * DIM + 4 * lane);
+                    const float4 e = ldg_f4(table4 + (size_t)(EMB4_E + ((x5 * 6 + x6) * 2 + x7) * 2 + x8) * DIM + 4 * lane);
+                    s[i] = make_float4(((a.x + bb.x) + c.x) + e.x, ((a.y + bb.y) + c.y) + e.y, ((a.z + bb.z) + c.z) + e.z, ((a.w + bb.w) + c.w) + e.w);
+                }
+                else
+                    s[i] = embed_chunk<DIM>(feat + (v + i) * ND_FEATURE, table9, concat_table_offsets(), lane);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+            if (lane < Q && v + i < v_end) stg_f4_stream(h + (v + i) * DIM + 4 * lane, s[i]);
     }
 }
 

@@ -227,9 +227,8 @@ int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int 
     float* h[2] = {b.act[0].as<float>(), b.act[1].as<float>()};
     int nl = 0;
     {
-        const long items = N * Q;
-        const int blocks = (int)std::min<long>(ceil_div<long>(items, 256), (long)sm_count * 16);
-        embed_table_kernel<D><<<blocks, 256, 0, s>>>(b.node_feature.as<int>(), w.ne_table.as<float>(), concat_table_offsets(), h[0], N);
+        const int blocks = (int)std::min<long>(ceil_div<long>(N, 8), (long)sm_count * 8);      // 8 warps per block, a warp per node
+        embed4_kernel<D><<<blocks, 256, 0, s>>>(b.node_feature.as<int>(), w.ne_table.as<float>(), w.ne_table4.as<float>(), h[0], N);
         FG_CUDA(cudaGetLastError());
         nl++;
     }
