@@ -414,10 +414,17 @@ def main():
         args.warmup = 3
     if args.model == "pna" and not args.base_graphs:
         args.base_graphs = 32768
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." when the box sets
+    # NCCL_DEBUG), so file descriptor 1 points at stderr while the arms run and sys.stdout keeps the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_b200_arm(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
