@@ -526,7 +526,7 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     int rc = prep_batch(b, flags, s);
     b.has_attr = keep_attr;
     FG_TRY(rc);
-    ctx->last_launches += 2;
+    ctx->last_launches += 3;      // scan_offsets + the two build_csr instantiations
     ctx->timer.marks = 0;
     ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
     switch (model)

@@ -13,6 +13,8 @@
 //   all  out-degree per node (degree_table)
 #include "internal.cuh"
 
+#include <algorithm>
+
 namespace fg {
 
 namespace {
@@ -89,8 +91,12 @@ __device__ __forceinline__ int4 empty_row_desc()
     return make_int4(e, e, e, e);
 }
 
-constexpr int CSR_WARPS = 4;
 constexpr int CSR_NCAP = 1024;     // nodes per graph supported by the warp-local tables (reference cap: 500)
+constexpr int CSR_NCAP_SMALL = 128;
+// The build is a chain of dependent memory round trips per graph (edges -> histogram -> sort scratch -> payload ->
+// descriptors), so it lives on occupancy.  Two instantiations run back to back: graphs of up to 128 nodes (every
+// molecule) take the small tables -- 1.5 KB of shared memory per warp, 64 warps per SM -- the others the 1,024-node
+// tables (12 KB per warp, 16 warps per SM); each kernel skips the graphs of the other.
 
 struct CsrParams {
     const int* nn; const int* ne; const int* node_off; const int* edge_off;
@@ -103,28 +109,20 @@ struct CsrParams {
 // One warp per graph.  Two stable counting-sort passes (by source, then by destination) give the
 // (destination, source, list-order) ordering; ranks inside a 32-edge chunk come from
 // __match_any_sync, chunks are consumed in order, so the sort is stable and deterministic.
-__global__ void __launch_bounds__(CSR_WARPS * 32) build_csr_kernel(CsrParams p)
+template <int NCAP>
+__device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int* deg, int* pu, int* pv)
 {
-    __shared__ int s_deg[CSR_WARPS][CSR_NCAP];     // out-degree
-    __shared__ int s_pu[CSR_WARPS][CSR_NCAP];      // running slot by source
-    __shared__ int s_pv[CSR_WARPS][CSR_NCAP];      // running slot by destination
-
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = blockIdx.x * CSR_WARPS + wid;
-    if (g >= p.num_graphs) return;
+    const int lane = threadIdx.x & 31;
     const int n = p.nn[g], e = p.ne[g];
     const int nb = p.node_off[g], eb = p.edge_off[g];
     if (g == p.num_graphs - 1 && lane == 0) p.in_ptr[nb + n] = eb + e;
-    if (n > CSR_NCAP || n < 0 || e < 0)
+    if (n > NCAP || n < 0 || e < 0)
     {
         if (lane == 0) atomicOr(p.status, 1);
         // keep downstream kernels in bounds: empty rows
         for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; if (p.row_desc) p.row_desc[nb + i] = empty_row_desc(); }
         return;
     }
-    int* deg = s_deg[wid];
-    int* pu = s_pu[wid];
-    int* pv = s_pv[wid];
     const int2* edges = reinterpret_cast<const int2*>(p.edge_list) + eb;
     const unsigned full = 0xffffffffu;
 
@@ -263,6 +261,45 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) build_csr_kernel(CsrParams p)
     }
 }
 
+// small graphs: one warp per graph, 8 warps per block
+__global__ void __launch_bounds__(8 * 32) build_csr_small_kernel(CsrParams p)
+{
+    __shared__ int s_tab[8][3][CSR_NCAP_SMALL];
+    const int wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * 8 + wid;
+    if (g >= p.num_graphs) return;
+    const int n = p.nn[g], e = p.ne[g];
+    if (!(n >= 0 && n <= CSR_NCAP_SMALL && e >= 0)) return;
+    build_graph_csr<CSR_NCAP_SMALL>(p, g, s_tab[wid][0], s_tab[wid][1], s_tab[wid][2]);
+}
+
+// the rest (more than 128 nodes, or invalid counts): a persistent grid whose warps scan 32 graphs at a time, so that a
+// batch of molecules costs this kernel a microsecond
+__global__ void __launch_bounds__(4 * 32) build_csr_large_kernel(CsrParams p)
+{
+    __shared__ int s_tab[4][3][CSR_NCAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warp = blockIdx.x * 4 + wid, nwarps = gridDim.x * 4;
+    for (int g0 = warp * 32; g0 < p.num_graphs; g0 += nwarps * 32)
+    {
+        const int g = g0 + lane;
+        bool mine = false;
+        if (g < p.num_graphs)
+        {
+            const int n = p.nn[g], e = p.ne[g];
+            mine = !(n >= 0 && n <= CSR_NCAP_SMALL && e >= 0);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, mine);
+        while (todo)
+        {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            build_graph_csr<CSR_NCAP>(p, g0 + k, s_tab[wid][0], s_tab[wid][1], s_tab[wid][2]);
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
@@ -299,7 +336,9 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
     p.sort_tmp = b.sort_tmp.as<int>(); p.status = b.status.as<int>();
     p.row_desc = (flags & PREP_ROW_DESC) ? b.row_desc.as<int4>() : nullptr;
     p.num_graphs = G; p.flags = flags; p.has_attr = b.has_attr ? 1 : 0;
-    build_csr_kernel<<<ceil_div(G, CSR_WARPS), CSR_WARPS * 32, 0, stream>>>(p);
+    build_csr_small_kernel<<<ceil_div(G, 8), 8 * 32, 0, stream>>>(p);
+    FG_CUDA(cudaGetLastError());
+    build_csr_large_kernel<<<std::max(1, std::min(ceil_div(G, 128), 148 * 4)), 4 * 32, 0, stream>>>(p);
     FG_CUDA(cudaGetLastError());
     return 0;
 }

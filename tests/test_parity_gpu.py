@@ -213,6 +213,53 @@ def test_limits_are_reported_not_crashed(ctx, weights):
     assert np.isfinite(ctx.run("gin", ok, weights["gin"])).all()
 
 
+@pytest.mark.parametrize("model", ["gin", "gcn", "pna"])
+def test_large_and_small_graphs_in_one_batch(model, ctx, weights, datasets):
+    """The CSR build runs two kernels (graphs of up to 128 nodes / the rest) and GIN's row descriptors hold four
+    in-edges: a batch that mixes molecules with graphs of 129..450 nodes and in-degrees up to ~20 goes through both
+    kernels, the long-row paths of the gather and the 'first four edges' descriptors, and must match the oracle."""
+    from flowgnn_b200.dataset import Batch
+    from oracle import refbind
+    rng = np.random.default_rng(7)
+    mol = datasets["molhiv"].slice(0, 6)
+    nn, ne, feat, edges, attr = [], [], [], [], []
+    lo = 0
+    for i, n in enumerate([450, 3, 129, 128, 200]):
+        e = int(n * 2.5)
+        v = rng.integers(0, n, e)
+        v[: e // 4] = rng.integers(0, max(1, n // 16), e // 4)              # a few hub nodes with long in-edge lists
+        u = rng.integers(0, n, e)
+        nn.append(n); ne.append(e)
+        feat.append(np.stack([rng.integers(0, k, n) for k in (119, 4, 12, 12, 10, 6, 6, 2, 2)], 1))
+        edges.append(np.stack([u, v], 1)); attr.append(np.stack([rng.integers(0, k, e) for k in (5, 6, 2)], 1))
+    big = Batch(np.array(nn), np.array(ne), np.concatenate(feat).astype(np.int32), np.concatenate(edges).astype(np.int32),
+                np.concatenate(attr).astype(np.int32))
+    b = Batch(np.concatenate([mol.nums_of_nodes[:3], big.nums_of_nodes, mol.nums_of_nodes[3:]]),
+              np.concatenate([mol.nums_of_edges[:3], big.nums_of_edges, mol.nums_of_edges[3:]]),
+              np.concatenate([mol.slice(0, 3).node_feature, big.node_feature, mol.slice(3, 6).node_feature]),
+              np.concatenate([mol.slice(0, 3).edge_list, big.edge_list, mol.slice(3, 6).edge_list]),
+              np.concatenate([mol.slice(0, 3).edge_attr, big.edge_attr, mol.slice(3, 6).edge_attr]))
+    got = ctx.run(model, b, weights[model])
+    want = refbind.run_port(model, b, weights[model])
+    assert_parity(got, want, what=f"{model} mixed small/large graphs")
+
+
+def test_out_of_vocabulary_features_read_what_the_reference_reads(ctx, weights, datasets):
+    """embed4_kernel uses combined tables that only cover in-vocabulary features; a node with a feature outside its
+    vocabulary (but inside the concatenated 173-row table, where the reference's lookup is still defined) must take
+    the nine-lookup path and agree with the oracle."""
+    from oracle import refbind
+    b = datasets["molhiv"].slice(0, 40)
+    feat = b.node_feature.copy()
+    feat[5, 1] = 7          # vocabulary of feature 1 is 4: the reference reads row 119 + 7 (a row of feature 2's table)
+    feat[17, 7] = 3         # vocabulary 2: row 169 + 3 (feature 8's table)
+    feat[30, 4] = 15        # vocabulary 10: row 147 + 15
+    from flowgnn_b200.dataset import Batch
+    bb = Batch(b.nums_of_nodes, b.nums_of_edges, feat, b.edge_list, b.edge_attr)
+    for model in ("gin", "pna"):
+        assert_parity(ctx.run(model, bb, weights[model]), refbind.run_port(model, bb, weights[model]), what=f"{model} out-of-vocabulary features")
+
+
 def test_mp_only_variant_is_the_pure_gather_scatter(ctx, weights, datasets):
     """The roofline variant (node transform = identity): h <- m + h per layer, checked against numpy."""
     b = datasets["molhiv"].slice(0, 500)
@@ -250,4 +297,4 @@ def test_full_size_synthetic_batch_properties(ctx, weights):
     assert np.array_equal(y.view(np.int32), ctx.run("gin", b).view(np.int32))
     ids = np.random.default_rng(5).choice(2048, 48, replace=False)
     assert_parity(y[ids], refbind.run_port("gin", base.select(ids), weights["gin"]), what="gin synthetic sample")
-    assert ctx.last_launch_count == 9
+    assert ctx.last_launch_count == 10
