@@ -211,6 +211,18 @@ __device__ __forceinline__ float relu_nan(float x)
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// two fp32 additions in one instruction (FADD2, sm_100): same IEEE round-to-nearest result per element
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    unsigned long long ua, ub, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+    return d;
+}
+
 // (x0, x1) -> packed bf16 pairs: hi = rn(x), lo = rn(x - hi); element 0 in the low half
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo)
 {
@@ -218,6 +230,14 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
     const float r0 = x0 - __uint_as_float(hi << 16);
     const float r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+// the same with the two residuals in one FADD2 (used where register pairs are cheap: the epilogue warps; in the gather
+// warps the pair alignment costs more registers than the 80 they have)
+__device__ __forceinline__ void split2_p(float x0, float x1, uint32_t& hi, uint32_t& lo)
+{
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float2 r = add2(make_float2(x0, x1), make_float2(-__uint_as_float(hi << 16), -__uint_as_float(hi & 0xFFFF0000u)));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
 }
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr)
@@ -340,7 +360,7 @@ __device__ __forceinline__ void convert_regs(uint32_t zaddr, const uint32_t (&r)
 {
     uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) split2(relu_nan(__uint_as_float(r[2 * j])), relu_nan(__uint_as_float(r[2 * j + 1])), hi[j], lo[j]);
+    for (int j = 0; j < 8; j++) split2_p(relu_nan(__uint_as_float(r[2 * j])), relu_nan(__uint_as_float(r[2 * j + 1])), hi[j], lo[j]);
     tc::st8(zaddr, hi);
     tc::st8(zaddr + 8, lo);
 }
