@@ -240,6 +240,16 @@ int load_gin(flowgnn_ctx* c, const float* const* w)
         FG_CUDA(cudaMemcpyAsync(g.wpack2.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
         FG_CUDA(cudaStreamSynchronize(s));
     }
+    {
+        const size_t per_layer = gin_tc3_pack_bytes();
+        std::vector<unsigned char> pack(5 * per_layer);
+        for (int l = 0; l < 5; l++)
+            gin_tc3_pack_layer(w[2] + (size_t)l * 200 * 100, w[3] + (size_t)l * 200, w[4] + (size_t)l * 100 * 200, w[5] + (size_t)l * 100,
+                               pack.data() + (size_t)l * per_layer, bf16_rn, bf16_to_float);
+        FG_TRY(g.wpack3.reserve(pack.size()));
+        FG_CUDA(cudaMemcpyAsync(g.wpack3.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
+        FG_CUDA(cudaStreamSynchronize(s));
+    }
     FG_TRY(upload(g.ee_raw, w[1], (size_t)5 * ED_FEATURE_PER_LAYER * 100, s));
     FG_TRY(upload(g.b2p, pad_rows(w[5], 5, 100, 112), s));
     FG_TRY(upload(g.pred_w, w[6], 100, s));
@@ -375,7 +385,20 @@ int check_status(flowgnn_ctx* ctx)
 
 }  // namespace
 
+namespace fg { extern unsigned long long* gin_tc2_trace_buffer; }
+
 extern "C" {
+
+// debugging aid (not part of include/flowgnn_b200.h): device buffer of 3 x 64 x 8 timestamps filled by pair 0 of the GIN layer kernel
+int flowgnn_b200_debug_trace(unsigned long long** dev_buffer, int enable)
+{
+    static unsigned long long* buf = nullptr;
+    if (!buf) FG_CUDA(cudaMalloc(&buf, 3 * 64 * 8 * sizeof(unsigned long long)));
+    if (enable) FG_CUDA(cudaMemset(buf, 0, 3 * 64 * 8 * sizeof(unsigned long long)));
+    fg::gin_tc2_trace_buffer = enable ? buf : nullptr;
+    if (dev_buffer) *dev_buffer = buf;
+    return 0;
+}
 
 const char* flowgnn_b200_last_error(void) { return g_last_error.c_str(); }
 
@@ -427,7 +450,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaStreamDestroy(ctx->copy_stream);
-    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
+    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.wpack3, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
                    &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
@@ -451,6 +474,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     if (!std::strcmp(name, "mp_only")) ctx->opt.mp_only = value;
     else if (!std::strcmp(name, "gin_ffma")) ctx->opt.gin_ffma = value;
     else if (!std::strcmp(name, "gin_tc1")) ctx->opt.gin_tc1 = value;
+    else if (!std::strcmp(name, "gin_tc3")) ctx->opt.gin_tc3 = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;
     else { set_last_error(std::string("unknown option ") + name); return FG_ERR_INVALID; }

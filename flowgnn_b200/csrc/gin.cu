@@ -257,7 +257,8 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         p.num_nodes = (int)N; p.num_tiles = num_tiles; p.relu_out = (l != 4);
         if (!opt.mp_only && !opt.gin_ffma)
         {
-            if (opt.gin_tc1) FG_TRY(gin_layer_tc_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
+            if (opt.gin_tc3) FG_TRY(gin_layer_tc3_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
+            else if (opt.gin_tc1) FG_TRY(gin_layer_tc_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
             else FG_TRY(gin_layer_tc2_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
             nl++;
             continue;

@@ -29,6 +29,7 @@
 #include "internal.cuh"
 #include "layers.cuh"
 #include "tc.cuh"
+#include "pair.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -97,173 +98,13 @@ struct GinTc2Params {
     const float* ee_comb;            // [60][100] this layer: ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]
     const unsigned char* wpack;      // [2 ranks][W_BYTES] this layer
     int num_nodes; int num_pair_tiles; int relu_out;
+    // experiments, compiled in with -DFG_TC2_TRACE only: dbg 1 = no in-edges, 2 = no h' stores, 4 = no z conversion (wrong
+    // results, for bottleneck elimination); trace = timeline of pair 0 (tools/trace_gin.py): [role][tile][event] globaltimer ns
+    int dbg;
+    unsigned long long* trace;
 };
 
-constexpr unsigned FULL = 0xFFFFFFFFu;
-
-// ---- cluster / pair primitives ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
-{
-    // default semantics (release, CTA scope) as in CUTLASS' ClusterBarrier::arrive(cta_id): what the waiter consumes was
-    // either written through the async proxy after fence.proxy.async or lives in tensor memory behind tcgen05 fences;
-    // .release.cluster would add a GPU-scope MEMBAR to every arrival
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// mbarrier wait with a suspend-time hint: the thread is parked by the hardware until the phase completes (or the hint
-// expires) instead of re-issuing try_wait in a tight loop -- the spinning warps of the other roles otherwise take a
-// fifth of all issue slots (and of the power budget the kernel runs into)
-__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-            : "memory");
-    } while (!done);
-}
-// wait with cluster-scope acquire: the arrivals may come from the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// arrive on the barrier at the same shared-memory offset in both CTAs once all MMAs issued so far have completed
-__device__ __forceinline__ void commit2(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-// D[tmem, 256 x N over the pair] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T, one K = 16 step
-__device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
-}
-
-// relu that lets NaN through, like the reference's compare-select (GIN/src/util.h:20-25), in ONE instruction
-__device__ __forceinline__ float relu_nan(float x)
-{
-    float y;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(0.0f));
-    return y;
-}
-
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-
-// two fp32 additions in one instruction (FADD2, sm_100): same IEEE round-to-nearest result per element
-__device__ __forceinline__ float2 add2(float2 a, float2 b)
-{
-    unsigned long long ua, ub, ud;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
-    return d;
-}
-
-// (x0, x1) -> packed bf16 pairs: hi = rn(x), lo = rn(x - hi); element 0 in the low half
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo)
-{
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-    const float r0 = x0 - __uint_as_float(hi << 16);
-    const float r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
-}
-// the same with the two residuals in one FADD2 (used where register pairs are cheap: the epilogue warps; in the gather
-// warps the pair alignment costs more registers than the 80 they have)
-__device__ __forceinline__ void split2_p(float x0, float x1, uint32_t& hi, uint32_t& lo)
-{
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-    const float2 r = add2(make_float2(x0, x1), make_float2(-__uint_as_float(hi << 16), -__uint_as_float(hi & 0xFFFF0000u)));
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
-}
-
-__device__ __forceinline__ float4 lds_f4(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b)
-{
-    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-// 16-byte load that is not issued when `on` is false (reads as zero).  Plain C++ on purpose: ptxas turns this into
-// "zero the quad, @p LDG into the same quad"; an inline-asm version made it load into a scratch quad and copy, i.e.
-// wait for every load right after issuing it.
-__device__ __forceinline__ float4 ldg_f4_if(const float* ptr, bool on)
-{
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on) v = __ldg(reinterpret_cast<const float4*>(ptr));
-    return v;
-}
-
-__device__ __forceinline__ void acc_edge(float4& m, const float4& t, const float4& h)
-{
-    m.x += relu_nan(t.x + h.x); m.y += relu_nan(t.y + h.y); m.z += relu_nan(t.z + h.z); m.w += relu_nan(t.w + h.w);
-}
+using namespace pair;
 
 // ---- one destination row as seen by one of its 8 threads ----------------------------------------------------------
 // Pointers to this thread's 16-byte chunk (step 0) of the row itself and of the source rows of its first four
@@ -344,46 +185,19 @@ __device__ __forceinline__ void row_finish(const GinTc2Params& p, const RowLoads
     }
 }
 
-// a register copy the compiler cannot fold: the consumer of a prefetched value waits for its load HERE, once, and
-// later uses of the copy carry no scoreboard dependency that would serialise them behind the feature-row loads
-__device__ __forceinline__ int reg_copy(int x)
+__device__ __forceinline__ unsigned long long gtime()
 {
-    int y;
-    asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
-    return y;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
-
-
-// z = relu(acc) for 16 accumulator columns of this thread's row (b1 is already in acc: the A tile carries a constant-1
-// column k = 100 and W1 the bias in that column) -> bf16 hi/lo, written back in place
-__device__ __forceinline__ void convert_regs(uint32_t zaddr, const uint32_t (&r)[16])
-{
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) split2_p(relu_nan(__uint_as_float(r[2 * j])), relu_nan(__uint_as_float(r[2 * j + 1])), hi[j], lo[j]);
-    tc::st8(zaddr, hi);
-    tc::st8(zaddr + 8, lo);
-}
-// chunks c, c + 2, ... < c_end of 16 columns each; the TMEM load of the next chunk is in flight while one is converted
-__device__ __forceinline__ void convert_range(uint32_t zbase, int c, int c_end)
-{
-    uint32_t r0[16], r1[16];
-    if (c >= c_end) return;
-    tc::ld16(zbase + 16 * c, r0);
-    while (true)
-    {
-        tc::wait_ld();
-        if (c + 2 < c_end) tc::ld16(zbase + 16 * (c + 2), r1);
-        convert_regs(zbase + 16 * c, r0);
-        c += 2;
-        if (c >= c_end) break;
-        tc::wait_ld();
-        if (c + 2 < c_end) tc::ld16(zbase + 16 * (c + 2), r0);
-        convert_regs(zbase + 16 * c, r1);
-        c += 2;
-        if (c >= c_end) break;
-    }
-}
+#ifdef FG_TC2_TRACE
+#define TRACE(role, it, ev) do { if (p.trace && pair == 0 && rank == 0 && (it) < 64) p.trace[((role) * 64 + (it)) * 8 + (ev)] = gtime(); } while (0)
+#define DBG(bit) (p.dbg & (bit))
+#else
+#define TRACE(role, it, ev) do { } while (0)
+#define DBG(bit) false
+#endif
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2_kernel(GinTc2Params p)
 {
@@ -443,6 +257,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
         if (warp == MMA_WARP)
         {
             // ===== MMA issuer: one thread of the leader CTA =====
+            // (issuing from the converged warp under elect.sync removes ptxas' per-MMA elect-and-retry loop, but measured
+            // 20 % slower: the MMAs then hit shared memory in bursts and starve the gather -- see DESIGN.md 5.1)
             if (rank == 0 && lane == 0)
             {
                 const uint32_t w_addr = smem_u32(smem + Smem::W);
@@ -452,8 +268,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                 for (int t = pair; t < p.num_pair_tiles; t += npairs, it++)
                 {
                     const uint32_t ph = it & 1, s = it & 1;
+                    TRACE(0, it, 0);
                     mbar_wait_park(&bar[BAR_A_FULL + s], (it >> 1) & 1);
                     tc::fence_after_sync();
+                    TRACE(0, it, 1);
                     // GEMM1, N half a (z columns 0..111) then half b (112..207)
 #pragma unroll
                     for (int nh = 0; nh < 2; nh++)
@@ -479,6 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                         commit2(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
                     }
                     commit2(&bar[BAR_A_FREE + s]);
+                    TRACE(0, it, 2);
                     // GEMM2, K half a (k-steps 0..6, operand columns converted from z half a) then half b (7..12)
                     bool acc = false;
 #pragma unroll
@@ -486,6 +305,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                     {
                         mbar_wait_park(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
                         tc::fence_after_sync();
+                        TRACE(0, it, 3 + kh);
 #pragma unroll
                         for (int prod = 0; prod < 3; prod++)
                         {
@@ -500,6 +320,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                         }
                     }
                     commit2(&bar[BAR_G2_DONE]);
+                    TRACE(0, it, 5);
                 }
             }
         }
@@ -560,6 +381,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             t[2] = ee_thr + ((d.z >> 16) & 0x3F) * (D * 4);
             t[3] = ee_thr + ((d.w >> 16) & 0x3F) * (D * 4);
             deg = node <= last ? (int)((unsigned)d.x >> 24) : 0;
+            if (DBG(1)) deg = 0;
             if (deg == 255) deg = __ldg(p.in_ptr + min(node, last) + 1) - __ldg(p.in_ptr + min(node, last));
             // longest in-edge list of the four rows of this pass (warp-uniform trip count of the tail rounds)
             maxdeg = max(deg, __shfl_xor_sync(FULL, deg, 8));
@@ -584,6 +406,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
         for (int t = pair; t < p.num_pair_tiles; t += npairs, it++)
         {
             const int s = it & 1;
+            if (gw == 0 && lane == 0) TRACE(2, it, 0);
             // one pass = 3 steps on 2 load buffers, so the buffers swap roles from pass to pass: X holds steps 0 and 2,
             // Y step 1 and then step 0 of the NEXT pass
             auto do_pass = [&](int pass, RowLoads& X, RowLoads& Y) {
@@ -599,7 +422,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                 row_loads<2>(hv, hu, deg, j, X);
                 row_finish<1>(p, Y, tab, deg, maxdeg, node, live, j, h_thr, ee_thr, a_dst);
                 // the pointers of this row are no longer needed: switch them to the next pass's row and start its loads
-                const int deg_next = node_next <= last ? (int)((unsigned)dc.x >> 24) : 0;
+                const int deg_next = (node_next <= last && !DBG(1)) ? (int)((unsigned)dc.x >> 24) : 0;
                 decode_ptrs(dc, node_next, hv, hu);
                 row_loads<0>(hv, hu, deg_next, j, Y);
                 dn = __ldg(p.row_desc + min(node + tile_rows, last));       // row of the pass after next
@@ -652,6 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             {
                 if (it == 0 && gw == 0) mbar_wait_park(&bar[BAR_W], 0);      // this CTA's weights have landed
                 mbar_arrive_cluster(bar_full0 + 8 * s);
+                if (gw == 0) TRACE(2, it, 1);
             }
         }
     }
@@ -671,22 +495,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
             // k-step c; the two warps of a quadrant take alternate chunks
             mbar_wait_park(&bar[BAR_G1A_DONE], ph);
             tc::fence_after_sync();
-            convert_range(lane_base + TC_Z, pp, N1A / 16);
+            if (tid == 0) TRACE(1, it, 0);
+            if (!DBG(4)) convert_range(lane_base + TC_Z, pp, N1A / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_a2a0);
+            if (tid == 0) TRACE(1, it, 1);
 
             mbar_wait_park(&bar[BAR_G1B_DONE], ph);
             tc::fence_after_sync();
-            convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
+            if (tid == 0) TRACE(1, it, 2);
+            if (!DBG(4)) convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_a2b0);
+            if (tid == 0) TRACE(1, it, 3);
 
             mbar_wait_park(&bar[BAR_G2_DONE], ph);
             tc::fence_after_sync();
+            if (tid == 0) TRACE(1, it, 4);
             // h' = acc (+ relu; b2 is already in acc through the bias column k = 200 of W2): 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and
             // t/4 + 8, so the four lanes of a row write one full 32-byte sector per store instruction; warp pp of the
             // quadrant takes its 16-row half
@@ -713,8 +542,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                             oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
                             ob = make_float2(relu_nan(ob.x), relu_nan(ob.y));
                         }
-                        if (row_a < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_a * D + col) = oa;
-                        if (row_b < p.num_nodes) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
+                        if (row_a < p.num_nodes && !DBG(2)) *reinterpret_cast<float2*>(p.h_out + (size_t)row_a * D + col) = oa;
+                        if (row_b < p.num_nodes && !DBG(2)) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
                     }
                 }
             };
@@ -726,6 +555,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                 tc::wait_ld(); ld_h(12, r1); st_h(8, r0);
                 tc::wait_ld(); st_h(12, r1);
             }
+            if (tid == 0) TRACE(1, it, 5);
         }
     }
 
@@ -781,6 +611,8 @@ void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const
     }
 }
 
+unsigned long long* gin_tc2_trace_buffer = nullptr;      // set through flowgnn_b200_debug_trace (api.cu)
+
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
 {
     static bool attr_set = false;
@@ -798,6 +630,9 @@ int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, c
     p.num_nodes = (int)b.total_nodes;
     p.num_pair_tiles = (int)ceil_div<long>(b.total_nodes, 2 * TM);
     p.relu_out = (layer != 4);
+    static const int dbg_env = [] { const char* e = std::getenv("FLOWGNN_B200_DBG"); return e ? std::atoi(e) : 0; }();
+    p.dbg = dbg_env;
+    p.trace = gin_tc2_trace_buffer;
     const int pairs = std::max(1, std::min(p.num_pair_tiles, sm_count / 2));
     gin_layer_tc2_kernel<<<2 * pairs, NT, Smem::BYTES, s>>>(p);
     FG_CUDA(cudaGetLastError());

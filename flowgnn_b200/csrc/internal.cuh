@@ -75,6 +75,7 @@ struct GinWeights {
     DevBuf b2p;          // [5][112]
     // CTA-pair tensor-core path (gin_tc2.cu): per layer and cluster rank, half of every weight block
     DevBuf wpack2;       // [5][2][gin_tc2_pack_bytes() / 2] bytes (weights and biases)
+    DevBuf wpack3;       // the same for gin_tc3.cu (N halves 128 + 96)
     DevBuf pred_w, pred_b;
 };
 struct GcnWeights {
@@ -121,6 +122,7 @@ struct RunOptions {
     int mp_only = 0;                 // GIN: node transform = identity (roofline variant)
     int gin_ffma = 0;                // GIN: node MLP on the FP32 FFMA pipe (on-device fp32 reference) instead of tcgen05
     int gin_tc1 = 0;                 // GIN: single-CTA tcgen05 kernel (gin_tc.cu) instead of the CTA-pair kernel (gin_tc2.cu)
+    int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
 };
@@ -128,6 +130,10 @@ struct RunOptions {
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+int gin_layer_tc3_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+size_t gin_tc3_pack_bytes();
+void gin_tc3_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
+                        float (*bf16_to_float)(uint16_t));
 size_t gin_tc2_pack_bytes();
 void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
                         float (*bf16_to_float)(uint16_t));

@@ -60,6 +60,20 @@ def test_gin_single_cta_kernel_agrees_with_cta_pair_kernel(ds, ctx, weights, dat
     assert_parity(pair, single, tol=5e-5, what=f"gin cta pair vs single cta/{ds}")
 
 
+@pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
+def test_gin_tma_staged_kernel_agrees(ds, ctx, weights, datasets, golden):
+    """gin_tc3.cu (option gin_tc3): the CTA-pair kernel with the tile's feature rows staged in shared memory by bulk
+    TMA and the A operand in tensor memory -- an alternative data path for the same math, kept under test."""
+    ctx.set_option("gin_tc3", 1)
+    try:
+        staged = ctx.run("gin", datasets[ds], weights["gin"])
+        few = ctx.run("gin", datasets[ds].slice(0, 11))
+    finally:
+        ctx.set_option("gin_tc3", 0)
+    assert_parity(staged, golden[ds]["gin"], what=f"gin tma-staged/{ds}")
+    assert_parity(few, golden[ds]["gin"][:11], what=f"gin tma-staged/{ds} first 11 graphs")
+
+
 @pytest.mark.parametrize("n_graphs", [1, 3, 10, 11, 21, 100])
 def test_gin_tile_boundaries(n_graphs, ctx, weights, datasets, golden):
     """Batches whose node count falls on either side of the 128-row CTA tile and the 256-row pair tile (a lone first
