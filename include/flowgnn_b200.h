@@ -126,7 +126,11 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx);
 
 /* Options: "mp_only" (GIN: node transform = identity; the edge gather-scatter roofline variant),
  * "gin_ffma" (GIN: run the node MLP on the FP32 FFMA pipe instead of the tcgen05 bf16x3 split path; the
- * on-device fp32 reference), "gat_node_offset_bug" (default 1), "time_layers" (see flowgnn_b200_last_layer_ms). */
+ * on-device fp32 reference), "gin_tc1" / "gin_tc3" (GIN: the single-CTA tcgen05 kernel / the CTA-pair kernel with
+ * TMA-staged tile rows instead of the default CTA-pair kernel; all three compute the same layer),
+ * "gat_node_offset_bug" (default 1), "time_layers" (see flowgnn_b200_last_layer_ms).
+ * Environment: FLOWGNN_B200_CHUNKS=n overrides the number of chunks the host-pointer entry points cut a batch into
+ * (default 3 for >= 16,384 graphs: upload of chunk i+1 overlaps the kernels of chunk i). */
 int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value);
 
 /* load_weights (GIN/src/load_inputs.cc:7-85 and per-model variants): upload ONE weight set and

@@ -1,5 +1,7 @@
 """Timeline of pair 0 of the GIN CTA-pair layer kernel (MMA issuer, one epilogue warp, one gather warp).
-usage: python tools/trace_gin.py   (prints per-tile event offsets in ns for the last layer launch)"""
+needs the library built with the hooks:  make -C flowgnn_b200/csrc clean && make -C flowgnn_b200/csrc EXTRA=-DFG_TC2_TRACE
+usage: python tools/trace_gin.py   (prints per-tile event offsets in ns for the last layer launch; env FLOWGNN_B200_DBG=1|2|4
+additionally switches off the in-edge loads / the h' stores / the z conversion: wrong results, for bottleneck elimination)"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
