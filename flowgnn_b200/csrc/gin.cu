@@ -245,6 +245,7 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         FG_CUDA(cudaFuncSetAttribute(gin_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GinSmem<true>::BYTES));
         attr_set = true;
     }
+    bool fused_head = false;
     for (int l = 0; l < 5; l++)
     {
         if (opt.timer) FG_TRY(opt.timer->mark(s));
@@ -259,6 +260,13 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         {
             if (opt.gin_tc3) FG_TRY(gin_layer_tc3_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
             else if (opt.gin_tc1) FG_TRY(gin_layer_tc_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
+            else if (l == 4 && !opt.gin_unfused_head)
+            {
+                // last layer: the epilogue applies the prediction weights per node, only 4 bytes per node leave the kernel
+                FG_TRY(b.node_dot.reserve(sizeof(float) * (size_t)(N + 1)));
+                FG_TRY(gin_layer_tc2_launch(b, w, l, p.h_in, p.h_out, sm_count, s, w.pred_w.as<float>(), b.node_dot.as<float>()));
+                fused_head = true;
+            }
             else FG_TRY(gin_layer_tc2_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
             nl++;
             continue;
@@ -278,6 +286,13 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
     }
 
     if (opt.timer) FG_TRY(opt.timer->mark(s));
+    if (fused_head)
+    {
+        FG_TRY(gin_pool_dot_launch(b.node_dot.as<float>(), b, w.pred_b.as<float>(), s));
+        nl++;
+        if (launches) *launches += nl;
+        return 0;
+    }
     HeadParams hp{};
     hp.x = h[1]; hp.dim = D; hp.node_off = b.node_off.as<int>(); hp.nn = b.nums_of_nodes.as<int>(); hp.num_graphs = b.num_graphs;
     hp.w[0] = w.pred_w.as<float>(); hp.b[0] = w.pred_b.as<float>(); hp.dims[0] = D; hp.dims[1] = 1; hp.num_layers = 1;

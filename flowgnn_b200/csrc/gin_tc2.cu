@@ -98,6 +98,9 @@ struct GinTc2Params {
     const float* ee_comb;            // [60][100] this layer: ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]
     const unsigned char* wpack;      // [2 ranks][W_BYTES] this layer
     int num_nodes; int num_pair_tiles; int relu_out;
+    // last layer only: instead of storing h' (400 B per node, re-read by the pooling kernel) the epilogue reduces every row
+    // with the prediction weights and stores node_dot[v] = <h'_v, w_pred> (4 B per node): mean_v(h'_v) . w == mean_v(h'_v . w)
+    const float* head_w; float* node_dot;
     // experiments, compiled in with -DFG_TC2_TRACE only: dbg 1 = no in-edges, 2 = no h' stores, 4 = no z conversion (wrong
     // results, for bottleneck elimination); trace = timeline of pair 0 (tools/trace_gin.py): [role][tile][event] globaltimer ns
     int dbg;
@@ -547,13 +550,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                     }
                 }
             };
+            float dot_a = 0.f, dot_b = 0.f;
+            auto dot_h = [&](int g4, const uint32_t (&r)[16]) {
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                {
+                    const int col = 8 * (g4 + g) + 2 * (lane & 3);
+                    if (8 * (g4 + g) < D && col < D)
+                    {
+                        const float2 wv = __ldg(reinterpret_cast<const float2*>(p.head_w + col));
+                        dot_a = fmaf(__uint_as_float(r[4 * g + 1]), wv.y, fmaf(__uint_as_float(r[4 * g]), wv.x, dot_a));
+                        dot_b = fmaf(__uint_as_float(r[4 * g + 3]), wv.y, fmaf(__uint_as_float(r[4 * g + 2]), wv.x, dot_b));
+                    }
+                }
+            };
             {
                 uint32_t r0[16], r1[16];
                 ld_h(0, r0);
-                tc::wait_ld(); ld_h(4, r1); st_h(0, r0);
-                tc::wait_ld(); ld_h(8, r0); st_h(4, r1);
-                tc::wait_ld(); ld_h(12, r1); st_h(8, r0);
-                tc::wait_ld(); st_h(12, r1);
+                if (p.head_w == nullptr)
+                {
+                    tc::wait_ld(); ld_h(4, r1); st_h(0, r0);
+                    tc::wait_ld(); ld_h(8, r0); st_h(4, r1);
+                    tc::wait_ld(); ld_h(12, r1); st_h(8, r0);
+                    tc::wait_ld(); st_h(12, r1);
+                }
+                else
+                {
+                    tc::wait_ld(); ld_h(4, r1); dot_h(0, r0);
+                    tc::wait_ld(); ld_h(8, r0); dot_h(4, r1);
+                    tc::wait_ld(); ld_h(12, r1); dot_h(8, r0);
+                    tc::wait_ld(); dot_h(12, r1);
+                    // the four lanes of a row hold disjoint columns: add them up in a fixed order
+                    dot_a += __shfl_xor_sync(FULL, dot_a, 1); dot_a += __shfl_xor_sync(FULL, dot_a, 2);
+                    dot_b += __shfl_xor_sync(FULL, dot_b, 1); dot_b += __shfl_xor_sync(FULL, dot_b, 2);
+                    if ((lane & 3) == 0)
+                    {
+                        if (row_a < p.num_nodes) p.node_dot[row_a] = dot_a;
+                        if (row_b < p.num_nodes) p.node_dot[row_b] = dot_b;
+                    }
+                }
             }
             if (tid == 0) TRACE(1, it, 5);
         }
@@ -611,9 +646,34 @@ void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const
     }
 }
 
+// mean over a graph's nodes of the per-node head products + bias (finalize, GIN/src/finalize.cc:36-115, with the
+// Linear(100 -> 1) already applied per node by the last layer's epilogue)
+__global__ void __launch_bounds__(256) gin_pool_dot_kernel(const float* __restrict__ node_dot, const int* __restrict__ node_off,
+                                                           const int* __restrict__ nn, const float* __restrict__ pred_b, float* __restrict__ out,
+                                                           int num_graphs)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= num_graphs) return;
+    const int n = nn[g];
+    const float* y = node_dot + node_off[g];
+    float s = 0.f;
+    for (int r = 0; r < n; r++) s += __ldg(y + r);
+    out[g] = s / (float)n + __ldg(pred_b);
+}
+
+int gin_pool_dot_launch(const float* node_dot, const DeviceBatch& b, const float* pred_b, cudaStream_t s)
+{
+    if (b.num_graphs <= 0) return 0;
+    gin_pool_dot_kernel<<<ceil_div(b.num_graphs, 256), 256, 0, s>>>(node_dot, b.node_off.as<int>(), b.nums_of_nodes.as<int>(), pred_b, b.out.as<float>(),
+                                                                     b.num_graphs);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
 unsigned long long* gin_tc2_trace_buffer = nullptr;      // set through flowgnn_b200_debug_trace (api.cu)
 
-int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
+int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
+                         const float* head_w, float* node_dot)
 {
     static bool attr_set = false;
     if (!attr_set)
@@ -630,6 +690,7 @@ int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, c
     p.num_nodes = (int)b.total_nodes;
     p.num_pair_tiles = (int)ceil_div<long>(b.total_nodes, 2 * TM);
     p.relu_out = (layer != 4);
+    p.head_w = head_w; p.node_dot = node_dot;
     static const int dbg_env = [] { const char* e = std::getenv("FLOWGNN_B200_DBG"); return e ? std::atoi(e) : 0; }();
     p.dbg = dbg_env;
     p.trace = gin_tc2_trace_buffer;

@@ -51,6 +51,7 @@ struct DeviceBatch {
     // activations
     DevBuf act[4];                         // float [N][<=100] ping/pong (+2 extra for GAT)
     DevBuf score[4];                       // float [N][4] GAT source/target scores ping/pong
+    DevBuf node_dot;                       // float [N]  GIN: <h'_v, w_pred> of the last layer (gin_tc2.cu)
     DevBuf out;                            // float [G]
 
     void release();
@@ -122,6 +123,7 @@ struct RunOptions {
     int mp_only = 0;                 // GIN: node transform = identity (roofline variant)
     int gin_ffma = 0;                // GIN: node MLP on the FP32 FFMA pipe (on-device fp32 reference) instead of tcgen05
     int gin_tc1 = 0;                 // GIN: single-CTA tcgen05 kernel (gin_tc.cu) instead of the CTA-pair kernel (gin_tc2.cu)
+    int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
     int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
@@ -129,7 +131,9 @@ struct RunOptions {
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
-int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
+                         const float* head_w = nullptr, float* node_dot = nullptr);
+int gin_pool_dot_launch(const float* node_dot, const DeviceBatch& b, const float* pred_b, cudaStream_t s);
 int gin_layer_tc3_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t gin_tc3_pack_bytes();
 void gin_tc3_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
