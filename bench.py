@@ -282,7 +282,10 @@ def run_b200_arm(args):
     ctx = Context(local)
     ctx.load_weights(model, weights)
     ctx.upload(hbatch)
-    ctx.set_option("time_layers", 1)
+    # GIN: one event pair around the five layer launches (events between them would break programmatic dependent launch);
+    # the per-launch time is that interval / 5 and includes the (overlapped) launch gaps
+    grouped = model in ("gin", "ginvn")
+    ctx.set_option("time_layers", 2 if grouped else 1)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
     if not gpu_id.startswith("GPU-"):
@@ -300,7 +303,8 @@ def run_b200_arm(args):
     layer_ms = []
     for _ in range(args.steps):
         ctx.compute(model, timed=True)
-        layer_ms.extend(ctx.last_layer_ms())
+        lm = ctx.last_layer_ms()
+        layer_ms.extend([lm[0] / ALGO[model][1]] * ALGO[model][1] if grouped and len(lm) == 1 else lm)
     ev1.record(stream)
     barrier()
     windows.append((w0, time.perf_counter()))
@@ -359,6 +363,7 @@ def run_b200_arm(args):
     edge_gather = None
     if model in ("gin", "ginvn"):
         ctx.set_option("mp_only", 1)
+        ctx.set_option("time_layers", 1)
         for _ in range(args.warmup):
             ctx.compute(model, timed=True)
         mp_ms = []

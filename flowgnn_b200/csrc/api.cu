@@ -554,6 +554,7 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     ctx->last_launches += 3;      // scan_offsets + the two build_csr instantiations
     ctx->timer.marks = 0;
     ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
+    ctx->opt.timer_group = ctx->time_layers == 2;
     switch (model)
     {
     case MODEL_GIN: FG_TRY(gin_forward(b, ctx->gin, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;

@@ -248,7 +248,7 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
     bool fused_head = false;
     for (int l = 0; l < 5; l++)
     {
-        if (opt.timer) FG_TRY(opt.timer->mark(s));
+        if (opt.timer && (l == 0 || !opt.timer_group)) FG_TRY(opt.timer->mark(s));
         GinLayerParams p;
         p.h_in = h[l & 1]; p.h_out = h[(l + 1) & 1];
         p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();

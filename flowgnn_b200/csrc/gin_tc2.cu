@@ -253,6 +253,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
     tc::fence_after_sync();
     const uint32_t tbase = *tmem_ptr;
     const uint32_t a_base = smem_u32(smem + Smem::A);
+    // Programmatic dependent launch: this grid may have been started while the previous kernel of the stream (the previous
+    // layer) was still draining -- everything above (barriers, tensor memory, weights, tables: nothing the previous kernel
+    // writes) overlapped its tail.  From here on the kernel reads h_in and writes h_out: wait for the previous grid, and let
+    // the next one start its own prologue as soon as this grid's CTAs retire.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp >= MMA_WARP)
     {
@@ -695,8 +701,13 @@ int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, c
     p.dbg = dbg_env;
     p.trace = gin_tc2_trace_buffer;
     const int pairs = std::max(1, std::min(p.num_pair_tiles, sm_count / 2));
-    gin_layer_tc2_kernel<<<2 * pairs, NT, Smem::BYTES, s>>>(p);
-    FG_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = Smem::BYTES; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FG_CUDA(cudaLaunchKernelEx(&cfg, gin_layer_tc2_kernel, p));
     return 0;
 }
 

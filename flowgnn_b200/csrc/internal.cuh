@@ -127,6 +127,8 @@ struct RunOptions {
     int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
+    int timer_group = 0;             // time_layers == 2: one interval around ALL layer launches (events between the launches
+                                     // would keep them from overlapping through programmatic dependent launch)
 };
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);

@@ -128,7 +128,8 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx);
  * "gin_ffma" (GIN: run the node MLP on the FP32 FFMA pipe instead of the tcgen05 bf16x3 split path; the
  * on-device fp32 reference), "gin_tc1" / "gin_tc3" (GIN: the single-CTA tcgen05 kernel / the CTA-pair kernel with
  * TMA-staged tile rows instead of the default CTA-pair kernel; all three compute the same layer),
- * "gat_node_offset_bug" (default 1), "time_layers" (see flowgnn_b200_last_layer_ms).
+ * "gat_node_offset_bug" (default 1), "time_layers" (1: see flowgnn_b200_last_layer_ms; 2 (GIN): ONE interval around all
+ * layer launches, which leaves them adjacent in the stream so that programmatic dependent launch can overlap them).
  * Environment: FLOWGNN_B200_CHUNKS=n overrides the number of chunks the host-pointer entry points cut a batch into
  * (default 3 for >= 16,384 graphs: upload of chunk i+1 overlaps the kernels of chunk i). */
 int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value);
