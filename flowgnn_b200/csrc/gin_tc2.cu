@@ -43,6 +43,14 @@ constexpr int D = 100;
 constexpr int Q = D / 4;
 constexpr int TM = 128;                       // nodes per CTA tile (pair tile = 256)
 constexpr int N1A = 112, N1B = 96, N1 = N1A + N1B;   // GEMM1 N halves (z columns), whole pair
+// Experiment (-DFG_G1_SINGLE=1): GEMM1 as ONE N = 208 MMA per k-step and product instead of two N halves -- the A tile is
+// read from shared memory 21 times per tile instead of 42 (86 KB less operand traffic), but the conversion of the first
+// z half no longer overlaps the second half of GEMM1.  Measured: 0.467 ms per layer against 0.39 ms, so the split stays.
+#ifndef FG_G1_SINGLE
+#define FG_G1_SINGLE 0
+#endif
+constexpr bool G1_SINGLE = FG_G1_SINGLE != 0;
+constexpr int LBO_W1 = (N1 / 2) * 16;           // single block: CTA r holds z columns 104 r .. 104 r + 103
 constexpr int N2 = 128;                       // GEMM2 N (100 used)
 constexpr int K1_STEPS = 7, K2_STEPS = 13;    // K = 16 per step
 constexpr int K1_CHUNKS = 13;                 // stored 8-element K chunks of A and W1 (k < 104; chunk 13 reads as zero)
@@ -282,6 +290,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                     tc::fence_after_sync();
                     TRACE(0, it, 1);
                     // GEMM1, N half a (z columns 0..111) then half b (112..207)
+                    if constexpr (G1_SINGLE)
+                    {
+                        const uint32_t idesc1 = tc::idesc_bf16(2 * TM, N1);
+                        bool acc = false;
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++)
+                        {
+                            const uint32_t a_addr = a_base + (2 * s + (prod == 1 ? 1 : 0)) * A_BYTES;
+                            const uint32_t b_addr = w_addr + (prod == 2 ? OFF_W1A_LO + W1B_BYTES : OFF_W1A_HI);      // W1_hi | W1_lo, 21,632 B each
+#pragma unroll
+                            for (int j = 0; j < K1_STEPS; j++)
+                            {
+                                const uint32_t a_start = a_addr + 2 * j * LBO_A;
+                                const uint32_t a_lbo = (j < K1_STEPS - 1) ? (uint32_t)LBO_A : zero_addr - a_start;
+                                mma_ss2(tbase + TC_Z, tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * LBO_W1, LBO_W1, 128), idesc1, acc);
+                                acc = true;
+                            }
+                        }
+                        commit2(&bar[BAR_G1A_DONE]);
+                        commit2(&bar[BAR_G1B_DONE]);
+                    }
+                    else
+                    {
 #pragma unroll
                     for (int nh = 0; nh < 2; nh++)
                     {
@@ -304,6 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                             }
                         }
                         commit2(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
+                    }
                     }
                     commit2(&bar[BAR_A_FREE + s]);
                     TRACE(0, it, 2);
@@ -640,8 +672,16 @@ void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const
     for (int r = 0; r < 2; r++)
     {
         unsigned char* img = dst + (size_t)r * W_BYTES;
-        for (int n = 0; n < N1A / 2; n++) w1_row(img + OFF_W1A_HI, img + OFF_W1A_LO, N1A / 2, n, (N1A / 2) * r + n);
-        for (int n = 0; n < N1B / 2; n++) w1_row(img + OFF_W1B_HI, img + OFF_W1B_LO, N1B / 2, n, N1A + (N1B / 2) * r + n);
+        if (G1_SINGLE)
+        {
+            // one block per CTA: W1_hi at offset 0, W1_lo behind it (the two half blocks of the other variant add up to the same size)
+            for (int n = 0; n < N1 / 2; n++) w1_row(img + OFF_W1A_HI, img + OFF_W1A_LO + W1B_BYTES, N1 / 2, n, (N1 / 2) * r + n);
+        }
+        else
+        {
+            for (int n = 0; n < N1A / 2; n++) w1_row(img + OFF_W1A_HI, img + OFF_W1A_LO, N1A / 2, n, (N1A / 2) * r + n);
+            for (int n = 0; n < N1B / 2; n++) w1_row(img + OFF_W1B_HI, img + OFF_W1B_LO, N1B / 2, n, N1A + (N1B / 2) * r + n);
+        }
         for (int n = 0; n < N2 / 2; n++)
         {
             const int o = (N2 / 2) * r + n;
