@@ -12,20 +12,24 @@
 // per row (128-byte pieces, 4 rows per instruction) and twice as many gather warps.
 //
 // Per CTA (896 threads):
-//   warps 0-7   epilogue: z = relu(acc + b1) -> bf16 hi/lo written back to tensor memory IN PLACE (A operand of GEMM2);
-//               h' = acc + b2 (+ relu) streamed to HBM, one full 32-byte sector per row and store
+//   warps 0-7   epilogue: z = relu(acc) -> bf16 hi/lo written back to tensor memory IN PLACE (A operand of GEMM2), the
+//               TMEM load of the next 16-column chunk in flight while one is converted; h' = acc (+ relu) streamed to
+//               HBM, one full 32-byte sector per row and store.  The biases are inside the GEMMs (constant-1 column
+//               k = 100 of the A tile, z column 200 == 1).  In the LAST layer the four lanes of a row multiply h' with the
+//               prediction weights instead and store one float per node (the head is fused, nothing else leaves)
 //   warps 8-23  gather: 8 rows each, as two passes of 4 rows; thread (g = lane / 8, j = lane % 8) owns row 4 pass + g
-//               and, per step ks < 4, the float4 chunk 8 ks + j of that row: own row + up to four source rows are
-//               loaded with addresses = pointer + immediate, the loads of step ks + 1 are issued before step ks is
-//               reduced (CSR order, deterministic), split to bf16 hi/lo and stored to the A tile.  The CSR slice of
-//               the NEXT tile (row pointers, packed source/code) is prefetched into registers one tile ahead and
-//               handed to the threads with warp shuffles.
+//               and, per step ks < 3, the float4 chunk 8 ks + j of that row: own row + up to four source rows are
+//               loaded with addresses = pointer + immediate (from the node's 16-byte row descriptor, prep.cu), reduced
+//               in CSR order (deterministic), split to bf16 hi/lo and stored to the A tile.  Software pipeline over
+//               steps, passes and tiles on two load buffers; chunk 24 is gathered once per tile with a lane per row
 //   warp 24     (leader CTA only) MMA issuer: GEMM1 = 3 products (hi*hi + lo*hi + hi*lo) x 7 k-steps from shared
 //               memory (SS), as two N halves (112 + 96) so that the conversion of the first half overlaps the second;
 //               GEMM2 = 3 x 13 k-steps with A = z from tensor memory (TS), N = 128 (TS needs N % 32 == 0 for pairs)
-//   warp 25     L2 prefetch of the feature rows two tiles ahead
+//   warp 25     L2 prefetch of the feature rows and the CSR slice two tiles ahead
 // Barriers that the MMA issuer waits on live in the leader CTA and are arrived on remotely by the peer's warps;
-// tcgen05.commit multicasts completion to both CTAs.
+// tcgen05.commit multicasts completion to both CTAs.  Launched with programmatic stream serialization: the prologue
+// (barriers, tensor memory, weights, tables) overlaps the previous layer's tail, griddepcontrol.wait guards h_in / h_out.
+// What bounds the kernel (the SM's shared-memory / L1 data path) and what was tried: DESIGN.md 5.1.
 #include "internal.cuh"
 #include "layers.cuh"
 #include "tc.cuh"
