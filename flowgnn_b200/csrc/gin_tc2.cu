@@ -587,8 +587,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_tc2
                             oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
                             ob = make_float2(relu_nan(ob.x), relu_nan(ob.y));
                         }
-                        if (row_a < p.num_nodes && !DBG(2)) *reinterpret_cast<float2*>(p.h_out + (size_t)row_a * D + col) = oa;
-                        if (row_b < p.num_nodes && !DBG(2)) *reinterpret_cast<float2*>(p.h_out + (size_t)row_b * D + col) = ob;
+                        // written once, read by the next launch: do not allocate in L1
+                        if (row_a < p.num_nodes && !DBG(2))
+                            asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p.h_out + (size_t)row_a * D + col), "f"(oa.x), "f"(oa.y) : "memory");
+                        if (row_b < p.num_nodes && !DBG(2))
+                            asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p.h_out + (size_t)row_b * D + col), "f"(ob.x), "f"(ob.y) : "memory");
                     }
                 }
             };
