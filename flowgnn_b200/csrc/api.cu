@@ -37,7 +37,7 @@ void DevBuf::release()
 void DeviceBatch::release()
 {
     DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
-                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &sort_tmp, &status, &node_dot,
+                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &status, &node_dot,
                      &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
     for (DevBuf* b : all) b->release();
 }
@@ -475,6 +475,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "gin_ffma")) ctx->opt.gin_ffma = value;
     else if (!std::strcmp(name, "gin_tc1")) ctx->opt.gin_tc1 = value;
     else if (!std::strcmp(name, "gin_tc3")) ctx->opt.gin_tc3 = value;
+    else if (!std::strcmp(name, "gin_staged")) ctx->opt.gin_staged = value;
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;

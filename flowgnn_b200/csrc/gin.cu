@@ -218,6 +218,142 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gin_gather_kernel(const flo
     }
 }
 
+
+// ---- staged gather: the message-passing half of a layer for DENSE graphs (hep10k kNN graphs: 16 in-edges per node) ------
+// With many in-edges per node every feature row is re-read once per out-edge, and the row-per-warp kernel above becomes
+// L2-bandwidth-bound (35 M edges x 400 B = 14 GB per launch on the hep10k workload: 2.04 ms = 6.9 TB/s out of L2).
+// The sources of a node are nodes of the SAME graph and a graph's rows are contiguous in HBM, so this kernel reads every
+// row from HBM exactly once: a persistent CTA per SM packs consecutive whole graphs into items of up to SG_ROWS rows,
+// one bulk-TMA copy per item (cp.async.bulk + mbarrier, double buffered: item i+1 streams in while item i is reduced)
+// lands them in shared memory and all in-edge reads hit shared memory.  Warp 0 packs and issues the copies, 31 warps
+// take a destination row each: the edge records of a row are read 32 at a time (coalesced) and broadcast by shuffle,
+// in-edges are added in CSR order (the reference's order, GIN/src/message_passing.cc:136-145).  Graphs with more than
+// SG_ROWS nodes are read from global memory by the same code.
+constexpr int SG_THREADS = 1024;
+constexpr int SG_ROWS = 240;
+struct SgSmem {
+    float stage[2][SG_ROWS * D];      // 2 x 96,000 B
+    float tab[ED_COMBOS * D];         // 24,000 B
+    uint64_t bar[2];
+    int item[2][4];                   // first node, end node, staged flag
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const float* tab, float* __restrict__ h_out,
+                                        const int* __restrict__ in_ptr, const int* __restrict__ src, const uint8_t* __restrict__ code,
+                                        int nb, int ne, int cw, int lane)
+{
+    // `rows` is indexed by (node - base): the stage for STAGED (base = nb), h_in otherwise (base = 0)
+    const int base = STAGED ? nb : 0;
+    const int col = 4 * min(lane, Q - 1);                        // lanes 25..31 shadow lane 24 (same addresses, no store)
+    for (int v = nb + cw; v < ne; v += SG_THREADS / 32 - 1)
+    {
+        const int eb = __ldg(in_ptr + v), ee = __ldg(in_ptr + v + 1);
+        const float4 hv = STAGED ? ld_f4(rows + (size_t)(v - base) * D + col) : ldg_f4(rows + (size_t)v * D + col);
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e0 = eb; e0 < ee; e0 += 32)
+        {
+            const int idx = e0 + lane;
+            int us = 0, cs = 0;
+            if (idx < ee) { us = __ldg(src + idx) - base; cs = (int)__ldg(code + idx); }
+            if (STAGED) us = (us << 6) | cs;                      // row < SG_ROWS, code < 64: one shuffle per edge
+            const int cnt = min(32, ee - e0);
+#pragma unroll 4
+            for (int k = 0; k < cnt; k++)
+            {
+                const int q = __shfl_sync(0xFFFFFFFFu, us, k);
+                const int c = STAGED ? (q & 63) : __shfl_sync(0xFFFFFFFFu, cs, k);
+                const float4 hu = STAGED ? ld_f4(rows + (q >> 6) * D + col) : ldg_f4(rows + (size_t)q * D + col);
+                const float4 t = ld_f4(tab + c * D + col);
+                m.x += relu_f(t.x + hu.x); m.y += relu_f(t.y + hu.y); m.z += relu_f(t.z + hu.z); m.w += relu_f(t.w + hu.w);
+            }
+        }
+        if (lane < Q) stg_f4_stream(h_out + (size_t)v * D + col, make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w));
+    }
+}
+
+__global__ void __launch_bounds__(SG_THREADS, 1) gin_gather_staged_kernel(const float* __restrict__ h_in, float* __restrict__ h_out,
+                                                                           const int* __restrict__ in_ptr, const int* __restrict__ src,
+                                                                           const uint8_t* __restrict__ code,
+                                                                           const float* __restrict__ ee_comb,
+                                                                           const int* __restrict__ node_off, int num_graphs)
+{
+    extern __shared__ __align__(128) unsigned char sg_raw[];
+    SgSmem& sm = *reinterpret_cast<SgSmem*>(sg_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g_hi = (int)((long)num_graphs * (blockIdx.x + 1) / gridDim.x);
+    int g_next = (int)((long)num_graphs * blockIdx.x / gridDim.x);           // used by thread 0 only
+
+    for (int i = tid; i < ED_COMBOS * Q; i += SG_THREADS) st_f4(sm.tab + 4 * i, ldg_f4(ee_comb + 4 * i));
+    if (tid == 0)
+    {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        fence_mbar_init();
+    }
+    // thread 0: pack the next run of whole graphs (<= SG_ROWS rows) into `slot` and start its copy
+    auto issue = [&](int slot) {
+        int nb = 0, ne = 0, staged = 0;
+        while (g_next < g_hi && ne == nb)                          // skip graphs without nodes
+        {
+            nb = __ldg(node_off + g_next);
+            ne = __ldg(node_off + g_next + 1);
+            g_next++;
+        }
+        if (ne > nb)
+        {
+            if (ne - nb <= SG_ROWS)
+            {
+                staged = 1;
+                while (g_next < g_hi)
+                {
+                    const int nx = __ldg(node_off + g_next + 1);
+                    if (nx - nb > SG_ROWS) break;
+                    ne = nx;
+                    g_next++;
+                }
+            }
+        }
+        sm.item[slot][0] = nb; sm.item[slot][1] = ne; sm.item[slot][2] = staged;
+        if (staged && ne > nb)
+        {
+            const uint32_t bytes = (uint32_t)(ne - nb) * (D * 4);
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&sm.bar[slot], bytes);
+            tma_load_1d(sm.stage[slot], h_in + (size_t)nb * D, bytes, &sm.bar[slot]);
+        }
+        else mbar_arrive(&sm.bar[slot]);                          // keeps the phase count in step with the item count
+    };
+    if (tid == 0) issue(0);
+    for (int it = 0;; it++)
+    {
+        const int s = it & 1;
+        __syncthreads();                                          // item it-1 is done: its slot may be refilled; item it's record is visible
+        if (tid == 0) issue(s ^ 1);
+        const int nb = sm.item[s][0], ne = sm.item[s][1], staged = sm.item[s][2];
+        if (ne == nb) break;                                      // CTA-uniform: no graphs left
+        if (warp == 0) continue;
+        if (staged)
+        {
+            mbar_wait(&sm.bar[s], (it >> 1) & 1);
+            sg_rows<true>(sm.stage[s], sm.tab, h_out, in_ptr, src, code, nb, ne, warp - 1, lane);
+        }
+        else sg_rows<false>(h_in, sm.tab, h_out, in_ptr, src, code, nb, ne, warp - 1, lane);
+    }
+}
+
+// Row descriptors "no in-edges" (prep.cu::empty_row_desc): the CTA-pair kernel run on them is the node MLP alone.
+__global__ void fill_empty_desc_kernel(int4* d, long n)
+{
+    const int e = 32768 | (ED_COMBOS << 16);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = make_int4(e, e, e, e);
+}
+
 }  // namespace
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches)
@@ -245,10 +381,51 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         FG_CUDA(cudaFuncSetAttribute(gin_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GinSmem<true>::BYTES));
         attr_set = true;
     }
+    // Dense graphs (average in-degree >= 6: hep10k kNN graphs, GIN-VN on them) run every layer as TWO launches: the staged
+    // gather (each row read from HBM once, in-edge reads from shared memory) writes x = m + h, and the CTA-pair kernel run
+    // on "no in-edges" descriptors applies the node MLP.  Sparse graphs (molecules) keep the single fused launch.
+    const bool staged = opt.gin_staged < 0 ? (b.total_edges >= 6 * N) : (opt.gin_staged != 0);
+    const bool split_layer = staged && !opt.mp_only && !opt.gin_ffma && !opt.gin_tc1 && !opt.gin_tc3;
+    auto staged_gather = [&](const float* x_in, float* x_out, int l) -> int {
+        static bool sg_attr = false;
+        if (!sg_attr)
+        {
+            FG_CUDA(cudaFuncSetAttribute(gin_gather_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgSmem)));
+            sg_attr = true;
+        }
+        const int grid = std::max(1, std::min(b.num_graphs, sm_count));
+        gin_gather_staged_kernel<<<grid, SG_THREADS, sizeof(SgSmem), s>>>(x_in, x_out, b.in_ptr.as<int>(), b.src.as<int>(), b.code.as<uint8_t>(),
+                                                                         w.ee_comb.as<float>() + (size_t)l * ED_COMBOS * D,
+                                                                         b.node_off.as<int>(), b.num_graphs);
+        FG_CUDA(cudaGetLastError());
+        return 0;
+    };
+    if (split_layer)
+    {
+        FG_TRY(b.row_desc0.reserve(sizeof(int4) * (size_t)(N + 1)));
+        fill_empty_desc_kernel<<<sm_count * 4, 256, 0, s>>>(b.row_desc0.as<int4>(), N + 1);
+        FG_CUDA(cudaGetLastError());
+        nl++;
+    }
     bool fused_head = false;
     for (int l = 0; l < 5; l++)
     {
         if (opt.timer && (l == 0 || !opt.timer_group)) FG_TRY(opt.timer->mark(s));
+        if (split_layer)
+        {
+            // h[0] -> gather -> h[1] -> node MLP -> h[0]
+            FG_TRY(staged_gather(h[0], h[1], l));
+            nl++;
+            if (l == 4 && !opt.gin_unfused_head)
+            {
+                FG_TRY(b.node_dot.reserve(sizeof(float) * (size_t)(N + 1)));
+                FG_TRY(gin_layer_tc2_launch(b, w, l, h[1], h[0], sm_count, s, w.pred_w.as<float>(), b.node_dot.as<float>(), b.row_desc0.as<int4>()));
+                fused_head = true;
+            }
+            else FG_TRY(gin_layer_tc2_launch(b, w, l, h[1], h[0], sm_count, s, nullptr, nullptr, b.row_desc0.as<int4>()));
+            nl++;
+            continue;
+        }
         GinLayerParams p;
         p.h_in = h[l & 1]; p.h_out = h[(l + 1) & 1];
         p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
@@ -271,7 +448,8 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
             nl++;
             continue;
         }
-        if (opt.mp_only)
+        if (opt.mp_only && staged) FG_TRY(staged_gather(p.h_in, p.h_out, l));
+        else if (opt.mp_only)
         {
             const int grid = (int)std::min<long>(ceil_div<long>(N, GATHER_WARPS), (long)sm_count * 8);
             gin_gather_kernel<<<grid, GATHER_WARPS * 32, 0, s>>>(p.h_in, p.h_out, p.in_ptr, p.src, p.code, p.ee_comb, (int)N);
@@ -294,7 +472,7 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         return 0;
     }
     HeadParams hp{};
-    hp.x = h[1]; hp.dim = D; hp.node_off = b.node_off.as<int>(); hp.nn = b.nums_of_nodes.as<int>(); hp.num_graphs = b.num_graphs;
+    hp.x = split_layer ? h[0] : h[1]; hp.dim = D; hp.node_off = b.node_off.as<int>(); hp.nn = b.nums_of_nodes.as<int>(); hp.num_graphs = b.num_graphs;
     hp.w[0] = w.pred_w.as<float>(); hp.b[0] = w.pred_b.as<float>(); hp.dims[0] = D; hp.dims[1] = 1; hp.num_layers = 1;
     hp.out = b.out.as<float>();
     FG_TRY(launch_pool_head(hp, s));

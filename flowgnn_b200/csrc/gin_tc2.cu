@@ -726,7 +726,7 @@ int gin_pool_dot_launch(const float* node_dot, const DeviceBatch& b, const float
 unsigned long long* gin_tc2_trace_buffer = nullptr;      // set through flowgnn_b200_debug_trace (api.cu)
 
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
-                         const float* head_w, float* node_dot)
+                         const float* head_w, float* node_dot, const int4* row_desc)
 {
     static bool attr_set = false;
     if (!attr_set)
@@ -737,7 +737,7 @@ int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, c
     GinTc2Params p;
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
-    p.row_desc = b.row_desc.as<int4>();
+    p.row_desc = row_desc ? row_desc : b.row_desc.as<int4>();     // override: "no in-edges" descriptors = node MLP only (gin.cu)
     p.ee_comb = w.ee_comb.as<float>() + (size_t)layer * ED_COMBOS * D;
     p.wpack = w.wpack2.as<unsigned char>() + (size_t)layer * 2 * W_BYTES;
     p.num_nodes = (int)b.total_nodes;

@@ -45,6 +45,7 @@ struct DeviceBatch {
     DevBuf out_deg;                        // int32 [N]
     DevBuf node_w0, node_w1;               // float [N]  DGN: sum|eig_w|, sum eig_w over in-edges
     DevBuf row_desc;                       // int4 [N]  GIN: first four in-edges of every node, packed (prep.cu)
+    DevBuf row_desc0;                      // int4 [N]  GIN, dense graphs: "no in-edges" descriptors (node MLP launch after the staged gather)
     DevBuf sort_tmp;                       // int32 [E] scratch for the two-pass stable sort
     DevBuf status;                         // int32 [1] device-side limit violations
 
@@ -125,6 +126,7 @@ struct RunOptions {
     int gin_tc1 = 0;                 // GIN: single-CTA tcgen05 kernel (gin_tc.cu) instead of the CTA-pair kernel (gin_tc2.cu)
     int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
     int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
+    int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
     int timer_group = 0;             // time_layers == 2: one interval around ALL layer launches (events between the launches
@@ -134,7 +136,7 @@ struct RunOptions {
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
-                         const float* head_w = nullptr, float* node_dot = nullptr);
+                         const float* head_w = nullptr, float* node_dot = nullptr, const int4* row_desc = nullptr);
 int gin_pool_dot_launch(const float* node_dot, const DeviceBatch& b, const float* pred_b, cudaStream_t s);
 int gin_layer_tc3_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t gin_tc3_pack_bytes();

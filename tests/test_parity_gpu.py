@@ -74,6 +74,30 @@ def test_gin_tma_staged_kernel_agrees(ds, ctx, weights, datasets, golden):
     assert_parity(few, golden[ds]["gin"][:11], what=f"gin tma-staged/{ds} first 11 graphs")
 
 
+@pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
+@pytest.mark.parametrize("vn", [False, True])
+def test_gin_staged_gather_layers_agree_with_fused_layers(ds, vn, ctx, weights, datasets, golden):
+    """Dense graphs (average in-degree >= 6: hep10k) run a layer as two launches -- gin_gather_staged_kernel (graph rows
+    staged in shared memory by bulk TMA, every row read from HBM once) and the CTA-pair kernel on 'no in-edges'
+    descriptors as the node MLP; molecules run the single fused launch.  Option gin_staged forces either path: both must
+    match the reference on both kinds of graphs (GIN and GIN-VN) and agree with each other."""
+    b = datasets[ds].with_virtual_node() if vn else datasets[ds]
+    want = golden[ds]["ginvn" if vn else "gin"]
+    out = {}
+    try:
+        for mode in (1, 0, -1):
+            ctx.set_option("gin_staged", mode)
+            out[mode] = ctx.run("gin", b, weights["gin"])
+            launches = ctx.last_launch_count
+            assert launches == (16 if mode == 1 or (mode == -1 and ds == "hep10k") else 10), (mode, launches)
+    finally:
+        ctx.set_option("gin_staged", -1)
+    for mode, y in out.items():
+        assert_parity(y, want, what=f"gin staged={mode} vn={vn}/{ds}")
+    assert_parity(out[1], out[0], tol=5e-5, what=f"gin staged vs fused/{ds}")
+    assert np.array_equal(out[-1].view(np.int32), out[1 if ds == "hep10k" else 0].view(np.int32))
+
+
 @pytest.mark.parametrize("n_graphs", [1, 3, 10, 11, 21, 100])
 def test_gin_tile_boundaries(n_graphs, ctx, weights, datasets, golden):
     """Batches whose node count falls on either side of the 128-row CTA tile and the 256-row pair tile (a lone first
@@ -256,6 +280,14 @@ def test_large_and_small_graphs_in_one_batch(model, ctx, weights, datasets):
     got = ctx.run(model, b, weights[model])
     want = refbind.run_port(model, b, weights[model])
     assert_parity(got, want, what=f"{model} mixed small/large graphs")
+    if model == "gin":
+        # the staged gather packs whole graphs into 240-row items; the graphs of 450 nodes take its global-memory path
+        ctx.set_option("gin_staged", 1)
+        try:
+            got = ctx.run(model, b)
+        finally:
+            ctx.set_option("gin_staged", -1)
+        assert_parity(got, want, what="gin staged gather, mixed small/large graphs")
 
 
 def test_out_of_vocabulary_features_read_what_the_reference_reads(ctx, weights, datasets):
@@ -293,9 +325,13 @@ def test_mp_only_variant_is_the_pure_gather_scatter(ctx, weights, datasets):
     ctx.set_option("mp_only", 1)
     try:
         got = ctx.run("gin", b, w)
+        ctx.set_option("gin_staged", 1)
+        got_staged = ctx.run("gin", b)
     finally:
         ctx.set_option("mp_only", 0)
+        ctx.set_option("gin_staged", -1)
     assert_parity(got, want.astype(np.float32), what="gin mp_only")
+    assert np.array_equal(got.view(np.int32), got_staged.view(np.int32)), "staged gather: same sums in the same order"
 
 
 def test_full_size_synthetic_batch_properties(ctx, weights):
