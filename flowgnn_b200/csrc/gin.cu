@@ -243,6 +243,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// two fp32 additions in one instruction (FADD2, sm_100): the same IEEE round-to-nearest result per element
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1)
+{
+    unsigned long long ua, ub, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b0), "f"(b1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(ud));
+}
+// signbit(x) ? 0 : x with NaN passing through, one instruction (FMNMX.NAN); the sign of a zero does not reach a sum
+__device__ __forceinline__ float relu_max(float x)
+{
+    float y;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(0.0f));
+    return y;
+}
+// m += relu(t + hu), four columns
+__device__ __forceinline__ void sg_edge(float4& m, const float4& t, const float4& hu)
+{
+    float4 x;
+    add2(x.x, x.y, t.x, t.y, hu.x, hu.y);
+    add2(x.z, x.w, t.z, t.w, hu.z, hu.w);
+    add2(m.x, m.y, m.x, m.y, relu_max(x.x), relu_max(x.y));
+    add2(m.z, m.w, m.z, m.w, relu_max(x.z), relu_max(x.w));
+}
+
 template <bool STAGED>
 __device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const float* tab, float* __restrict__ h_out,
                                         const int* __restrict__ in_ptr, const int* __restrict__ src, const uint8_t* __restrict__ code,
@@ -251,26 +277,43 @@ __device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const fl
     // `rows` is indexed by (node - base): the stage for STAGED (base = nb), h_in otherwise (base = 0)
     const int base = STAGED ? nb : 0;
     const int col = 4 * min(lane, Q - 1);                        // lanes 25..31 shadow lane 24 (same addresses, no store)
+    rows += col;
+    tab += col;
+    // The edge-embedding row of the current bond code stays in registers: kNN graphs carry ONE code on every edge
+    // (hep10k: edge_attr == 0), which halves the shared-memory reads per edge.  Chunks with mixed codes look every edge up.
+    int c_cur = -1;
+    float4 t_cur = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int v = nb + cw; v < ne; v += SG_THREADS / 32 - 1)
     {
         const int eb = __ldg(in_ptr + v), ee = __ldg(in_ptr + v + 1);
-        const float4 hv = STAGED ? ld_f4(rows + (size_t)(v - base) * D + col) : ldg_f4(rows + (size_t)v * D + col);
+        const float4 hv = STAGED ? ld_f4(rows + (v - base) * D) : ldg_f4(rows + (size_t)v * D);
         float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int e0 = eb; e0 < ee; e0 += 32)
         {
             const int idx = e0 + lane;
-            int us = 0, cs = 0;
+            int us = 0, cs = -1;
             if (idx < ee) { us = __ldg(src + idx) - base; cs = (int)__ldg(code + idx); }
-            if (STAGED) us = (us << 6) | cs;                      // row < SG_ROWS, code < 64: one shuffle per edge
             const int cnt = min(32, ee - e0);
-#pragma unroll 4
-            for (int k = 0; k < cnt; k++)
+            const int c0 = __shfl_sync(0xFFFFFFFFu, cs, 0);
+            if (__all_sync(0xFFFFFFFFu, cs == c0 || cs < 0))
             {
-                const int q = __shfl_sync(0xFFFFFFFFu, us, k);
-                const int c = STAGED ? (q & 63) : __shfl_sync(0xFFFFFFFFu, cs, k);
-                const float4 hu = STAGED ? ld_f4(rows + (q >> 6) * D + col) : ldg_f4(rows + (size_t)q * D + col);
-                const float4 t = ld_f4(tab + c * D + col);
-                m.x += relu_f(t.x + hu.x); m.y += relu_f(t.y + hu.y); m.z += relu_f(t.z + hu.z); m.w += relu_f(t.w + hu.w);
+                if (c0 != c_cur) { t_cur = ld_f4(tab + c0 * D); c_cur = c0; }
+                if (STAGED) us *= D;                              // element offset of the source row inside the stage
+#pragma unroll 4
+                for (int k = 0; k < cnt; k++)
+                {
+                    const int q = __shfl_sync(0xFFFFFFFFu, us, k);
+                    sg_edge(m, t_cur, STAGED ? ld_f4(rows + q) : ldg_f4(rows + (size_t)q * D));
+                }
+            }
+            else
+            {
+#pragma unroll 4
+                for (int k = 0; k < cnt; k++)
+                {
+                    const int q = __shfl_sync(0xFFFFFFFFu, us, k), c = __shfl_sync(0xFFFFFFFFu, cs, k);
+                    sg_edge(m, ld_f4(tab + c * D), STAGED ? ld_f4(rows + q * D) : ldg_f4(rows + (size_t)q * D));
+                }
             }
         }
         if (lane < Q) stg_f4_stream(h_out + (size_t)v * D + col, make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w));
