@@ -235,7 +235,8 @@ struct SgSmem {
     float stage[2][SG_ROWS * D];      // 2 x 96,000 B
     float tab[ED_COMBOS * D];         // 24,000 B
     uint64_t bar[2];
-    int item[2][4];                   // first node, end node, staged flag
+    int item[2][4];                   // first node, end node, staged flag, the one bond code of all edges (or -1)
+    int next_row[2];                  // next row of the item to hand out
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
@@ -269,31 +270,66 @@ __device__ __forceinline__ void sg_edge(float4& m, const float4& t, const float4
     add2(m.z, m.w, m.z, m.w, relu_max(x.z), relu_max(x.w));
 }
 
-template <bool STAGED>
-__device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const float* tab, float* __restrict__ h_out,
-                                        const int* __restrict__ in_ptr, const int* __restrict__ src, const uint8_t* __restrict__ code,
-                                        int nb, int ne, int cw, int lane)
+// Rows of an item are handed out one at a time through a counter in shared memory (a virtual node's row has three times
+// the in-edges of the others: a static split leaves the other warps waiting at the item barrier).  The row loop is a
+// two-deep software pipeline in registers: while row v is reduced, the first 32 edge records of the next row and the
+// in_ptr pair of the row after next are in flight, so no global-load latency sits between two rows.
+// PRE: every edge of the item carries the same bond code c and the stage already holds relu(h_u + EE[c]) (transformed in
+// place, once per node instead of once per edge): an edge is one shuffle, one 16-byte shared-memory read and two FADD2.
+template <bool STAGED, bool PRE>
+__device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const float* tab, const float* __restrict__ h_glob,
+                                        float* __restrict__ h_out, const int* __restrict__ in_ptr, const int* __restrict__ src,
+                                        const uint8_t* __restrict__ code, int nb, int ne, int* next_row, int lane)
 {
     // `rows` is indexed by (node - base): the stage for STAGED (base = nb), h_in otherwise (base = 0)
     const int base = STAGED ? nb : 0;
     const int col = 4 * min(lane, Q - 1);                        // lanes 25..31 shadow lane 24 (same addresses, no store)
     rows += col;
     tab += col;
+    auto grab = [&]() {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(next_row, 1);
+        return nb + __shfl_sync(0xFFFFFFFFu, r, 0);
+    };
+    auto chunk = [&](int e0, int ee, int& us, int& cs) {
+        const int idx = e0 + lane;
+        us = 0; cs = -1;
+        if (idx < ee) { us = __ldg(src + idx) - base; cs = (int)__ldg(code + idx); }
+    };
     // The edge-embedding row of the current bond code stays in registers: kNN graphs carry ONE code on every edge
     // (hep10k: edge_attr == 0), which halves the shared-memory reads per edge.  Chunks with mixed codes look every edge up.
     int c_cur = -1;
     float4 t_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int v = nb + cw; v < ne; v += SG_THREADS / 32 - 1)
+
+    int v = grab(), eb = 0, ee = 0, us = 0, cs = -1;
+    if (v < ne) { eb = __ldg(in_ptr + v); ee = __ldg(in_ptr + v + 1); }
+    int vn = grab(), ebn = 0, een = 0;
+    if (vn < ne) { ebn = __ldg(in_ptr + vn); een = __ldg(in_ptr + vn + 1); }
+    chunk(eb, ee, us, cs);
+    while (v < ne)
     {
-        const int eb = __ldg(in_ptr + v), ee = __ldg(in_ptr + v + 1);
-        const float4 hv = STAGED ? ld_f4(rows + (v - base) * D) : ldg_f4(rows + (size_t)v * D);
+        const int v2 = grab();
+        int eb2 = 0, ee2 = 0, usn, csn;
+        if (v2 < ne) { eb2 = __ldg(in_ptr + v2); ee2 = __ldg(in_ptr + v2 + 1); }
+        chunk(ebn, een, usn, csn);
+        const float4 hv = (STAGED && !PRE) ? ld_f4(rows + (v - base) * D) : ldg_f4(h_glob + (size_t)v * D + col);
         float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int e0 = eb; e0 < ee; e0 += 32)
         {
-            const int idx = e0 + lane;
-            int us = 0, cs = -1;
-            if (idx < ee) { us = __ldg(src + idx) - base; cs = (int)__ldg(code + idx); }
+            if (e0 != eb) chunk(e0, ee, us, cs);
             const int cnt = min(32, ee - e0);
+            if (PRE)
+            {
+                us *= D;
+#pragma unroll 8
+                for (int k = 0; k < cnt; k++)
+                {
+                    const float4 r = ld_f4(rows + __shfl_sync(0xFFFFFFFFu, us, k));
+                    add2(m.x, m.y, m.x, m.y, r.x, r.y);
+                    add2(m.z, m.w, m.z, m.w, r.z, r.w);
+                }
+                continue;
+            }
             const int c0 = __shfl_sync(0xFFFFFFFFu, cs, 0);
             if (__all_sync(0xFFFFFFFFu, cs == c0 || cs < 0))
             {
@@ -308,7 +344,7 @@ __device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const fl
             }
             else
             {
-#pragma unroll 4
+#pragma unroll 2
                 for (int k = 0; k < cnt; k++)
                 {
                     const int q = __shfl_sync(0xFFFFFFFFu, us, k), c = __shfl_sync(0xFFFFFFFFu, cs, k);
@@ -317,6 +353,8 @@ __device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const fl
             }
         }
         if (lane < Q) stg_f4_stream(h_out + (size_t)v * D + col, make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w));
+        v = vn; eb = ebn; ee = een; us = usn; cs = csn;
+        vn = v2; ebn = eb2; een = ee2;
     }
 }
 
@@ -339,18 +377,19 @@ __global__ void __launch_bounds__(SG_THREADS, 1) gin_gather_staged_kernel(const 
         mbar_init(&sm.bar[1], 1);
         fence_mbar_init();
     }
-    // thread 0: pack the next run of whole graphs (<= SG_ROWS rows) into `slot` and start its copy
+    // warp 0: pack the next run of whole graphs (<= SG_ROWS rows) into `slot`, start its copy, and -- while the copy is in
+    // flight -- check whether all in-edges of the item carry one bond code (record[3]: that code, else -1)
     auto issue = [&](int slot) {
         int nb = 0, ne = 0, staged = 0;
-        while (g_next < g_hi && ne == nb)                          // skip graphs without nodes
+        if (lane == 0)
         {
-            nb = __ldg(node_off + g_next);
-            ne = __ldg(node_off + g_next + 1);
-            g_next++;
-        }
-        if (ne > nb)
-        {
-            if (ne - nb <= SG_ROWS)
+            while (g_next < g_hi && ne == nb)                      // skip graphs without nodes
+            {
+                nb = __ldg(node_off + g_next);
+                ne = __ldg(node_off + g_next + 1);
+                g_next++;
+            }
+            if (ne > nb && ne - nb <= SG_ROWS)
             {
                 staged = 1;
                 while (g_next < g_hi)
@@ -362,31 +401,73 @@ __global__ void __launch_bounds__(SG_THREADS, 1) gin_gather_staged_kernel(const 
                 }
             }
         }
-        sm.item[slot][0] = nb; sm.item[slot][1] = ne; sm.item[slot][2] = staged;
-        if (staged && ne > nb)
+        nb = __shfl_sync(0xFFFFFFFFu, nb, 0); ne = __shfl_sync(0xFFFFFFFFu, ne, 0); staged = __shfl_sync(0xFFFFFFFFu, staged, 0);
+        int ucode = -1;
+        if (staged)
         {
-            const uint32_t bytes = (uint32_t)(ne - nb) * (D * 4);
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&sm.bar[slot], bytes);
-            tma_load_1d(sm.stage[slot], h_in + (size_t)nb * D, bytes, &sm.bar[slot]);
+            if (lane == 0)
+            {
+                const uint32_t bytes = (uint32_t)(ne - nb) * (D * 4);
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&sm.bar[slot], bytes);
+                tma_load_1d(sm.stage[slot], h_in + (size_t)nb * D, bytes, &sm.bar[slot]);
+            }
+            const int eb = __ldg(in_ptr + nb), ee = __ldg(in_ptr + ne);
+            if (ee > eb)
+            {
+                // 16 bytes per load; the bytes outside [eb, ee) of the first and last vector are masked out
+                const int c0 = (int)__ldg(code + eb);
+                const uint32_t pat = (uint32_t)c0 * 0x01010101u;
+                const long lo = (long)eb, hi = (long)ee;
+                uint32_t diff = 0;
+#pragma unroll 2
+                for (long p = (lo & ~15L) + 16 * lane; p < hi; p += 512)
+                {
+                    const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(code + p));
+                    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const long pw = p + 4 * k;
+                        const int b0 = (int)max(lo - pw, 0L), b1 = (int)min(hi - pw, 4L);      // valid bytes [b0, b1) of this word
+                        if (b1 > b0) diff |= (w[k] ^ pat) & (0xFFFFFFFFu >> (8 * (4 - b1))) & (0xFFFFFFFFu << (8 * b0));
+                    }
+                }
+                if (__all_sync(0xFFFFFFFFu, diff == 0)) ucode = c0;
+            }
         }
-        else mbar_arrive(&sm.bar[slot]);                          // keeps the phase count in step with the item count
+        else if (lane == 0) mbar_arrive(&sm.bar[slot]);            // keeps the phase count in step with the item count
+        if (lane == 0)
+        {
+            sm.item[slot][0] = nb; sm.item[slot][1] = ne; sm.item[slot][2] = staged; sm.item[slot][3] = ucode;
+            sm.next_row[slot] = 0;
+        }
     };
-    if (tid == 0) issue(0);
+    if (warp == 0) issue(0);
     for (int it = 0;; it++)
     {
         const int s = it & 1;
         __syncthreads();                                          // item it-1 is done: its slot may be refilled; item it's record is visible
-        if (tid == 0) issue(s ^ 1);
-        const int nb = sm.item[s][0], ne = sm.item[s][1], staged = sm.item[s][2];
+        const int nb = sm.item[s][0], ne = sm.item[s][1], staged = sm.item[s][2], ucode = sm.item[s][3];
         if (ne == nb) break;                                      // CTA-uniform: no graphs left
-        if (warp == 0) continue;
-        if (staged)
+        if (warp == 0) { issue(s ^ 1); continue; }
+        if (!staged) { sg_rows<false, false>(h_in, sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], lane); continue; }
+        mbar_wait(&sm.bar[s], (it >> 1) & 1);
+        if (ucode < 0) { sg_rows<true, false>(sm.stage[s], sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], lane); continue; }
+        // one code on every edge: stage <- relu(stage + EE[code]) in place, then the edges only add
+        if (lane < Q)
         {
-            mbar_wait(&sm.bar[s], (it >> 1) & 1);
-            sg_rows<true>(sm.stage[s], sm.tab, h_out, in_ptr, src, code, nb, ne, warp - 1, lane);
+            const float4 t = ld_f4(sm.tab + ucode * D + 4 * lane);
+            for (int r = warp - 1; r < ne - nb; r += SG_THREADS / 32 - 1)
+            {
+                float* x = sm.stage[s] + r * D + 4 * lane;
+                const float4 h = ld_f4(x);
+                st_f4(x, make_float4(relu_max(h.x + t.x), relu_max(h.y + t.y), relu_max(h.z + t.z), relu_max(h.w + t.w)));
+            }
         }
-        else sg_rows<false>(h_in, sm.tab, h_out, in_ptr, src, code, nb, ne, warp - 1, lane);
+        asm volatile("bar.sync 1, %0;" ::"n"(SG_THREADS - 32) : "memory");          // the 31 row warps
+        sg_rows<true, true>(sm.stage[s], sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], lane);
+        fence_proxy_async();                                      // these generic writes precede the next bulk copy into this stage
     }
 }
 
