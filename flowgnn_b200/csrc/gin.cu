@@ -237,6 +237,7 @@ struct SgSmem {
     uint64_t bar[2];
     int item[2][4];                   // first node, end node, staged flag, the one bond code of all edges (or -1)
     int next_row[2];                  // next row of the item to hand out
+    alignas(16) int scratch[SG_THREADS];   // per warp: the row offsets of 32 edge records
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
@@ -279,7 +280,7 @@ __device__ __forceinline__ void sg_edge(float4& m, const float4& t, const float4
 template <bool STAGED, bool PRE>
 __device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const float* tab, const float* __restrict__ h_glob,
                                         float* __restrict__ h_out, const int* __restrict__ in_ptr, const int* __restrict__ src,
-                                        const uint8_t* __restrict__ code, int nb, int ne, int* next_row, int lane)
+                                        const uint8_t* __restrict__ code, int nb, int ne, int* next_row, int* scratch, int lane)
 {
     // `rows` is indexed by (node - base): the stage for STAGED (base = nb), h_in otherwise (base = 0)
     const int base = STAGED ? nb : 0;
@@ -293,8 +294,8 @@ __device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const fl
     };
     auto chunk = [&](int e0, int ee, int& us, int& cs) {
         const int idx = e0 + lane;
-        us = 0; cs = -1;
-        if (idx < ee) { us = __ldg(src + idx) - base; cs = (int)__ldg(code + idx); }
+        us = base; cs = -1;                                       // raw node id: `- base` happens where the record is consumed,
+        if (idx < ee) { us = __ldg(src + idx); cs = (int)__ldg(code + idx); }      // not here, where it would wait for the load
     };
     // The edge-embedding row of the current bond code stays in registers: kNN graphs carry ONE code on every edge
     // (hep10k: edge_attr == 0), which halves the shared-memory reads per edge.  Chunks with mixed codes look every edge up.
@@ -318,16 +319,27 @@ __device__ __forceinline__ void sg_rows(const float* __restrict__ rows, const fl
         {
             if (e0 != eb) chunk(e0, ee, us, cs);
             const int cnt = min(32, ee - e0);
+            us -= base;
             if (PRE)
             {
-                us *= D;
-#pragma unroll 8
-                for (int k = 0; k < cnt; k++)
+                // the 32 row offsets go through a per-warp scratch line: one 16-byte broadcast read hands four of them to
+                // every lane (a shuffle per edge would cost the shared-memory pipe four times as many wavefronts)
+                scratch[lane] = us * D;
+                __syncwarp();
+                for (int k = 0; k < cnt; k += 4)
                 {
-                    const float4 r = ld_f4(rows + __shfl_sync(0xFFFFFFFFu, us, k));
-                    add2(m.x, m.y, m.x, m.y, r.x, r.y);
-                    add2(m.z, m.w, m.z, m.w, r.z, r.w);
+                    const int4 o = *reinterpret_cast<const int4*>(scratch + k);
+                    const float4 r0 = ld_f4(rows + o.x);
+                    const float4 r1 = ld_f4(rows + (k + 1 < cnt ? o.y : o.x));
+                    const float4 r2 = ld_f4(rows + (k + 2 < cnt ? o.z : o.x));
+                    const float4 r3 = ld_f4(rows + (k + 3 < cnt ? o.w : o.x));
+                    add2(m.x, m.y, m.x, m.y, r0.x, r0.y);
+                    add2(m.z, m.w, m.z, m.w, r0.z, r0.w);
+                    if (k + 1 < cnt) { add2(m.x, m.y, m.x, m.y, r1.x, r1.y); add2(m.z, m.w, m.z, m.w, r1.z, r1.w); }
+                    if (k + 2 < cnt) { add2(m.x, m.y, m.x, m.y, r2.x, r2.y); add2(m.z, m.w, m.z, m.w, r2.z, r2.w); }
+                    if (k + 3 < cnt) { add2(m.x, m.y, m.x, m.y, r3.x, r3.y); add2(m.z, m.w, m.z, m.w, r3.z, r3.w); }
                 }
+                __syncwarp();
                 continue;
             }
             const int c0 = __shfl_sync(0xFFFFFFFFu, cs, 0);
@@ -451,9 +463,9 @@ __global__ void __launch_bounds__(SG_THREADS, 1) gin_gather_staged_kernel(const 
         const int nb = sm.item[s][0], ne = sm.item[s][1], staged = sm.item[s][2], ucode = sm.item[s][3];
         if (ne == nb) break;                                      // CTA-uniform: no graphs left
         if (warp == 0) { issue(s ^ 1); continue; }
-        if (!staged) { sg_rows<false, false>(h_in, sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], lane); continue; }
+        if (!staged) { sg_rows<false, false>(h_in, sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], sm.scratch + 32 * warp, lane); continue; }
         mbar_wait(&sm.bar[s], (it >> 1) & 1);
-        if (ucode < 0) { sg_rows<true, false>(sm.stage[s], sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], lane); continue; }
+        if (ucode < 0) { sg_rows<true, false>(sm.stage[s], sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], sm.scratch + 32 * warp, lane); continue; }
         // one code on every edge: stage <- relu(stage + EE[code]) in place, then the edges only add
         if (lane < Q)
         {
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) gin_gather_staged_kernel(const 
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(SG_THREADS - 32) : "memory");          // the 31 row warps
-        sg_rows<true, true>(sm.stage[s], sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], lane);
+        sg_rows<true, true>(sm.stage[s], sm.tab, h_in, h_out, in_ptr, src, code, nb, ne, &sm.next_row[s], sm.scratch + 32 * warp, lane);
         fence_proxy_async();                                      // these generic writes precede the next bulk copy into this stage
     }
 }
