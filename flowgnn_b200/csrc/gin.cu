@@ -143,15 +143,19 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_kernel(GinLayerParams p)
 #pragma unroll
                     for (int n = 0; n < 8; n++) acc[i][n] = 0.f;
                 Gemm1::run(As, D, p.w1t, wbuf, acc);
-                if (ty < Gemm1::RT && tx * 8 < H)
+                if (ty < Gemm1::RT)
                 {
-                    const float4 ba = ldg_f4(p.b1 + tx * 8), bb = ldg_f4(p.b1 + tx * 8 + 4);
+                    // two groups of four hidden columns per thread (layers.cuh); the second group of the last two column
+                    // threads is padding (columns 200..207)
+                    const int c0 = Gemm1::col(tx, 0), c1 = Gemm1::col(tx, 1);
+                    const float4 ba = ldg_f4(p.b1 + c0), bb = ldg_f4(p.b1 + c1);
 #pragma unroll
                     for (int i = 0; i < 8; i++)
                     {
-                        float* z = Zs + (ty + Gemm1::RT * i) * LDZ + tx * 8;
-                        st_f4(z, make_float4(relu_f(acc[i][0] + ba.x), relu_f(acc[i][1] + ba.y), relu_f(acc[i][2] + ba.z), relu_f(acc[i][3] + ba.w)));
-                        st_f4(z + 4, make_float4(relu_f(acc[i][4] + bb.x), relu_f(acc[i][5] + bb.y), relu_f(acc[i][6] + bb.z), relu_f(acc[i][7] + bb.w)));
+                        float* z = Zs + (ty + Gemm1::RT * i) * LDZ;
+                        st_f4(z + c0, make_float4(relu_f(acc[i][0] + ba.x), relu_f(acc[i][1] + ba.y), relu_f(acc[i][2] + ba.z), relu_f(acc[i][3] + ba.w)));
+                        if (c1 < H)
+                            st_f4(z + c1, make_float4(relu_f(acc[i][4] + bb.x), relu_f(acc[i][5] + bb.y), relu_f(acc[i][6] + bb.z), relu_f(acc[i][7] + bb.w)));
                     }
                 }
             }

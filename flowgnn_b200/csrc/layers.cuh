@@ -57,7 +57,10 @@ __device__ __forceinline__ void stage_tile_csr(TileCsr& t, const int* __restrict
 // Wt: global (L2-resident), k-major, row length NP (zero-padded N), streamed in chunks of GEMM_KC rows
 //     through wbuf[2][GEMM_KC * NP] (GEMM_KC = k-rows per cp.async stage).
 // Thread (tx, ty) = (tid % CT, tid / CT) with CT = NP / TN owns rows ty + RT*i (i < 8, RT = TILE_M/8)
-// and columns tx*TN .. tx*TN+TN-1; threads with ty >= RT only help with the copies.
+// and TN/4 groups of four columns, group g at col(tx, g) = g * (NP / (TN/4)) + tx*4 (acc[i][4g .. 4g+3]): every weight
+// read is then 16 contiguous bytes per lane.  (TN contiguous columns per thread made each 16-byte read of an 8-wide
+// tile a 2-way bank conflict, and the PNA GEMM LSU-bound: 80 shared-memory wavefronts per 256 FFMA and warp.)
+// Threads with ty >= RT only help with the copies.
 template <int K, int NP, int TN, int NT, int GEMM_KC = 20>
 struct TileGemm {
     static constexpr int CT = NP / TN;
@@ -67,6 +70,9 @@ struct TileGemm {
     static_assert(K % GEMM_KC == 0 && GEMM_KC % 4 == 0, "k tiling");
     static_assert(CT * RT <= NT, "not enough threads for the output tile");
     static constexpr int WBUF_FLOATS = 2 * GEMM_KC * NP;
+    static constexpr int GROUPS = TN / 4;
+    static constexpr int GROUP_STRIDE = NP / GROUPS;              // = 4 * CT
+    __host__ __device__ static constexpr int col(int tx, int g) { return g * GROUP_STRIDE + tx * 4; }
 
     __device__ static __forceinline__ void load_chunk(float* dst, const float* __restrict__ wt, int chunk)
     {
@@ -100,7 +106,7 @@ struct TileGemm {
             __syncthreads();
             if (active)
             {
-                const float* wb = wbuf + (c & 1) * GEMM_KC * NP + tx * TN;
+                const float* wb = wbuf + (c & 1) * GEMM_KC * NP + tx * 4;
                 const float* ab = As + ty * lda + c * GEMM_KC;
 #pragma unroll
                 for (int kk = 0; kk < GEMM_KC; kk += 4)
@@ -115,7 +121,7 @@ struct TileGemm {
 #pragma unroll
                         for (int n = 0; n < TN; n += 4)
                         {
-                            const float4 w4 = ld_f4(wb + (kk + j) * NP + n);
+                            const float4 w4 = ld_f4(wb + (kk + j) * NP + (n / 4) * GROUP_STRIDE);
                             w[n] = w4.x; w[n + 1] = w4.y; w[n + 2] = w4.z; w[n + 3] = w4.w;
                         }
 #pragma unroll

@@ -184,9 +184,9 @@ __global__ void __launch_bounds__(NT, 1) pna_layer_kernel(PnaLayerParams p)
 #pragma unroll
             for (int i = 0; i < 8; i++)
             {
-                float* z = Zs + (ty + Gemm::RT * i) * NC + tx * 8;
-                st_f4(z, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-                st_f4(z + 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+                float* z = Zs + (ty + Gemm::RT * i) * NC;
+                st_f4(z + Gemm::col(tx, 0), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+                st_f4(z + Gemm::col(tx, 1), make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
             }
         }
         __syncthreads();
