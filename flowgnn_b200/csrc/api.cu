@@ -37,7 +37,7 @@ void DevBuf::release()
 void DeviceBatch::release()
 {
     DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
-                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &status, &node_dot,
+                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &status, &node_dot, &apack, &nonfinite,
                      &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
     for (DevBuf* b : all) b->release();
 }
@@ -331,6 +331,13 @@ int load_pna(flowgnn_ctx* c, const float* const* w)
                     for (int i = 0; i < 80; i++)
                         wcat[((size_t)l * 320 + a * 80 + i) * 240 + sc * 80 + o] = w[1][((((size_t)l * 80 + o) * 3 + sc) * 4 + a) * 80 + i];
     FG_TRY(upload(g.wcat, wcat, s));
+    {
+        std::vector<unsigned char> pack(4 * pna_tc_pack_bytes());
+        for (int l = 0; l < 4; l++) pna_tc_pack_layer(wcat.data() + (size_t)l * 320 * 240, pack.data() + (size_t)l * pna_tc_pack_bytes(), bf16_rn, bf16_to_float);
+        FG_TRY(g.wpack_tc.reserve(pack.size()));
+        FG_CUDA(cudaMemcpyAsync(g.wpack_tc.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
+        FG_CUDA(cudaStreamSynchronize(s));
+    }
     FG_TRY(upload(g.w_ref, w[1], (size_t)4 * 80 * 12 * 80, s));
     FG_TRY(upload(g.b, w[2], 320, s));
     FG_TRY(upload(g.m1w, w[3], 40 * 80, s));
@@ -453,7 +460,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.wpack3, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
-                   &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
+                   &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.wpack_tc, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
                    &ctx->pna.m3w, &ctx->pna.m3b,
                    &ctx->dgn.emb, &ctx->dgn.wt, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
                    &ctx->dgn.m2w, &ctx->dgn.m2b,
@@ -476,6 +483,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "gin_tc1")) ctx->opt.gin_tc1 = value;
     else if (!std::strcmp(name, "gin_tc3")) ctx->opt.gin_tc3 = value;
     else if (!std::strcmp(name, "gin_staged")) ctx->opt.gin_staged = value;
+    else if (!std::strcmp(name, "pna_tc")) ctx->opt.pna_tc = value;
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;

@@ -53,6 +53,8 @@ struct DeviceBatch {
     DevBuf act[4];                         // float [N][<=100] ping/pong (+2 extra for GAT)
     DevBuf score[4];                       // float [N][4] GAT source/target scores ping/pong
     DevBuf node_dot;                       // float [N]  GIN: <h'_v, w_pred> of the last layer (gin_tc2.cu)
+    DevBuf apack;                          // PNA tensor-core path: bf16 hi/lo aggregate blocks [tiles][5][32768] (pna_tc.cu)
+    DevBuf nonfinite;                      // uint8 [N]  PNA tensor-core path: rows whose aggregates are not finite
     DevBuf out;                            // float [G]
 
     void release();
@@ -92,6 +94,7 @@ struct PnaWeights {
     DevBuf ne_table4;           // [431][80] combined tables of embed4_kernel (layers.cuh)
     DevBuf wcat;                // [4][320][240]  k = aggr*80+in, n = scaler*80+out
     DevBuf w_ref;               // [4][80][3][4][80] reference layout (exact path for out-degree-0 nodes)
+    DevBuf wpack_tc;            // [4][5][61440] bytes: wcat as bf16 hi | lo K-chunks for pna_gemm_kernel (pna_tc.cu)
     DevBuf b;                   // [4][80]
     DevBuf m1w, m1b, m2w, m2b, m3w, m3b;
     float avg_deg = 0.f;
@@ -127,6 +130,7 @@ struct RunOptions {
     int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
     int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
+    int pna_tc = 0;                  // PNA: node transform on tcgen05 (pna_tc.cu: aggregate -> bf16x3 GEMM -> exact rows) instead of FFMA
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
     int timer_group = 0;             // time_layers == 2: one interval around ALL layer launches (events between the launches
@@ -145,6 +149,9 @@ void gin_tc3_pack_layer(const float* w1, const float* b1, const float* w2, const
 size_t gin_tc2_pack_bytes();
 void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
                         float (*bf16_to_float)(uint16_t));
+int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+size_t pna_tc_pack_bytes();
+void pna_tc_pack_layer(const float* wcat, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
 int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);

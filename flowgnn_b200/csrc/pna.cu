@@ -243,6 +243,12 @@ int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int 
     for (int l = 0; l < 4; l++)
     {
         if (opt.timer) FG_TRY(opt.timer->mark(s));
+        if (opt.pna_tc)
+        {
+            FG_TRY(pna_layer_tc_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
+            nl += 3;
+            continue;
+        }
         PnaLayerParams p{};
         p.h_in = h[l & 1]; p.h_out = h[(l + 1) & 1];
         p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.out_deg = b.out_deg.as<int>();
