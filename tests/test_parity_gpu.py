@@ -121,25 +121,26 @@ def test_gin_ffma_reference_path_agrees_with_tensor_core_path(ds, ctx, weights, 
     assert_parity(tc, ffma, tol=5e-5, what=f"gin tcgen05 vs ffma/{ds}")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("FLOWGNN_B200_TEST_PNA_TC") != "1", reason="pna_tc is not verified on hardware yet")
 @pytest.mark.parametrize("ds", ["molhiv", "molpcba", "hep10k"])
 def test_pna_tensor_core_path_matches_reference(ds, ctx, weights, datasets, golden):
-    """Option pna_tc (pna_tc.cu): message passing -> bf16 hi/lo aggregate blocks, [128 x 320] x [320 x 240] on tcgen05
+    """Default PNA path (pna_tc.cu; option pna_tc = 0 selects the FFMA kernel pna.cu, kept as the on-device fp32
+    reference): message passing -> bf16 hi/lo aggregate blocks, [128 x 320] x [320 x 240] on tcgen05
     (3 products), fused combine/relu/residual epilogue; out-degree-0 rows and rows with non-finite aggregates in fp32.
     Must sit inside the 1e-4 contract (non-finite values positionally) and agree with the FFMA kernel, also on batches
     that end inside a 128-row tile."""
-    ffma = ctx.run("pna", datasets[ds], weights["pna"])
-    ctx.set_option("pna_tc", 1)
+    ctx.set_option("pna_tc", 0)
     try:
-        tc = ctx.run("pna", datasets[ds])
-        few = ctx.run("pna", datasets[ds].slice(0, 3))
-        some = ctx.run("pna", datasets[ds].slice(0, 47))
+        ffma = ctx.run("pna", datasets[ds], weights["pna"])
     finally:
-        ctx.set_option("pna_tc", 0)
+        ctx.set_option("pna_tc", 1)
+    tc = ctx.run("pna", datasets[ds])
+    few = ctx.run("pna", datasets[ds].slice(0, 3))
+    some = ctx.run("pna", datasets[ds].slice(0, 47))
+    assert_parity(ffma, golden[ds]["pna"], what=f"pna ffma/{ds}")
     assert_parity(tc, golden[ds]["pna"], what=f"pna tcgen05/{ds}")
     assert_parity(few, golden[ds]["pna"][:3], what=f"pna tcgen05/{ds} first 3 graphs")
     assert_parity(some, golden[ds]["pna"][:47], what=f"pna tcgen05/{ds} first 47 graphs")
-    assert_parity(tc, ffma, tol=5e-5, what=f"pna tcgen05 vs ffma/{ds}")
+    assert_parity(tc, ffma, tol=1e-4, what=f"pna tcgen05 vs ffma/{ds}")
 
 
 def test_gat_hep10k_is_the_prediction_bias(ctx, weights, datasets, golden):
