@@ -5,7 +5,7 @@
 //   acc = b + sum_in [T0 + T1 t + T2 s]  ==  b + G0 + t G1 + s G2  with  G = A [320] x Wcat [320 x 240];  h <- h + relu(acc)
 // The FFMA kernel (pna.cu) spends 154 kFLOP per node on the FP32 pipe (56 ms per layer on molpcba, 42 % of the FFMA peak).
 // Here a layer is three launches:
-//   1. pna_aggregate_kernel   message passing on the CUDA cores; every A value is split into bf16 hi + bf16 lo
+//   1. pna_aggregate_kernel   message passing on the CUDA cores (lane = row, eight columns per thread); every A value is split into bf16 hi + bf16 lo
 //                             (x = hi + lo + O(2^-17 |x|)) and written to HBM in the tcgen05 no-swizzle K-major canonical
 //                             layout, blocked per tile of 128 nodes and K chunk of 64:
 //                                 block(t, c) = [hi 16 KB | lo 16 KB],  byte(r, k) = (k / 8) * 2048 + r * 16 + (k % 8) * 2
@@ -137,29 +137,70 @@ __device__ __forceinline__ bool finite4(const float (&x)[4])
 }
 
 // ---- 1. message passing -> bf16 hi/lo A blocks ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pna_aggregate_kernel(const float* __restrict__ h_in, const int* __restrict__ in_ptr,
-                                                            const int* __restrict__ src, unsigned char* __restrict__ apack,
-                                                            unsigned char* __restrict__ nonfinite, long num_nodes)
+// A warp owns 32 consecutive rows (lane = row, the blocks are 128 rows tall) and eight columns: every gathered piece of a
+// source row is one full 32-byte sector, and every store instruction writes 32 x 16 bytes = 512 contiguous bytes of a
+// block (eight consecutive k of one row are 16 contiguous bytes in the canonical layout).  The first version mapped
+// threads to (row, four columns) like pna.cu: its 8-byte stores scattered over eleven sectors per instruction.
+constexpr int AG_WARPS = 8;
+constexpr int Q2 = D / 8;                    // column groups of eight
+__global__ void __launch_bounds__(AG_WARPS * 32) pna_aggregate_kernel(const float* __restrict__ h_in, const int* __restrict__ in_ptr,
+                                                                      const int* __restrict__ src, unsigned char* __restrict__ apack,
+                                                                      unsigned char* __restrict__ nonfinite, long num_nodes)
 {
-    const long total = num_nodes * Q;
-    for (long item = blockIdx.x * (long)blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x)
+    const int lane = threadIdx.x & 31;
+    const long warp = blockIdx.x * (long)AG_WARPS + (threadIdx.x >> 5), nwarps = (long)gridDim.x * AG_WARPS;
+    const long items = ((num_nodes + 31) / 32) * Q2;
+    for (long item = warp; item < items; item += nwarps)
     {
-        const int v = (int)(item / Q), q = (int)(item - (long)v * Q);
-        float a[4][4];                                            // [mean | min | max | std] (aggregator_t order, PNA/src/dcl.h:29-35)
-        aggregate4(h_in, in_ptr, src, v, q, a[0], a[1], a[2], a[3]);
-        if (!(finite4(a[0]) && finite4(a[1]) && finite4(a[2]) && finite4(a[3]))) nonfinite[v] = 1;
-        const int t = v / TM, r = v % TM;
+        const long rb = item / Q2;
+        const int q2 = (int)(item - rb * Q2);
+        const long v = rb * 32 + lane;
+        if (v >= num_nodes) continue;
+        const int eb = __ldg(in_ptr + v), ee = __ldg(in_ptr + v + 1);
+        float s[8], sq[8], mn[8], mx[8];
 #pragma unroll
-        for (int g = 0; g < 4; g++)
+        for (int j = 0; j < 8; j++) { s[j] = 0.f; sq[j] = 0.f; mn[j] = FM_MAX; mx[j] = FM_MIN; }
+        for (int e = eb; e < ee; e++)
         {
-            const int k = g * D + 4 * q, c = k / KC, kk = k % KC;
-            unsigned char* blk = apack + ((size_t)t * NCHUNK + c) * A_BLOCK + (kk / 8) * LBO_A + r * 16 + (kk % 8) * 2;
-            uint32_t h0, l0, h1, l1;
-            split2(a[g][0], a[g][1], h0, l0);
-            split2(a[g][2], a[g][3], h1, l1);
-            *reinterpret_cast<uint2*>(blk) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(blk + A_HALF) = make_uint2(l0, l1);
+            const float* hu = h_in + (size_t)__ldg(src + e) * D + 8 * q2;
+            const float4 x0 = ldg_f4(hu), x1 = ldg_f4(hu + 4);
+            const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+            {
+                s[j] += x[j];
+                sq[j] += x[j] * x[j];
+                if (x[j] < mn[j]) mn[j] = x[j];
+                if (x[j] > mx[j]) mx[j] = x[j];
+            }
         }
+        int in_deg = ee - eb;
+        if (in_deg == 0) in_deg = 1;
+        const float fn = (float)in_deg;
+        float mean[8], sd[8];
+        bool fin = true;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            mean[j] = s[j] / fn;
+            sd[j] = sqrtf(relu_f(sq[j] / fn - mean[j] * mean[j]));
+            fin = fin && isfinite(mean[j]) && isfinite(mn[j]) && isfinite(mx[j]) && isfinite(sd[j]);
+        }
+        if (!fin) nonfinite[v] = 1;
+        const long t = v / TM;
+        const int r = (int)(v - t * TM);
+        auto put = [&](int g, const float (&x)[8]) {              // aggregator_t order (PNA/src/dcl.h:29-35): mean, min, max, std
+            const int k = g * D + 8 * q2, c = k / KC, kk = k % KC;
+            unsigned char* blk = apack + ((size_t)t * NCHUNK + c) * A_BLOCK + (kk / 8) * LBO_A + r * 16;
+            uint4 hi, lo;
+            split2(x[0], x[1], hi.x, lo.x);
+            split2(x[2], x[3], hi.y, lo.y);
+            split2(x[4], x[5], hi.z, lo.z);
+            split2(x[6], x[7], hi.w, lo.w);
+            *reinterpret_cast<uint4*>(blk) = hi;
+            *reinterpret_cast<uint4*>(blk + A_HALF) = lo;
+        };
+        put(0, mean); put(1, mn); put(2, mx); put(3, sd);
     }
 }
 
@@ -435,8 +476,8 @@ int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const fl
     FG_TRY(b.nonfinite.reserve((size_t)N + 16));
     FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
     {
-        const int blocks = (int)std::min<long>(ceil_div<long>(N * Q, 256), (long)sm_count * 16);
-        pna_aggregate_kernel<<<blocks, 256, 0, s>>>(h_in, b.in_ptr.as<int>(), b.src.as<int>(), b.apack.as<unsigned char>(),
+        const int blocks = (int)std::min<long>(ceil_div<long>(ceil_div<long>(N, 32) * Q2, AG_WARPS), (long)sm_count * 8);
+        pna_aggregate_kernel<<<blocks, AG_WARPS * 32, 0, s>>>(h_in, b.in_ptr.as<int>(), b.src.as<int>(), b.apack.as<unsigned char>(),
                                                     b.nonfinite.as<unsigned char>(), N);
         FG_CUDA(cudaGetLastError());
     }
