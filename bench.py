@@ -50,7 +50,7 @@ WORKLOADS = {
 ALGO = {"gin": (100, 5, 3, 0), "ginvn": (100, 5, 3, 0), "gcn": (100, 5, 3, 0), "gat": (64, 5, 0, 64), "pna": (80, 4, 0, 0),
         "dgn": (100, 4, 0, 0)}
 LAYER_KERNEL = {"gin": "gin_layer_tc2_kernel", "ginvn": "gin_layer_tc2_kernel", "gcn": "gcn_layer_kernel", "gat": "gat_layer_kernel",
-                "pna": "pna_layer_kernel", "dgn": "dgn_layer_kernel"}
+                "pna": "pna_aggregate_kernel + pna_gemm_kernel + pna_exact_rows_kernel (three launches per layer)", "dgn": "dgn_layer_kernel"}
 
 
 def layer_bytes(model: str, total_nodes: int, total_edges: int) -> int:
