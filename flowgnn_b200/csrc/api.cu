@@ -265,6 +265,13 @@ int load_gcn(flowgnn_ctx* c, const float* const* w)
     FG_TRY(upload(g.ee_comb, combine_edge_embedding(w[1], 5, 100), s));
     FG_TRY(upload(g.wt, transpose_pad(w[2], 5, 100, 100, 104), s));
     FG_TRY(upload(g.b, pad_rows(w[3], 5, 100, 104), s));
+    {
+        std::vector<unsigned char> pack(5 * gcn_tc_pack_bytes());
+        for (int l = 0; l < 5; l++) gcn_tc_pack_layer(w[2] + (size_t)l * 100 * 100, pack.data() + (size_t)l * gcn_tc_pack_bytes(), bf16_rn, bf16_to_float);
+        FG_TRY(g.wpack_tc.reserve(pack.size()));
+        FG_CUDA(cudaMemcpyAsync(g.wpack_tc.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
+        FG_CUDA(cudaStreamSynchronize(s));
+    }
     FG_TRY(upload(g.root, w[4], 500, s));
     FG_TRY(upload(g.bn_weight, w[5], 500, s));
     FG_TRY(upload(g.bn_bias, w[6], 500, s));
@@ -357,6 +364,13 @@ int load_dgn(flowgnn_ctx* c, const float* const* w)
     FG_TRY(upload(g.emb, w[0], (size_t)9 * 119 * 100, s));
     FG_TRY(upload(g.wt, transpose_pad(w[1], 4, 100, 200, 104), s));
     FG_TRY(upload(g.w_ref, w[1], (size_t)4 * 100 * 200, s));
+    {
+        std::vector<unsigned char> pack(4 * dgn_tc_pack_bytes());
+        for (int l = 0; l < 4; l++) dgn_tc_pack_layer(w[1] + (size_t)l * 100 * 200, pack.data() + (size_t)l * dgn_tc_pack_bytes(), bf16_rn, bf16_to_float);
+        FG_TRY(g.wpack_tc.reserve(pack.size()));
+        FG_CUDA(cudaMemcpyAsync(g.wpack_tc.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
+        FG_CUDA(cudaStreamSynchronize(s));
+    }
     FG_TRY(upload(g.b, pad_rows(w[2], 4, 100, 104), s));
     FG_TRY(upload(g.m0w, w[3], 50 * 100, s));
     FG_TRY(upload(g.m0b, w[4], 50, s));
@@ -427,6 +441,8 @@ int flowgnn_b200_create(flowgnn_ctx** out, int device)
     std::unique_ptr<flowgnn_ctx> c(new flowgnn_ctx);
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    // FLOWGNN_B200_TC_ALL=0/1 overrides the default of the "gcn_tc" / "dgn_tc" options (used to run the whole GPU suite on either path)
+    if (const char* e = std::getenv("FLOWGNN_B200_TC_ALL")) c->opt.gcn_tc = c->opt.dgn_tc = std::atoi(e) != 0;
     FG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < flowgnn_ctx::PIPE; i++)
@@ -458,11 +474,11 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaStreamDestroy(ctx->copy_stream);
     DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.wpack3, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
-                   &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
+                   &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wpack_tc, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
                    &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.wpack_tc, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
                    &ctx->pna.m3w, &ctx->pna.m3b,
-                   &ctx->dgn.emb, &ctx->dgn.wt, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
+                   &ctx->dgn.emb, &ctx->dgn.wt, &ctx->dgn.wpack_tc, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
                    &ctx->dgn.m2w, &ctx->dgn.m2b,
                    &ctx->gat.proj0, &ctx->gat.projt, &ctx->gat.skipt, &ctx->gat.a_src, &ctx->gat.a_tgt, &ctx->gat.pred_w, &ctx->gat.pred_b};
     for (DevBuf* b : w) b->release();
@@ -484,6 +500,8 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "gin_tc3")) ctx->opt.gin_tc3 = value;
     else if (!std::strcmp(name, "gin_staged")) ctx->opt.gin_staged = value;
     else if (!std::strcmp(name, "pna_tc")) ctx->opt.pna_tc = value;
+    else if (!std::strcmp(name, "gcn_tc")) ctx->opt.gcn_tc = value;
+    else if (!std::strcmp(name, "dgn_tc")) ctx->opt.dgn_tc = value;
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;

@@ -177,6 +177,12 @@ int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int 
     for (int l = 0; l < 4; l++)
     {
         if (opt.timer) FG_TRY(opt.timer->mark(s));
+        if (opt.dgn_tc)
+        {
+            FG_TRY(dgn_layer_tc_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
+            nl += 3;
+            continue;
+        }
         DgnLayerParams p{};
         p.h_in = h[l & 1]; p.h_out = h[(l + 1) & 1];
         p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.eig_w = b.edge_w.as<float>(); p.out_deg = b.out_deg.as<int>();

@@ -1,0 +1,169 @@
+// GCN forward with the Linear_l node transform on the B200 tensor cores (option "gcn_tc"; gcn.cu is the FFMA version and
+// documents the reference pipeline, GCN/src/GCN_compute.cc:50-102, node_embedding.cc:98-146, message_passing.cc).
+//
+// Per step l = 0..4 two launches (tcgemm.cuh):
+//   gcn_aggregate_kernel<FIRST>    a = x0 (input embedding)                                            } bf16 hi/lo A blocks,
+//   gcn_aggregate_kernel<MIDDLE>   message passing over p_{l-1}, self term, BatchNorm_{l-1}, relu -> a } K = 100 padded to 128
+//   tcg::gemm_kernel<2, 112>       p_l = W_l a + b_l   (hi*hi + lo*hi + hi*lo on tcgen05, epilogue adds the bias)
+// and the last step (message passing over p_4, BatchNorm_4, no relu, no Linear) stays gcn_layer_kernel<FINAL> (gcn.cu).
+// The expressions of the aggregate kernel are those of gcn.cu, in the same order.
+#include "internal.cuh"
+#include "layers.cuh"
+#include "tcgemm.cuh"
+
+#include <algorithm>
+
+namespace fg {
+
+namespace {
+
+constexpr int D = 100;
+constexpr int NCHUNK = 2;                    // K = 128
+constexpr int NPAD = 112;
+constexpr int G8 = 13;                       // column groups of eight that hold real columns (the last one: 96..99)
+constexpr int AG_WARPS = 8;
+
+struct GcnAggParams {
+    const float* p_in;
+    const int* feat; const float* ne_table;                       // FIRST
+    const int* in_ptr; const int* src; const uint8_t* code; const float* norm; const int* out_deg;
+    const float* ee_comb;                                         // [60][100] of the layer being finished
+    const float* root; const float* bn_mean; const float* bn_sqrt_var; const float* bn_weight; const float* bn_bias;
+    unsigned char* apack;
+    long num_nodes;
+};
+
+template <bool FIRST>
+__global__ void __launch_bounds__(AG_WARPS * 32) gcn_aggregate_kernel(GcnAggParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const long warp = blockIdx.x * (long)AG_WARPS + (threadIdx.x >> 5), nwarps = (long)gridDim.x * AG_WARPS;
+    const long items = ((p.num_nodes + 31) / 32) * G8;
+    const EmbedOffsets eo = concat_table_offsets();
+    for (long item = warp; item < items; item += nwarps)
+    {
+        const long rb = item / G8;
+        const int g8 = (int)(item - rb * G8);
+        const long v = rb * 32 + lane;
+        if (v >= p.num_nodes) continue;
+        const int c0 = 8 * g8;
+        const bool two = c0 + 4 < D;                              // the last group holds columns 96..99 only
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (FIRST)
+        {
+            // layer 0 consumes the input embedding directly (GCN/src/node_embedding.cc:124-127)
+            const float4 x0 = embed_chunk<D>(p.feat + (size_t)v * ND_FEATURE, p.ne_table, eo, 2 * g8);
+            a[0] = x0.x; a[1] = x0.y; a[2] = x0.z; a[3] = x0.w;
+            if (two)
+            {
+                const float4 x1 = embed_chunk<D>(p.feat + (size_t)v * ND_FEATURE, p.ne_table, eo, 2 * g8 + 1);
+                a[4] = x1.x; a[5] = x1.y; a[6] = x1.z; a[7] = x1.w;
+            }
+        }
+        else
+        {
+            const int eb = __ldg(p.in_ptr + v), ee = __ldg(p.in_ptr + v + 1);
+            const float degp1 = (float)(__ldg(p.out_deg + v) + 1);
+#pragma unroll
+            for (int half = 0; half < 2; half++)
+            {
+                if (half == 1 && !two) break;
+                const int c = c0 + 4 * half;
+                float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int e = eb; e < ee; e++)
+                {
+                    const int u = __ldg(p.src + e), cd = __ldg(p.code + e);
+                    const float nrm = __ldg(p.norm + e);
+                    const float4 pu = ldg_f4(p.p_in + (size_t)u * D + c);
+                    const float4 t = ldg_f4(p.ee_comb + cd * D + c);
+                    m.x += nrm * relu_f(t.x + pu.x); m.y += nrm * relu_f(t.y + pu.y);
+                    m.z += nrm * relu_f(t.z + pu.z); m.w += nrm * relu_f(t.w + pu.w);
+                }
+                // finish the layer: self term, BatchNorm (inference), relu
+                const float4 pv = ldg_f4(p.p_in + (size_t)v * D + c);
+                const float4 rt = ldg_f4(p.root + c), mu = ldg_f4(p.bn_mean + c), sv = ldg_f4(p.bn_sqrt_var + c);
+                const float4 ga = ldg_f4(p.bn_weight + c), be = ldg_f4(p.bn_bias + c);
+                float4 r;
+                r.x = (m.x + relu_f(pv.x + rt.x) / degp1 - mu.x) / sv.x * ga.x + be.x;
+                r.y = (m.y + relu_f(pv.y + rt.y) / degp1 - mu.y) / sv.y * ga.y + be.y;
+                r.z = (m.z + relu_f(pv.z + rt.z) / degp1 - mu.z) / sv.z * ga.z + be.z;
+                r.w = (m.w + relu_f(pv.w + rt.w) / degp1 - mu.w) / sv.w * ga.w + be.w;
+                a[4 * half] = relu_f(r.x); a[4 * half + 1] = relu_f(r.y); a[4 * half + 2] = relu_f(r.z); a[4 * half + 3] = relu_f(r.w);
+            }
+        }
+        tcg::put8<NCHUNK>(p.apack, v, c0, a);
+        if (g8 == G8 - 1)
+            for (int k0 = 8 * G8; k0 < NCHUNK * tcg::KC; k0 += 8) tcg::put8_zero<NCHUNK>(p.apack, v, k0);      // K padding
+    }
+}
+
+// p_l[v][d] = acc[d] + b_l[d]
+struct GcnEpi {
+    const float* b; float* p_out;
+    struct State {};
+    __device__ State begin(int, bool) const { return State{}; }
+    __device__ void store(const State&, int v, int d0, const uint32_t (&acc)[16]) const
+    {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            if (d0 + j < D)
+            {
+                const float4 bb = ldg_f4(b + d0 + j);
+                stg_f4_stream(p_out + (size_t)v * D + d0 + j, make_float4(__uint_as_float(acc[j]) + bb.x, __uint_as_float(acc[j + 1]) + bb.y,
+                                                                         __uint_as_float(acc[j + 2]) + bb.z, __uint_as_float(acc[j + 3]) + bb.w));
+            }
+    }
+};
+
+}  // namespace
+
+size_t gcn_tc_pack_bytes() { return (size_t)NCHUNK * tcg::Cfg<NPAD>::B_BLOCK; }
+
+// W_l [100][100] ("[out][in]") -> two [112 x 64] hi | lo chunks
+void gcn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t))
+{
+    tcg::pack_weights<NPAD>(w, D, D, NCHUNK, [](int k) { return k < D ? k : -1; }, dst, bf16_rn, bf16_to_float);
+}
+
+int gcn_step_tc_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s)
+{
+    using C = tcg::Cfg<NPAD>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        FG_CUDA(cudaFuncSetAttribute(tcg::gemm_kernel<NCHUNK, NPAD, GcnEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES));
+        attr_set = true;
+    }
+    const long N = b.total_nodes;
+    const int num_tiles = (int)ceil_div<long>(N, tcg::TM);
+    FG_TRY(b.apack.reserve((size_t)num_tiles * NCHUNK * tcg::A_BLOCK));
+    GcnAggParams p{};
+    p.p_in = p_in;
+    p.feat = b.node_feature.as<int>(); p.ne_table = w.ne_table.as<float>();
+    p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>(); p.norm = b.edge_w.as<float>();
+    p.out_deg = b.out_deg.as<int>();
+    if (l > 0)
+    {
+        const size_t k = (size_t)(l - 1);
+        p.ee_comb = w.ee_comb.as<float>() + k * ED_COMBOS * D;
+        p.root = w.root.as<float>() + k * D; p.bn_mean = w.bn_mean.as<float>() + k * D; p.bn_sqrt_var = w.bn_sqrt_var.as<float>() + k * D;
+        p.bn_weight = w.bn_weight.as<float>() + k * D; p.bn_bias = w.bn_bias.as<float>() + k * D;
+    }
+    p.apack = b.apack.as<unsigned char>();
+    p.num_nodes = N;
+    const int blocks = (int)std::min<long>(ceil_div<long>(ceil_div<long>(N, 32) * G8, AG_WARPS), (long)sm_count * 8);
+    if (l == 0) gcn_aggregate_kernel<true><<<blocks, AG_WARPS * 32, 0, s>>>(p);
+    else gcn_aggregate_kernel<false><<<blocks, AG_WARPS * 32, 0, s>>>(p);
+    FG_CUDA(cudaGetLastError());
+
+    tcg::GemmArgs g{};
+    g.apack = b.apack.as<unsigned char>();
+    g.wpack = w.wpack_tc.as<unsigned char>() + (size_t)l * gcn_tc_pack_bytes();
+    g.num_nodes = (int)N; g.num_tiles = num_tiles;
+    GcnEpi epi{w.b.as<float>() + (size_t)l * 104, p_out};
+    tcg::gemm_kernel<NCHUNK, NPAD, GcnEpi><<<std::min(num_tiles, sm_count), tcg::NT, C::BYTES, s>>>(g, epi);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fg

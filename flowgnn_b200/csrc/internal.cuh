@@ -85,6 +85,7 @@ struct GinWeights {
 struct GcnWeights {
     DevBuf ne_table, ee_comb;   // as GIN
     DevBuf wt, b;               // [5][100][104], [5][104]
+    DevBuf wpack_tc;            // [5][2][28672] bytes: W_l as bf16 hi | lo K-chunks for tcg::gemm_kernel (gcn_tc.cu)
     DevBuf root;                // [5][100]
     DevBuf bn_mean, bn_sqrt_var, bn_weight, bn_bias;   // [5][100]; sqrt_var = sqrt(var + 2^-10)
     DevBuf pred_w, pred_b;
@@ -103,6 +104,7 @@ struct DgnWeights {
     DevBuf emb;                 // [9][119][100]
     DevBuf wt;                  // [4][200][104]  k = part*100+in
     DevBuf w_ref;               // [4][100][200] reference layout (exact path for out-degree-0 nodes)
+    DevBuf wpack_tc;            // [4][4][28672] bytes: W_l as bf16 hi | lo K-chunks for tcg::gemm_kernel (dgn_tc.cu)
     DevBuf b;                   // [4][104]
     DevBuf m0w, m0b, m1w, m1b, m2w, m2b;
 };
@@ -130,6 +132,8 @@ struct RunOptions {
     int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
     int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
+    int gcn_tc = 0;                  // GCN: Linear_l on tcgen05 (gcn_tc.cu: aggregate -> bf16x3 GEMM) instead of the fused FFMA kernel
+    int dgn_tc = 0;                  // DGN: node transform on tcgen05 (dgn_tc.cu: aggregate -> bf16x3 GEMM -> fp32 rows) instead of FFMA
     int pna_tc = 1;                  // PNA: node transform on tcgen05 (pna_tc.cu: aggregate -> bf16x3 GEMM -> exact rows); 0: FFMA kernel (pna.cu)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
@@ -152,6 +156,12 @@ void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const
 int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t pna_tc_pack_bytes();
 void pna_tc_pack_layer(const float* wcat, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
+int gcn_step_tc_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s);
+size_t gcn_tc_pack_bytes();
+void gcn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
+int dgn_layer_tc_launch(DeviceBatch& b, const DgnWeights& w, int l, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+size_t dgn_tc_pack_bytes();
+void dgn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
 int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);

@@ -12,6 +12,7 @@ import pytest
 from conftest import ALL_MODELS, assert_parity
 
 pytestmark = pytest.mark.gpu
+DEFAULT_TC = "0"          # library default of the gcn_tc / dgn_tc options
 
 
 @pytest.fixture(scope="module")
@@ -141,6 +142,30 @@ def test_pna_tensor_core_path_matches_reference(ds, ctx, weights, datasets, gold
     assert_parity(few, golden[ds]["pna"][:3], what=f"pna tcgen05/{ds} first 3 graphs")
     assert_parity(some, golden[ds]["pna"][:47], what=f"pna tcgen05/{ds} first 47 graphs")
     assert_parity(tc, ffma, tol=1e-4, what=f"pna tcgen05 vs ffma/{ds}")
+
+
+@pytest.mark.parametrize("model", ["gcn", "dgn"])
+@pytest.mark.parametrize("ds", ["molhiv", "molpcba", "hep10k"])
+def test_gcn_dgn_tensor_core_paths_match_reference(model, ds, ctx, weights, datasets, golden):
+    """Options gcn_tc / dgn_tc (gcn_tc.cu, dgn_tc.cu on tcgemm.cuh): the aggregate kernel writes bf16 hi/lo A blocks, the
+    dense layer runs on tcgen05 (3 products), DGN's non-finite rows (out-degree 0) are evaluated in fp32.  Both settings
+    must sit inside the 1e-4 contract (non-finite values positionally) and agree with each other, also on batches that
+    end inside a 128-row tile."""
+    opt = model + "_tc"
+    out = {}
+    try:
+        for mode in (0, 1):
+            ctx.set_option(opt, mode)
+            out[mode] = ctx.run(model, datasets[ds], weights[model])
+        few = ctx.run(model, datasets[ds].slice(0, 3))
+        some = ctx.run(model, datasets[ds].slice(0, 47))
+    finally:
+        ctx.set_option(opt, int(__import__("os").environ.get("FLOWGNN_B200_TC_ALL", DEFAULT_TC)))
+    assert_parity(out[0], golden[ds][model], what=f"{model} ffma/{ds}")
+    assert_parity(out[1], golden[ds][model], what=f"{model} tcgen05/{ds}")
+    assert_parity(few, golden[ds][model][:3], what=f"{model} tcgen05/{ds} first 3 graphs")
+    assert_parity(some, golden[ds][model][:47], what=f"{model} tcgen05/{ds} first 47 graphs")
+    assert_parity(out[1], out[0], tol=1e-4, what=f"{model} tcgen05 vs ffma/{ds}")
 
 
 def test_gat_hep10k_is_the_prediction_bias(ctx, weights, datasets, golden):
