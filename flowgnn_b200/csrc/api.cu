@@ -441,7 +441,7 @@ int flowgnn_b200_create(flowgnn_ctx** out, int device)
     std::unique_ptr<flowgnn_ctx> c(new flowgnn_ctx);
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    // FLOWGNN_B200_TC_ALL=0/1 overrides the default of the "gcn_tc" / "dgn_tc" options (used to run the whole GPU suite on either path)
+    // FLOWGNN_B200_TC_ALL=0/1 overrides the default (1) of the "gcn_tc" / "dgn_tc" options (used to run the whole GPU suite on either path)
     if (const char* e = std::getenv("FLOWGNN_B200_TC_ALL")) c->opt.gcn_tc = c->opt.dgn_tc = std::atoi(e) != 0;
     FG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));

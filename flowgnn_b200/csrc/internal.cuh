@@ -132,8 +132,8 @@ struct RunOptions {
     int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
     int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
-    int gcn_tc = 0;                  // GCN: Linear_l on tcgen05 (gcn_tc.cu: aggregate -> bf16x3 GEMM) instead of the fused FFMA kernel
-    int dgn_tc = 0;                  // DGN: node transform on tcgen05 (dgn_tc.cu: aggregate -> bf16x3 GEMM -> fp32 rows) instead of FFMA
+    int gcn_tc = 1;                  // GCN: Linear_l on tcgen05 (gcn_tc.cu: aggregate -> bf16x3 GEMM); 0: the fused FFMA kernel (gcn.cu)
+    int dgn_tc = 1;                  // DGN: node transform on tcgen05 (dgn_tc.cu: aggregate -> bf16x3 GEMM -> fp32 rows); 0: FFMA kernel (dgn.cu)
     int pna_tc = 1;                  // PNA: node transform on tcgen05 (pna_tc.cu: aggregate -> bf16x3 GEMM -> exact rows); 0: FFMA kernel (pna.cu)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on

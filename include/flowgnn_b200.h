@@ -132,6 +132,8 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx);
  * the node MLP; -1 (default): when the batch averages >= 6 in-edges per node (hep10k kNN graphs), 0 / 1: never / always),
  * "pna_tc" (PNA, default 1: node transform on tcgen05 -- aggregate kernel, bf16x3 GEMM, fp32 rows kernel; 0: the fused
  * FP32 FFMA kernel, kept as the on-device fp32 reference),
+ * "gcn_tc" / "dgn_tc" (default 1: the dense layer of GCN / DGN on tcgen05 through the aggregate -> GEMM path of tcgemm.cuh;
+ * 0: the fused FFMA kernels; environment FLOWGNN_B200_TC_ALL=0/1 sets both defaults),
  * "gat_node_offset_bug" (default 1), "time_layers" (1: see flowgnn_b200_last_layer_ms; 2 (GIN): ONE interval around all
  * layer launches, which leaves them adjacent in the stream so that programmatic dependent launch can overlap them).
  * Environment: FLOWGNN_B200_CHUNKS=n overrides the number of chunks the host-pointer entry points cut a batch into
