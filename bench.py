@@ -49,8 +49,8 @@ WORKLOADS = {
 #: (D, L, attr words A, extra bytes per node X) of SURVEY.md 8(d): B_layer = 8*D*N + E*(8+4A) + X*N
 ALGO = {"gin": (100, 5, 3, 0), "ginvn": (100, 5, 3, 0), "gcn": (100, 5, 3, 0), "gat": (64, 5, 0, 64), "pna": (80, 4, 0, 0),
         "dgn": (100, 4, 0, 0)}
-LAYER_KERNEL = {"gin": "gin_layer_tc2_kernel", "ginvn": "gin_layer_tc2_kernel", "gcn": "gcn_layer_kernel", "gat": "gat_layer_kernel",
-                "pna": "pna_aggregate_kernel + pna_gemm_kernel + pna_exact_rows_kernel (three launches per layer)", "dgn": "dgn_layer_kernel"}
+LAYER_KERNEL = {"gin": "gin_layer_tc2_kernel", "ginvn": "gin_layer_tc2_kernel", "gcn": "gcn_aggregate_kernel + tcg::gemm_kernel (two launches per step)", "gat": "gat_layer_kernel",
+                "pna": "pna_aggregate_kernel + pna_gemm_kernel + pna_exact_rows_kernel (three launches per layer)", "dgn": "dgn_aggregate_kernel + tcg::gemm_kernel + dgn_exact_rows_kernel (three launches per layer)"}
 
 
 def layer_bytes(model: str, total_nodes: int, total_edges: int) -> int:
