@@ -18,6 +18,9 @@ Printed (rank 0, one JSON line):
                gather-scatter figure of BASELINE.json's metric
   cpu_baseline the reference's own kernel sources (oracle/_ref, fp32 flavour) on this box's host cores,
                bounded sample of the same workload (rank 0, N = 1 only)
+  e2e_pageable the end-to-end call again with the caller's arrays in pageable memory, and after pinning them in place
+  extras       BASELINE configs C4 / C5 on the same N GPUs: ONE 437,929-graph PNA batch sharded by graph index
+               (strong scaling) and GIN-VN on hep10k-shaped graphs (weak scaling + batch-size sweep)
 
 --impl reference times that CPU build alone (one process per core; its state is in file-scope
 globals, */src/globals.cc, so it is not re-entrant) and prints the same line with "impl": "reference".
@@ -51,6 +54,11 @@ ALGO = {"gin": (100, 5, 3, 0), "ginvn": (100, 5, 3, 0), "gcn": (100, 5, 3, 0), "
         "dgn": (100, 4, 0, 0)}
 LAYER_KERNEL = {"gin": "gin_layer_tc2_kernel", "ginvn": "gin_layer_tc2_kernel", "gcn": "gcn_aggregate_kernel + tcg::gemm_kernel (two launches per step)", "gat": "gat_layer_kernel",
                 "pna": "pna_aggregate_kernel + pna_gemm_kernel + pna_exact_rows_kernel (three launches per layer)", "dgn": "dgn_aggregate_kernel + tcg::gemm_kernel + dgn_exact_rows_kernel (three launches per layer)"}
+
+
+def metric_name(model: str) -> str:
+    """The SAME string on both arms (the driver matches them to form its ratios)."""
+    return f"graphs/sec ({WORKLOADS[model][0]}-shaped, {model.upper()} forward)"
 
 
 def layer_bytes(model: str, total_nodes: int, total_edges: int) -> int:
@@ -195,7 +203,7 @@ def run_reference_arm(args):
     sample_txt = (f"first {sample.num_graphs} graphs ({per_core} per core) of the synthetic {shape}-shaped workload per step, "
                   f"one process per core, timed around <MODEL>_compute_graphs only")
     line = {
-        "impl": "reference", "metric": f"graphs/sec ({shape}-shaped, {model.upper()} forward)", "value": value, "unit": "graphs/s",
+        "impl": "reference", "metric": metric_name(model), "value": value, "unit": "graphs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{model.upper()} forward, {full} synthetic {shape}-shaped graphs per GPU per step",
@@ -215,6 +223,133 @@ def pinned_copy(a):
     return t, v
 
 
+
+def bind_to_gpu_numa(dev_index: int):
+    """Pin this process to the CPU cores of the GPU's NUMA node (if the cpuset allows any of them), BEFORE any pinned host
+    memory is allocated: first-touch then places the staging buffers next to the GPU's PCIe root.  Returns a record for the
+    JSON line.  (r1: all 8 ranks sat on NUMA node 0 and the end-to-end arm lost 33 % at 8 GPUs.)"""
+    import torch
+    rec = {"numa_node": None, "cpus_before": None, "cpus_after": None}
+    try:
+        allowed = os.sched_getaffinity(0)
+        rec["cpus_before"] = len(allowed)
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        rec["numa_node"] = node
+        if node < 0:
+            return rec
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        want = cpus & allowed
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+        rec["cpus_after"] = len(os.sched_getaffinity(0))
+        rec["local_cpus_in_cpuset"] = len(want)
+    except (OSError, ValueError, AttributeError) as e:
+        rec["error"] = str(e)[:80]
+    return rec
+
+
+def measure_resident(ctx, model, steps, warmup, stream, barrier, grouped):
+    """W untimed + K timed passes of the hot path over the batch resident in `ctx`; returns (ms of the K steps on this rank,
+    per-layer-launch ms list, launches)."""
+    import torch
+    L = ALGO[model][1]
+    for _ in range(warmup):
+        ctx.compute(model, timed=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    layer_ms = []
+    for _ in range(steps):
+        ctx.compute(model, timed=True)
+        lm = ctx.last_layer_ms()
+        layer_ms.extend([lm[0] / L] * L if grouped and len(lm) == 1 else lm)
+    ev1.record(stream)
+    barrier()
+    return ev0.elapsed_time(ev1), layer_ms, ctx.last_launch_count * steps
+
+
+def run_extra_configs(args, rank, world, local, dev, barrier, max_over_ranks, sum_over_ranks, hbm_peak):
+    """BASELINE configs C4 and C5 inside the same JSON line (the driver only runs `bench.py --gpus N`):
+      pna_molpcba_sharded  ONE batch of 437,929 molpcba-shaped graphs cut by graph index over the N ranks
+                           (flowgnn_b200.sharding.shard_of -- strong scaling; NCCL only tallies);
+      ginvn_hep10k         GIN-VN on hep10k-shaped graphs, 40,000 per GPU (weak), plus a batch-size sweep.
+    Device-timed, max over ranks; fewer steps than the headline (each PNA step is ~50 ms on one GPU)."""
+    import torch
+    from flowgnn_b200.capi import Context
+    from flowgnn_b200.sharding import shard_of
+    from flowgnn_b200.weights import load_weights
+    steps, warmup = max(3, min(args.steps, 8)), 3
+    out = {}
+
+    def one(model, batch, grouped):
+        ctx = Context(local)
+        try:
+            ctx.load_weights(model, load_weights(model, os.path.join(GOLDEN, "weights", WEIGHT_DIRS[model])))
+            ctx.upload(batch)
+            ctx.set_option("time_layers", 2 if grouped else 1)
+            stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+            ms, layer_ms, launches = measure_resident(ctx, model, steps, warmup, stream, barrier, grouped)
+            y = ctx.download()
+        finally:
+            ctx.close()
+        return ms, layer_ms, launches, y
+
+    # ---- C4: PNA, one molpcba-sized batch sharded by graph index ------------------------------------------
+    model = "pna"
+    full = make_workload(model, WORKLOADS[model][1], base_graphs=8192)          # same on every rank
+    shard, g0, g1 = shard_of(full, rank, world)
+    ms, layer_ms, launches, y = one(model, shard, False)
+    ms = max_over_ranks(ms)
+    done = sum_over_ranks(float(g1 - g0))
+    finite = sum_over_ranks(float(np.isfinite(y).sum()))
+    lb = layer_bytes(model, full.total_nodes, full.total_edges)                # whole job
+    mean_layer = max_over_ranks(float(np.mean(layer_ms)))
+    out["pna_molpcba_sharded"] = {
+        "metric": metric_name(model), "value": done * steps / (ms * 1e-3), "unit": "graphs/s", "scaling": "strong",
+        "workload": f"PNA forward, ONE batch of {full.num_graphs} synthetic molpcba-shaped graphs (sum N = {full.total_nodes}, "
+                    f"sum E = {full.total_edges}) cut into {world} contiguous graph ranges (shard_of)",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "graphs_done_per_step": done, "finite_outputs": finite,
+        "gpu_launches": int(launches), "layer_ms_max_over_ranks": mean_layer,
+        "roofline": {"bound": "hbm", "kernel": LAYER_KERNEL[model], "achieved": lb / world / (mean_layer * 1e-3) / 1e9, "peak": hbm_peak,
+                     "unit": "GB/s per GPU", "frac": lb / world / (mean_layer * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_layer_whole_job": lb},
+    }
+    del full, shard
+
+    # ---- C5: GIN-VN on hep10k-shaped graphs, weak scaling + batch-size sweep -------------------------------
+    model = "ginvn"
+    sweep = []
+    for G in (2500, 10000, WORKLOADS[model][1]):
+        batch = make_workload(model, G, seed_offset=rank, base_graphs=2048)
+        ms, layer_ms, launches, y = one(model, batch, True)
+        ms = max_over_ranks(ms)
+        done = sum_over_ranks(float(G))
+        lb = layer_bytes(model, batch.total_nodes, batch.total_edges)
+        mean_layer = max_over_ranks(float(np.mean(layer_ms)))
+        rec = {"graphs_per_gpu": G, "value": done * steps / (ms * 1e-3), "ms_per_step": ms / steps, "layer_ms": mean_layer,
+               "roofline_frac": lb / (mean_layer * 1e-3) / 1e9 / hbm_peak, "gpu_launches": int(launches),
+               "finite_outputs": sum_over_ranks(float(np.isfinite(y).sum()))}
+        sweep.append(rec)
+    top = sweep[-1]
+    out["ginvn_hep10k"] = {
+        "metric": metric_name(model), "value": top["value"], "unit": "graphs/s", "scaling": "weak",
+        "workload": f"GIN-VN forward, {WORKLOADS[model][1]} synthetic hep10k-shaped graphs per GPU per step (virtual node added)",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": top["ms_per_step"],
+        "roofline": {"bound": "hbm", "kernel": "GIN layer on dense graphs", "frac": top["roofline_frac"], "peak": hbm_peak, "unit": "GB/s",
+                     "mean_layer_ms": top["layer_ms"]},
+        "sweep": sweep,
+    }
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -230,6 +365,7 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU build)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -332,6 +468,42 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: device-resident and end-to-end predictions differ")
     clocks = sampler.stop(windows) if sampler else None
 
+    # ---- the same call with PAGEABLE caller buffers (what the reference host owns: aligned_allocator vectors,
+    # common/includes/xcl2/xcl2.hpp:61-76), and again after pinning them in place through flowgnn_b200_pin_host ----
+    e2e_pageable = None
+    if not args.no_pageable:
+        from flowgnn_b200.capi import pin_host, unpin_host
+        pbatch = Batch(batch.nums_of_nodes, batch.nums_of_edges, batch.node_feature.copy(), batch.edge_list.copy(),
+                       None if batch.edge_attr is None else batch.edge_attr.copy(), None if batch.node_eigen is None else batch.node_eigen.copy(),
+                       name=batch.name)
+        pcall = ReferenceCall(model, pbatch, weights)
+        ksteps = max(3, args.steps // 2)
+
+        def timed_calls():
+            for _ in range(3):
+                y = pcall.run()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                y = pcall.run()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            return total_graphs * ksteps / dt, y.copy()
+
+        v_page, y_page = timed_calls()
+        big = [a for a in (pbatch.node_feature, pbatch.edge_list, pbatch.edge_attr, pbatch.node_eigen) if a is not None]
+        for a in big:
+            pin_host(a)
+        v_reg, y_reg = timed_calls()
+        for a in big:
+            unpin_host(a)
+        if not (np.array_equal(y_page.view(np.int32), y_dev.view(np.int32)) and np.array_equal(y_reg.view(np.int32), y_dev.view(np.int32))):
+            raise SystemExit("bench.py: pageable-buffer predictions differ")
+        e2e_pageable = {"value": v_page, "unit": "graphs/s", "steps": ksteps,
+                        "after_flowgnn_b200_pin_host": v_reg,
+                        "note": "same C-ABI call; caller arrays in ordinary (pageable) memory, then page-locked in place"}
+
     # ---- roofline of the dominant kernel (per-layer CUDA events recorded inside the timed region) ---
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
@@ -382,6 +554,10 @@ def run_b200_arm(args):
                        "mean_launch_ms": float(np.mean(mp_ms)), "algorithmic_bytes_per_launch": lb_full}
     ctx.close()
 
+    extras = None
+    if not args.no_extras and model == "gin":
+        extras = run_extra_configs(args, rank, world, local, dev, barrier, max_over_ranks, sum_over_ranks, hbm_peak)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
@@ -397,11 +573,11 @@ def run_b200_arm(args):
 
     if rank == 0:
         line = {
-            "metric": f"graphs/sec ({shape}-shaped, {model.upper()} forward, device-timed)", "value": value, "unit": "graphs/s",
+            "metric": metric_name(model), "value": value, "unit": "graphs/s", "timer": "CUDA events on the context's stream (device-timed)",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{model.upper()} forward, {G} synthetic {shape}-shaped graphs per GPU per step "
-                                   f"(sum N = {N}, sum E = {E} on rank 0); trained weights shipped with the reference",
+            "config": {"workload": f"{model.upper()} forward, {G} synthetic {shape}-shaped graphs per GPU per step",
+                       "batch": f"sum N = {N}, sum E = {E} on rank 0; trained weights shipped with the reference",
                        "l2": "inputs larger than L2 (activations 2 x %.0f MB per GPU)" % (N * ALGO[model][0] * 4 / 1e6),
                        "parallelism": f"graphs sharded by index over {world} GPU(s), no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -412,6 +588,9 @@ def run_b200_arm(args):
             "edge_gather": edge_gather,
             "algorithmic_bytes_per_graph": graph_bytes(model, G, N, E) / G,
             "cpu_baseline": cpu_baseline,
+            "e2e_pageable": e2e_pageable,
+            "extras": extras,
+            "affinity": affinity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -429,6 +608,8 @@ def main():
     ap.add_argument("--base-graphs", type=int, default=0, help="generate this many distinct graphs and tile them")
     ap.add_argument("--cpu-graphs-per-core", type=int, default=256, help="reference arm: graphs per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C4 (PNA sharded) / C5 (GIN-VN hep10k) lines")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-caller end-to-end line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
     "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_compute", "flowgnn_b200_download",
     "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
+    "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host",
 )
 
 
@@ -60,6 +61,8 @@ def load_library() -> ctypes.CDLL:
         lib.flowgnn_b200_last_launch_count.argtypes = [ctypes.c_void_p]
         lib.flowgnn_b200_synchronize.argtypes = [ctypes.c_void_p]
         lib.flowgnn_b200_last_layer_ms.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
+        lib.flowgnn_b200_pin_host.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+        lib.flowgnn_b200_unpin_host.argtypes = [ctypes.c_void_p]
         _lib = lib
     return _lib
 
@@ -81,6 +84,15 @@ def _addr(a) -> Optional[int]:
     if hasattr(a, "data_ptr"):
         return int(a.data_ptr())
     raise TypeError(type(a))
+
+
+def pin_host(a: np.ndarray) -> None:
+    """Page-lock a caller-owned array (what a C++ host does once after building its batch vectors)."""
+    _check(load_library().flowgnn_b200_pin_host(a.ctypes.data, a.nbytes), "pin_host")
+
+
+def unpin_host(a: np.ndarray) -> None:
+    _check(load_library().flowgnn_b200_unpin_host(a.ctypes.data), "unpin_host")
 
 
 class Context:

@@ -6,7 +6,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/flowgnn_b200.h"
@@ -17,6 +20,19 @@ namespace fg {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int opt_in_smem(const void* kernel, int bytes)
+{
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    FG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({kernel, dev})) return 0;
+    FG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({kernel, dev});
+    return 0;
+}
 
 int DevBuf::reserve(size_t bytes)
 {
@@ -37,7 +53,7 @@ void DevBuf::release()
 void DeviceBatch::release()
 {
     DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
-                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &status, &node_dot, &apack, &nonfinite,
+                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &big_tab, &status, &node_dot, &apack, &nonfinite,
                      &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
     for (DevBuf* b : all) b->release();
 }
@@ -394,14 +410,22 @@ int copy_in(DevBuf& dst, const void* src, size_t bytes, cudaStream_t s)
     return 0;
 }
 
+// device-side rejections (prep.cu) -> error code + text
+int status_error(int st)
+{
+    if (st & 2) { set_last_error("edge_list holds a node id outside [0, num_of_nodes)"); return FG_ERR_INVALID; }
+    if (st & 4) { set_last_error("edge_attr holds a value outside the bond vocabulary {5, 6, 2} (GIN/src/host_load.cc:5-6)"); return FG_ERR_INVALID; }
+    if (st & 1) { set_last_error("invalid node / edge count of a graph"); return FG_ERR_LIMIT; }
+    if (st & 8) { set_last_error("GIN: an edge spans more than 32,767 node positions (reference cap: MAX_NODE = 500 nodes per graph)"); return FG_ERR_LIMIT; }
+    return 0;
+}
+
 int check_status(flowgnn_ctx* ctx)
 {
     int st = 0;
     FG_CUDA(cudaMemcpyAsync(&st, ctx->batch.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (st & 1) { set_last_error("a graph has more than 1024 nodes (reference cap: MAX_NODE = 500)"); return FG_ERR_LIMIT; }
-    if (st & 2) { set_last_error("edge_list holds a node id outside [0, num_of_nodes)"); return FG_ERR_INVALID; }
-    return 0;
+    return status_error(st);
 }
 
 }  // namespace
@@ -554,7 +578,23 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
         set_last_error("null batch array");
         return FG_ERR_INVALID;
     }
+    // the counts drive every offset on the device: check them here, where they are host memory (O(G), microseconds)
+    int64_t sum_n = 0, sum_e = 0;
+    int max_n = 0;
+    for (int g = 0; g < num_graphs; g++)
+    {
+        const int n = nums_of_nodes[g], e = nums_of_edges[g];
+        if (n < 0 || e < 0) { set_last_error("negative entry in nums_of_nodes / nums_of_edges (graph " + std::to_string(g) + ")"); return FG_ERR_INVALID; }
+        sum_n += n; sum_e += e;
+        max_n = std::max(max_n, n);
+    }
+    if (sum_n != total_nodes || sum_e != total_edges)
+    {
+        set_last_error("total_nodes / total_edges do not match the sums of nums_of_nodes / nums_of_edges");
+        return FG_ERR_INVALID;
+    }
     b.num_graphs = num_graphs; b.total_nodes = total_nodes; b.total_edges = total_edges;
+    b.max_graph_nodes = max_n;
     b.has_attr = edge_attr != nullptr; b.has_eigen = node_eigen != nullptr;
     FG_TRY(copy_in(b.nums_of_nodes, nums_of_nodes, sizeof(int) * (size_t)num_graphs, s));
     FG_TRY(copy_in(b.nums_of_edges, nums_of_edges, sizeof(int) * (size_t)num_graphs, s));
@@ -660,6 +700,24 @@ int flowgnn_b200_last_layer_ms(flowgnn_ctx* ctx, float* out, int max_layers)
 }
 void* flowgnn_b200_stream(flowgnn_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+// Page-lock caller-owned host memory so that the host-pointer entry points can overlap its upload with the kernels
+// (pageable memory is staged by the driver, synchronously).  The caller unpins before freeing.
+int flowgnn_b200_pin_host(void* ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) return 0;      // pinned already
+    (void)cudaGetLastError();
+    FG_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int flowgnn_b200_unpin_host(void* ptr)
+{
+    if (!ptr) return 0;
+    FG_CUDA(cudaHostUnregister(ptr));
+    return 0;
+}
+
 int flowgnn_b200_synchronize(flowgnn_ctx* ctx)
 {
     FG_TRY(check_ctx(ctx));
@@ -699,6 +757,16 @@ uint64_t hash_weights(const float* const* w, const size_t* counts, int n, size_t
         const unsigned char* p = reinterpret_cast<const unsigned char*>(w[i] + set * counts[i]);
         const size_t bytes = counts[i] * sizeof(float);
         size_t k = 0;
+        // four independent multiply chains (the single FNV chain is latency-bound at ~2.5 GB/s; ~1 MB of weights per call)
+        uint64_t a = h, b = h ^ 0x9E3779B97F4A7C15ull, c = h ^ 0xC2B2AE3D27D4EB4Full, d = h ^ 0x165667B19E3779F9ull;
+        for (; k + 32 <= bytes; k += 32)
+        {
+            uint64_t v[4];
+            std::memcpy(v, p + k, 32);
+            a = (a ^ v[0]) * 1099511628211ull; b = (b ^ v[1]) * 1099511628211ull;
+            c = (c ^ v[2]) * 1099511628211ull; d = (d ^ v[3]) * 1099511628211ull;
+        }
+        h = ((a ^ (b >> 29)) * 1099511628211ull ^ c) * 1099511628211ull ^ (d >> 31);
         for (; k + 8 <= bytes; k += 8) { uint64_t v; std::memcpy(&v, p + k, 8); h = (h ^ v) * 1099511628211ull; }
         for (; k < bytes; k++) h = (h ^ p[k]) * 1099511628211ull;
     }
@@ -777,6 +845,12 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             nb += n_c; eb += e_c;
             return 0;
         };
+        // any early return below leaves copies and kernels in flight that read the caller's buffers and write the pinned
+        // staging words: drain both streams before handing control back
+        struct Drain {
+            flowgnn_ctx* c; bool armed = true;
+            ~Drain() { if (armed) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); } }
+        } drain{ctx};
         FG_TRY(issue_upload(0));
 
         const uint64_t h = hash_weights(weights, counts, nw, (size_t)set);
@@ -805,11 +879,11 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             if (ci + P < nchunks) FG_TRY(issue_upload(ci + P));                     // reuses this chunk's buffer once it is free
         }
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
+        drain.armed = false;
         FG_CUDA(cudaGetLastError());
         int st = 0;
         for (int ci = 0; ci < nchunks; ci++) st |= ctx->h_status[ci];
-        if (st & 1) { set_last_error("a graph has more than 1024 nodes (reference cap: MAX_NODE = 500)"); return FG_ERR_LIMIT; }
-        if (st & 2) { set_last_error("edge_list holds a node id outside [0, num_of_nodes)"); return FG_ERR_INVALID; }
+        FG_TRY(status_error(st));
         std::memcpy(out + g, ctx->h_out, sizeof(float) * (size_t)run_graphs);
         node_base += n_run; edge_base += e_run;
         g = g1;

@@ -27,6 +27,10 @@ void set_last_error(const std::string& msg);
         if (_r != 0) return _r;                                                                    \
     } while (0)
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory, once per (kernel, device): function attributes are
+// per device, and a process may hold one context per GPU (api.cu)
+int opt_in_smem(const void* kernel, int bytes);
+
 constexpr int FG_ERR_INVALID = 10001;      // bad argument
 constexpr int FG_ERR_LIMIT = 10002;        // graph exceeds a documented limit
 constexpr int FG_ERR_STATE = 10003;        // call order (no weights / no batch)

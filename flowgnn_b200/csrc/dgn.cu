@@ -166,12 +166,7 @@ int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int 
         FG_CUDA(cudaGetLastError());
         nl++;
     }
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(dgn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DgnSmem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&dgn_layer_kernel), DgnSmem::BYTES));
     const int num_tiles = (int)ceil_div<long>(N, TILE_M);
     const int grid = min(num_tiles, sm_count);
     for (int l = 0; l < 4; l++)

@@ -177,12 +177,7 @@ void dgn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(f
 int dgn_layer_tc_launch(DeviceBatch& b, const DgnWeights& w, int l, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
 {
     using C = tcg::Cfg<NPAD>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(tcg::gemm_kernel<NCHUNK, NPAD, DgnEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&tcg::gemm_kernel<NCHUNK, NPAD, DgnEpi>), C::BYTES));
     const long N = b.total_nodes;
     const int num_tiles = (int)ceil_div<long>(N, tcg::TM);
     FG_TRY(b.apack.reserve((size_t)num_tiles * NCHUNK * tcg::A_BLOCK));

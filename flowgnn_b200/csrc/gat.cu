@@ -284,13 +284,8 @@ int gat_forward(DeviceBatch& b, const GatWeights& w, const RunOptions& opt, int 
                                                              w.a_src.as<float>(), w.a_tgt.as<float>(), hp[0], o[0], S[0], T[0]);
     FG_CUDA(cudaGetLastError());
     nl++;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(gat_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GatSmem::BYTES));
-        FG_CUDA(cudaFuncSetAttribute(gat_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GatSmem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gat_layer_kernel<false>), GatSmem::BYTES));
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gat_layer_kernel<true>), GatSmem::BYTES));
     const int num_tiles = (int)ceil_div<long>(N, TILE_M);
     const int grid = min(num_tiles, sm_count * 2);
     for (int l = 0; l < 5; l++)

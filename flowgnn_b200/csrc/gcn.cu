@@ -194,14 +194,9 @@ int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int 
     FG_TRY(b.act[0].reserve(sizeof(float) * (size_t)N * D));
     FG_TRY(b.act[1].reserve(sizeof(float) * (size_t)N * D));
     float* h[2] = {b.act[0].as<float>(), b.act[1].as<float>()};
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(gcn_layer_kernel<FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcnSmem::BYTES));
-        FG_CUDA(cudaFuncSetAttribute(gcn_layer_kernel<MIDDLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcnSmem::BYTES));
-        FG_CUDA(cudaFuncSetAttribute(gcn_layer_kernel<FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcnSmem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gcn_layer_kernel<FIRST>), GcnSmem::BYTES));
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gcn_layer_kernel<MIDDLE>), GcnSmem::BYTES));
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gcn_layer_kernel<FINAL>), GcnSmem::BYTES));
     const int num_tiles = (int)ceil_div<long>(N, TILE_M);
     const int grid = min(num_tiles, sm_count);
     int nl = 0;

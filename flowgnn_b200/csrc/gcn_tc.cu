@@ -128,12 +128,7 @@ void gcn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(f
 int gcn_step_tc_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s)
 {
     using C = tcg::Cfg<NPAD>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(tcg::gemm_kernel<NCHUNK, NPAD, GcnEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&tcg::gemm_kernel<NCHUNK, NPAD, GcnEpi>), C::BYTES));
     const long N = b.total_nodes;
     const int num_tiles = (int)ceil_div<long>(N, tcg::TM);
     FG_TRY(b.apack.reserve((size_t)num_tiles * NCHUNK * tcg::A_BLOCK));

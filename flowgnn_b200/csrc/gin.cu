@@ -514,25 +514,15 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
     }
 
     const int num_tiles = (int)ceil_div<long>(N, TILE_M);
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(gin_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GinSmem<false>::BYTES));
-        FG_CUDA(cudaFuncSetAttribute(gin_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GinSmem<true>::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_layer_kernel<false>), GinSmem<false>::BYTES));
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_layer_kernel<true>), GinSmem<true>::BYTES));
     // Dense graphs (average in-degree >= 6: hep10k kNN graphs, GIN-VN on them) run every layer as TWO launches: the staged
     // gather (each row read from HBM once, in-edge reads from shared memory) writes x = m + h, and the CTA-pair kernel run
     // on "no in-edges" descriptors applies the node MLP.  Sparse graphs (molecules) keep the single fused launch.
     const bool staged = opt.gin_staged < 0 ? (b.total_edges >= 6 * N) : (opt.gin_staged != 0);
     const bool split_layer = staged && !opt.mp_only && !opt.gin_ffma && !opt.gin_tc1 && !opt.gin_tc3;
     auto staged_gather = [&](const float* x_in, float* x_out, int l) -> int {
-        static bool sg_attr = false;
-        if (!sg_attr)
-        {
-            FG_CUDA(cudaFuncSetAttribute(gin_gather_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgSmem)));
-            sg_attr = true;
-        }
+        FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_gather_staged_kernel), (int)sizeof(SgSmem)));
         const int grid = std::max(1, std::min(b.num_graphs, sm_count));
         gin_gather_staged_kernel<<<grid, SG_THREADS, sizeof(SgSmem), s>>>(x_in, x_out, b.in_ptr.as<int>(), b.src.as<int>(), b.code.as<uint8_t>(),
                                                                          w.ee_comb.as<float>() + (size_t)l * ED_COMBOS * D,

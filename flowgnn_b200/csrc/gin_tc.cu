@@ -550,12 +550,7 @@ __global__ void __launch_bounds__(NT, 1) gin_layer_tc_kernel(GinTcParams p)
 
 int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(gin_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_layer_tc_kernel), Smem::BYTES));
     GinTcParams p;
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();

@@ -728,12 +728,7 @@ unsigned long long* gin_tc2_trace_buffer = nullptr;      // set through flowgnn_
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
                          const float* head_w, float* node_dot, const int4* row_desc)
 {
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(gin_layer_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_layer_tc2_kernel), Smem::BYTES));
     GinTc2Params p;
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();

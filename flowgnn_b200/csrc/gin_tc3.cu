@@ -510,12 +510,7 @@ void gin_tc3_pack_layer(const float* w1, const float* b1, const float* w2, const
 
 int gin_layer_tc3_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(gin_layer_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_layer_tc3_kernel), Smem::BYTES));
     GinTc3Params p;
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();

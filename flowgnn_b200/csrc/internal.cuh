@@ -28,6 +28,7 @@ struct DeviceBatch {
     long total_edges = 0;
     bool has_attr = false;
     bool has_eigen = false;
+    int max_graph_nodes = 0;               // largest nums_of_nodes entry (host-side scan in upload_into, api.cu)
 
     // inputs (caller layout)
     DevBuf nums_of_nodes, nums_of_edges;   // int32 [G]
@@ -47,6 +48,7 @@ struct DeviceBatch {
     DevBuf row_desc;                       // int4 [N]  GIN: first four in-edges of every node, packed (prep.cu)
     DevBuf row_desc0;                      // int4 [N]  GIN, dense graphs: "no in-edges" descriptors (node MLP launch after the staged gather)
     DevBuf sort_tmp;                       // int32 [E] scratch for the two-pass stable sort
+    DevBuf big_tab;                        // int32 [3][N] CSR-build tables of graphs above 1,024 nodes (allocated only if there is one)
     DevBuf status;                         // int32 [1] device-side limit violations
 
     // activations

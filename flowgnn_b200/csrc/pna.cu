@@ -232,12 +232,7 @@ int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int 
         FG_CUDA(cudaGetLastError());
         nl++;
     }
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(pna_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PnaSmem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&pna_layer_kernel), PnaSmem::BYTES));
     const int num_tiles = (int)ceil_div<long>(N, TILE_M);
     const int grid = min(num_tiles, sm_count);
     for (int l = 0; l < 4; l++)

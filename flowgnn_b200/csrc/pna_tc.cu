@@ -464,12 +464,7 @@ void pna_tc_pack_layer(const float* wcat, unsigned char* dst, uint16_t (*bf16_rn
 
 int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        FG_CUDA(cudaFuncSetAttribute(pna_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::BYTES));
-        attr_set = true;
-    }
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&pna_gemm_kernel), Smem::BYTES));
     const long N = b.total_nodes;
     const int num_tiles = (int)ceil_div<long>(N, TM);
     FG_TRY(b.apack.reserve((size_t)num_tiles * NCHUNK * A_BLOCK));

@@ -91,7 +91,8 @@ __device__ __forceinline__ int4 empty_row_desc()
     return make_int4(e, e, e, e);
 }
 
-constexpr int CSR_NCAP = 1024;     // nodes per graph supported by the warp-local tables (reference cap: 500)
+constexpr int CSR_NCAP = 1024;     // nodes per graph supported by the warp-local shared-memory tables (reference cap: 500);
+                                   // larger graphs use tables in global memory (big_tab), the same code, slower
 constexpr int CSR_NCAP_SMALL = 128;
 // The build is a chain of dependent memory round trips per graph (edges -> histogram -> sort scratch -> payload ->
 // descriptors), so it lives on occupancy.  Two instantiations run back to back: graphs of up to 128 nodes (every
@@ -103,24 +104,46 @@ struct CsrParams {
     const int* edge_list; const int* edge_attr; const float* node_eigen;
     int* in_ptr; int* src; uint8_t* code; float* edge_w; int* out_deg; float* node_w0; float* node_w1; int4* row_desc;
     int* sort_tmp; int* status;
+    int* big_tab;                    // [3][N] histogram / cursor tables of graphs above CSR_NCAP nodes (nullptr: the batch has none)
+    long total_nodes;
     int num_graphs; int flags; int has_attr;
 };
+
+// A graph the build rejects (status bit set; the call returns an error after the forward): every row empty, and the
+// graph's edge slots -- which the row pointers of the neighbouring rows still span -- filled with defined values, so
+// that the layer kernels that run before the status is read stay in bounds (sources = the graph's first node, or node 0
+// for a graph without nodes; code 0; weight 0).
+__device__ __forceinline__ void neutralise_graph(const CsrParams& p, int nb, int n, int eb, int e)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n; i += 32)
+    {
+        p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0;
+        if (p.row_desc) p.row_desc[nb + i] = empty_row_desc();
+        if (p.flags & PREP_DGN_EIG) { p.node_w0[nb + i] = 0.f; p.node_w1[nb + i] = 0.f; }
+    }
+    const int safe = n > 0 ? nb : 0;
+    for (int i = lane; i < e; i += 32)
+    {
+        p.src[eb + i] = safe;
+        if (p.has_attr) p.code[eb + i] = 0;
+        if (p.flags & (PREP_GCN_NORM | PREP_DGN_EIG)) p.edge_w[eb + i] = 0.f;
+    }
+}
 
 // One warp per graph.  Two stable counting-sort passes (by source, then by destination) give the
 // (destination, source, list-order) ordering; ranks inside a 32-edge chunk come from
 // __match_any_sync, chunks are consumed in order, so the sort is stable and deterministic.
-template <int NCAP>
-__device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int* deg, int* pu, int* pv)
+__device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int ncap, int* deg, int* pu, int* pv)
 {
     const int lane = threadIdx.x & 31;
     const int n = p.nn[g], e = p.ne[g];
     const int nb = p.node_off[g], eb = p.edge_off[g];
     if (g == p.num_graphs - 1 && lane == 0) p.in_ptr[nb + n] = eb + e;
-    if (n > NCAP || n < 0 || e < 0)
+    if (n > ncap || n < 0 || e < 0)
     {
         if (lane == 0) atomicOr(p.status, 1);
-        // keep downstream kernels in bounds: empty rows
-        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; if (p.row_desc) p.row_desc[nb + i] = empty_row_desc(); }
+        neutralise_graph(p, nb, n, eb, e);
         return;
     }
     const int2* edges = reinterpret_cast<const int2*>(p.edge_list) + eb;
@@ -139,7 +162,7 @@ __device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int* 
     if (__any_sync(full, bad))
     {
         if (lane == 0) atomicOr(p.status, 2);
-        for (int i = lane; i < n; i += 32) { p.in_ptr[nb + i] = eb; p.out_deg[nb + i] = 0; if (p.row_desc) p.row_desc[nb + i] = empty_row_desc(); }
+        neutralise_graph(p, nb, n, eb, e);
         return;
     }
     __syncwarp();
@@ -204,7 +227,12 @@ __device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int* 
             if (p.has_attr)
             {
                 const int* a = p.edge_attr + 3 * (size_t)(eb + i);
-                p.code[pos] = (uint8_t)(__ldg(a) * 12 + __ldg(a + 1) * 2 + __ldg(a + 2));
+                const int a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+                // bond features outside the vocabulary {5, 6, 2} (GIN/src/host_load.cc:5-6) would alias another triple
+                // or index past the combined table: reject the batch (code 0 keeps the layer kernels in bounds)
+                const bool oov = (unsigned)a0 >= 5u || (unsigned)a1 >= 6u || (unsigned)a2 >= 2u;
+                if (oov) atomicOr(p.status, 4);
+                p.code[pos] = oov ? (uint8_t)0 : (uint8_t)(a0 * 12 + a1 * 2 + a2);
             }
             if (p.flags & PREP_GCN_NORM)
             {
@@ -234,7 +262,11 @@ __device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int* 
             int4 d = empty_row_desc();
             int* dq = reinterpret_cast<int*>(&d);
             for (int q = 0; q < 4 && beg + q < end; q++)
-                dq[q] = ((p.src[beg + q] - (nb + v) + 32768) & 0xFFFF) | ((p.has_attr ? (int)p.code[beg + q] : 0) << 16);
+            {
+                const int rel = p.src[beg + q] - (nb + v);
+                if (rel < -32768 || rel > 32767) atomicOr(p.status, 8);      // the descriptor holds 16-bit relative positions
+                dq[q] = ((rel + 32768) & 0xFFFF) | ((p.has_attr ? (int)p.code[beg + q] : 0) << 16);
+            }
             d.x |= min(end - beg, 255) << 24;
             p.row_desc[nb + v] = d;
         }
@@ -270,7 +302,7 @@ __global__ void __launch_bounds__(8 * 32) build_csr_small_kernel(CsrParams p)
     if (g >= p.num_graphs) return;
     const int n = p.nn[g], e = p.ne[g];
     if (!(n >= 0 && n <= CSR_NCAP_SMALL && e >= 0)) return;
-    build_graph_csr<CSR_NCAP_SMALL>(p, g, s_tab[wid][0], s_tab[wid][1], s_tab[wid][2]);
+    build_graph_csr(p, g, CSR_NCAP_SMALL, s_tab[wid][0], s_tab[wid][1], s_tab[wid][2]);
 }
 
 // the rest (more than 128 nodes, or invalid counts): a persistent grid whose warps scan 32 graphs at a time, so that a
@@ -294,7 +326,15 @@ __global__ void __launch_bounds__(4 * 32) build_csr_large_kernel(CsrParams p)
         {
             const int k = __ffs(todo) - 1;
             todo &= todo - 1;
-            build_graph_csr<CSR_NCAP>(p, g0 + k, s_tab[wid][0], s_tab[wid][1], s_tab[wid][2]);
+            const int gk = g0 + k, nk = p.nn[gk];
+            if (nk > CSR_NCAP && p.big_tab)
+            {
+                // a graph beyond the shared-memory tables: the same build on tables in global memory (node ranges of
+                // different graphs are disjoint, so the batch-wide arrays are indexed by global node id)
+                int* t = p.big_tab + p.node_off[gk];
+                build_graph_csr(p, gk, 0x7fffffff, t, t + p.total_nodes, t + 2 * p.total_nodes);
+            }
+            else build_graph_csr(p, gk, CSR_NCAP, s_tab[wid][0], s_tab[wid][1], s_tab[wid][2]);
             __syncwarp();
         }
     }
@@ -334,6 +374,12 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>(); p.edge_w = b.edge_w.as<float>();
     p.out_deg = b.out_deg.as<int>(); p.node_w0 = b.node_w0.as<float>(); p.node_w1 = b.node_w1.as<float>();
     p.sort_tmp = b.sort_tmp.as<int>(); p.status = b.status.as<int>();
+    p.big_tab = nullptr; p.total_nodes = b.total_nodes;
+    if (b.max_graph_nodes > CSR_NCAP)
+    {
+        FG_TRY(b.big_tab.reserve(sizeof(int) * 3 * (size_t)(b.total_nodes + 1)));
+        p.big_tab = b.big_tab.as<int>();
+    }
     p.row_desc = (flags & PREP_ROW_DESC) ? b.row_desc.as<int4>() : nullptr;
     p.num_graphs = G; p.flags = flags; p.has_attr = b.has_attr ? 1 : 0;
     build_csr_small_kernel<<<ceil_div(G, 8), 8 * 32, 0, stream>>>(p);

@@ -32,7 +32,9 @@ extern "C" {
 #endif
 
 #define FLOWGNN_ERR_INVALID 10001   /* bad argument */
-#define FLOWGNN_ERR_LIMIT   10002   /* a graph exceeds a documented limit (1024 nodes per graph) */
+#define FLOWGNN_ERR_LIMIT   10002   /* the batch exceeds a documented limit (32-bit node / edge positions per batch; GIN: an edge may
+                                       span at most 32,767 node positions).  Graphs of any node count are accepted: up to 1,024
+                                       nodes the CSR build keeps its tables in shared memory, above that in global memory */
 #define FLOWGNN_ERR_STATE   10003   /* wrong call order (no weights / no batch) */
 
 /* ------------------------------------------------------------------------------------------------
@@ -171,6 +173,13 @@ int flowgnn_b200_last_layer_ms(flowgnn_ctx* ctx, float* out, int max_layers);
 void* flowgnn_b200_stream(flowgnn_ctx* ctx);
 
 int flowgnn_b200_synchronize(flowgnn_ctx* ctx);
+
+/* Page-lock / release caller-owned host memory (cudaHostRegister without CUDA headers).  The reference host keeps its
+ * batch in 4 KiB-aligned pageable vectors (common/includes/xcl2/xcl2.hpp:61-76) that XRT maps with CL_MEM_USE_HOST_PTR
+ * (GIN/src/host.cc:141-182); pinning them once after the batch is built lets the Part-1 entry points overlap the upload
+ * of chunk i+1 with the kernels of chunk i.  Pageable buffers work too, the copies are then staged by the driver. */
+int flowgnn_b200_pin_host(void* ptr, size_t bytes);
+int flowgnn_b200_unpin_host(void* ptr);
 
 #ifdef __cplusplus
 }

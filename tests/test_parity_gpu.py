@@ -284,19 +284,100 @@ def test_edge_cases_empty_batch_and_edgeless_graph(ctx, weights):
         assert_parity(got, want, what=f"{model} edgeless/directed")
 
 
-def test_limits_are_reported_not_crashed(ctx, weights):
-    from flowgnn_b200.capi import FlowGNNError
+def _chain_graph(n, rng, with_eigen=False):
+    """One connected graph of n nodes: a path plus n random chords, both directions listed (molecule-like degrees)."""
     from flowgnn_b200.dataset import Batch
-    n = 1100                                   # above the 1024-node per-graph limit (reference cap: 500)
-    e = np.stack([np.arange(n - 1), np.arange(1, n)], 1).astype(np.int32)
-    big = Batch(np.array([n]), np.array([n - 1]), np.zeros((n, 9), np.int32), e, np.zeros((n - 1, 3), np.int32))
-    with pytest.raises(FlowGNNError, match="1024"):
-        ctx.run("gin", big, weights["gin"])
-    bad = Batch(np.array([2]), np.array([1]), np.zeros((2, 9), np.int32), np.array([[0, 5]], np.int32), np.zeros((1, 3), np.int32))
-    with pytest.raises(FlowGNNError, match="node id"):
-        ctx.run("gin", bad, weights["gin"])
-    ok = Batch(np.array([2]), np.array([1]), np.zeros((2, 9), np.int32), np.array([[0, 1]], np.int32), np.zeros((1, 3), np.int32))
-    assert np.isfinite(ctx.run("gin", ok, weights["gin"])).all()
+    a = np.concatenate([np.arange(n - 1), rng.integers(0, n, n)])
+    b = np.concatenate([np.arange(1, n), rng.integers(0, n, n)])
+    keep = a != b
+    a, b = a[keep], b[keep]
+    e = np.stack([np.stack([a, b], 1), np.stack([b, a], 1)], 1).reshape(-1, 2).astype(np.int32)
+    attr1 = np.stack([rng.integers(0, k, len(a)) for k in (5, 6, 2)], 1)
+    attr = np.repeat(attr1, 2, axis=0).astype(np.int32)
+    feat = np.stack([rng.integers(0, k, n) for k in (119, 4, 12, 12, 10, 6, 6, 2, 2)], 1).astype(np.int32)
+    eig = rng.standard_normal((n, 4)).astype(np.float32) if with_eigen else None
+    return Batch(np.array([n]), np.array([len(e)]), feat, e, attr, eig)
+
+
+@pytest.mark.parametrize("model", ["gin", "gcn", "gat", "pna", "dgn"])
+def test_graphs_above_the_shared_memory_tables(model, ctx, weights, datasets):
+    """No per-graph node cap (SURVEY.md 8b 'Limits'; the reference stops at MAX_NODE = 500, GIN/src/dcl.h:17): graphs of
+    1,100 and 3,000 nodes take the CSR build on global-memory tables (prep.cu) and must match the oracle, in one batch
+    with ordinary molecules on either side."""
+    from flowgnn_b200.dataset import Batch, concat
+    from oracle import refbind
+    rng = np.random.default_rng(21)
+    eig = model == "dgn"
+    mol = datasets["molhiv"].slice(0, 4)
+    if eig:
+        from flowgnn_b200.dataset import synthetic_molecules
+        mol = synthetic_molecules(4, "molhiv", seed=5, with_eigen=True)
+    elif mol.node_eigen is not None:
+        mol = Batch(mol.nums_of_nodes, mol.nums_of_edges, mol.node_feature, mol.edge_list, mol.edge_attr)
+    b = concat([mol.slice(0, 2), _chain_graph(1100, rng, eig), mol.slice(2, 3), _chain_graph(3000, rng, eig), mol.slice(3, 4)])
+    ctx.set_option("gat_node_offset_bug", 0)
+    try:
+        got = ctx.run(model, b, weights[model])
+    finally:
+        ctx.set_option("gat_node_offset_bug", 1)
+    want = refbind.run_port(model, b, weights[model], gat_node_offset_bug=False)
+    assert_parity(got, want, what=f"{model} with 1,100- and 3,000-node graphs")
+
+
+def test_rejected_batches_are_reported_not_crashed(ctx, weights, datasets):
+    """Every rejection is an error code + text, never a fault, and leaves the context usable: a bad edge id, a bond
+    feature outside its vocabulary, negative counts, totals that do not match the counts -- through the extended
+    interface and through the reference entry point, for kernels that gather through the CSR (GCN, PNA) as well as GIN's
+    row descriptors (the rejected graph's edge slots must hold defined values: the layer kernels run before the status is read)."""
+    from flowgnn_b200.capi import FlowGNNError, compute_graphs
+    from flowgnn_b200.dataset import Batch, concat
+    good = datasets["molhiv"].slice(0, 50)
+    good = Batch(good.nums_of_nodes, good.nums_of_edges, good.node_feature, good.edge_list, good.edge_attr)
+    want = {m: ctx.run(m, good, weights[m]).copy() for m in ("gin", "gcn", "pna")}
+
+    def with_graph(bad):
+        return concat([good.slice(0, 20), bad, good.slice(20, 50)])
+
+    z9 = lambda n: np.zeros((n, 9), np.int32)
+    bad_id = Batch(np.array([4]), np.array([5]), z9(4), np.array([[0, 1], [1, 0], [2, 7], [3, 2], [-1, 0]], np.int32), np.zeros((5, 3), np.int32))
+    bad_attr = Batch(np.array([3]), np.array([2]), z9(3), np.array([[0, 1], [1, 0]], np.int32), np.array([[0, 0, 0], [5, 0, 0]], np.int32))
+    for model in ("gin", "gcn", "pna"):
+        for bad, pattern in ((bad_id, "node id"), (bad_attr, "vocabulary")):
+            if model == "pna" and bad is bad_attr:
+                continue                                   # PNA takes no edge_attr
+            with pytest.raises(FlowGNNError, match=pattern):
+                ctx.run(model, with_graph(bad), weights[model])
+            with pytest.raises(FlowGNNError, match=pattern):
+                compute_graphs(model, with_graph(bad), weights[model])
+            assert np.array_equal(ctx.run(model, good).view(np.int32), want[model].view(np.int32)), "context unusable after a rejection"
+            assert np.array_equal(compute_graphs(model, good, weights[model]).view(np.int32), want[model].view(np.int32))
+    neg = Batch(good.nums_of_nodes.copy(), good.nums_of_edges.copy(), good.node_feature, good.edge_list, good.edge_attr)
+    neg.nums_of_nodes[3] = -5
+    with pytest.raises(FlowGNNError, match="negative"):
+        compute_graphs("gin", neg, weights["gin"])
+    with pytest.raises(FlowGNNError, match="negative|match"):
+        ctx.upload_arrays(neg.num_graphs, good.total_nodes, good.total_edges, neg.nums_of_nodes, neg.nums_of_edges, neg.node_feature,
+                          neg.edge_list, neg.edge_attr)
+    with pytest.raises(FlowGNNError, match="match"):
+        ctx.upload_arrays(good.num_graphs, good.total_nodes + 1, good.total_edges, good.nums_of_nodes, good.nums_of_edges,
+                          good.node_feature, good.edge_list, good.edge_attr)
+    assert np.array_equal(ctx.run("gin", good).view(np.int32), want["gin"].view(np.int32))
+
+
+def test_two_contexts_on_two_devices_in_one_process(weights, datasets, golden):
+    """Function attributes (the shared-memory opt-in of every big kernel) are per device: a second context on another GPU
+    of the same process must launch the same kernels (a process-wide 'attribute set' flag broke this)."""
+    import torch
+    from flowgnn_b200.capi import Context
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    b = datasets["molhiv"].slice(0, 400)
+    with Context(0) as c0, Context(1) as c1:
+        for model in ("gin", "gcn", "gat", "pna", "dgn"):
+            y0 = c0.run(model, b, weights[model])
+            y1 = c1.run(model, b, weights[model])
+            assert_parity(y0, golden["molhiv"][model][:400], what=f"{model} on device 0")
+            assert np.array_equal(y0.view(np.int32), y1.view(np.int32)), model
 
 
 @pytest.mark.parametrize("model", ["gin", "gcn", "pna"])
@@ -396,3 +477,36 @@ def test_full_size_synthetic_batch_properties(ctx, weights):
     ids = np.random.default_rng(5).choice(2048, 48, replace=False)
     assert_parity(y[ids], refbind.run_port("gin", base.select(ids), weights["gin"]), what="gin synthetic sample")
     assert ctx.last_launch_count == 10
+
+
+FULL_SIZE = {"gcn": ("molhiv", 41127), "gat": ("molhiv", 41127), "dgn": ("molhiv", 41127), "pna": ("molpcba", 437929),
+             "ginvn": ("hep10k", 40000)}
+
+
+@pytest.mark.parametrize("model", sorted(FULL_SIZE))
+def test_full_size_batches_of_the_other_configs(model, ctx, weights):
+    """BASELINE configs C3 (GAT, 41,127 molhiv-shaped graphs), C4 (PNA, 437,929 molpcba-shaped graphs), C5 (GIN-VN,
+    40,000 hep10k-shaped graphs) and GCN / DGN at the C2 size: the full-size launch sequence (multi-GB activation planes,
+    every persistent CTA with many tiles) -- determinism, agreement of the tiled copies, and a random sample re-checked
+    against the oracle."""
+    from flowgnn_b200.dataset import synthetic_hep, synthetic_molecules
+    from oracle import refbind
+    shape, G = FULL_SIZE[model]
+    nbase = 1024 if shape == "hep10k" else 2048
+    base = synthetic_hep(nbase, seed=13) if shape == "hep10k" else synthetic_molecules(nbase, shape, seed=13, with_eigen=(model == "dgn"))
+    b = base.tile(G)
+    ctx.set_option("gat_node_offset_bug", 0)           # per-graph semantics, so that tiled copies and the oracle sample are comparable
+    try:
+        y = ctx.run(model, b, weights[model])
+        again = ctx.run(model, b)
+    finally:
+        ctx.set_option("gat_node_offset_bug", 1)
+    assert y.shape == (G,) and np.isfinite(y).all()
+    assert np.array_equal(y.view(np.int32), again.view(np.int32)), "not deterministic"
+    assert np.array_equal(y[:nbase].view(np.int32), y[nbase:2 * nbase].view(np.int32)), "tiled copies differ"
+    last = (G // nbase) * nbase
+    assert np.array_equal(y[last:].view(np.int32), y[:G - last].view(np.int32)), "tail of the batch differs from the head"
+    ids = np.random.default_rng(5).choice(nbase, 48, replace=False)
+    sel = base.select(ids)
+    want = refbind.run_port(model, sel.with_virtual_node() if model == "ginvn" else sel, weights[model], gat_node_offset_bug=False)
+    assert_parity(y[ids], want, what=f"{model} full-size sample")

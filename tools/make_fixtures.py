@@ -6,7 +6,7 @@ What it writes (all consumed by tests/ on machines that do NOT have the referenc
 * tests/golden/weights/<MODEL>/...   the trained weight blobs, in the reference's own file formats
                                      (inputs the host loads; SURVEY.md App. B);
 * tests/golden/<dataset>.npz          packed graphs: all 4,113 shipped molhiv graphs, the first 4,113
-                                     molpcba graphs, the first 500 hep10k graphs (with DGN eigenvectors);
+                                     molpcba graphs, the first 1,000 hep10k graphs (with DGN eigenvectors; SURVEY.md 8d config C5);
 * tests/golden/golden_<dataset>.npz   per-graph predictions of the UNMODIFIED reference kernels compiled
                                      against oracle/shim (oracle/_ref, canonical -O2 -ffp-contract=off
                                      build), one array per model.  `gat` is the whole dataset as ONE batch
@@ -14,7 +14,7 @@ What it writes (all consumed by tests/ on machines that do NOT have the referenc
                                      `gat_per_graph` evaluates each graph as its own batch (offset bug
                                      cannot trigger).  `ginvn` runs on the virtual-node-augmented batch.
 
-Usage:  make -C oracle ref && python tools/make_fixtures.py
+Usage:  make -C oracle ref && python tools/make_fixtures.py [dataset ...]     (default: all three)
 """
 from __future__ import annotations
 
@@ -45,7 +45,7 @@ WEIGHT_FILES = {
         "linear_proj_weight_0", "linear_proj_weight_1", "skip_proj_weight_0", "skip_proj_weight_1")],
 }
 MODEL_DIR = {"gin": "GIN", "ginvn": "GIN", "gcn": "GCN", "gat": "GAT", "pna": "PNA", "dgn": "DGN"}
-DATASETS = {"molhiv": 4113, "molpcba": 4113, "hep10k": 500}
+DATASETS = {"molhiv": 4113, "molpcba": 4113, "hep10k": 1000}
 
 
 def main() -> None:
@@ -72,7 +72,10 @@ def main() -> None:
 
     weights = {m: load_weights(m, os.path.join(GOLD, "weights", d)) for m, d in MODEL_DIR.items()}
 
+    only = set(sys.argv[1:])
     for ds, count in DATASETS.items():
+        if only and ds not in only:
+            continue
         t = time.time()
         batch = load_dataset_zip(os.path.join(REF, f"{ds}.zip"), count, with_eigen=True)
         batch.save_npz(os.path.join(GOLD, f"{ds}.npz"))
