@@ -12,8 +12,22 @@
 //
 // The OpenCL/XRT plumbing (xcl2, cl::Buffer, bitstream programming) has no counterpart: the library owns the GPU.
 //
-//   host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE]
+// Beyond the reference (one FPGA, one in-order queue: GIN/config_slr.cfg:2, GIN/src/host.cc:207-209):
+//   --gpus N         graphs are independent (the kernel's graph loop carries only offsets, GIN/src/GIN_compute.cc:44,96-97),
+//                    so the batch is cut into N contiguous graph ranges balanced by nodes + edges/4; one host thread per
+//                    GPU owns a context (Part 2 of the header), uploads its range once and runs the trials on it; the
+//                    predictions land in disjoint slices of out[G].  NCCL is used for ONE thing: the throughput tally
+//                    (all-reduce SUM of the graphs done, MAX of the device time) -- there is no collective on the data path
+//   <dataset>.fgb    the packed single-file dataset (flowgnn_b200/dataset.py::save_packed) instead of 3-4 tiny files per graph
+//
+//   host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir | file.fgb> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE] [--gpus N]
+#include <cuda_runtime.h>
+#include <nccl.h>
+
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -230,6 +244,183 @@ Graphs load_graphs(const std::string& root, int first, int count, bool with_eige
     return g;
 }
 
+// FGNNPACK v1 (flowgnn_b200/dataset.py): magic[8] | u32 version | u32 flags | u64 G | u64 N | u64 E |
+// nums_of_nodes[G] | nums_of_edges[G] | node_feature[N][9] | edge_list[E][2] | (flags & 1) edge_attr[E][3] | (flags & 2) eigen[N][4]
+Graphs load_packed(const std::string& path, int first, int count, bool with_eigen, bool virtual_node)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) die("cannot open " + path);
+    char magic[8];
+    uint32_t version = 0, flags = 0;
+    uint64_t G = 0, N = 0, E = 0;
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "FGNNPACK", 8) != 0) die(path + ": not a FGNNPACK file");
+    if (std::fread(&version, 4, 1, f) != 1 || std::fread(&flags, 4, 1, f) != 1 || std::fread(&G, 8, 1, f) != 1 || std::fread(&N, 8, 1, f) != 1 ||
+        std::fread(&E, 8, 1, f) != 1 || version != 1)
+        die(path + ": bad header");
+    auto rd_i = [&](size_t n) { std::vector<int32_t> v(n); if (n && std::fread(v.data(), 4, n, f) != n) die(path + ": truncated"); return v; };
+    const auto nn = rd_i(G), ne = rd_i(G);
+    const auto nf = rd_i(N * ND_FEATURE), el = rd_i(E * 2);
+    std::vector<int32_t> ea = (flags & 1) ? rd_i(E * EDGE_ATTR) : std::vector<int32_t>(E * EDGE_ATTR, 0);
+    std::vector<float> eg;
+    if (flags & 2) { eg.resize(N * 4); if (N && std::fread(eg.data(), 4, N * 4, f) != N * 4) die(path + ": truncated"); }
+    std::fclose(f);
+    if (with_eigen && !(flags & 2)) die(path + ": DGN needs the eigenvectors, the file has none");
+    if (count < 0) count = (int)G - (first - 1);
+    if (first < 1 || (uint64_t)(first - 1 + count) > G) die(path + ": graph range outside the file");
+    Graphs g;
+    size_t nb = 0, eb = 0;
+    for (int id = 1; id < first; id++) { nb += (size_t)nn[id - 1]; eb += (size_t)ne[id - 1]; }
+    for (int id = first; id < first + count; id++)
+    {
+        int n = nn[id - 1], e = ne[id - 1];
+        g.feat.insert(g.feat.end(), nf.begin() + nb * ND_FEATURE, nf.begin() + (nb + n) * ND_FEATURE);
+        g.edges.insert(g.edges.end(), el.begin() + eb * 2, el.begin() + (eb + e) * 2);
+        g.attr.insert(g.attr.end(), ea.begin() + eb * EDGE_ATTR, ea.begin() + (eb + e) * EDGE_ATTR);
+        if (with_eigen) g.eig.insert(g.eig.end(), eg.begin() + nb * 4, eg.begin() + (nb + n) * 4);
+        nb += (size_t)n; eb += (size_t)e;
+        if (virtual_node)
+        {
+            g.feat.insert(g.feat.end(), ND_FEATURE, 0);
+            for (int i = 0; i < n; i++)
+            {
+                const int32_t pair[4] = {i, n, n, i};
+                g.edges.insert(g.edges.end(), pair, pair + 4);
+                g.attr.insert(g.attr.end(), 2 * EDGE_ATTR, 0);
+            }
+            e += 2 * n;
+            n += 1;
+        }
+        g.nn.push_back(n);
+        g.ne.push_back(e);
+        g.reload.push_back(id == first ? 1 : 0);
+    }
+    return g;
+}
+
+int model_id(const std::string& model)
+{
+    if (model == "gin" || model == "ginvn") return FLOWGNN_GIN;
+    if (model == "gcn") return FLOWGNN_GCN;
+    if (model == "gat") return FLOWGNN_GAT;
+    if (model == "pna") return FLOWGNN_PNA;
+    return FLOWGNN_DGN;
+}
+
+// contiguous graph ranges balanced by sum(N + E / 4) (the same rule as flowgnn_b200/dataset.py::shard_ranges)
+std::vector<int> shard_bounds(const Graphs& g, int parts)
+{
+    const int G = (int)g.nn.size();
+    std::vector<double> cum(G + 1, 0.0);
+    for (int i = 0; i < G; i++) cum[i + 1] = cum[i] + g.nn[i] + 0.25 * g.ne[i];
+    std::vector<int> b(parts + 1, G);
+    b[0] = 0;
+    for (int k = 1; k < parts; k++)
+    {
+        const double target = cum[G] * k / parts;
+        b[k] = std::max(b[k - 1], (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin()));
+    }
+    return b;
+}
+
+struct Barrier {
+    std::mutex m; std::condition_variable cv; int n, waiting = 0, gen = 0;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> l(m);
+        const int g = gen;
+        if (++waiting == n) { waiting = 0; gen++; cv.notify_all(); }
+        else cv.wait(l, [&] { return gen != g; });
+    }
+};
+
+struct Tally { double graphs = 0, ms = 0; };
+
+// One thread per GPU: context, weights, its graph range resident in HBM, `trials` device-timed passes, predictions into
+// out[g0..g1).  The tally goes through NCCL over NVLink: SUM of the graphs, MAX of the best device time.
+void run_sharded(const std::string& model, Graphs& g, Weights& w, std::vector<float>& out, int gpus, int trials, Tally& tally)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < gpus) die("--gpus " + std::to_string(gpus) + ": only " + std::to_string(ndev) + " CUDA device(s) visible");
+    const std::vector<int> bounds = shard_bounds(g, gpus);
+    std::vector<size_t> noff(g.nn.size() + 1, 0), eoff(g.nn.size() + 1, 0);
+    for (size_t i = 0; i < g.nn.size(); i++) { noff[i + 1] = noff[i] + (size_t)g.nn[i]; eoff[i + 1] = eoff[i] + (size_t)g.ne[i]; }
+    std::vector<int> devs(gpus);
+    for (int k = 0; k < gpus; k++) devs[k] = k;
+    std::vector<ncclComm_t> comms(gpus);
+    if (ncclCommInitAll(comms.data(), gpus, devs.data()) != ncclSuccess) die("ncclCommInitAll failed");
+    Barrier bar(gpus);
+    std::vector<std::string> errors(gpus);
+    std::vector<Tally> local(gpus), global(gpus);
+    const int mid = model_id(model);
+    const bool with_attr = (mid == FLOWGNN_GIN || mid == FLOWGNN_GCN), with_eig = (mid == FLOWGNN_DGN);
+    auto worker = [&](int k) {
+        auto fail = [&](const std::string& what) { errors[k] = what + ": " + flowgnn_b200_last_error(); };
+        cudaSetDevice(k);
+        flowgnn_ctx* ctx = nullptr;
+        const int g0 = bounds[k], g1 = bounds[k + 1];
+        bool ok = flowgnn_b200_create(&ctx, k) == 0;
+        if (!ok) fail("create");
+        if (ok)
+        {
+            std::vector<const float*> a;
+            for (auto& v : w.arrays) a.push_back(v.data());
+            ok = flowgnn_b200_load_weights(ctx, mid, a.data(), (int)a.size()) == 0;
+            if (!ok) fail("load_weights");
+        }
+        if (ok)
+        {
+            // the reference's GAT reads node features from the START of the batch buffer for every graph; a
+            // range of a larger batch keeps that behaviour by handing the kernel the batch's first rows
+            const int32_t* feat = (mid == FLOWGNN_GAT) ? g.feat.data() : g.feat.data() + ND_FEATURE * noff[g0];
+            ok = flowgnn_b200_upload_batch(ctx, g1 - g0, (int64_t)(noff[g1] - noff[g0]), (int64_t)(eoff[g1] - eoff[g0]), g.nn.data() + g0,
+                                           g.ne.data() + g0, feat, g.edges.data() + 2 * eoff[g0],
+                                           with_attr ? g.attr.data() + EDGE_ATTR * eoff[g0] : nullptr,
+                                           with_eig ? g.eig.data() + 4 * noff[g0] : nullptr) == 0;
+            if (!ok) fail("upload_batch");
+        }
+        double best = 1e30;
+        for (int t = 0; t < std::max(trials, 1); t++)
+        {
+            bar.wait();                                       // all GPUs start a trial together
+            float ms = 0.f;
+            if (ok && g1 > g0)
+            {
+                ok = flowgnn_b200_compute(ctx, mid, &ms) == 0 && flowgnn_b200_download(ctx, out.data() + g0, g1 - g0) == 0;
+                if (!ok) fail("compute");
+            }
+            if (t > 0 || trials == 1) best = std::min(best, (double)ms);
+        }
+        local[k].graphs = ok ? g1 - g0 : 0;
+        local[k].ms = best < 1e29 ? best : 0.0;
+        // ---- the tally: the only use of NCCL ----
+        double* d = nullptr;
+        cudaStream_t s;
+        cudaStreamCreate(&s);
+        cudaMalloc(&d, 2 * sizeof(double));
+        cudaMemcpyAsync(d, &local[k], 2 * sizeof(double), cudaMemcpyHostToDevice, s);
+        bar.wait();
+        ncclGroupStart();
+        ncclAllReduce(d, d, 1, ncclDouble, ncclSum, comms[k], s);
+        ncclAllReduce(d + 1, d + 1, 1, ncclDouble, ncclMax, comms[k], s);
+        ncclGroupEnd();
+        cudaMemcpyAsync(&global[k], d, 2 * sizeof(double), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        cudaFree(d);
+        cudaStreamDestroy(s);
+        if (ctx) flowgnn_b200_destroy(ctx);
+    };
+    std::vector<std::thread> th;
+    for (int k = 0; k < gpus; k++) th.emplace_back(worker, k);
+    for (auto& t : th) t.join();
+    for (int k = 0; k < gpus; k++) ncclCommDestroy(comms[k]);
+    for (int k = 0; k < gpus; k++)
+        if (!errors[k].empty()) die("GPU " + std::to_string(k) + ": " + errors[k]);
+    tally = global[0];
+    for (int k = 0; k < gpus; k++)
+        std::printf("  GPU %d: graphs [%d, %d)  best %.3f ms (device-timed)\n", k, bounds[k] + 1, bounds[k + 1] + 1, local[k].ms);
+}
+
 int run_model(const std::string& model, Graphs& g, Weights& w, std::vector<float>& out)
 {
     const int G = (int)g.nn.size();
@@ -256,9 +447,9 @@ int run_model(const std::string& model, Graphs& g, Weights& w, std::vector<float
 int main(int argc, char** argv)
 {
     if (argc < 4)
-        die("usage: host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE]");
+        die("usage: host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir | file.fgb> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE] [--gpus N]");
     const std::string model = argv[1], root = argv[2], wdir = argv[3];
-    int count = -1, first = 1, trials = 25;                      // NUM_TRIALS = 25, GIN/src/host.h:8
+    int count = -1, first = 1, trials = 25, gpus = 0;            // NUM_TRIALS = 25, GIN/src/host.h:8
     std::string out_path = "B200_output.txt";
     for (int i = 4; i + 1 < argc; i += 2)
     {
@@ -267,9 +458,11 @@ int main(int argc, char** argv)
         else if (k == "--first") first = std::atoi(argv[i + 1]);
         else if (k == "--trials") trials = std::atoi(argv[i + 1]);
         else if (k == "--out") out_path = argv[i + 1];
+        else if (k == "--gpus") gpus = std::atoi(argv[i + 1]);
         else die("unknown option " + k);
     }
-    if (count < 0)
+    const bool packed = root.size() > 4 && root.compare(root.size() - 4, 4, ".fgb") == 0;
+    if (count < 0 && !packed)
     {
         // NUM_GRAPHS comes from common/includes/dataset/dataset_size.txt in the reference (dataset.hpp:1-3)
         FILE* f = std::fopen((root + "/common/includes/dataset/dataset_size.txt").c_str(), "r");
@@ -279,10 +472,24 @@ int main(int argc, char** argv)
     }
     Weights w = load_weights(model, wdir);
     std::printf("******* Weights loading done *******\n");
-    Graphs g = load_graphs(root, first, count, model == "dgn", model == "ginvn");
+    Graphs g = packed ? load_packed(root, first, count, model == "dgn", model == "ginvn") : load_graphs(root, first, count, model == "dgn", model == "ginvn");
+    count = (int)g.nn.size();
     std::printf("******* Graphs loading done: %d graphs *******\n", count);
 
     std::vector<float> out((size_t)count, 0.0f);
+    if (gpus > 0)
+    {
+        Tally tally;
+        run_sharded(model, g, w, out, gpus, trials, tally);
+        std::printf("%s: %d graphs on %d GPU(s), %d trials: %.0f graphs in %.3f ms (NCCL tally: SUM of graphs, MAX of the best device time) = %.0f graphs/s\n",
+                    model.c_str(), count, gpus, trials, tally.graphs, tally.ms, tally.ms > 0 ? tally.graphs / (tally.ms * 1e-3) : 0.0);
+        FILE* fo = std::fopen(out_path.c_str(), "w");
+        if (!fo) die("cannot write " + out_path);
+        for (int i = 0; i < count; i++) std::fprintf(fo, "g%d: %.8f\n", first + i, out[i]);
+        std::fclose(fo);
+        std::printf("******* %s written *******\n", out_path.c_str());
+        return 0;
+    }
     double best_ms = 1e30, sum_ms = 0;
     for (int t = 0; t < std::max(trials, 1); t++)
     {
