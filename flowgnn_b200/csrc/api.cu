@@ -53,7 +53,7 @@ void DevBuf::release()
 void DeviceBatch::release()
 {
     DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
-                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &big_tab, &status, &node_dot, &apack, &nonfinite,
+                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &big_tab, &status, &tiles, &tile_count, &node_dot, &apack, &nonfinite,
                      &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
     for (DevBuf* b : all) b->release();
 }
@@ -521,6 +521,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     if (!std::strcmp(name, "mp_only")) ctx->opt.mp_only = value;
     else if (!std::strcmp(name, "gin_ffma")) ctx->opt.gin_ffma = value;
     else if (!std::strcmp(name, "gin_tc1")) ctx->opt.gin_tc1 = value;
+    else if (!std::strcmp(name, "gin_tc2")) ctx->opt.gin_tc2 = value;
     else if (!std::strcmp(name, "gin_tc3")) ctx->opt.gin_tc3 = value;
     else if (!std::strcmp(name, "gin_staged")) ctx->opt.gin_staged = value;
     else if (!std::strcmp(name, "pna_tc")) ctx->opt.pna_tc = value;
@@ -612,13 +613,13 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     if (b.num_graphs == 0) return 0;
     if (model == MODEL_DGN && !b.has_eigen) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
     if ((model == MODEL_GIN || model == MODEL_GCN) && !b.has_attr) { set_last_error("GIN/GCN need edge_attr"); return FG_ERR_INVALID; }
-    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN) ? PREP_ROW_DESC : 0;
+    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN) ? (PREP_ROW_DESC | PREP_TILES) : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
     int rc = prep_batch(b, flags, s);
     b.has_attr = keep_attr;
     FG_TRY(rc);
-    ctx->last_launches += 3;      // scan_offsets + the two build_csr instantiations
+    ctx->last_launches += 3 + (model == MODEL_GIN ? 1 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN: pack_tiles)
     ctx->timer.marks = 0;
     ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
     ctx->opt.timer_group = ctx->time_layers == 2;

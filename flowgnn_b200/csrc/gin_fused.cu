@@ -1,0 +1,656 @@
+// GIN / GIN-VN layer, ONE kernel per layer: TMA-staged graph-aligned tiles, shared-memory edge gather, tcgen05 node MLP.
+//
+// Reference work per layer (GIN/src/message_passing.cc:77-150, node_embedding.cc:23-201):
+//   m_v = sum_{(u,v)} relu(h_u + EE_l[attr_uv]);  a_v = m_v + h_v  (eps is never loaded: SURVEY.md F4)
+//   z = relu(W1 a + b1);  h'_v = W2 z + b2  (+ relu unless last layer)
+//
+// What changed against gin_tc2.cu (same CTA pair, same weight image, same MMA / epilogue protocol): the edge gather no
+// longer goes through the L1 / LSU global path.  In-edge sources are nodes of the SAME graph and a graph's rows are
+// contiguous in HBM, so prep.cu packs whole graphs into tiles of <= 128 rows and the kernel lands a tile's feature rows
+// in shared memory with ONE bulk-TMA copy (cp.async.bulk + mbarrier, issued by a producer warp, no LSU wavefronts, every
+// row read from HBM exactly once).  The gather warps then read own row, source rows and edge-embedding rows with
+// conflict-free 128-byte shared-memory pieces (29-cycle latency instead of L2 round trips: no software pipeline, no
+// register ring), reduce in CSR order and write the bf16 hi/lo A tile.  The shared memory for the stage comes from
+// single-buffering the A tile: gather(t+1) starts when GEMM1(t) has consumed A, and overlaps the z conversion, GEMM2
+// and the h' epilogue of tile t.
+//
+// Per CTA (896 threads; cluster of two CTAs = one UMMA M = 256 tile = two graph-aligned tiles):
+//   warps 0-7   epilogue (as gin_tc2.cu): z = relu(acc) -> bf16 hi/lo in tensor memory, h' = acc (+relu) -> HBM, or the fused head
+//   warps 8-23  gather: 8 rows each as two passes of 4 rows, 8 lanes per row, chunk 8 ks + j in step ks < 3; chunk 24 by lane j == 0
+//   warp 24     (leader CTA) MMA issuer: GEMM1 SS (3 products x 7 k-steps, N halves 112 + 96), GEMM2 TS (3 x 13, N = 128)
+//   warp 25     producer: bulk-TMA copy of the next tile's rows into the stage, L2 prefetch two tiles ahead
+// Option mp_only (node transform = identity): the same gather writes x = m + h straight to h_out, the MMA
+// and epilogue warps idle, and the A-tile region serves as a second stage buffer.
+// Tiles whose graph exceeds 128 nodes are flagged external: their source rows are read from global memory.
+#include "internal.cuh"
+#include "layers.cuh"
+#include "tc.cuh"
+#include "pair.cuh"
+#include "gin_wpack.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace fg {
+
+namespace {
+
+using namespace ginw;
+using namespace pair;
+
+constexpr int LBO_A = TM * 16 + 32;                     // +32: the 8-byte stores of a warp hit every bank group exactly twice
+constexpr int A_BYTES = K1_CHUNKS * LBO_A;              // one hi or lo buffer
+constexpr int ZERO_BYTES = TM * 16;
+constexpr int ROW_BYTES = D * 4;                        // 400
+constexpr int STAGE_BYTES = TM * ROW_BYTES;             // 51,200
+constexpr int DESC_BYTES = TM * 16;                     // 2,048
+
+constexpr int EPI_WARPS = 8, GATHER_WARPS = 16;
+constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, LOAD_WARP = MMA_WARP + 1;
+constexpr int NT = (MMA_WARP + 4) * 32;       // 896
+constexpr int REGS_LAUNCH = 72;
+constexpr int REGS_EPI = 80, REGS_MISC = 56, REGS_GATHER = 72;
+static_assert(32 * (EPI_WARPS * REGS_EPI + GATHER_WARPS * REGS_GATHER + 4 * REGS_MISC) <= NT * REGS_LAUNCH, "setmaxnreg pool");
+constexpr int ROWS_PER_WARP = TM / GATHER_WARPS;   // 8
+
+constexpr uint32_t TC_Z = 0, TC_H = 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct Smem {
+    static constexpr int W = 0;
+    static constexpr int A = W + W_BYTES;                           // [hi, lo][A_BYTES]; mp_only: second stage buffer
+    static constexpr int ZERO = A + 2 * A_BYTES;                    // K chunk 13 of the A buffers (must lie above them: LBO >= 0)
+    static constexpr int EE = ZERO + ZERO_BYTES;                    // [61][100] fp32 combined edge-embedding rows; row 60 = sentinel
+    static constexpr int STAGE = EE + (ED_COMBOS + 1) * D * 4;      // [128][100] fp32 feature rows of the tile (bulk TMA)
+    static constexpr int DESC = STAGE + STAGE_BYTES;                // [128] int4 row descriptors of the tile (second bulk copy)
+    static constexpr int BAR = DESC + DESC_BYTES;
+    static constexpr int TMEM_PTR = BAR + 16 * 8;
+    static constexpr int TILE = TMEM_PTR + 16;                      // [2] int2 tile record of the stage (written by the producer)
+    static constexpr int BYTES = TILE + 16;
+};
+static_assert(Smem::ZERO % 16 == 0 && Smem::A % 16 == 0 && Smem::EE % 16 == 0 && Smem::STAGE % 16 == 0 && Smem::BAR % 8 == 0, "alignment");
+static_assert(2 * A_BYTES >= STAGE_BYTES + DESC_BYTES, "mp_only uses the A region as the second stage");
+static_assert(Smem::BYTES <= 232448, "shared memory budget");
+
+enum { BAR_W = 0, BAR_A_FULL, BAR_A_FREE, BAR_G1A_DONE, BAR_G1B_DONE, BAR_A2A_FULL, BAR_A2B_FULL, BAR_G2_DONE,
+       BAR_STAGE_FULL /* 2 */, BAR_STAGE_FREE = BAR_STAGE_FULL + 2 /* 2 */, BAR_COUNT = BAR_STAGE_FREE + 2 };
+static_assert(BAR_COUNT <= 16, "barrier slots");
+
+struct GinFusedParams {
+    const float* h_in; float* h_out;
+    const int* in_ptr; const int* src; const uint8_t* code;
+    const int4* row_desc;            // [N] first four in-edges of every node, packed (prep.cu)
+    const int2* tiles;               // graph-aligned tiles (first node, rows | external << 30) (prep.cu::pack_tiles_kernel)
+    const int* tile_count;
+    const float* ee_comb;            // [60][100] this layer
+    const unsigned char* wpack;      // [2 ranks][W_BYTES] this layer
+    int num_nodes; int relu_out; int mp_only;
+    const float* head_w; float* node_dot;      // last layer: fused prediction head (see gin_tc2.cu)
+};
+
+__device__ __forceinline__ int2 tile_of(const GinFusedParams& p, int t, int ntiles)
+{
+    int2 v = make_int2(0, 0);
+    if (t < ntiles) asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p.tiles + t));
+    return v;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ int4 lds_i4(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void stg_f4(float* ptr, const float4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// One destination row as seen by one of its 8 threads: shared-memory byte addresses of this thread's 16-byte chunk
+// (step 0) of the row itself, of the source rows of its first four in-edges and of their edge-embedding rows.
+// Absent slots point at the row itself and the sentinel table row (relu(h - 3e38) adds exactly 0); a row beyond the end of
+// the tile reads the shared zero block, so its x is 0 without a select.
+struct RowCtx {
+    uint32_t own;
+    uint32_t so[4];
+    uint32_t tb[4];
+    int deg;
+    int node;            // global node id
+};
+
+// m += relu(t + h) with the two additions as FADD2 (same IEEE result per element as four FADD)
+__device__ __forceinline__ void acc_edge2(float4& m, const float4& t, const float4& h)
+{
+    const float2 a = add2(make_float2(t.x, t.y), make_float2(h.x, h.y)), b = add2(make_float2(t.z, t.w), make_float2(h.z, h.w));
+    const float2 ma = add2(make_float2(m.x, m.y), make_float2(relu_nan(a.x), relu_nan(a.y)));
+    const float2 mb = add2(make_float2(m.z, m.w), make_float2(relu_nan(b.x), relu_nan(b.y)));
+    m = make_float4(ma.x, ma.y, mb.x, mb.y);
+}
+
+// x = h_v + sum over in-edges (CSR order) of relu(h_u + EE[code]) for this thread's chunk at byte offset OFF of the row.
+// NQ = number of descriptor slots the four rows of this warp instruction need (the longest of their in-edge lists, at
+// most 4): the loads are unconditional -- an absent slot costs a shared-memory wavefront but no instruction to predicate
+// it, and the kernel is bound by instruction issue, not by the shared-memory pipe.  LONG: a row has more than four
+// in-edges (virtual nodes, kNN graphs): rounds of four further edges from the CSR arrays.
+template <int NQ, bool LONG, int OFF>
+__device__ __forceinline__ float4 gather_chunk(const GinFusedParams& p, const RowCtx& r, int maxdeg, uint32_t stage_thr, uint32_t ee_thr, int tile_start)
+{
+    const float4 hv = lds_f4(r.own + OFF);
+    float4 hu[4], tt[4];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) { hu[q] = lds_f4(r.so[q] + OFF); tt[q] = lds_f4(r.tb[q] + OFF); }
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < NQ; q++) acc_edge2(m, tt[q], hu[q]);
+    if constexpr (LONG)
+    {
+        const int eb = __ldg(p.in_ptr + r.node);
+        int u[4], c[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const bool ok = 4 + q < r.deg;
+            u[q] = ok ? __ldg(p.src + eb + 4 + q) : r.node;
+            c[q] = ok ? (int)__ldg(p.code + eb + 4 + q) : ED_COMBOS;
+        }
+#pragma unroll 1
+        for (int e4 = 4; e4 < maxdeg; e4 += 4)
+        {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                // an exhausted slot reads the row itself (u = node) with the sentinel table row: adds exactly 0
+                hu[q] = lds_f4(stage_thr + (uint32_t)(u[q] - tile_start) * ROW_BYTES + OFF);
+                tt[q] = lds_f4(ee_thr + c[q] * ROW_BYTES + OFF);
+                const bool ok = e4 + 4 + q < r.deg;
+                u[q] = ok ? __ldg(p.src + eb + e4 + 4 + q) : r.node;
+                c[q] = ok ? (int)__ldg(p.code + eb + e4 + 4 + q) : ED_COMBOS;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc_edge2(m, tt[q], hu[q]);
+        }
+    }
+    const float2 xa = add2(make_float2(m.x, m.y), make_float2(hv.x, hv.y)), xb = add2(make_float2(m.z, m.w), make_float2(hv.z, hv.w));
+    return make_float4(xa.x, xa.y, xb.x, xb.y);
+}
+
+// where a chunk of x goes: the bf16 hi / lo A tile (shared memory), or -- mp_only -- h_out
+__device__ __forceinline__ void put_chunk(const float4& x, bool mp_only, bool live, float* out_chunk, uint32_t a_dst)
+{
+    if (mp_only) { if (live) stg_f4(out_chunk, x); }
+    else
+    {
+        uint32_t h0, l0, h1, l1;
+        split2(x.x, x.y, h0, l0);
+        split2(x.z, x.w, h1, l1);
+        sts_v2(a_dst, h0, h1);
+        sts_v2(a_dst + A_BYTES, l0, l1);
+    }
+}
+
+// chunks 8 ks + j, ks < 3, of the pass's row (this thread: lane j of the row)
+template <int NQ, bool LONG>
+__device__ __forceinline__ void gather_pass(const GinFusedParams& p, const RowCtx& r, int maxdeg, uint32_t stage_thr, uint32_t ee_thr, int tile_start,
+                                            bool mp_only, bool live, float* out_thr, uint32_t a_thr)
+{
+    const float4 x0 = gather_chunk<NQ, LONG, 0>(p, r, maxdeg, stage_thr, ee_thr, tile_start);
+    put_chunk(x0, mp_only, live, out_thr, a_thr);
+    const float4 x1 = gather_chunk<NQ, LONG, 128>(p, r, maxdeg, stage_thr, ee_thr, tile_start);
+    put_chunk(x1, mp_only, live, out_thr + 32, a_thr + 4 * LBO_A);
+    const float4 x2 = gather_chunk<NQ, LONG, 256>(p, r, maxdeg, stage_thr, ee_thr, tile_start);
+    put_chunk(x2, mp_only, live, out_thr + 64, a_thr + 8 * LBO_A);
+}
+
+// The last float4 of a row (columns 96..99, chunk 24) does not fit 8 lanes x 3 steps: once per tile lanes 0..7 of a warp
+// take it for the warp's 8 rows, a lane per row, walking the row's in-edges one by one (same CSR order).
+__device__ __forceinline__ float4 tail_chunk(const GinFusedParams& p, const int4& d, int node, int deg, uint32_t own, uint32_t ee_tail, bool ext,
+                                             uint32_t stage_tail, int tile_start)
+{
+    const float4 hv = lds_f4(own);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int dq[4] = {d.x, d.y, d.z, d.w};
+    const float* h_tail = p.h_in + 4 * (Q - 1);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (q < deg)
+        {
+            const int rel = (dq[q] & 0xFFFF) - 32768;
+            const float4 hu = ext ? ldg_f4(h_tail + (size_t)(node + rel) * D) : lds_f4(own + (uint32_t)(rel * ROW_BYTES));
+            acc_edge2(m, lds_f4(ee_tail + ((dq[q] >> 16) & 0x3F) * ROW_BYTES), hu);
+        }
+    if (deg > 4)
+    {
+        const int eb = __ldg(p.in_ptr + node);
+        for (int e = 4; e < deg; e++)
+        {
+            const int u = __ldg(p.src + eb + e), c = __ldg(p.code + eb + e);
+            const float4 hu = ext ? ldg_f4(h_tail + (size_t)u * D) : lds_f4(stage_tail + (uint32_t)(u - tile_start) * ROW_BYTES);
+            acc_edge2(m, lds_f4(ee_tail + c * ROW_BYTES), hu);
+        }
+    }
+    return make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w);
+}
+
+// A chunk of a row of a graph with more than 128 nodes: source rows may lie outside the stage and are read from global
+// memory.  Rare (molhiv: 0.1 % of the graphs), kept out of line so that it does not cost the fast path registers.
+__device__ __noinline__ float4 gather_chunk_ext(const float* h_chunk, const int* in_ptr, const int* src, const uint8_t* code, int node, int deg,
+                                                uint32_t own, uint32_t ee_chunk)
+{
+    const float4 hv = lds_f4(own);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int eb = __ldg(in_ptr + node);
+    for (int e = 0; e < deg; e++)
+    {
+        const int u = __ldg(src + eb + e), c = __ldg(code + eb + e);
+        acc_edge2(m, lds_f4(ee_chunk + c * ROW_BYTES), ldg_f4(h_chunk + (size_t)u * D));
+    }
+    return make_float4(m.x + hv.x, m.y + hv.y, m.z + hv.z, m.w + hv.w);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fused_kernel(GinFusedParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* ee = reinterpret_cast<float*>(smem + Smem::EE);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::BAR);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const bool mp_only = p.mp_only != 0;
+    const int nstage = mp_only ? 2 : 1;
+
+    if (tid == 0)
+    {
+        mbar_init(&bar[BAR_W], 1);
+        mbar_init(&bar[BAR_A_FULL], 2 * GATHER_WARPS);
+        mbar_init(&bar[BAR_A_FREE], 1);
+        mbar_init(&bar[BAR_G1A_DONE], 1);
+        mbar_init(&bar[BAR_G1B_DONE], 1);
+        mbar_init(&bar[BAR_A2A_FULL], 2 * EPI_WARPS);
+        mbar_init(&bar[BAR_A2B_FULL], 2 * EPI_WARPS);
+        mbar_init(&bar[BAR_G2_DONE], 1);
+        for (int i = 0; i < 2; i++)
+        {
+            mbar_init(&bar[BAR_STAGE_FULL + i], 1);
+            mbar_init(&bar[BAR_STAGE_FREE + i], GATHER_WARPS);
+        }
+        fence_mbar_init();
+        if (!mp_only)
+        {
+            mbar_arrive_expect_tx(&bar[BAR_W], W_BYTES);
+            tma_load_1d(smem + Smem::W, p.wpack + (size_t)rank * W_BYTES, W_BYTES, &bar[BAR_W]);
+        }
+    }
+    __syncthreads();
+    cluster_sync();          // both CTAs are running and their barriers are initialised
+    if (warp == MMA_WARP)
+    {
+        tmem_alloc2(tmem_ptr, TMEM_COLS);
+        tmem_relinquish2();
+    }
+    for (int i = tid; i < ED_COMBOS * Q; i += NT) st_f4(ee + 4 * i, ldg_f4(p.ee_comb + 4 * i));
+    for (int i = tid; i < D; i += NT) ee[ED_COMBOS * D + i] = -3.0e38f;       // absent edge slots: relu(-3e38 + h) adds exactly 0
+    // A buffers + zero block (k = 101..103 of every row stays zero for the whole launch)
+    for (int i = tid; i < (Smem::EE - Smem::A) / 16; i += NT) st_f4(reinterpret_cast<float*>(smem + Smem::A) + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+    __syncthreads();
+    // bias column: a_hi[row][k = 100] = 1, never overwritten (the gather writes k < 100 only)
+    if (!mp_only)
+        for (int i = tid; i < TM; i += NT) *reinterpret_cast<uint16_t*>(smem + Smem::A + (D / 8) * LBO_A + i * 16 + (D % 8) * 2) = 0x3F80;
+    fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    cluster_sync();
+    tc::fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+    const uint32_t a_base = smem_u32(smem + Smem::A);
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on the kernel reads
+    // what the previous kernels of the stream wrote (h_in, and in the first layer the tiles / descriptors of prep.cu)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int ntiles = __ldg(p.tile_count);
+    const int npt = (ntiles + 1) >> 1;                       // pair tiles
+
+    if (warp >= MMA_WARP)
+    {
+        reg_dec<REGS_MISC>();
+        if (warp == MMA_WARP)
+        {
+            // ===== MMA issuer: one thread of the leader CTA (see gin_tc2.cu for the protocol) =====
+            if (rank == 0 && lane == 0 && !mp_only)
+            {
+                const uint32_t w_addr = smem_u32(smem + Smem::W);
+                const uint32_t zero_addr = smem_u32(smem + Smem::ZERO);
+                const uint32_t idesc1a = tc::idesc_bf16(2 * TM, N1A), idesc1b = tc::idesc_bf16(2 * TM, N1B), idesc2 = tc::idesc_bf16(2 * TM, N2);
+                int it = 0;
+                for (int pt = pair; pt < npt; pt += npairs, it++)
+                {
+                    const uint32_t ph = it & 1;
+                    mbar_wait_park(&bar[BAR_A_FULL], ph);
+                    tc::fence_after_sync();
+#pragma unroll
+                    for (int nh = 0; nh < 2; nh++)
+                    {
+                        bool acc = false;
+                        const uint32_t lbo_b = nh ? LBO_W1B : LBO_W1A;
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++)
+                        {
+                            const uint32_t a_addr = a_base + (prod == 1 ? 1 : 0) * A_BYTES;
+                            const uint32_t b_addr = w_addr + (nh ? (prod == 2 ? OFF_W1B_LO : OFF_W1B_HI) : (prod == 2 ? OFF_W1A_LO : OFF_W1A_HI));
+#pragma unroll
+                            for (int j = 0; j < K1_STEPS; j++)
+                            {
+                                const uint32_t a_start = a_addr + 2 * j * LBO_A;
+                                // the last k-step pairs chunk 12 with the shared zero block (k = 104..111 does not exist)
+                                const uint32_t a_lbo = (j < K1_STEPS - 1) ? (uint32_t)LBO_A : zero_addr - a_start;
+                                mma_ss2(tbase + TC_Z + (nh ? N1A : 0), tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128),
+                                        nh ? idesc1b : idesc1a, acc);
+                                acc = true;
+                            }
+                        }
+                        commit2(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
+                    }
+                    commit2(&bar[BAR_A_FREE]);
+                    bool acc = false;
+#pragma unroll
+                    for (int kh = 0; kh < 2; kh++)
+                    {
+                        mbar_wait_park(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
+                        tc::fence_after_sync();
+#pragma unroll
+                        for (int prod = 0; prod < 3; prod++)
+                        {
+                            const uint32_t a_col = tbase + TC_Z + (prod == 1 ? 8 : 0);
+                            const uint32_t b_addr = w_addr + (prod == 2 ? OFF_W2_LO : OFF_W2_HI);
+#pragma unroll
+                            for (int j = (kh ? N1A / 16 : 0); j < (kh ? K2_STEPS : N1A / 16); j++)
+                            {
+                                mma_ts2(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * LBO_W2, LBO_W2, 128), idesc2, acc);
+                                acc = true;
+                            }
+                        }
+                    }
+                    commit2(&bar[BAR_G2_DONE]);
+                }
+            }
+        }
+        else if (warp == LOAD_WARP)
+        {
+            // ===== producer: the tile's feature rows -> stage (ONE bulk copy), L2 prefetch of the tile after next =====
+            if (lane == 0)
+            {
+                int it = 0;
+                for (int pt = pair; pt < npt; pt += npairs, it++)
+                {
+                    const int s = mp_only ? (it & 1) : 0;
+                    const int2 ti = tile_of(p, 2 * pt + (int)rank, ntiles);
+                    const uint32_t bytes = (uint32_t)(ti.y & 0xFFFF) * ROW_BYTES;
+                    if (it >= nstage) mbar_wait_park(&bar[BAR_STAGE_FREE + s], (mp_only ? ((it >> 1) - 1) : (it - 1)) & 1);
+                    unsigned char* dst = smem + ((mp_only && s == 1) ? Smem::A : Smem::STAGE);
+                    unsigned char* ddst = smem + ((mp_only && s == 1) ? Smem::A + STAGE_BYTES : Smem::DESC);
+                    const int nrows = ti.y & 0xFFFF;
+                    reinterpret_cast<int2*>(smem + Smem::TILE)[s] = ti;          // released to the gather warps by the arrival below
+                    mbar_arrive_expect_tx(&bar[BAR_STAGE_FULL + s], bytes + nrows * 16);
+                    if (bytes)
+                    {
+                        tma_load_1d(dst, p.h_in + (size_t)ti.x * D, bytes, &bar[BAR_STAGE_FULL + s]);
+                        tma_load_1d(ddst, p.row_desc + ti.x, nrows * 16, &bar[BAR_STAGE_FULL + s]);
+                    }
+                    const int2 tn = tile_of(p, 2 * (pt + 2 * npairs) + (int)rank, ntiles);
+                    if (tn.y & 0xFFFF)
+                    {
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (size_t)tn.x * D), "r"((tn.y & 0xFFFF) * ROW_BYTES) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.row_desc + tn.x), "r"((tn.y & 0xFFFF) * 16) : "memory");
+                    }
+                }
+            }
+        }
+    }
+    else if (warp >= EPI_WARPS)
+    {
+        if constexpr (REGS_GATHER > REGS_LAUNCH) reg_inc<REGS_GATHER>(); else reg_dec<REGS_GATHER>();
+        // ===== gather warps =====
+        const int gw = warp - EPI_WARPS;
+        const int g = lane >> 3, j = lane & 7;
+        const uint32_t ee_thr = smem_u32(ee) + 16 * j;
+        const uint32_t bar_full0 = mapa(smem_u32(&bar[BAR_A_FULL]), 0);
+        const uint32_t zero_thr = smem_u32(smem + Smem::ZERO) + 16 * j;            // 2 KB of zeros: the "row" of a slot beyond the tile
+        // this thread's 8-byte slot in row (8 gw + g) of the A tile, step 0: chunk j -> K chunk pair j / 2, half j % 2
+        const uint32_t a_thr = a_base + (j >> 1) * LBO_A + (j & 1) * 8 + (gw * ROWS_PER_WARP + g) * 16;
+        const int4 empty = make_int4(32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16));
+
+        int it = 0;
+        for (int pt = pair; pt < npt; pt += npairs, it++)
+        {
+            const int s = mp_only ? (it & 1) : 0;
+            mbar_wait_park(&bar[BAR_STAGE_FULL + s], (mp_only ? (it >> 1) : it) & 1);
+            if (!mp_only && it >= 1) mbar_wait_park(&bar[BAR_A_FREE], (it - 1) & 1);
+            // the tile's record and row descriptors arrived with its rows: no global load, no register prefetch in these warps
+            const int2 ti = reinterpret_cast<const int2*>(smem + Smem::TILE)[s];
+            const int start = ti.x, rows = ti.y & 0xFFFF;
+            const bool ext = (ti.y >> 30) & 1;
+            const uint32_t stage_thr = smem_u32(smem + ((mp_only && s == 1) ? Smem::A : Smem::STAGE)) + 16 * j;
+            const uint32_t desc_base = smem_u32(smem + ((mp_only && s == 1) ? Smem::A + STAGE_BYTES : Smem::DESC));
+#pragma unroll 1
+            for (int ps = 0; ps < 2; ps++)
+            {
+                const int R = gw * ROWS_PER_WARP + 4 * ps + g;
+                const bool live = R < rows;
+                const int4 d = live ? lds_i4(desc_base + R * 16) : empty;
+                RowCtx r;
+                r.node = start + (live ? R : 0);
+                r.own = live ? stage_thr + (uint32_t)R * ROW_BYTES : zero_thr;
+                r.so[0] = r.own + (uint32_t)(((d.x & 0xFFFF) - 32768) * ROW_BYTES);
+                r.so[1] = r.own + (uint32_t)(((d.y & 0xFFFF) - 32768) * ROW_BYTES);
+                r.so[2] = r.own + (uint32_t)(((d.z & 0xFFFF) - 32768) * ROW_BYTES);
+                r.so[3] = r.own + (uint32_t)(((d.w & 0xFFFF) - 32768) * ROW_BYTES);
+                r.tb[0] = ee_thr + ((d.x >> 16) & 0x3F) * ROW_BYTES;
+                r.tb[1] = ee_thr + ((d.y >> 16) & 0x3F) * ROW_BYTES;
+                r.tb[2] = ee_thr + ((d.z >> 16) & 0x3F) * ROW_BYTES;
+                r.tb[3] = ee_thr + ((d.w >> 16) & 0x3F) * ROW_BYTES;
+                r.deg = live ? (int)((unsigned)d.x >> 24) : 0;
+                if (r.deg == 255) r.deg = __ldg(p.in_ptr + r.node + 1) - __ldg(p.in_ptr + r.node);
+                int maxdeg = max(r.deg, __shfl_xor_sync(FULL, r.deg, 8));
+                maxdeg = max(maxdeg, __shfl_xor_sync(FULL, maxdeg, 16));
+                float* out_thr = p.h_out + (size_t)r.node * D + 4 * j;
+                const uint32_t a_dst = a_thr + ps * (4 * 16);
+                if (ext)
+                {
+#pragma unroll 1
+                    for (int ks = 0; ks < 3; ks++)
+                    {
+                        const float4 x = gather_chunk_ext(p.h_in + 4 * (8 * ks + j), p.in_ptr, p.src, p.code, r.node, r.deg, r.own + 128 * ks, ee_thr + 128 * ks);
+                        put_chunk(x, mp_only, live, out_thr + 32 * ks, a_dst + ks * (4 * LBO_A));
+                    }
+                }
+                else
+                {
+                    // one specialisation per slot count of this warp instruction's four rows: a single uniform branch per pass
+                    switch (maxdeg)
+                    {
+                    case 0: gather_pass<0, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
+                    case 1: gather_pass<1, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
+                    case 2: gather_pass<2, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
+                    case 3: gather_pass<3, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
+                    case 4: gather_pass<4, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
+                    default: gather_pass<4, true>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
+                    }
+                }
+            }
+            // chunk 24 of the warp's 8 rows: lanes 0..7, a lane per row
+            if (lane < ROWS_PER_WARP)
+            {
+                const int R = gw * ROWS_PER_WARP + lane;
+                const bool live = R < rows;
+                const int4 d = live ? lds_i4(desc_base + R * 16) : empty;
+                const int node = start + (live ? R : 0);
+                int deg = live ? (int)((unsigned)d.x >> 24) : 0;
+                if (deg == 255) deg = __ldg(p.in_ptr + node + 1) - __ldg(p.in_ptr + node);
+                const uint32_t stage_tail = stage_thr - 16 * j + 16 * (Q - 1);
+                const uint32_t own = live ? stage_tail + (uint32_t)R * ROW_BYTES : zero_thr - 16 * j;
+                const float4 x = tail_chunk(p, d, node, deg, own, ee_thr - 16 * j + 16 * (Q - 1), ext, stage_tail, start);
+                put_chunk(x, mp_only, live, p.h_out + (size_t)node * D + 4 * (Q - 1), a_base + ((Q - 1) >> 1) * LBO_A + R * 16);
+            }
+            __syncwarp();
+            // the stage may be refilled; the tile is visible to the tensor core (async proxy) and reported to the leader CTA
+            if (!mp_only) fence_proxy_async();
+            __syncwarp();
+            if (lane == 0)
+            {
+                mbar_arrive(&bar[BAR_STAGE_FREE + s]);
+                if (!mp_only)
+                {
+                    if (it == 0 && gw == 0) mbar_wait_park(&bar[BAR_W], 0);      // this CTA's weights have landed
+                    mbar_arrive_cluster(bar_full0);
+                }
+            }
+        }
+    }
+    else if (!mp_only)
+    {
+        if constexpr (REGS_EPI > REGS_LAUNCH) reg_inc<REGS_EPI>(); else reg_dec<REGS_EPI>();
+        // ===== epilogue warps: two per TMEM lane quadrant (as gin_tc2.cu; rows beyond the tile are not stored) =====
+        const int quad = warp & 3, pp = warp >> 2;
+        const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
+        const uint32_t bar_a2a0 = mapa(smem_u32(&bar[BAR_A2A_FULL]), 0), bar_a2b0 = mapa(smem_u32(&bar[BAR_A2B_FULL]), 0);
+        int it = 0;
+        for (int pt = pair; pt < npt; pt += npairs, it++)
+        {
+            const uint32_t ph = it & 1;
+            const int2 ti = tile_of(p, 2 * pt + (int)rank, ntiles);
+            const int rows = ti.y & 0xFFFF;
+            mbar_wait_park(&bar[BAR_G1A_DONE], ph);
+            tc::fence_after_sync();
+            convert_range(lane_base + TC_Z, pp, N1A / 16);
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_a2a0);
+
+            mbar_wait_park(&bar[BAR_G1B_DONE], ph);
+            tc::fence_after_sync();
+            convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_a2b0);
+
+            mbar_wait_park(&bar[BAR_G2_DONE], ph);
+            tc::fence_after_sync();
+            // 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and t/4 + 8
+            const int ra = quad * 32 + pp * 16 + (lane >> 2), rb = ra + 8;
+            const bool va = ra < rows, vb = rb < rows;
+            const long row_a = (long)ti.x + ra, row_b = (long)ti.x + rb;
+            const uint32_t ta = lane_base + ((uint32_t)(pp * 16) << 16) + TC_H;
+            auto ld_h = [&](int g4, uint32_t (&r)[16]) {
+                asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                               "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(ta + 8 * g4)
+                             : "memory");
+            };
+            auto st_h = [&](int g4, const uint32_t (&r)[16]) {
+#pragma unroll
+                for (int gg = 0; gg < 4; gg++)
+                {
+                    const int col = 8 * (g4 + gg) + 2 * (lane & 3);
+                    if (8 * (g4 + gg) < D && col < D)
+                    {
+                        float2 oa = make_float2(__uint_as_float(r[4 * gg]), __uint_as_float(r[4 * gg + 1]));
+                        float2 ob = make_float2(__uint_as_float(r[4 * gg + 2]), __uint_as_float(r[4 * gg + 3]));
+                        if (p.relu_out)
+                        {
+                            oa = make_float2(relu_nan(oa.x), relu_nan(oa.y));
+                            ob = make_float2(relu_nan(ob.x), relu_nan(ob.y));
+                        }
+                        if (va) asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p.h_out + (size_t)row_a * D + col), "f"(oa.x), "f"(oa.y) : "memory");
+                        if (vb) asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p.h_out + (size_t)row_b * D + col), "f"(ob.x), "f"(ob.y) : "memory");
+                    }
+                }
+            };
+            float dot_a = 0.f, dot_b = 0.f;
+            auto dot_h = [&](int g4, const uint32_t (&r)[16]) {
+#pragma unroll
+                for (int gg = 0; gg < 4; gg++)
+                {
+                    const int col = 8 * (g4 + gg) + 2 * (lane & 3);
+                    if (8 * (g4 + gg) < D && col < D)
+                    {
+                        const float2 wv = __ldg(reinterpret_cast<const float2*>(p.head_w + col));
+                        dot_a = fmaf(__uint_as_float(r[4 * gg + 1]), wv.y, fmaf(__uint_as_float(r[4 * gg]), wv.x, dot_a));
+                        dot_b = fmaf(__uint_as_float(r[4 * gg + 3]), wv.y, fmaf(__uint_as_float(r[4 * gg + 2]), wv.x, dot_b));
+                    }
+                }
+            };
+            {
+                uint32_t r0[16], r1[16];
+                ld_h(0, r0);
+                if (p.head_w == nullptr)
+                {
+                    tc::wait_ld(); ld_h(4, r1); st_h(0, r0);
+                    tc::wait_ld(); ld_h(8, r0); st_h(4, r1);
+                    tc::wait_ld(); ld_h(12, r1); st_h(8, r0);
+                    tc::wait_ld(); st_h(12, r1);
+                }
+                else
+                {
+                    tc::wait_ld(); ld_h(4, r1); dot_h(0, r0);
+                    tc::wait_ld(); ld_h(8, r0); dot_h(4, r1);
+                    tc::wait_ld(); ld_h(12, r1); dot_h(8, r0);
+                    tc::wait_ld(); dot_h(12, r1);
+                    dot_a += __shfl_xor_sync(FULL, dot_a, 1); dot_a += __shfl_xor_sync(FULL, dot_a, 2);
+                    dot_b += __shfl_xor_sync(FULL, dot_b, 1); dot_b += __shfl_xor_sync(FULL, dot_b, 2);
+                    if ((lane & 3) == 0)
+                    {
+                        if (va) p.node_dot[row_a] = dot_a;
+                        if (vb) p.node_dot[row_b] = dot_b;
+                    }
+                }
+            }
+        }
+    }
+
+    // both CTAs must be done with tensor memory, shared memory and each other's barriers before either leaves
+    tc::fence_before_sync();
+    __syncthreads();
+    __syncwarp();
+    cluster_sync();
+    if (warp == MMA_WARP) tmem_dealloc2(tbase, TMEM_COLS);
+}
+
+}  // namespace
+
+int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
+                           const float* head_w, float* node_dot, const int4* row_desc, int mp_only)
+{
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_layer_fused_kernel), Smem::BYTES));
+    GinFusedParams p;
+    p.h_in = h_in; p.h_out = h_out;
+    p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
+    p.row_desc = row_desc ? row_desc : b.row_desc.as<int4>();     // override: "no in-edges" descriptors = node MLP only (gin.cu)
+    p.tiles = b.tiles.as<int2>(); p.tile_count = b.tile_count.as<int>();
+    p.ee_comb = w.ee_comb.as<float>() + (size_t)layer * ED_COMBOS * D;
+    p.wpack = w.wpack2.as<unsigned char>() + (size_t)layer * 2 * W_BYTES;
+    p.num_nodes = (int)b.total_nodes;
+    p.relu_out = (layer != 4);
+    p.mp_only = mp_only;
+    p.head_w = head_w; p.node_dot = node_dot;
+    const int pairs = (int)std::max<long>(1, std::min<long>((b.max_tiles + 1) / 2, sm_count / 2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = Smem::BYTES; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FG_CUDA(cudaLaunchKernelEx(&cfg, gin_layer_fused_kernel, p));
+    return 0;
+}
+
+}  // namespace fg

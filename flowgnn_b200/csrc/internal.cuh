@@ -50,6 +50,9 @@ struct DeviceBatch {
     DevBuf sort_tmp;                       // int32 [E] scratch for the two-pass stable sort
     DevBuf big_tab;                        // int32 [3][N] CSR-build tables of graphs above 1,024 nodes (allocated only if there is one)
     DevBuf status;                         // int32 [1] device-side limit violations
+    DevBuf tiles;                          // int2 [max_tiles] GIN: graph-aligned tiles (first node, rows | external << 30) (prep.cu)
+    DevBuf tile_count;                     // int32 [1] number of tiles
+    long max_tiles = 0;                    // host-side upper bound of tile_count (grid sizing)
 
     // activations
     DevBuf act[4];                         // float [N][<=100] ping/pong (+2 extra for GAT)
@@ -62,7 +65,7 @@ struct DeviceBatch {
     void release();
 };
 
-enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2, PREP_ROW_DESC = 4 };
+enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2, PREP_ROW_DESC = 4, PREP_TILES = 8 };
 
 // graph preprocessing: offsets scan + per-graph CSR build (prep.cu)
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream);
@@ -128,9 +131,11 @@ struct LayerTimer {
 };
 
 struct RunOptions {
-    int mp_only = 0;                 // GIN: node transform = identity (roofline variant)
+    int mp_only = 0;                 // GIN: node transform = identity (roofline variant): 1 = the mp_only mode of the layer
+                                     // kernel itself (gin_fused.cu), 2 = the stand-alone row-per-warp gather kernel (gin.cu)
     int gin_ffma = 0;                // GIN: node MLP on the FP32 FFMA pipe (on-device fp32 reference) instead of tcgen05
-    int gin_tc1 = 0;                 // GIN: single-CTA tcgen05 kernel (gin_tc.cu) instead of the CTA-pair kernel (gin_tc2.cu)
+    int gin_tc1 = 0;                 // GIN: single-CTA tcgen05 kernel (gin_tc.cu) instead of the default
+    int gin_tc2 = 0;                 // GIN: the round-1 CTA-pair kernel (gin_tc2.cu: gather through L1 from global memory) instead of gin_fused.cu
     int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
     int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
@@ -147,6 +152,8 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
 int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
                          const float* head_w = nullptr, float* node_dot = nullptr, const int4* row_desc = nullptr);
+int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
+                           const float* head_w = nullptr, float* node_dot = nullptr, const int4* row_desc = nullptr, int mp_only = 0);
 int gin_pool_dot_launch(const float* node_dot, const DeviceBatch& b, const float* pred_b, cudaStream_t s);
 int gin_layer_tc3_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t gin_tc3_pack_bytes();

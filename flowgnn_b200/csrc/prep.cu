@@ -340,6 +340,80 @@ __global__ void __launch_bounds__(4 * 32) build_csr_large_kernel(CsrParams p)
     }
 }
 
+
+// ---- graph-aligned tiles for the GIN layer kernel (gin_fused.cu) ---------------------------------------------------
+// The layer kernel stages the feature rows of one tile (<= 128 consecutive nodes) in shared memory with ONE bulk copy
+// and gathers the in-edges from that stage.  In-edge sources are nodes of the SAME graph, so tiles are packed from
+// whole graphs: no gather ever leaves its stage.  A graph of more than 128 nodes is cut into 128-row tiles flagged
+// "external" (bit 30 of .y): their gathers read source rows from global memory.
+// One block: thread i packs a contiguous chunk of graphs greedily (a tile closes when the next graph does not fit, and at
+// the end of the chunk), a block-wide scan of the per-chunk tile counts places the chunks' tiles, a second pass writes
+// them.  tiles[t] = (first node, rows | ext << 30); tile_count[0] = number of tiles.
+constexpr int TILE_ROWS = 128;
+constexpr int PACK_THREADS = 1024;
+
+template <bool WRITE>
+__device__ __forceinline__ int pack_chunk(const int* __restrict__ nn, const int* __restrict__ node_off, int g0, int g1, int2* out)
+{
+    int count = 0, start = 0, rows = 0;
+    for (int g = g0; g < g1; g++)
+    {
+        const int n = nn[g];
+        if (n <= 0) continue;
+        if (n > TILE_ROWS)
+        {
+            if (rows > 0) { if (WRITE) out[count] = make_int2(start, rows); count++; rows = 0; }
+            const int nb = node_off[g];
+            for (int r = 0; r < n; r += TILE_ROWS)
+            {
+                if (WRITE) out[count] = make_int2(nb + r, min(TILE_ROWS, n - r) | (1 << 30));
+                count++;
+            }
+            continue;
+        }
+        if (rows + n > TILE_ROWS) { if (WRITE) out[count] = make_int2(start, rows); count++; rows = 0; }
+        if (rows == 0) start = node_off[g];
+        rows += n;
+    }
+    if (rows > 0) { if (WRITE) out[count] = make_int2(start, rows); count++; }
+    return count;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) pack_tiles_kernel(const int* __restrict__ nn, const int* __restrict__ node_off, int num_graphs,
+                                                                  int2* __restrict__ tiles, int* __restrict__ tile_count)
+{
+    __shared__ int warp_tot[PACK_THREADS / 32];
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (num_graphs + PACK_THREADS - 1) / PACK_THREADS;
+    const int g0 = min(tid * per, num_graphs), g1 = min(g0 + per, num_graphs);
+    const int mine = pack_chunk<false>(nn, node_off, g0, g1, nullptr);
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int a = __shfl_up_sync(full, incl, d);
+        if (lane >= d) incl += a;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0)
+    {
+        const int t = warp_tot[lane];
+        int ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const int a = __shfl_up_sync(full, ti, d);
+            if (lane >= d) ti += a;
+        }
+        warp_tot[lane] = ti - t;
+        if (lane == 31) tile_count[0] = ti;
+    }
+    __syncthreads();
+    pack_chunk<true>(nn, node_off, g0, g1, tiles + warp_tot[wid] + incl - mine);
+}
+
 }  // namespace
 
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
@@ -366,6 +440,16 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
     scan_offsets_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.nums_of_edges.as<int>(), b.node_off.as<int>(),
                                                          b.edge_off.as<int>(), G);
     FG_CUDA(cudaGetLastError());
+
+    if (flags & PREP_TILES)
+    {
+        // upper bound: a tile closes at most once per graph, per 128 rows of a large graph and per packing chunk
+        b.max_tiles = (long)G + b.total_nodes / TILE_ROWS + PACK_THREADS + 1;
+        FG_TRY(b.tiles.reserve(sizeof(int2) * (size_t)b.max_tiles));
+        FG_TRY(b.tile_count.reserve(sizeof(int)));
+        pack_tiles_kernel<<<1, PACK_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.node_off.as<int>(), G, b.tiles.as<int2>(), b.tile_count.as<int>());
+        FG_CUDA(cudaGetLastError());
+    }
 
     CsrParams p;
     p.nn = b.nums_of_nodes.as<int>(); p.ne = b.nums_of_edges.as<int>();

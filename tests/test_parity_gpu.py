@@ -23,6 +23,21 @@ def ctx():
     c.close()
 
 
+def _chain_graph(n, rng, with_eigen=False):
+    """One connected graph of n nodes: a path plus n random chords, both directions listed (molecule-like degrees)."""
+    from flowgnn_b200.dataset import Batch
+    a = np.concatenate([np.arange(n - 1), rng.integers(0, n, n)])
+    b = np.concatenate([np.arange(1, n), rng.integers(0, n, n)])
+    keep = a != b
+    a, b = a[keep], b[keep]
+    e = np.stack([np.stack([a, b], 1), np.stack([b, a], 1)], 1).reshape(-1, 2).astype(np.int32)
+    attr1 = np.stack([rng.integers(0, k, len(a)) for k in (5, 6, 2)], 1)
+    attr = np.repeat(attr1, 2, axis=0).astype(np.int32)
+    feat = np.stack([rng.integers(0, k, n) for k in (119, 4, 12, 12, 10, 6, 6, 2, 2)], 1).astype(np.int32)
+    eig = rng.standard_normal((n, 4)).astype(np.float32) if with_eigen else None
+    return Batch(np.array([n]), np.array([len(e)]), feat, e, attr, eig)
+
+
 def _gold_key(model):
     return model
 
@@ -61,6 +76,49 @@ def test_gin_single_cta_kernel_agrees_with_cta_pair_kernel(ds, ctx, weights, dat
     assert_parity(pair, single, tol=5e-5, what=f"gin cta pair vs single cta/{ds}")
 
 
+@pytest.mark.parametrize("ds", ["molhiv", "molpcba", "hep10k"])
+@pytest.mark.parametrize("vn", [False, True])
+def test_gin_fused_kernel_agrees_with_round1_pair_kernel(ds, vn, ctx, weights, datasets, golden):
+    """The default GIN layer kernel (gin_fused.cu): graph-aligned tiles staged in shared memory by bulk TMA, in-edges
+    gathered from the stage.  Option gin_tc2 selects the round-1 CTA-pair kernel (gather from global memory through L1).
+    Both add a node's in-edges in CSR order and run the same GEMMs, so they must agree BIT FOR BIT, on molecules and on
+    dense graphs run as ONE launch per layer (gin_staged = 0), with and without the virtual node."""
+    b = datasets[ds].with_virtual_node() if vn else datasets[ds]
+    want = golden[ds]["ginvn" if vn else "gin"]
+    try:
+        ctx.set_option("gin_staged", 0)
+        fused = ctx.run("gin", b, weights["gin"])
+        ctx.set_option("gin_tc2", 1)
+        pair = ctx.run("gin", b)
+    finally:
+        ctx.set_option("gin_tc2", 0)
+        ctx.set_option("gin_staged", -1)
+    assert_parity(fused, want, what=f"gin fused vn={vn}/{ds}")
+    assert np.array_equal(fused.view(np.int32), pair.view(np.int32)), f"gin fused vs round-1 pair kernel, vn={vn}/{ds}"
+
+
+def test_gin_tiles_pack_whole_graphs(ctx, weights, datasets):
+    """Tile packing (prep.cu::pack_tiles_kernel): graphs of exactly 128 / 129 / 127+1 / 1 nodes, a run of single-node graphs
+    that fills tiles exactly, graphs above 128 nodes (external tiles: sources from global memory) -- against the oracle."""
+    from flowgnn_b200.dataset import concat
+    from oracle import refbind
+    rng = np.random.default_rng(3)
+    parts = [_chain_graph(n, rng) for n in (128, 129, 127, 1, 128, 5, 256, 257, 64, 64, 1, 300)] + [_chain_graph(1, rng) for _ in range(260)] + \
+            [datasets["molhiv"].slice(0, 30)]
+    parts = [type(x)(x.nums_of_nodes, x.nums_of_edges, x.node_feature, x.edge_list, x.edge_attr) for x in parts]
+    b = concat(parts)
+    want = refbind.run_port("gin", b, weights["gin"])
+    assert_parity(ctx.run("gin", b, weights["gin"]), want, what="gin tile packing")
+    ctx.set_option("mp_only", 1)
+    try:
+        fused_mp = ctx.run("gin", b)
+        ctx.set_option("mp_only", 2)
+        side_mp = ctx.run("gin", b)
+    finally:
+        ctx.set_option("mp_only", 0)
+    assert np.array_equal(fused_mp.view(np.int32), side_mp.view(np.int32)), "mp_only: layer kernel vs stand-alone gather kernel"
+
+
 @pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
 def test_gin_tma_staged_kernel_agrees(ds, ctx, weights, datasets, golden):
     """gin_tc3.cu (option gin_tc3): the CTA-pair kernel with the tile's feature rows staged in shared memory by bulk
@@ -90,7 +148,7 @@ def test_gin_staged_gather_layers_agree_with_fused_layers(ds, vn, ctx, weights, 
             ctx.set_option("gin_staged", mode)
             out[mode] = ctx.run("gin", b, weights["gin"])
             launches = ctx.last_launch_count
-            assert launches == (16 if mode == 1 or (mode == -1 and ds == "hep10k") else 10), (mode, launches)
+            assert launches == (17 if mode == 1 or (mode == -1 and ds == "hep10k") else 11), (mode, launches)
     finally:
         ctx.set_option("gin_staged", -1)
     for mode, y in out.items():
@@ -284,21 +342,6 @@ def test_edge_cases_empty_batch_and_edgeless_graph(ctx, weights):
         assert_parity(got, want, what=f"{model} edgeless/directed")
 
 
-def _chain_graph(n, rng, with_eigen=False):
-    """One connected graph of n nodes: a path plus n random chords, both directions listed (molecule-like degrees)."""
-    from flowgnn_b200.dataset import Batch
-    a = np.concatenate([np.arange(n - 1), rng.integers(0, n, n)])
-    b = np.concatenate([np.arange(1, n), rng.integers(0, n, n)])
-    keep = a != b
-    a, b = a[keep], b[keep]
-    e = np.stack([np.stack([a, b], 1), np.stack([b, a], 1)], 1).reshape(-1, 2).astype(np.int32)
-    attr1 = np.stack([rng.integers(0, k, len(a)) for k in (5, 6, 2)], 1)
-    attr = np.repeat(attr1, 2, axis=0).astype(np.int32)
-    feat = np.stack([rng.integers(0, k, n) for k in (119, 4, 12, 12, 10, 6, 6, 2, 2)], 1).astype(np.int32)
-    eig = rng.standard_normal((n, 4)).astype(np.float32) if with_eigen else None
-    return Batch(np.array([n]), np.array([len(e)]), feat, e, attr, eig)
-
-
 @pytest.mark.parametrize("model", ["gin", "gcn", "gat", "pna", "dgn"])
 def test_graphs_above_the_shared_memory_tables(model, ctx, weights, datasets):
     """No per-graph node cap (SURVEY.md 8b 'Limits'; the reference stops at MAX_NODE = 500, GIN/src/dcl.h:17): graphs of
@@ -453,7 +496,9 @@ def test_mp_only_variant_is_the_pure_gather_scatter(ctx, weights, datasets):
     want = pooled / b.nums_of_nodes[:, None] @ w["graph_pred_weights"][0].astype(np.float64) + w["graph_pred_bias"][0]
     ctx.set_option("mp_only", 1)
     try:
-        got = ctx.run("gin", b, w)
+        got = ctx.run("gin", b, w)                    # the mp_only mode of the layer kernel itself (gin_fused.cu)
+        ctx.set_option("mp_only", 2)
+        got_side = ctx.run("gin", b)                  # the stand-alone row-per-warp gather kernel (gin.cu)
         ctx.set_option("gin_staged", 1)
         got_staged = ctx.run("gin", b)
     finally:
@@ -461,6 +506,7 @@ def test_mp_only_variant_is_the_pure_gather_scatter(ctx, weights, datasets):
         ctx.set_option("gin_staged", -1)
     assert_parity(got, want.astype(np.float32), what="gin mp_only")
     assert np.array_equal(got.view(np.int32), got_staged.view(np.int32)), "staged gather: same sums in the same order"
+    assert np.array_equal(got.view(np.int32), got_side.view(np.int32)), "stand-alone gather kernel: same sums in the same order"
 
 
 def test_full_size_synthetic_batch_properties(ctx, weights):
@@ -476,7 +522,7 @@ def test_full_size_synthetic_batch_properties(ctx, weights):
     assert np.array_equal(y.view(np.int32), ctx.run("gin", b).view(np.int32))
     ids = np.random.default_rng(5).choice(2048, 48, replace=False)
     assert_parity(y[ids], refbind.run_port("gin", base.select(ids), weights["gin"]), what="gin synthetic sample")
-    assert ctx.last_launch_count == 10
+    assert ctx.last_launch_count == 11       # scan, pack_tiles, 2 x build_csr, embed, 5 layers, pool
 
 
 FULL_SIZE = {"gcn": ("molhiv", 41127), "gat": ("molhiv", 41127), "dgn": ("molhiv", 41127), "pna": ("molpcba", 437929),
