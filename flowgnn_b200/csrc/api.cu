@@ -53,7 +53,7 @@ void DevBuf::release()
 void DeviceBatch::release()
 {
     DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
-                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc0, &sort_tmp, &big_tab, &status, &tiles, &tile_count, &node_dot, &apack, &nonfinite,
+                     &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc_sorted, &row_desc0, &sort_tmp, &big_tab, &status, &tiles, &tile_count, &node_dot, &apack, &nonfinite,
                      &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
     for (DevBuf* b : all) b->release();
 }
@@ -619,7 +619,7 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     int rc = prep_batch(b, flags, s);
     b.has_attr = keep_attr;
     FG_TRY(rc);
-    ctx->last_launches += 3 + (model == MODEL_GIN ? 1 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN: pack_tiles)
+    ctx->last_launches += 3 + (model == MODEL_GIN ? 2 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN: pack_tiles, sort_tile_rows)
     ctx->timer.marks = 0;
     ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
     ctx->opt.timer_group = ctx->time_layers == 2;

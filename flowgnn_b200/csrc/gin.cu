@@ -530,7 +530,7 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         FG_CUDA(cudaGetLastError());
         return 0;
     };
-    if (split_layer)
+    if (split_layer && opt.gin_tc2)
     {
         FG_TRY(b.row_desc0.reserve(sizeof(int4) * (size_t)(N + 1)));
         fill_empty_desc_kernel<<<sm_count * 4, 256, 0, s>>>(b.row_desc0.as<int4>(), N + 1);
@@ -539,9 +539,10 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
     }
     // the layer kernel: gin_fused.cu (TMA-staged graph-aligned tiles, shared-memory gather), or with option gin_tc2 the
     // round-1 CTA-pair kernel that gathers through L1 from global memory
-    auto pair_layer = [&](int l, const float* x_in, float* x_out, const float* head_w, float* node_dot, const int4* desc) -> int {
-        if (opt.gin_tc2) return gin_layer_tc2_launch(b, w, l, x_in, x_out, sm_count, s, head_w, node_dot, desc);
-        return gin_layer_fused_launch(b, w, l, x_in, x_out, sm_count, s, head_w, node_dot, desc, 0);
+    // mlp_only: every row without in-edges = the node MLP alone (second launch of a dense-graph layer)
+    auto pair_layer = [&](int l, const float* x_in, float* x_out, const float* head_w, float* node_dot, bool mlp_only) -> int {
+        if (opt.gin_tc2) return gin_layer_tc2_launch(b, w, l, x_in, x_out, sm_count, s, head_w, node_dot, mlp_only ? b.row_desc0.as<int4>() : nullptr);
+        return gin_layer_fused_launch(b, w, l, x_in, x_out, sm_count, s, head_w, node_dot, mlp_only, 0);
     };
     bool fused_head = false;
     for (int l = 0; l < 5; l++)
@@ -555,10 +556,10 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
             if (l == 4 && !opt.gin_unfused_head)
             {
                 FG_TRY(b.node_dot.reserve(sizeof(float) * (size_t)(N + 1)));
-                FG_TRY(pair_layer(l, h[1], h[0], w.pred_w.as<float>(), b.node_dot.as<float>(), b.row_desc0.as<int4>()));
+                FG_TRY(pair_layer(l, h[1], h[0], w.pred_w.as<float>(), b.node_dot.as<float>(), true));
                 fused_head = true;
             }
-            else FG_TRY(pair_layer(l, h[1], h[0], nullptr, nullptr, b.row_desc0.as<int4>()));
+            else FG_TRY(pair_layer(l, h[1], h[0], nullptr, nullptr, true));
             nl++;
             continue;
         }
@@ -577,14 +578,14 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
             {
                 // last layer: the epilogue applies the prediction weights per node, only 4 bytes per node leave the kernel
                 FG_TRY(b.node_dot.reserve(sizeof(float) * (size_t)(N + 1)));
-                FG_TRY(pair_layer(l, p.h_in, p.h_out, w.pred_w.as<float>(), b.node_dot.as<float>(), nullptr));
+                FG_TRY(pair_layer(l, p.h_in, p.h_out, w.pred_w.as<float>(), b.node_dot.as<float>(), false));
                 fused_head = true;
             }
-            else FG_TRY(pair_layer(l, p.h_in, p.h_out, nullptr, nullptr, nullptr));
+            else FG_TRY(pair_layer(l, p.h_in, p.h_out, nullptr, nullptr, false));
             nl++;
             continue;
         }
-        if (opt.mp_only == 1 && opt.gin_staged <= 0) FG_TRY(gin_layer_fused_launch(b, w, l, p.h_in, p.h_out, sm_count, s, nullptr, nullptr, nullptr, 1));
+        if (opt.mp_only == 1 && opt.gin_staged <= 0) FG_TRY(gin_layer_fused_launch(b, w, l, p.h_in, p.h_out, sm_count, s, nullptr, nullptr, false, 1));
         else if (opt.mp_only && staged) FG_TRY(staged_gather(p.h_in, p.h_out, l));
         else if (opt.mp_only)
         {

@@ -79,14 +79,28 @@ static_assert(BAR_COUNT <= 16, "barrier slots");
 struct GinFusedParams {
     const float* h_in; float* h_out;
     const int* in_ptr; const int* src; const uint8_t* code;
-    const int4* row_desc;            // [N] first four in-edges of every node, packed (prep.cu)
+    const int4* row_desc;            // [N] per tile: the rows' descriptors (first four in-edges, packed) ordered by in-degree, the row's
+                                     // position inside the tile in .y bits 24..30 (prep.cu::sort_tile_rows_kernel); nullptr: no in-edges at all
     const int2* tiles;               // graph-aligned tiles (first node, rows | external << 30) (prep.cu::pack_tiles_kernel)
     const int* tile_count;
     const float* ee_comb;            // [60][100] this layer
     const unsigned char* wpack;      // [2 ranks][W_BYTES] this layer
     int num_nodes; int relu_out; int mp_only;
     const float* head_w; float* node_dot;      // last layer: fused prediction head (see gin_tc2.cu)
+    unsigned long long* trace;                 // -DFG_TC2_TRACE only: timeline of pair 0 (tools/trace_fused.py): [role][tile][event] globaltimer ns
 };
+
+#ifdef FG_TC2_TRACE
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(role, it, ev) do { if (p.trace && pair == 0 && rank == 0 && (it) < 64) p.trace[((role) * 64 + (it)) * 8 + (ev)] = gtime(); } while (0)
+#else
+#define TRACE(role, it, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ int2 tile_of(const GinFusedParams& p, int t, int ntiles)
 {
@@ -322,8 +336,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
         reg_dec<REGS_MISC>();
         if (warp == MMA_WARP)
         {
-            // ===== MMA issuer: one thread of the leader CTA (see gin_tc2.cu for the protocol) =====
-            if (rank == 0 && lane == 0 && !mp_only)
+            // ===== MMA issuer: the converged warp of the leader CTA, the tcgen05 instructions predicated on elect.sync.  (In
+            // gin_tc2.cu this made the layer slower: the MMAs then hit shared memory in bursts and starved the gather.  Here
+            // the gather warps are waiting for GEMM1 to release the A tile, so GEMM1 should run as fast as the tensor pipe can.)
+            if (rank == 0 && !mp_only)
             {
                 const uint32_t w_addr = smem_u32(smem + Smem::W);
                 const uint32_t zero_addr = smem_u32(smem + Smem::ZERO);
@@ -332,8 +348,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                 for (int pt = pair; pt < npt; pt += npairs, it++)
                 {
                     const uint32_t ph = it & 1;
+                    if (lane == 0) TRACE(0, it, 0);
                     mbar_wait_park(&bar[BAR_A_FULL], ph);
                     tc::fence_after_sync();
+                    if (lane == 0) TRACE(0, it, 1);
 #pragma unroll
                     for (int nh = 0; nh < 2; nh++)
                     {
@@ -350,20 +368,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                                 const uint32_t a_start = a_addr + 2 * j * LBO_A;
                                 // the last k-step pairs chunk 12 with the shared zero block (k = 104..111 does not exist)
                                 const uint32_t a_lbo = (j < K1_STEPS - 1) ? (uint32_t)LBO_A : zero_addr - a_start;
-                                mma_ss2(tbase + TC_Z + (nh ? N1A : 0), tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128),
+                                mma_ss2_elect(tbase + TC_Z + (nh ? N1A : 0), tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128),
                                         nh ? idesc1b : idesc1a, acc);
                                 acc = true;
                             }
                         }
-                        commit2(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
+                        commit2_elect(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
                     }
-                    commit2(&bar[BAR_A_FREE]);
+                    commit2_elect(&bar[BAR_A_FREE]);
+                    if (lane == 0) TRACE(0, it, 2);
                     bool acc = false;
 #pragma unroll
                     for (int kh = 0; kh < 2; kh++)
                     {
                         mbar_wait_park(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
                         tc::fence_after_sync();
+                        if (lane == 0) TRACE(0, it, 3 + kh);
 #pragma unroll
                         for (int prod = 0; prod < 3; prod++)
                         {
@@ -372,12 +392,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
 #pragma unroll
                             for (int j = (kh ? N1A / 16 : 0); j < (kh ? K2_STEPS : N1A / 16); j++)
                             {
-                                mma_ts2(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * LBO_W2, LBO_W2, 128), idesc2, acc);
+                                mma_ts2_elect(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * LBO_W2, LBO_W2, 128), idesc2, acc);
                                 acc = true;
                             }
                         }
                     }
-                    commit2(&bar[BAR_G2_DONE]);
+                    commit2_elect(&bar[BAR_G2_DONE]);
+                    if (lane == 0) TRACE(0, it, 5);
                 }
             }
         }
@@ -396,18 +417,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                     unsigned char* dst = smem + ((mp_only && s == 1) ? Smem::A : Smem::STAGE);
                     unsigned char* ddst = smem + ((mp_only && s == 1) ? Smem::A + STAGE_BYTES : Smem::DESC);
                     const int nrows = ti.y & 0xFFFF;
+                    TRACE(2, it, 4);
                     reinterpret_cast<int2*>(smem + Smem::TILE)[s] = ti;          // released to the gather warps by the arrival below
-                    mbar_arrive_expect_tx(&bar[BAR_STAGE_FULL + s], bytes + nrows * 16);
+                    mbar_arrive_expect_tx(&bar[BAR_STAGE_FULL + s], bytes + (p.row_desc ? nrows * 16 : 0));
                     if (bytes)
                     {
                         tma_load_1d(dst, p.h_in + (size_t)ti.x * D, bytes, &bar[BAR_STAGE_FULL + s]);
-                        tma_load_1d(ddst, p.row_desc + ti.x, nrows * 16, &bar[BAR_STAGE_FULL + s]);
+                        if (p.row_desc) tma_load_1d(ddst, p.row_desc + ti.x, nrows * 16, &bar[BAR_STAGE_FULL + s]);
                     }
                     const int2 tn = tile_of(p, 2 * (pt + 2 * npairs) + (int)rank, ntiles);
                     if (tn.y & 0xFFFF)
                     {
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (size_t)tn.x * D), "r"((tn.y & 0xFFFF) * ROW_BYTES) : "memory");
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.row_desc + tn.x), "r"((tn.y & 0xFFFF) * 16) : "memory");
+                        if (p.row_desc) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.row_desc + tn.x), "r"((tn.y & 0xFFFF) * 16) : "memory");
                     }
                 }
             }
@@ -422,16 +444,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
         const uint32_t ee_thr = smem_u32(ee) + 16 * j;
         const uint32_t bar_full0 = mapa(smem_u32(&bar[BAR_A_FULL]), 0);
         const uint32_t zero_thr = smem_u32(smem + Smem::ZERO) + 16 * j;            // 2 KB of zeros: the "row" of a slot beyond the tile
-        // this thread's 8-byte slot in row (8 gw + g) of the A tile, step 0: chunk j -> K chunk pair j / 2, half j % 2
-        const uint32_t a_thr = a_base + (j >> 1) * LBO_A + (j & 1) * 8 + (gw * ROWS_PER_WARP + g) * 16;
+        // this thread's 8-byte slot in row 0 of the A tile, step 0: chunk j -> K chunk pair j / 2, half j % 2
+        const uint32_t a_thr = a_base + (j >> 1) * LBO_A + (j & 1) * 8;
+        const bool has_desc = p.row_desc != nullptr;
         const int4 empty = make_int4(32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16));
 
         int it = 0;
         for (int pt = pair; pt < npt; pt += npairs, it++)
         {
             const int s = mp_only ? (it & 1) : 0;
+            if (gw == 0 && lane == 0) TRACE(2, it, 0);
             mbar_wait_park(&bar[BAR_STAGE_FULL + s], (mp_only ? (it >> 1) : it) & 1);
+            if (gw == 0 && lane == 0) TRACE(2, it, 2);
             if (!mp_only && it >= 1) mbar_wait_park(&bar[BAR_A_FREE], (it - 1) & 1);
+            if (gw == 0 && lane == 0) TRACE(2, it, 3);
             // the tile's record and row descriptors arrived with its rows: no global load, no register prefetch in these warps
             const int2 ti = reinterpret_cast<const int2*>(smem + Smem::TILE)[s];
             const int start = ti.x, rows = ti.y & 0xFFFF;
@@ -441,9 +467,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
 #pragma unroll 1
             for (int ps = 0; ps < 2; ps++)
             {
-                const int R = gw * ROWS_PER_WARP + 4 * ps + g;
-                const bool live = R < rows;
-                const int4 d = live ? lds_i4(desc_base + R * 16) : empty;
+                // slot -> row: the tile's descriptors are ordered by in-degree, so the four rows of this warp instruction
+                // (almost always) have in-edge lists of one length; a slot beyond the tile stands for itself
+                const int slot = gw * ROWS_PER_WARP + 4 * ps + g;
+                const bool live = slot < rows;
+                const int4 d = (live && has_desc) ? lds_i4(desc_base + slot * 16) : empty;
+                const int R = (live && has_desc) ? ((d.y >> 24) & 0x7F) : slot;
                 RowCtx r;
                 r.node = start + (live ? R : 0);
                 r.own = live ? stage_thr + (uint32_t)R * ROW_BYTES : zero_thr;
@@ -460,7 +489,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                 int maxdeg = max(r.deg, __shfl_xor_sync(FULL, r.deg, 8));
                 maxdeg = max(maxdeg, __shfl_xor_sync(FULL, maxdeg, 16));
                 float* out_thr = p.h_out + (size_t)r.node * D + 4 * j;
-                const uint32_t a_dst = a_thr + ps * (4 * 16);
+                const uint32_t a_dst = a_thr + R * 16;
                 if (ext)
                 {
 #pragma unroll 1
@@ -487,9 +516,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             // chunk 24 of the warp's 8 rows: lanes 0..7, a lane per row
             if (lane < ROWS_PER_WARP)
             {
-                const int R = gw * ROWS_PER_WARP + lane;
-                const bool live = R < rows;
-                const int4 d = live ? lds_i4(desc_base + R * 16) : empty;
+                const int slot = gw * ROWS_PER_WARP + lane;
+                const bool live = slot < rows;
+                const int4 d = (live && has_desc) ? lds_i4(desc_base + slot * 16) : empty;
+                const int R = (live && has_desc) ? ((d.y >> 24) & 0x7F) : slot;
                 const int node = start + (live ? R : 0);
                 int deg = live ? (int)((unsigned)d.x >> 24) : 0;
                 if (deg == 255) deg = __ldg(p.in_ptr + node + 1) - __ldg(p.in_ptr + node);
@@ -510,6 +540,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                     if (it == 0 && gw == 0) mbar_wait_park(&bar[BAR_W], 0);      // this CTA's weights have landed
                     mbar_arrive_cluster(bar_full0);
                 }
+                if (gw == 0) TRACE(2, it, 1);
             }
         }
     }
@@ -528,22 +559,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             const int rows = ti.y & 0xFFFF;
             mbar_wait_park(&bar[BAR_G1A_DONE], ph);
             tc::fence_after_sync();
+            if (tid == 0) TRACE(1, it, 0);
             convert_range(lane_base + TC_Z, pp, N1A / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_a2a0);
+            if (tid == 0) TRACE(1, it, 1);
 
             mbar_wait_park(&bar[BAR_G1B_DONE], ph);
             tc::fence_after_sync();
+            if (tid == 0) TRACE(1, it, 2);
             convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_a2b0);
+            if (tid == 0) TRACE(1, it, 3);
 
             mbar_wait_park(&bar[BAR_G2_DONE], ph);
             tc::fence_after_sync();
+            if (tid == 0) TRACE(1, it, 4);
             // 16-lane x 256-bit TMEM loads give thread t columns 8g + 2(t%4), +1 of rows t/4 and t/4 + 8
             const int ra = quad * 32 + pp * 16 + (lane >> 2), rb = ra + 8;
             const bool va = ra < rows, vb = rb < rows;
@@ -614,6 +650,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                     }
                 }
             }
+            if (tid == 0) TRACE(1, it, 5);
         }
     }
 
@@ -627,14 +664,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
 
 }  // namespace
 
+extern unsigned long long* gin_tc2_trace_buffer;      // set through flowgnn_b200_debug_trace (api.cu)
+
 int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
-                           const float* head_w, float* node_dot, const int4* row_desc, int mp_only)
+                           const float* head_w, float* node_dot, bool mlp_only, int mp_only)
 {
     FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_layer_fused_kernel), Smem::BYTES));
     GinFusedParams p;
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
-    p.row_desc = row_desc ? row_desc : b.row_desc.as<int4>();     // override: "no in-edges" descriptors = node MLP only (gin.cu)
+    p.row_desc = mlp_only ? nullptr : b.row_desc_sorted.as<int4>();      // nullptr: every row without in-edges = the node MLP alone (dense graphs, gin.cu)
     p.tiles = b.tiles.as<int2>(); p.tile_count = b.tile_count.as<int>();
     p.ee_comb = w.ee_comb.as<float>() + (size_t)layer * ED_COMBOS * D;
     p.wpack = w.wpack2.as<unsigned char>() + (size_t)layer * 2 * W_BYTES;
@@ -642,6 +681,7 @@ int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer,
     p.relu_out = (layer != 4);
     p.mp_only = mp_only;
     p.head_w = head_w; p.node_dot = node_dot;
+    p.trace = gin_tc2_trace_buffer;
     const int pairs = (int)std::max<long>(1, std::min<long>((b.max_tiles + 1) / 2, sm_count / 2));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = Smem::BYTES; cfg.stream = s;

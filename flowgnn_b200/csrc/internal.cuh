@@ -46,6 +46,7 @@ struct DeviceBatch {
     DevBuf out_deg;                        // int32 [N]
     DevBuf node_w0, node_w1;               // float [N]  DGN: sum|eig_w|, sum eig_w over in-edges
     DevBuf row_desc;                       // int4 [N]  GIN: first four in-edges of every node, packed (prep.cu)
+    DevBuf row_desc_sorted;                // int4 [N]  GIN: the descriptors of every tile ordered by in-degree, row position in .y bits 24..30 (prep.cu)
     DevBuf row_desc0;                      // int4 [N]  GIN, dense graphs: "no in-edges" descriptors (node MLP launch after the staged gather)
     DevBuf sort_tmp;                       // int32 [E] scratch for the two-pass stable sort
     DevBuf big_tab;                        // int32 [3][N] CSR-build tables of graphs above 1,024 nodes (allocated only if there is one)
@@ -153,7 +154,7 @@ int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, co
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
                          const float* head_w = nullptr, float* node_dot = nullptr, const int4* row_desc = nullptr);
 int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
-                           const float* head_w = nullptr, float* node_dot = nullptr, const int4* row_desc = nullptr, int mp_only = 0);
+                           const float* head_w = nullptr, float* node_dot = nullptr, bool mlp_only = false, int mp_only = 0);
 int gin_pool_dot_launch(const float* node_dot, const DeviceBatch& b, const float* pred_b, cudaStream_t s);
 int gin_layer_tc3_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t gin_tc3_pack_bytes();

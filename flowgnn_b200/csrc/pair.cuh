@@ -125,6 +125,40 @@ __device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64
         : "memory");
 }
 
+// The same three instructions issued by the elected lane of a CONVERGED warp: elect.sync inside the asm block, the tcgen05
+// instruction predicated on it.  The loop around them then runs on all 32 lanes (uniform datapath, descriptors in uniform
+// registers) and ptxas emits one predicated UTCHMMA per MMA -- issued from a `lane == 0` branch every MMA is wrapped in an
+// elect-and-retry loop with R2UR moves (~150 cycles per MMA, three times the time the tensor pipe needs to execute it).
+__device__ __forceinline__ void commit2_elect(uint64_t* bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xFFFFFFFF;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ss2_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xFFFFFFFF;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts2_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xFFFFFFFF;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
 // relu that lets NaN through, like the reference's compare-select (GIN/src/util.h:20-25), in ONE instruction
 __device__ __forceinline__ float relu_nan(float x)
 {
