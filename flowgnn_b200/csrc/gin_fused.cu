@@ -7,20 +7,20 @@
 // What changed against gin_tc2.cu (same CTA pair, same weight image, same MMA / epilogue protocol): the edge gather no
 // longer goes through the L1 / LSU global path.  In-edge sources are nodes of the SAME graph and a graph's rows are
 // contiguous in HBM, so prep.cu packs whole graphs into tiles of <= 128 rows and the kernel lands a tile's feature rows
-// in shared memory with ONE bulk-TMA copy (cp.async.bulk + mbarrier, issued by a producer warp, no LSU wavefronts, every
-// row read from HBM exactly once).  The gather warps then read own row, source rows and edge-embedding rows with
-// conflict-free 128-byte shared-memory pieces (29-cycle latency instead of L2 round trips: no software pipeline, no
-// register ring), reduce in CSR order and write the bf16 hi/lo A tile.  The shared memory for the stage comes from
-// single-buffering the A tile: gather(t+1) starts when GEMM1(t) has consumed A, and overlaps the z conversion, GEMM2
-// and the h' epilogue of tile t.
+// (and its row descriptors) in shared memory with bulk-TMA copies (cp.async.bulk + mbarrier, issued by a producer warp:
+// no LSU wavefronts, every row read from HBM exactly once).  The gather warps read own row, source rows and
+// edge-embedding rows with conflict-free 128-byte shared-memory pieces, reduce in CSR order and keep the tile's x = m + h
+// as packed bf16 hi/lo IN REGISTERS (24 per thread); once all 16 gather warps are done reading, the A tile of the GEMM
+// is written IN PLACE over the stage.  Two such buffers alternate: while GEMM1 consumes the A tile of tile t in one, the
+// gather reads the stage of tile t+1 in the other, and the buffer GEMM1 releases receives the rows of tile t+2.
 //
 // Per CTA (896 threads; cluster of two CTAs = one UMMA M = 256 tile = two graph-aligned tiles):
 //   warps 0-7   epilogue (as gin_tc2.cu): z = relu(acc) -> bf16 hi/lo in tensor memory, h' = acc (+relu) -> HBM, or the fused head
-//   warps 8-23  gather: 8 rows each as two passes of 4 rows, 8 lanes per row, chunk 8 ks + j in step ks < 3; chunk 24 by lane j == 0
+//   warps 8-23  gather: 8 rows each as two passes of 4 rows, 8 lanes per row, chunk 8 ks + j in step ks < 3; chunk 24 by lanes 0..7
 //   warp 24     (leader CTA) MMA issuer: GEMM1 SS (3 products x 7 k-steps, N halves 112 + 96), GEMM2 TS (3 x 13, N = 128)
-//   warp 25     producer: bulk-TMA copy of the next tile's rows into the stage, L2 prefetch two tiles ahead
+//   warp 25     producer: bulk-TMA copies of a tile's rows + descriptors into the free buffer, L2 prefetch two tiles ahead
 // Option mp_only (node transform = identity): the same gather writes x = m + h straight to h_out, the MMA
-// and epilogue warps idle, and the A-tile region serves as a second stage buffer.
+// and epilogue warps idle.
 // Tiles whose graph exceeds 128 nodes are flagged external: their source rows are read from global memory.
 #include "internal.cuh"
 #include "layers.cuh"
@@ -49,31 +49,30 @@ constexpr int EPI_WARPS = 8, GATHER_WARPS = 16;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, LOAD_WARP = MMA_WARP + 1;
 constexpr int NT = (MMA_WARP + 4) * 32;       // 896
 constexpr int REGS_LAUNCH = 72;
-constexpr int REGS_EPI = 80, REGS_MISC = 56, REGS_GATHER = 72;
+constexpr int REGS_EPI = 80, REGS_MISC = 24, REGS_GATHER = 80;
 static_assert(32 * (EPI_WARPS * REGS_EPI + GATHER_WARPS * REGS_GATHER + 4 * REGS_MISC) <= NT * REGS_LAUNCH, "setmaxnreg pool");
 constexpr int ROWS_PER_WARP = TM / GATHER_WARPS;   // 8
 
 constexpr uint32_t TC_Z = 0, TC_H = 256;
 constexpr uint32_t TMEM_COLS = 512;
 
+constexpr int BUF_BYTES = 2 * A_BYTES;                  // one buffer: stage rows [128][100] fp32 + descriptors [128] int4, later A hi | A lo
 struct Smem {
     static constexpr int W = 0;
-    static constexpr int A = W + W_BYTES;                           // [hi, lo][A_BYTES]; mp_only: second stage buffer
-    static constexpr int ZERO = A + 2 * A_BYTES;                    // K chunk 13 of the A buffers (must lie above them: LBO >= 0)
+    static constexpr int BUF = W + W_BYTES;                         // [2][BUF_BYTES]
+    static constexpr int ZERO = BUF + 2 * BUF_BYTES;                // K chunk 13 of the A tiles (must lie above them: LBO >= 0); rows beyond a tile
     static constexpr int EE = ZERO + ZERO_BYTES;                    // [61][100] fp32 combined edge-embedding rows; row 60 = sentinel
-    static constexpr int STAGE = EE + (ED_COMBOS + 1) * D * 4;      // [128][100] fp32 feature rows of the tile (bulk TMA)
-    static constexpr int DESC = STAGE + STAGE_BYTES;                // [128] int4 row descriptors of the tile (second bulk copy)
-    static constexpr int BAR = DESC + DESC_BYTES;
+    static constexpr int BAR = EE + (ED_COMBOS + 1) * D * 4;
     static constexpr int TMEM_PTR = BAR + 16 * 8;
-    static constexpr int TILE = TMEM_PTR + 16;                      // [2] int2 tile record of the stage (written by the producer)
+    static constexpr int TILE = TMEM_PTR + 16;                      // [2] int2 tile record of each buffer (written by the producer)
     static constexpr int BYTES = TILE + 16;
 };
-static_assert(Smem::ZERO % 16 == 0 && Smem::A % 16 == 0 && Smem::EE % 16 == 0 && Smem::STAGE % 16 == 0 && Smem::BAR % 8 == 0, "alignment");
-static_assert(2 * A_BYTES >= STAGE_BYTES + DESC_BYTES, "mp_only uses the A region as the second stage");
+static_assert(Smem::ZERO % 16 == 0 && Smem::BUF % 16 == 0 && BUF_BYTES % 16 == 0 && Smem::EE % 16 == 0 && Smem::BAR % 8 == 0, "alignment");
+static_assert(BUF_BYTES >= STAGE_BYTES + DESC_BYTES, "a buffer holds the stage rows and the descriptors");
 static_assert(Smem::BYTES <= 232448, "shared memory budget");
 
-enum { BAR_W = 0, BAR_A_FULL, BAR_A_FREE, BAR_G1A_DONE, BAR_G1B_DONE, BAR_A2A_FULL, BAR_A2B_FULL, BAR_G2_DONE,
-       BAR_STAGE_FULL /* 2 */, BAR_STAGE_FREE = BAR_STAGE_FULL + 2 /* 2 */, BAR_COUNT = BAR_STAGE_FREE + 2 };
+enum { BAR_W = 0, BAR_A_FULL /* 2 */, BAR_G1A_DONE = BAR_A_FULL + 2, BAR_G1B_DONE, BAR_A2A_FULL, BAR_A2B_FULL, BAR_G2_DONE,
+       BAR_STAGE_FULL /* 2 */, BAR_BUF_FREE = BAR_STAGE_FULL + 2 /* 2 */, BAR_COUNT = BAR_BUF_FREE + 2 };
 static_assert(BAR_COUNT <= 16, "barrier slots");
 
 struct GinFusedParams {
@@ -156,12 +155,18 @@ template <int NQ, bool LONG, int OFF>
 __device__ __forceinline__ float4 gather_chunk(const GinFusedParams& p, const RowCtx& r, int maxdeg, uint32_t stage_thr, uint32_t ee_thr, int tile_start)
 {
     const float4 hv = lds_f4(r.own + OFF);
-    float4 hu[4], tt[4];
-#pragma unroll
-    for (int q = 0; q < NQ; q++) { hu[q] = lds_f4(r.so[q] + OFF); tt[q] = lds_f4(r.tb[q] + OFF); }
+    float4 hu[2], tt[2];
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    // two slots per batch of loads: 20 registers of loads in flight instead of 36 (the 24 packed results of the tile live in
+    // registers too), and the other 15 gather warps cover the second round trip to shared memory
 #pragma unroll
-    for (int q = 0; q < NQ; q++) acc_edge2(m, tt[q], hu[q]);
+    for (int q0 = 0; q0 < NQ; q0 += 2)
+    {
+#pragma unroll
+        for (int q = q0; q < q0 + 2 && q < NQ; q++) { hu[q - q0] = lds_f4(r.so[q] + OFF); tt[q - q0] = lds_f4(r.tb[q] + OFF); }
+#pragma unroll
+        for (int q = q0; q < q0 + 2 && q < NQ; q++) acc_edge2(m, tt[q - q0], hu[q - q0]);
+    }
     if constexpr (LONG)
     {
         const int eb = __ldg(p.in_ptr + r.node);
@@ -177,48 +182,55 @@ __device__ __forceinline__ float4 gather_chunk(const GinFusedParams& p, const Ro
         for (int e4 = 4; e4 < maxdeg; e4 += 4)
         {
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q0 = 0; q0 < 4; q0 += 2)
             {
-                // an exhausted slot reads the row itself (u = node) with the sentinel table row: adds exactly 0
-                hu[q] = lds_f4(stage_thr + (uint32_t)(u[q] - tile_start) * ROW_BYTES + OFF);
-                tt[q] = lds_f4(ee_thr + c[q] * ROW_BYTES + OFF);
-                const bool ok = e4 + 4 + q < r.deg;
-                u[q] = ok ? __ldg(p.src + eb + e4 + 4 + q) : r.node;
-                c[q] = ok ? (int)__ldg(p.code + eb + e4 + 4 + q) : ED_COMBOS;
-            }
 #pragma unroll
-            for (int q = 0; q < 4; q++) acc_edge2(m, tt[q], hu[q]);
+                for (int q = q0; q < q0 + 2; q++)
+                {
+                    // an exhausted slot reads the row itself (u = node) with the sentinel table row: adds exactly 0
+                    hu[q - q0] = lds_f4(stage_thr + (uint32_t)(u[q] - tile_start) * ROW_BYTES + OFF);
+                    tt[q - q0] = lds_f4(ee_thr + c[q] * ROW_BYTES + OFF);
+                    const bool ok = e4 + 4 + q < r.deg;
+                    u[q] = ok ? __ldg(p.src + eb + e4 + 4 + q) : r.node;
+                    c[q] = ok ? (int)__ldg(p.code + eb + e4 + 4 + q) : ED_COMBOS;
+                }
+#pragma unroll
+                for (int q = q0; q < q0 + 2; q++) acc_edge2(m, tt[q - q0], hu[q - q0]);
+            }
         }
     }
     const float2 xa = add2(make_float2(m.x, m.y), make_float2(hv.x, hv.y)), xb = add2(make_float2(m.z, m.w), make_float2(hv.z, hv.w));
     return make_float4(xa.x, xa.y, xb.x, xb.y);
 }
 
-// where a chunk of x goes: the bf16 hi / lo A tile (shared memory), or -- mp_only -- h_out
-__device__ __forceinline__ void put_chunk(const float4& x, bool mp_only, bool live, float* out_chunk, uint32_t a_dst)
+// One chunk of x: mp_only -> stored to h_out right away; otherwise split into packed bf16 hi / lo pairs that stay in
+// registers until the whole tile has been read (the A tile is then written over the stage, in place).
+struct Packed { uint32_t h0, h1, l0, l1; };
+__device__ __forceinline__ Packed keep_chunk(const float4& x, bool mp_only, bool live, float* out_chunk)
 {
+    Packed k = {0u, 0u, 0u, 0u};
     if (mp_only) { if (live) stg_f4(out_chunk, x); }
     else
     {
-        uint32_t h0, l0, h1, l1;
-        split2(x.x, x.y, h0, l0);
-        split2(x.z, x.w, h1, l1);
-        sts_v2(a_dst, h0, h1);
-        sts_v2(a_dst + A_BYTES, l0, l1);
+        split2(x.x, x.y, k.h0, k.l0);
+        split2(x.z, x.w, k.h1, k.l1);
     }
+    return k;
+}
+__device__ __forceinline__ void sts_packed(uint32_t a_dst, const Packed& k)
+{
+    sts_v2(a_dst, k.h0, k.h1);
+    sts_v2(a_dst + A_BYTES, k.l0, k.l1);
 }
 
 // chunks 8 ks + j, ks < 3, of the pass's row (this thread: lane j of the row)
 template <int NQ, bool LONG>
 __device__ __forceinline__ void gather_pass(const GinFusedParams& p, const RowCtx& r, int maxdeg, uint32_t stage_thr, uint32_t ee_thr, int tile_start,
-                                            bool mp_only, bool live, float* out_thr, uint32_t a_thr)
+                                            bool mp_only, bool live, float* out_thr, Packed (&k)[3])
 {
-    const float4 x0 = gather_chunk<NQ, LONG, 0>(p, r, maxdeg, stage_thr, ee_thr, tile_start);
-    put_chunk(x0, mp_only, live, out_thr, a_thr);
-    const float4 x1 = gather_chunk<NQ, LONG, 128>(p, r, maxdeg, stage_thr, ee_thr, tile_start);
-    put_chunk(x1, mp_only, live, out_thr + 32, a_thr + 4 * LBO_A);
-    const float4 x2 = gather_chunk<NQ, LONG, 256>(p, r, maxdeg, stage_thr, ee_thr, tile_start);
-    put_chunk(x2, mp_only, live, out_thr + 64, a_thr + 8 * LBO_A);
+    k[0] = keep_chunk(gather_chunk<NQ, LONG, 0>(p, r, maxdeg, stage_thr, ee_thr, tile_start), mp_only, live, out_thr);
+    k[1] = keep_chunk(gather_chunk<NQ, LONG, 128>(p, r, maxdeg, stage_thr, ee_thr, tile_start), mp_only, live, out_thr + 32);
+    k[2] = keep_chunk(gather_chunk<NQ, LONG, 256>(p, r, maxdeg, stage_thr, ee_thr, tile_start), mp_only, live, out_thr + 64);
 }
 
 // The last float4 of a row (columns 96..99, chunk 24) does not fit 8 lanes x 3 steps: once per tile lanes 0..7 of a warp
@@ -278,13 +290,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const bool mp_only = p.mp_only != 0;
-    const int nstage = mp_only ? 2 : 1;
 
     if (tid == 0)
     {
         mbar_init(&bar[BAR_W], 1);
+        // one barrier per buffer: the gather of tile t+1 does not wait for GEMM1(t), so both A tiles can be complete before the
+        // MMA warp looks -- a single barrier would advance two phases and the parity wait would never return
         mbar_init(&bar[BAR_A_FULL], 2 * GATHER_WARPS);
-        mbar_init(&bar[BAR_A_FREE], 1);
+        mbar_init(&bar[BAR_A_FULL + 1], 2 * GATHER_WARPS);
         mbar_init(&bar[BAR_G1A_DONE], 1);
         mbar_init(&bar[BAR_G1B_DONE], 1);
         mbar_init(&bar[BAR_A2A_FULL], 2 * EPI_WARPS);
@@ -293,7 +306,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
         for (int i = 0; i < 2; i++)
         {
             mbar_init(&bar[BAR_STAGE_FULL + i], 1);
-            mbar_init(&bar[BAR_STAGE_FREE + i], GATHER_WARPS);
+            // a buffer is free again when GEMM1 has consumed the A tile written over it (one tcgen05.commit, multicast to both
+            // CTAs); mp_only: when the 16 gather warps are done reading it
+            mbar_init(&bar[BAR_BUF_FREE + i], mp_only ? GATHER_WARPS : 1);
         }
         fence_mbar_init();
         if (!mp_only)
@@ -311,19 +326,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
     }
     for (int i = tid; i < ED_COMBOS * Q; i += NT) st_f4(ee + 4 * i, ldg_f4(p.ee_comb + 4 * i));
     for (int i = tid; i < D; i += NT) ee[ED_COMBOS * D + i] = -3.0e38f;       // absent edge slots: relu(-3e38 + h) adds exactly 0
-    // A buffers + zero block (k = 101..103 of every row stays zero for the whole launch)
-    for (int i = tid; i < (Smem::EE - Smem::A) / 16; i += NT) st_f4(reinterpret_cast<float*>(smem + Smem::A) + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
-    __syncthreads();
-    // bias column: a_hi[row][k = 100] = 1, never overwritten (the gather writes k < 100 only)
-    if (!mp_only)
-        for (int i = tid; i < TM; i += NT) *reinterpret_cast<uint16_t*>(smem + Smem::A + (D / 8) * LBO_A + i * 16 + (D % 8) * 2) = 0x3F80;
+    for (int i = tid; i < ZERO_BYTES / 16; i += NT) st_f4(reinterpret_cast<float*>(smem + Smem::ZERO) + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
     fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     cluster_sync();
     tc::fence_after_sync();
     const uint32_t tbase = *tmem_ptr;
-    const uint32_t a_base = smem_u32(smem + Smem::A);
+    const uint32_t buf_base = smem_u32(smem + Smem::BUF);
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on the kernel reads
     // what the previous kernels of the stream wrote (h_in, and in the first layer the tiles / descriptors of prep.cu)
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -341,60 +351,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             // the gather warps are waiting for GEMM1 to release the A tile, so GEMM1 should run as fast as the tensor pipe can.)
             if (rank == 0 && !mp_only)
             {
-                const uint32_t w_addr = smem_u32(smem + Smem::W);
-                const uint32_t zero_addr = smem_u32(smem + Smem::ZERO);
+                const uint32_t w_addr0 = smem_u32(smem + Smem::W);
+                const uint32_t zero_addr0 = smem_u32(smem + Smem::ZERO);
                 const uint32_t idesc1a = tc::idesc_bf16(2 * TM, N1A), idesc1b = tc::idesc_bf16(2 * TM, N1B), idesc2 = tc::idesc_bf16(2 * TM, N2);
                 int it = 0;
                 for (int pt = pair; pt < npt; pt += npairs, it++)
                 {
                     const uint32_t ph = it & 1;
+                    const uint32_t a_base = buf_base + (it & 1) * BUF_BYTES;
+                    // opaque copies: the 81 operand descriptors are rebuilt per tile (a few uniform-datapath instructions each)
+                    // instead of being hoisted out of the loop into registers this warp does not have
+                    uint32_t w_addr, zero_addr;
+                    asm volatile("mov.u32 %0, %1;" : "=r"(w_addr) : "r"(w_addr0));
+                    asm volatile("mov.u32 %0, %1;" : "=r"(zero_addr) : "r"(zero_addr0));
                     if (lane == 0) TRACE(0, it, 0);
-                    mbar_wait_park(&bar[BAR_A_FULL], ph);
+                    mbar_wait_park(&bar[BAR_A_FULL + (it & 1)], (it >> 1) & 1);
                     tc::fence_after_sync();
                     if (lane == 0) TRACE(0, it, 1);
-#pragma unroll
+                    // rolled loops on purpose: this warp runs on 24 registers (setmaxnreg), the descriptors are a few integer
+                    // instructions per MMA
+#pragma unroll 1
                     for (int nh = 0; nh < 2; nh++)
                     {
-                        bool acc = false;
                         const uint32_t lbo_b = nh ? LBO_W1B : LBO_W1A;
-#pragma unroll
+                        const uint32_t idesc1 = nh ? idesc1b : idesc1a;
+                        const uint32_t d_col = tbase + TC_Z + (nh ? N1A : 0);
+#pragma unroll 1
                         for (int prod = 0; prod < 3; prod++)
                         {
-                            const uint32_t a_addr = a_base + (prod == 1 ? 1 : 0) * A_BYTES;
+                            const uint32_t a_addr = a_base + (prod == 1 ? A_BYTES : 0);
                             const uint32_t b_addr = w_addr + (nh ? (prod == 2 ? OFF_W1B_LO : OFF_W1B_HI) : (prod == 2 ? OFF_W1A_LO : OFF_W1A_HI));
-#pragma unroll
+#pragma unroll 1
                             for (int j = 0; j < K1_STEPS; j++)
                             {
                                 const uint32_t a_start = a_addr + 2 * j * LBO_A;
                                 // the last k-step pairs chunk 12 with the shared zero block (k = 104..111 does not exist)
                                 const uint32_t a_lbo = (j < K1_STEPS - 1) ? (uint32_t)LBO_A : zero_addr - a_start;
-                                mma_ss2_elect(tbase + TC_Z + (nh ? N1A : 0), tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128),
-                                        nh ? idesc1b : idesc1a, acc);
-                                acc = true;
+                                mma_ss2_elect(d_col, tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128), idesc1,
+                                              (prod | j) != 0);
                             }
                         }
                         commit2_elect(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
                     }
-                    commit2_elect(&bar[BAR_A_FREE]);
                     if (lane == 0) TRACE(0, it, 2);
-                    bool acc = false;
-#pragma unroll
+#pragma unroll 1
                     for (int kh = 0; kh < 2; kh++)
                     {
                         mbar_wait_park(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
                         tc::fence_after_sync();
                         if (lane == 0) TRACE(0, it, 3 + kh);
-#pragma unroll
+                        const int j0 = kh ? N1A / 16 : 0, j1 = kh ? K2_STEPS : N1A / 16;
+#pragma unroll 1
                         for (int prod = 0; prod < 3; prod++)
                         {
                             const uint32_t a_col = tbase + TC_Z + (prod == 1 ? 8 : 0);
                             const uint32_t b_addr = w_addr + (prod == 2 ? OFF_W2_LO : OFF_W2_HI);
-#pragma unroll
-                            for (int j = (kh ? N1A / 16 : 0); j < (kh ? K2_STEPS : N1A / 16); j++)
-                            {
-                                mma_ts2_elect(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * LBO_W2, LBO_W2, 128), idesc2, acc);
-                                acc = true;
-                            }
+#pragma unroll 1
+                            for (int j = j0; j < j1; j++)
+                                mma_ts2_elect(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * LBO_W2, LBO_W2, 128), idesc2, (kh | prod | (j - j0)) != 0);
                         }
                     }
                     commit2_elect(&bar[BAR_G2_DONE]);
@@ -410,12 +424,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                 int it = 0;
                 for (int pt = pair; pt < npt; pt += npairs, it++)
                 {
-                    const int s = mp_only ? (it & 1) : 0;
+                    const int s = it & 1;
                     const int2 ti = tile_of(p, 2 * pt + (int)rank, ntiles);
                     const uint32_t bytes = (uint32_t)(ti.y & 0xFFFF) * ROW_BYTES;
-                    if (it >= nstage) mbar_wait_park(&bar[BAR_STAGE_FREE + s], (mp_only ? ((it >> 1) - 1) : (it - 1)) & 1);
-                    unsigned char* dst = smem + ((mp_only && s == 1) ? Smem::A : Smem::STAGE);
-                    unsigned char* ddst = smem + ((mp_only && s == 1) ? Smem::A + STAGE_BYTES : Smem::DESC);
+                    if (it >= 2) mbar_wait_park(&bar[BAR_BUF_FREE + s], ((it >> 1) - 1) & 1);
+                    unsigned char* dst = smem + Smem::BUF + s * BUF_BYTES;
+                    unsigned char* ddst = dst + STAGE_BYTES;
                     const int nrows = ti.y & 0xFFFF;
                     TRACE(2, it, 4);
                     reinterpret_cast<int2*>(smem + Smem::TILE)[s] = ti;          // released to the gather warps by the arrival below
@@ -444,102 +458,121 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
         const uint32_t ee_thr = smem_u32(ee) + 16 * j;
         const uint32_t bar_full0 = mapa(smem_u32(&bar[BAR_A_FULL]), 0);
         const uint32_t zero_thr = smem_u32(smem + Smem::ZERO) + 16 * j;            // 2 KB of zeros: the "row" of a slot beyond the tile
-        // this thread's 8-byte slot in row 0 of the A tile, step 0: chunk j -> K chunk pair j / 2, half j % 2
-        const uint32_t a_thr = a_base + (j >> 1) * LBO_A + (j & 1) * 8;
         const bool has_desc = p.row_desc != nullptr;
         const int4 empty = make_int4(32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16), 32768 | (ED_COMBOS << 16));
+
+        // one pass = the four rows of this warp instruction (thread: lane j of row slot), chunks 8 ks + j -> k[0..2]
+        auto do_pass = [&](int slot, int start, int rows, bool ext, uint32_t stage_thr, uint32_t desc_base, Packed (&k)[3], int& R_out) {
+            // slot -> row: the tile's descriptors are ordered by in-degree, so the four rows of a warp instruction (almost
+            // always) have in-edge lists of one length; a slot beyond the tile stands for itself
+            const bool live = slot < rows;
+            const int4 d = (live && has_desc) ? lds_i4(desc_base + slot * 16) : empty;
+            const int R = (live && has_desc) ? ((d.y >> 24) & 0x7F) : slot;
+            R_out = R;
+            RowCtx r;
+            r.node = start + (live ? R : 0);
+            r.own = live ? stage_thr + (uint32_t)R * ROW_BYTES : zero_thr;
+            r.so[0] = r.own + (uint32_t)(((d.x & 0xFFFF) - 32768) * ROW_BYTES);
+            r.so[1] = r.own + (uint32_t)(((d.y & 0xFFFF) - 32768) * ROW_BYTES);
+            r.so[2] = r.own + (uint32_t)(((d.z & 0xFFFF) - 32768) * ROW_BYTES);
+            r.so[3] = r.own + (uint32_t)(((d.w & 0xFFFF) - 32768) * ROW_BYTES);
+            r.tb[0] = ee_thr + ((d.x >> 16) & 0x3F) * ROW_BYTES;
+            r.tb[1] = ee_thr + ((d.y >> 16) & 0x3F) * ROW_BYTES;
+            r.tb[2] = ee_thr + ((d.z >> 16) & 0x3F) * ROW_BYTES;
+            r.tb[3] = ee_thr + ((d.w >> 16) & 0x3F) * ROW_BYTES;
+            r.deg = live ? (int)((unsigned)d.x >> 24) : 0;
+            if (r.deg == 255) r.deg = __ldg(p.in_ptr + r.node + 1) - __ldg(p.in_ptr + r.node);
+            int maxdeg = max(r.deg, __shfl_xor_sync(FULL, r.deg, 8));
+            maxdeg = max(maxdeg, __shfl_xor_sync(FULL, maxdeg, 16));
+            float* out_thr = p.h_out + (size_t)r.node * D + 4 * j;
+            if (ext)
+            {
+#pragma unroll
+                for (int ks = 0; ks < 3; ks++)
+                    k[ks] = keep_chunk(gather_chunk_ext(p.h_in + 4 * (8 * ks + j), p.in_ptr, p.src, p.code, r.node, r.deg, r.own + 128 * ks, ee_thr + 128 * ks),
+                                       mp_only, live, out_thr + 32 * ks);
+            }
+            else
+            {
+                // one specialisation per slot count of this warp instruction's four rows: a single uniform branch per pass
+                switch (maxdeg)
+                {
+                case 0: gather_pass<0, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, k); break;
+                case 1: gather_pass<1, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, k); break;
+                case 2: gather_pass<2, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, k); break;
+                case 3: gather_pass<3, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, k); break;
+                case 4: gather_pass<4, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, k); break;
+                default: gather_pass<4, true>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, k); break;
+                }
+            }
+        };
 
         int it = 0;
         for (int pt = pair; pt < npt; pt += npairs, it++)
         {
-            const int s = mp_only ? (it & 1) : 0;
+            const int s = it & 1;
             if (gw == 0 && lane == 0) TRACE(2, it, 0);
-            mbar_wait_park(&bar[BAR_STAGE_FULL + s], (mp_only ? (it >> 1) : it) & 1);
+            mbar_wait_park(&bar[BAR_STAGE_FULL + s], (it >> 1) & 1);
             if (gw == 0 && lane == 0) TRACE(2, it, 2);
-            if (!mp_only && it >= 1) mbar_wait_park(&bar[BAR_A_FREE], (it - 1) & 1);
-            if (gw == 0 && lane == 0) TRACE(2, it, 3);
             // the tile's record and row descriptors arrived with its rows: no global load, no register prefetch in these warps
             const int2 ti = reinterpret_cast<const int2*>(smem + Smem::TILE)[s];
             const int start = ti.x, rows = ti.y & 0xFFFF;
             const bool ext = (ti.y >> 30) & 1;
-            const uint32_t stage_thr = smem_u32(smem + ((mp_only && s == 1) ? Smem::A : Smem::STAGE)) + 16 * j;
-            const uint32_t desc_base = smem_u32(smem + ((mp_only && s == 1) ? Smem::A + STAGE_BYTES : Smem::DESC));
-#pragma unroll 1
-            for (int ps = 0; ps < 2; ps++)
-            {
-                // slot -> row: the tile's descriptors are ordered by in-degree, so the four rows of this warp instruction
-                // (almost always) have in-edge lists of one length; a slot beyond the tile stands for itself
-                const int slot = gw * ROWS_PER_WARP + 4 * ps + g;
-                const bool live = slot < rows;
-                const int4 d = (live && has_desc) ? lds_i4(desc_base + slot * 16) : empty;
-                const int R = (live && has_desc) ? ((d.y >> 24) & 0x7F) : slot;
-                RowCtx r;
-                r.node = start + (live ? R : 0);
-                r.own = live ? stage_thr + (uint32_t)R * ROW_BYTES : zero_thr;
-                r.so[0] = r.own + (uint32_t)(((d.x & 0xFFFF) - 32768) * ROW_BYTES);
-                r.so[1] = r.own + (uint32_t)(((d.y & 0xFFFF) - 32768) * ROW_BYTES);
-                r.so[2] = r.own + (uint32_t)(((d.z & 0xFFFF) - 32768) * ROW_BYTES);
-                r.so[3] = r.own + (uint32_t)(((d.w & 0xFFFF) - 32768) * ROW_BYTES);
-                r.tb[0] = ee_thr + ((d.x >> 16) & 0x3F) * ROW_BYTES;
-                r.tb[1] = ee_thr + ((d.y >> 16) & 0x3F) * ROW_BYTES;
-                r.tb[2] = ee_thr + ((d.z >> 16) & 0x3F) * ROW_BYTES;
-                r.tb[3] = ee_thr + ((d.w >> 16) & 0x3F) * ROW_BYTES;
-                r.deg = live ? (int)((unsigned)d.x >> 24) : 0;
-                if (r.deg == 255) r.deg = __ldg(p.in_ptr + r.node + 1) - __ldg(p.in_ptr + r.node);
-                int maxdeg = max(r.deg, __shfl_xor_sync(FULL, r.deg, 8));
-                maxdeg = max(maxdeg, __shfl_xor_sync(FULL, maxdeg, 16));
-                float* out_thr = p.h_out + (size_t)r.node * D + 4 * j;
-                const uint32_t a_dst = a_thr + R * 16;
-                if (ext)
-                {
-#pragma unroll 1
-                    for (int ks = 0; ks < 3; ks++)
-                    {
-                        const float4 x = gather_chunk_ext(p.h_in + 4 * (8 * ks + j), p.in_ptr, p.src, p.code, r.node, r.deg, r.own + 128 * ks, ee_thr + 128 * ks);
-                        put_chunk(x, mp_only, live, out_thr + 32 * ks, a_dst + ks * (4 * LBO_A));
-                    }
-                }
-                else
-                {
-                    // one specialisation per slot count of this warp instruction's four rows: a single uniform branch per pass
-                    switch (maxdeg)
-                    {
-                    case 0: gather_pass<0, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
-                    case 1: gather_pass<1, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
-                    case 2: gather_pass<2, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
-                    case 3: gather_pass<3, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
-                    case 4: gather_pass<4, false>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
-                    default: gather_pass<4, true>(p, r, maxdeg, stage_thr, ee_thr, start, mp_only, live, out_thr, a_dst); break;
-                    }
-                }
-            }
+            const uint32_t buf = buf_base + s * BUF_BYTES;
+            const uint32_t stage_thr = buf + 16 * j, desc_base = buf + STAGE_BYTES;
+            Packed k0[3], k1[3], kt = {0u, 0u, 0u, 0u};
+            int R0, R1, Rt = 0;
+            do_pass(gw * ROWS_PER_WARP + g, start, rows, ext, stage_thr, desc_base, k0, R0);
+            do_pass(gw * ROWS_PER_WARP + 4 + g, start, rows, ext, stage_thr, desc_base, k1, R1);
             // chunk 24 of the warp's 8 rows: lanes 0..7, a lane per row
             if (lane < ROWS_PER_WARP)
             {
                 const int slot = gw * ROWS_PER_WARP + lane;
                 const bool live = slot < rows;
                 const int4 d = (live && has_desc) ? lds_i4(desc_base + slot * 16) : empty;
-                const int R = (live && has_desc) ? ((d.y >> 24) & 0x7F) : slot;
-                const int node = start + (live ? R : 0);
+                Rt = (live && has_desc) ? ((d.y >> 24) & 0x7F) : slot;
+                const int node = start + (live ? Rt : 0);
                 int deg = live ? (int)((unsigned)d.x >> 24) : 0;
                 if (deg == 255) deg = __ldg(p.in_ptr + node + 1) - __ldg(p.in_ptr + node);
-                const uint32_t stage_tail = stage_thr - 16 * j + 16 * (Q - 1);
-                const uint32_t own = live ? stage_tail + (uint32_t)R * ROW_BYTES : zero_thr - 16 * j;
-                const float4 x = tail_chunk(p, d, node, deg, own, ee_thr - 16 * j + 16 * (Q - 1), ext, stage_tail, start);
-                put_chunk(x, mp_only, live, p.h_out + (size_t)node * D + 4 * (Q - 1), a_base + ((Q - 1) >> 1) * LBO_A + R * 16);
+                const uint32_t stage_tail = buf + 16 * (Q - 1);
+                const uint32_t own = live ? stage_tail + (uint32_t)Rt * ROW_BYTES : zero_thr - 16 * j;
+                const float4 x = tail_chunk(p, d, node, deg, own, smem_u32(ee) + 16 * (Q - 1), ext, stage_tail, start);
+                kt = keep_chunk(x, mp_only, live, p.h_out + (size_t)node * D + 4 * (Q - 1));
             }
             __syncwarp();
-            // the stage may be refilled; the tile is visible to the tensor core (async proxy) and reported to the leader CTA
-            if (!mp_only) fence_proxy_async();
+            if (gw == 0 && lane == 0) TRACE(2, it, 3);
+            if (mp_only)
+            {
+                if (lane == 0) mbar_arrive(&bar[BAR_BUF_FREE + s]);          // the buffer may be refilled
+                continue;
+            }
+            // every gather warp is done reading the stage: the A tile goes over it, in place (bf16 hi at +0, lo at +A_BYTES;
+            // thread's 8-byte slot of row R in step ks: K chunk pair 4 ks + j / 2, half j % 2)
+            asm volatile("bar.sync 1, %0;" ::"n"(GATHER_WARPS * 32) : "memory");
+            {
+                const uint32_t a_thr = buf + (j >> 1) * LBO_A + (j & 1) * 8;
+#pragma unroll
+                for (int ks = 0; ks < 3; ks++)
+                {
+                    sts_packed(a_thr + R0 * 16 + ks * (4 * LBO_A), k0[ks]);
+                    sts_packed(a_thr + R1 * 16 + ks * (4 * LBO_A), k1[ks]);
+                }
+                if (lane < ROWS_PER_WARP)
+                {
+                    // K chunk 12 of the row: k = 96..99 from chunk 24, the bias column k = 100 (constant 1 in the hi tile: W1 carries
+                    // b1 there), k = 101..103 zero
+                    const uint32_t dst = buf + ((Q - 1) >> 1) * LBO_A + Rt * 16;
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(kt.h0), "r"(kt.h1), "r"(0x00003F80u), "r"(0u) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + A_BYTES), "r"(kt.l0), "r"(kt.l1), "r"(0u), "r"(0u) : "memory");
+                }
+            }
+            // the tile is visible to the tensor core (async proxy) and reported to the leader CTA
+            fence_proxy_async();
             __syncwarp();
             if (lane == 0)
             {
-                mbar_arrive(&bar[BAR_STAGE_FREE + s]);
-                if (!mp_only)
-                {
-                    if (it == 0 && gw == 0) mbar_wait_park(&bar[BAR_W], 0);      // this CTA's weights have landed
-                    mbar_arrive_cluster(bar_full0);
-                }
+                if (it == 0 && gw == 0) mbar_wait_park(&bar[BAR_W], 0);      // this CTA's weights have landed
+                mbar_arrive_cluster(bar_full0 + 8 * s);
                 if (gw == 0) TRACE(2, it, 1);
             }
         }
@@ -569,6 +602,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
 
             mbar_wait_park(&bar[BAR_G1B_DONE], ph);
             tc::fence_after_sync();
+            // GEMM1 is complete (both N halves; the commit is multicast to both CTAs): the A tile is consumed, this CTA's buffer
+            // may receive the rows of tile it + 2
+            if (tid == 0) mbar_arrive(&bar[BAR_BUF_FREE + (it & 1)]);
             if (tid == 0) TRACE(1, it, 2);
             convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
             tc::wait_st();

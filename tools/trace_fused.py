@@ -40,18 +40,18 @@ for name, a, b in (("A_FULL wait", (0, 0), (0, 1)), ("G1 issue", (0, 1), (0, 2))
                    ("G2 issued -> next A wait", None, None), ("EPI: got G1A -> arrived A2A (convert a)", (1, 0), (1, 1)), ("EPI: arrived A2A -> got G1B", (1, 1), (1, 2)),
                    ("EPI: convert b", (1, 2), (1, 3)), ("EPI: arrived A2B -> got G2", (1, 3), (1, 4)), ("EPI: H store", (1, 4), (1, 5)),
                    ("MMA G1 issued -> EPI got G1A", (0, 2), (1, 0)), ("EPI arrived A2A -> MMA got A2A", (1, 1), (0, 3)), ("MMA G2 issued -> EPI got G2", (0, 5), (1, 4)),
-                   ("GATHER tile time (start -> arrived)", (2, 0), (2, 1)), ("GATHER wait for the stage", (2, 0), (2, 2)), ("GATHER wait for A free", (2, 2), (2, 3)),
-                   ("GATHER compute (A free -> arrived)", (2, 3), (2, 1)), 
+                   ("GATHER tile time (start -> arrived)", (2, 0), (2, 1)), ("GATHER wait for the stage", (2, 0), (2, 2)), ("GATHER compute (stage full -> all chunks in registers)", (2, 2), (2, 3)),
+                   ("GATHER barrier + A stores (-> arrived)", (2, 3), (2, 1)), 
                    ("GATHER arrived -> MMA got A", (2, 1), (0, 1)), ("producer TMA issue -> GATHER got stage", (2, 4), (2, 2))):
     if a is None: continue
     d = t[b[0], 8:50, b[1]] - t[a[0], 8:50, a[1]]
     print(f"{name:45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
 
 # cross-tile intervals: GEMM1 of tile i releases the A tile for the gather of tile i + 1; the stage of tile i + 1 is requested when the gather of tile i is done
-d = t[2, 9:51, 3] - t[0, 8:50, 2]
-print(f"{'MMA G1(i) issued -> GATHER(i+1) got A free':45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
-d = t[2, 9:51, 4] - t[2, 8:50, 1]
-print(f"{'GATHER(i) arrived -> producer issues TMA(i+1)':45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
+d = t[2, 10:52, 4] - t[0, 8:50, 2]
+print(f"{'MMA G1(i) issued -> producer issues TMA(i+2)':45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
+d = t[2, 9:51, 2] - t[2, 8:50, 1]
+print(f"{'GATHER(i) arrived -> GATHER(i+1) got its stage':45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
 d = t[2, 9:51, 2] - t[2, 9:51, 4]
 print(f"{'producer TMA(i+1) issue -> stage(i+1) full':45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
 d = t[0, 9:51, 1] - t[0, 8:50, 5]
