@@ -438,8 +438,8 @@ extern "C" {
 int flowgnn_b200_debug_trace(unsigned long long** dev_buffer, int enable)
 {
     static unsigned long long* buf = nullptr;
-    if (!buf) FG_CUDA(cudaMalloc(&buf, 3 * 64 * 8 * sizeof(unsigned long long)));
-    if (enable) FG_CUDA(cudaMemset(buf, 0, 3 * 64 * 8 * sizeof(unsigned long long)));
+    if (!buf) FG_CUDA(cudaMalloc(&buf, 4096 * sizeof(unsigned long long)));
+    if (enable) FG_CUDA(cudaMemset(buf, 0, 4096 * sizeof(unsigned long long)));
     fg::gin_tc2_trace_buffer = enable ? buf : nullptr;
     if (dev_buffer) *dev_buffer = buf;
     return 0;

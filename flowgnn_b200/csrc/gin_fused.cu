@@ -30,6 +30,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <set>
+#include <type_traits>
 
 namespace fg {
 
@@ -46,16 +49,25 @@ constexpr int STAGE_BYTES = TM * ROW_BYTES;             // 51,200
 constexpr int DESC_BYTES = TM * 16;                     // 2,048
 
 constexpr int EPI_WARPS = 8, GATHER_WARPS = 16;
-constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, LOAD_WARP = MMA_WARP + 1;
+constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS;
+// 28 warps (7 per scheduler): launched with 72 registers per thread, setmaxnreg moves them to where they are needed -- the
+// gather warps keep a tile's x in registers (80), the epilogue stays at 72, the last warpgroup (the MMA issuer and three
+// idle warps) gets 40: every operand descriptor of the issuer is a compile-time constant (the tile loop is unrolled by
+// two, one body per buffer), so it holds next to nothing.  (Tried: 24 registers with the descriptors in a shared-memory /
+// constant-memory table -- ptxas moves them through vector registers and local memory, GEMM1 then takes 2.2 us to issue
+// instead of ~1; 25 warps x 80 registers without setmaxnreg does not launch: 7 warps x 2,560 registers on one scheduler
+// exceed its 16,384.)  The TMA producer is thread 0 of the epilogue: it learns that GEMM1(t) has consumed a buffer from
+// the barrier it waits on anyway.
 constexpr int NT = (MMA_WARP + 4) * 32;       // 896
 constexpr int REGS_LAUNCH = 72;
-constexpr int REGS_EPI = 80, REGS_MISC = 24, REGS_GATHER = 80;
+constexpr int REGS_EPI = 72, REGS_MISC = 40, REGS_GATHER = 80;
 static_assert(32 * (EPI_WARPS * REGS_EPI + GATHER_WARPS * REGS_GATHER + 4 * REGS_MISC) <= NT * REGS_LAUNCH, "setmaxnreg pool");
 constexpr int ROWS_PER_WARP = TM / GATHER_WARPS;   // 8
 
 constexpr uint32_t TC_Z = 0, TC_H = 256;
 constexpr uint32_t TMEM_COLS = 512;
 
+constexpr int G1_MMAS = 2 * 3 * K1_STEPS, G2_MMAS = 3 * K2_STEPS;       // 42, 39
 constexpr int BUF_BYTES = 2 * A_BYTES;                  // one buffer: stage rows [128][100] fp32 + descriptors [128] int4, later A hi | A lo
 struct Smem {
     static constexpr int W = 0;
@@ -97,7 +109,10 @@ __device__ __forceinline__ unsigned long long gtime()
     return t;
 }
 #define TRACE(role, it, ev) do { if (p.trace && pair == 0 && rank == 0 && (it) < 64) p.trace[((role) * 64 + (it)) * 8 + (ev)] = gtime(); } while (0)
+// whole-kernel marks of CTA 0 (slot 60) and of the last CTA (slot 61): entry, prologue done, loops done
+#define TRACE_K(ev) do { if (p.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) p.trace[(1 * 64 + (blockIdx.x == 0 ? 0 : 2) + ((ev) >> 1)) * 8 + 6 + ((ev) & 1)] = gtime(); } while (0)
 #else
+#define TRACE_K(ev) do { } while (0)
 #define TRACE(role, it, ev) do { } while (0)
 #endif
 
@@ -118,6 +133,25 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr)
     int4 v;
     asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
+}
+
+// Shared-memory address of dynamic shared memory in a kernel without static shared memory (the kernel checks it): with it
+// every operand descriptor of the MMA issuer is a compile-time constant.
+constexpr uint32_t SMEM_BASE = 0x400;
+__host__ __device__ constexpr uint64_t desc_imm(uint32_t off, uint32_t lbo)
+{
+    return (uint64_t)(((SMEM_BASE + off) >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+
+// compile-time loop: f(std::integral_constant<int, I>) for I = 0 .. N-1
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N)
+    {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
 }
 
 __device__ __forceinline__ void stg_f4(float* ptr, const float4& v)
@@ -290,6 +324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const bool mp_only = p.mp_only != 0;
+    TRACE_K(0);
 
     if (tid == 0)
     {
@@ -306,9 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
         for (int i = 0; i < 2; i++)
         {
             mbar_init(&bar[BAR_STAGE_FULL + i], 1);
-            // a buffer is free again when GEMM1 has consumed the A tile written over it (one tcgen05.commit, multicast to both
-            // CTAs); mp_only: when the 16 gather warps are done reading it
-            mbar_init(&bar[BAR_BUF_FREE + i], mp_only ? GATHER_WARPS : 1);
+            mbar_init(&bar[BAR_BUF_FREE + i], GATHER_WARPS);        // mp_only: the 16 gather warps are done reading the buffer
         }
         fence_mbar_init();
         if (!mp_only)
@@ -336,10 +369,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
     const uint32_t buf_base = smem_u32(smem + Smem::BUF);
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail; from here on the kernel reads
     // what the previous kernels of the stream wrote (h_in, and in the first layer the tiles / descriptors of prep.cu)
+    TRACE_K(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    TRACE_K(2);
+#ifdef FG_TC2_TRACE
+    if (p.trace && tid == 0) p.trace[2048 + blockIdx.x] = gtime();             // per-CTA loop start / end (tools/trace_fused.py)
+#endif
     const int ntiles = __ldg(p.tile_count);
+    if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[7] = (unsigned long long)ntiles;
     const int npt = (ntiles + 1) >> 1;                       // pair tiles
+    // producer (one thread): the tile's feature rows + row descriptors -> buffer s (two bulk copies onto one barrier), its
+    // record for the gather warps, and an L2 prefetch for the tile two further on
+    auto produce = [&](int it, int pt) {
+        const int s = it & 1;
+        const int2 ti = tile_of(p, 2 * pt + (int)rank, ntiles);
+        const int nrows = ti.y & 0xFFFF;
+        const uint32_t bytes = (uint32_t)nrows * ROW_BYTES;
+        unsigned char* dst = smem + Smem::BUF + s * BUF_BYTES;
+        TRACE(2, it, 4);
+        reinterpret_cast<int2*>(smem + Smem::TILE)[s] = ti;          // released to the gather warps by the arrival below
+        mbar_arrive_expect_tx(&bar[BAR_STAGE_FULL + s], bytes + (p.row_desc ? nrows * 16 : 0));
+        if (bytes)
+        {
+            tma_load_1d(dst, p.h_in + (size_t)ti.x * D, bytes, &bar[BAR_STAGE_FULL + s]);
+            if (p.row_desc) tma_load_1d(dst + STAGE_BYTES, p.row_desc + ti.x, nrows * 16, &bar[BAR_STAGE_FULL + s]);
+        }
+        const int2 tn = tile_of(p, 2 * (pt + 2 * npairs) + (int)rank, ntiles);
+        if (tn.y & 0xFFFF)
+        {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (size_t)tn.x * D), "r"((tn.y & 0xFFFF) * ROW_BYTES) : "memory");
+            if (p.row_desc) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.row_desc + tn.x), "r"((tn.y & 0xFFFF) * 16) : "memory");
+        }
+    };
 
     if (warp >= MMA_WARP)
     {
@@ -351,107 +413,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             // the gather warps are waiting for GEMM1 to release the A tile, so GEMM1 should run as fast as the tensor pipe can.)
             if (rank == 0 && !mp_only)
             {
-                const uint32_t w_addr0 = smem_u32(smem + Smem::W);
-                const uint32_t zero_addr0 = smem_u32(smem + Smem::ZERO);
-                const uint32_t idesc1a = tc::idesc_bf16(2 * TM, N1A), idesc1b = tc::idesc_bf16(2 * TM, N1B), idesc2 = tc::idesc_bf16(2 * TM, N2);
-                int it = 0;
-                for (int pt = pair; pt < npt; pt += npairs, it++)
-                {
+                constexpr uint32_t IDESC1A = tc::idesc_bf16(2 * TM, N1A), IDESC1B = tc::idesc_bf16(2 * TM, N1B), IDESC2 = tc::idesc_bf16(2 * TM, N2);
+                // the immediates of mma_*_tab assume these two bases
+                if ((smem_u32(smem) & 0xFFFFFFu) != SMEM_BASE || tbase != 0) asm volatile("trap;");
+                // one tile: every descriptor index is a compile-time constant (B selects the buffer); the operands come from the
+                // constant bank inside the asm blocks and nothing lives in this warp's 24 vector registers
+                auto mma_tile = [&](auto BSEL, int it) {
+                    constexpr int B = decltype(BSEL)::value;
                     const uint32_t ph = it & 1;
-                    const uint32_t a_base = buf_base + (it & 1) * BUF_BYTES;
-                    // opaque copies: the 81 operand descriptors are rebuilt per tile (a few uniform-datapath instructions each)
-                    // instead of being hoisted out of the loop into registers this warp does not have
-                    uint32_t w_addr, zero_addr;
-                    asm volatile("mov.u32 %0, %1;" : "=r"(w_addr) : "r"(w_addr0));
-                    asm volatile("mov.u32 %0, %1;" : "=r"(zero_addr) : "r"(zero_addr0));
                     if (lane == 0) TRACE(0, it, 0);
-                    mbar_wait_park(&bar[BAR_A_FULL + (it & 1)], (it >> 1) & 1);
+                    mbar_wait_park(&bar[BAR_A_FULL + B], (it >> 1) & 1);
                     tc::fence_after_sync();
                     if (lane == 0) TRACE(0, it, 1);
-                    // rolled loops on purpose: this warp runs on 24 registers (setmaxnreg), the descriptors are a few integer
-                    // instructions per MMA
-#pragma unroll 1
-                    for (int nh = 0; nh < 2; nh++)
-                    {
-                        const uint32_t lbo_b = nh ? LBO_W1B : LBO_W1A;
-                        const uint32_t idesc1 = nh ? idesc1b : idesc1a;
-                        const uint32_t d_col = tbase + TC_Z + (nh ? N1A : 0);
-#pragma unroll 1
-                        for (int prod = 0; prod < 3; prod++)
-                        {
-                            const uint32_t a_addr = a_base + (prod == 1 ? A_BYTES : 0);
-                            const uint32_t b_addr = w_addr + (nh ? (prod == 2 ? OFF_W1B_LO : OFF_W1B_HI) : (prod == 2 ? OFF_W1A_LO : OFF_W1A_HI));
-#pragma unroll 1
-                            for (int j = 0; j < K1_STEPS; j++)
-                            {
-                                const uint32_t a_start = a_addr + 2 * j * LBO_A;
-                                // the last k-step pairs chunk 12 with the shared zero block (k = 104..111 does not exist)
-                                const uint32_t a_lbo = (j < K1_STEPS - 1) ? (uint32_t)LBO_A : zero_addr - a_start;
-                                mma_ss2_elect(d_col, tc::smem_desc(a_start, a_lbo, 128), tc::smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128), idesc1,
-                                              (prod | j) != 0);
-                            }
-                        }
-                        commit2_elect(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
-                    }
+                    static_for<0, 2 * 3 * K1_STEPS>([&](auto I) {
+                        constexpr int e = decltype(I)::value, nh = e / (3 * K1_STEPS), prod = (e / K1_STEPS) % 3, j = e % K1_STEPS;
+                        constexpr uint32_t lbo_b = nh ? LBO_W1B : LBO_W1A;
+                        constexpr uint32_t a_start = Smem::BUF + B * BUF_BYTES + (prod == 1 ? A_BYTES : 0) + 2 * j * LBO_A;
+                        // the last k-step pairs chunk 12 with the shared zero block (k = 104..111 does not exist)
+                        constexpr uint64_t a_desc = desc_imm(a_start, j < K1_STEPS - 1 ? (uint32_t)LBO_A : (uint32_t)Smem::ZERO - a_start);
+                        constexpr uint64_t b_desc = desc_imm(Smem::W + (nh ? (prod == 2 ? OFF_W1B_LO : OFF_W1B_HI) : (prod == 2 ? OFF_W1A_LO : OFF_W1A_HI)) + 2 * j * lbo_b, lbo_b);
+                        mma_ss2_elect(TC_Z + (nh ? N1A : 0), a_desc, b_desc, nh ? IDESC1B : IDESC1A, (prod | j) != 0);
+                        if constexpr (prod == 2 && j == K1_STEPS - 1) commit2_elect(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
+                    });
                     if (lane == 0) TRACE(0, it, 2);
-#pragma unroll 1
-                    for (int kh = 0; kh < 2; kh++)
-                    {
-                        mbar_wait_park(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
-                        tc::fence_after_sync();
-                        if (lane == 0) TRACE(0, it, 3 + kh);
-                        const int j0 = kh ? N1A / 16 : 0, j1 = kh ? K2_STEPS : N1A / 16;
-#pragma unroll 1
-                        for (int prod = 0; prod < 3; prod++)
-                        {
-                            const uint32_t a_col = tbase + TC_Z + (prod == 1 ? 8 : 0);
-                            const uint32_t b_addr = w_addr + (prod == 2 ? OFF_W2_LO : OFF_W2_HI);
-#pragma unroll 1
-                            for (int j = j0; j < j1; j++)
-                                mma_ts2_elect(tbase + TC_H, a_col + 16 * j, tc::smem_desc(b_addr + 2 * j * LBO_W2, LBO_W2, 128), idesc2, (kh | prod | (j - j0)) != 0);
-                        }
-                    }
+                    // GEMM2: A = z (tensor memory: hi at +0, lo at +8 of every 16-column k-step)
+                    constexpr int NJA = N1A / 16;
+                    mbar_wait_park(&bar[BAR_A2A_FULL], ph);
+                    tc::fence_after_sync();
+                    if (lane == 0) TRACE(0, it, 3);
+                    static_for<0, 3 * NJA>([&](auto I) {
+                        constexpr int i = decltype(I)::value, prod = i / NJA, j = i % NJA;
+                        mma_ts2_elect(TC_H, TC_Z + (prod == 1 ? 8 : 0) + 16 * j, desc_imm(Smem::W + (prod == 2 ? OFF_W2_LO : OFF_W2_HI) + 2 * j * LBO_W2, LBO_W2), IDESC2, i != 0);
+                    });
+                    mbar_wait_park(&bar[BAR_A2B_FULL], ph);
+                    tc::fence_after_sync();
+                    if (lane == 0) TRACE(0, it, 4);
+                    static_for<0, 3 * (K2_STEPS - NJA)>([&](auto I) {
+                        constexpr int i = decltype(I)::value, prod = i / (K2_STEPS - NJA), j = NJA + i % (K2_STEPS - NJA);
+                        mma_ts2_elect(TC_H, TC_Z + (prod == 1 ? 8 : 0) + 16 * j, desc_imm(Smem::W + (prod == 2 ? OFF_W2_LO : OFF_W2_HI) + 2 * j * LBO_W2, LBO_W2), IDESC2, true);
+                    });
                     commit2_elect(&bar[BAR_G2_DONE]);
                     if (lane == 0) TRACE(0, it, 5);
-                }
-            }
-        }
-        else if (warp == LOAD_WARP)
-        {
-            // ===== producer: the tile's feature rows -> stage (ONE bulk copy), L2 prefetch of the tile after next =====
-            if (lane == 0)
-            {
+                };
                 int it = 0;
-                for (int pt = pair; pt < npt; pt += npairs, it++)
+                for (int pt = pair; pt < npt; pt += 2 * npairs, it += 2)
                 {
-                    const int s = it & 1;
-                    const int2 ti = tile_of(p, 2 * pt + (int)rank, ntiles);
-                    const uint32_t bytes = (uint32_t)(ti.y & 0xFFFF) * ROW_BYTES;
-                    if (it >= 2) mbar_wait_park(&bar[BAR_BUF_FREE + s], ((it >> 1) - 1) & 1);
-                    unsigned char* dst = smem + Smem::BUF + s * BUF_BYTES;
-                    unsigned char* ddst = dst + STAGE_BYTES;
-                    const int nrows = ti.y & 0xFFFF;
-                    TRACE(2, it, 4);
-                    reinterpret_cast<int2*>(smem + Smem::TILE)[s] = ti;          // released to the gather warps by the arrival below
-                    mbar_arrive_expect_tx(&bar[BAR_STAGE_FULL + s], bytes + (p.row_desc ? nrows * 16 : 0));
-                    if (bytes)
-                    {
-                        tma_load_1d(dst, p.h_in + (size_t)ti.x * D, bytes, &bar[BAR_STAGE_FULL + s]);
-                        if (p.row_desc) tma_load_1d(ddst, p.row_desc + ti.x, nrows * 16, &bar[BAR_STAGE_FULL + s]);
-                    }
-                    const int2 tn = tile_of(p, 2 * (pt + 2 * npairs) + (int)rank, ntiles);
-                    if (tn.y & 0xFFFF)
-                    {
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.h_in + (size_t)tn.x * D), "r"((tn.y & 0xFFFF) * ROW_BYTES) : "memory");
-                        if (p.row_desc) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.row_desc + tn.x), "r"((tn.y & 0xFFFF) * 16) : "memory");
-                    }
+                    mma_tile(std::integral_constant<int, 0>{}, it);
+                    if (pt + npairs < npt) mma_tile(std::integral_constant<int, 1>{}, it + 1);
                 }
             }
         }
     }
     else if (warp >= EPI_WARPS)
     {
-        if constexpr (REGS_GATHER > REGS_LAUNCH) reg_inc<REGS_GATHER>(); else reg_dec<REGS_GATHER>();
+        reg_inc<REGS_GATHER>();
         // ===== gather warps =====
         const int gw = warp - EPI_WARPS;
         const int g = lane >> 3, j = lane & 7;
@@ -522,12 +537,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             const uint32_t stage_thr = buf + 16 * j, desc_base = buf + STAGE_BYTES;
             Packed k0[3], k1[3], kt = {0u, 0u, 0u, 0u};
             int R0, R1, Rt = 0;
-            do_pass(gw * ROWS_PER_WARP + g, start, rows, ext, stage_thr, desc_base, k0, R0);
-            do_pass(gw * ROWS_PER_WARP + 4 + g, start, rows, ext, stage_thr, desc_base, k1, R1);
+            // the slots are ordered by in-degree: pass 0 takes a group of four from the lower half, pass 1 from the upper half, so
+            // that every warp gets a cheap and an expensive group (the A tile waits for the slowest warp)
+            do_pass(gw * 4 + g, start, rows, ext, stage_thr, desc_base, k0, R0);
+            do_pass(TM / 2 + gw * 4 + g, start, rows, ext, stage_thr, desc_base, k1, R1);
             // chunk 24 of the warp's 8 rows: lanes 0..7, a lane per row
             if (lane < ROWS_PER_WARP)
             {
-                const int slot = gw * ROWS_PER_WARP + lane;
+                const int slot = (lane & 4) * (TM / 8) + gw * 4 + (lane & 3);       // the warp's 8 slots: gw*4 + {0..3}, 64 + gw*4 + {0..3}
                 const bool live = slot < rows;
                 const int4 d = (live && has_desc) ? lds_i4(desc_base + slot * 16) : empty;
                 Rt = (live && has_desc) ? ((d.y >> 24) & 0x7F) : slot;
@@ -577,10 +594,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             }
         }
     }
-    else if (!mp_only)
+    else if (mp_only)
     {
-        if constexpr (REGS_EPI > REGS_LAUNCH) reg_inc<REGS_EPI>(); else reg_dec<REGS_EPI>();
+        // mp_only: no MMA, no epilogue -- thread 0 is just the producer, a buffer is free when the 16 gather warps have read it
+        if (tid == 0)
+        {
+            int it = 0;
+            for (int pt = pair; pt < npt; pt += npairs, it++)
+            {
+                if (it >= 2) mbar_wait_park(&bar[BAR_BUF_FREE + (it & 1)], ((it >> 1) - 1) & 1);
+                produce(it, pt);
+            }
+        }
+    }
+    else
+    {
         // ===== epilogue warps: two per TMEM lane quadrant (as gin_tc2.cu; rows beyond the tile are not stored) =====
+        // thread 0 is also the TMA producer: tiles 0 and 1 up front, tile it + 2 as soon as GEMM1(it) has consumed its buffer
+        if (tid == 0)
+        {
+            if (pair < npt) produce(0, pair);
+            if (pair + npairs < npt) produce(1, pair + npairs);
+        }
         const int quad = warp & 3, pp = warp >> 2;
         const uint32_t lane_base = tbase + ((uint32_t)(quad * 32) << 16);
         const uint32_t bar_a2a0 = mapa(smem_u32(&bar[BAR_A2A_FULL]), 0), bar_a2b0 = mapa(smem_u32(&bar[BAR_A2B_FULL]), 0);
@@ -603,8 +638,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             mbar_wait_park(&bar[BAR_G1B_DONE], ph);
             tc::fence_after_sync();
             // GEMM1 is complete (both N halves; the commit is multicast to both CTAs): the A tile is consumed, this CTA's buffer
-            // may receive the rows of tile it + 2
-            if (tid == 0) mbar_arrive(&bar[BAR_BUF_FREE + (it & 1)]);
+            // receives the rows of tile it + 2
+            if (tid == 0 && pt + 2 * npairs < npt) produce(it + 2, pt + 2 * npairs);
             if (tid == 0) TRACE(1, it, 2);
             convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
             tc::wait_st();
@@ -693,6 +728,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
     // both CTAs must be done with tensor memory, shared memory and each other's barriers before either leaves
     tc::fence_before_sync();
     __syncthreads();
+    TRACE_K(3);
+#ifdef FG_TC2_TRACE
+    if (p.trace && tid == 0) p.trace[2048 + 256 + blockIdx.x] = gtime();
+#endif
     __syncwarp();
     cluster_sync();
     if (warp == MMA_WARP) tmem_dealloc2(tbase, TMEM_COLS);

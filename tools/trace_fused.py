@@ -21,12 +21,13 @@ with Context(0) as c:
     assert lib.flowgnn_b200_debug_trace(ctypes.byref(ptr), 1) == 0
     c.compute("gin"); c.synchronize()
     lib.flowgnn_b200_debug_trace(ctypes.byref(ptr), 0)
-    buf = np.zeros(3 * 64 * 8, dtype=np.uint64)
+    buf = np.zeros(4096, dtype=np.uint64)
     torch.cuda.synchronize()
     import ctypes as ct
     cudart = ct.CDLL("libcudart.so.12")
     cudart.cudaMemcpy(buf.ctypes.data_as(ct.c_void_p), ptr, buf.nbytes, 2)
-t = buf.reshape(3, 64, 8).astype(np.int64)
+cta = buf[2048:].astype(np.int64)
+t = buf[:3 * 64 * 8].reshape(3, 64, 8).astype(np.int64)
 t0 = t[0, 0, 0]
 np.set_printoptions(linewidth=200)
 print("events (ns since the MMA thread started tile 0); MMA: wait_A, got_A, G1 issued, got_A2A, got_A2B, G2 issued")
@@ -56,3 +57,17 @@ d = t[2, 9:51, 2] - t[2, 9:51, 4]
 print(f"{'producer TMA(i+1) issue -> stage(i+1) full':45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
 d = t[0, 9:51, 1] - t[0, 8:50, 5]
 print(f"{'MMA G2(i) issued -> got A(i+1)':45s} mean {d.mean():8.0f} ns  min {d.min():6d} max {d.max():6d}")
+
+k0 = np.array([t[1, 0, 6], t[1, 0, 7], t[1, 1, 6], t[1, 1, 7]]) - t0
+k1 = np.array([t[1, 2, 6], t[1, 2, 7], t[1, 3, 6], t[1, 3, 7]]) - t0
+print("CTA 0   : entry %d, prologue done %d, previous grid done %d, loops done %d  (ns relative to the first tile of pair 0)" % tuple(k0))
+print("last CTA: entry %d, prologue done %d, previous grid done %d, loops done %d" % tuple(k1))
+nt = int(t[0, 0, 7])
+print("tiles:", nt, " pair tiles per pair: %.1f" % (nt / 2 / 74))
+last = max(i for i in range(64) if t[0, i, 5] > 0)
+print("pair 0: last recorded tile %d, G2 issued at %d ns" % (last, t[0, last, 5] - t0))
+
+dur = (cta[256:256 + 148] - cta[:148]) / 1e3
+start = (cta[:148] - cta[:148].min()) / 1e3
+print("per-CTA loop time (us): min %.1f mean %.1f max %.1f;  loop start spread %.1f us" % (dur.min(), dur.mean(), dur.max(), start.max()))
+print("per pair (even CTA):", np.round(dur[0::2], 0).astype(int).tolist())
