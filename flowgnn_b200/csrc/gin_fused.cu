@@ -64,7 +64,11 @@ constexpr int REGS_EPI = 72, REGS_MISC = 40, REGS_GATHER = 80;
 static_assert(32 * (EPI_WARPS * REGS_EPI + GATHER_WARPS * REGS_GATHER + 4 * REGS_MISC) <= NT * REGS_LAUNCH, "setmaxnreg pool");
 constexpr int ROWS_PER_WARP = TM / GATHER_WARPS;   // 8
 
-constexpr uint32_t TC_Z = 0, TC_H = 256;
+// tensor-memory columns: a ring of three 112-column z halves (tile t: GEMM1 half a -> ring slot 2t % 3, half b -> (2t + 1) % 3;
+// 96 of the 112 columns used by half b) and the h' accumulator.  With three halves GEMM1 of tile t+1 can run while the
+// epilogue still converts and GEMM2 still reads the z of tile t.
+constexpr uint32_t TC_ZR = 0, ZR_COLS = N1A, TC_H = 3 * ZR_COLS;
+static_assert(TC_H + N2 <= 512, "tensor memory columns");
 constexpr uint32_t TMEM_COLS = 512;
 
 constexpr int G1_MMAS = 2 * 3 * K1_STEPS, G2_MMAS = 3 * K2_STEPS;       // 42, 39
@@ -83,7 +87,7 @@ static_assert(Smem::ZERO % 16 == 0 && Smem::BUF % 16 == 0 && BUF_BYTES % 16 == 0
 static_assert(BUF_BYTES >= STAGE_BYTES + DESC_BYTES, "a buffer holds the stage rows and the descriptors");
 static_assert(Smem::BYTES <= 232448, "shared memory budget");
 
-enum { BAR_W = 0, BAR_A_FULL /* 2 */, BAR_G1A_DONE = BAR_A_FULL + 2, BAR_G1B_DONE, BAR_A2A_FULL, BAR_A2B_FULL, BAR_G2_DONE,
+enum { BAR_W = 0, BAR_A_FULL /* 2 */, BAR_G1A_DONE = BAR_A_FULL + 2 /* 2 */, BAR_G1B_DONE = BAR_G1A_DONE + 2 /* 2 */, BAR_A2A_FULL = BAR_G1B_DONE + 2, BAR_A2B_FULL, BAR_G2_DONE,
        BAR_STAGE_FULL /* 2 */, BAR_BUF_FREE = BAR_STAGE_FULL + 2 /* 2 */, BAR_COUNT = BAR_BUF_FREE + 2 };
 static_assert(BAR_COUNT <= 16, "barrier slots");
 
@@ -333,8 +337,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
         // MMA warp looks -- a single barrier would advance two phases and the parity wait would never return
         mbar_init(&bar[BAR_A_FULL], 2 * GATHER_WARPS);
         mbar_init(&bar[BAR_A_FULL + 1], 2 * GATHER_WARPS);
-        mbar_init(&bar[BAR_G1A_DONE], 1);
-        mbar_init(&bar[BAR_G1B_DONE], 1);
+        // two each, by tile parity: GEMM1(t+1) is issued before the epilogue has looked at GEMM1(t), a single barrier could
+        // advance two phases and the parity wait would never return
+        for (int i = 0; i < 2; i++) { mbar_init(&bar[BAR_G1A_DONE + i], 1); mbar_init(&bar[BAR_G1B_DONE + i], 1); }
         mbar_init(&bar[BAR_A2A_FULL], 2 * EPI_WARPS);
         mbar_init(&bar[BAR_A2B_FULL], 2 * EPI_WARPS);
         mbar_init(&bar[BAR_G2_DONE], 1);
@@ -416,43 +421,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                 constexpr uint32_t IDESC1A = tc::idesc_bf16(2 * TM, N1A), IDESC1B = tc::idesc_bf16(2 * TM, N1B), IDESC2 = tc::idesc_bf16(2 * TM, N2);
                 // the immediates of mma_*_tab assume these two bases
                 if ((smem_u32(smem) & 0xFFFFFFu) != SMEM_BASE || tbase != 0) asm volatile("trap;");
-                // one tile: every descriptor index is a compile-time constant (B selects the buffer); the operands come from the
-                // constant bank inside the asm blocks and nothing lives in this warp's 24 vector registers
-                auto mma_tile = [&](auto BSEL, int it) {
-                    constexpr int B = decltype(BSEL)::value;
-                    const uint32_t ph = it & 1;
-                    if (lane == 0) TRACE(0, it, 0);
-                    mbar_wait_park(&bar[BAR_A_FULL + B], (it >> 1) & 1);
-                    tc::fence_after_sync();
-                    if (lane == 0) TRACE(0, it, 1);
-                    static_for<0, 2 * 3 * K1_STEPS>([&](auto I) {
-                        constexpr int e = decltype(I)::value, nh = e / (3 * K1_STEPS), prod = (e / K1_STEPS) % 3, j = e % K1_STEPS;
+                // Issue order: GEMM1 of tile t is interleaved with GEMM2 of tile t-1 --
+                //   wait A(t), G1a(t) -> ring slot 2t % 3;  wait z_a(t-1) converted, G2a(t-1);  G1b(t) -> slot (2t+1) % 3 (the slot
+                //   G2a(t-1) has just read);  wait z_b(t-1) converted, G2b(t-1)
+                // so the tensor pipe works on GEMM1(t) while the epilogue converts tile t-1.  Every smem descriptor is a compile-time
+                // constant (B selects the buffer, the tile loop is unrolled by two); ring columns are run-time values.
+                auto g1_half = [&](auto BSEL, auto NH, uint32_t zcol) {
+                    constexpr int B = decltype(BSEL)::value, nh = decltype(NH)::value;
+                    static_for<0, 3 * K1_STEPS>([&](auto I) {
+                        constexpr int e = decltype(I)::value, prod = e / K1_STEPS, j = e % K1_STEPS;
                         constexpr uint32_t lbo_b = nh ? LBO_W1B : LBO_W1A;
                         constexpr uint32_t a_start = Smem::BUF + B * BUF_BYTES + (prod == 1 ? A_BYTES : 0) + 2 * j * LBO_A;
                         // the last k-step pairs chunk 12 with the shared zero block (k = 104..111 does not exist)
                         constexpr uint64_t a_desc = desc_imm(a_start, j < K1_STEPS - 1 ? (uint32_t)LBO_A : (uint32_t)Smem::ZERO - a_start);
                         constexpr uint64_t b_desc = desc_imm(Smem::W + (nh ? (prod == 2 ? OFF_W1B_LO : OFF_W1B_HI) : (prod == 2 ? OFF_W1A_LO : OFF_W1A_HI)) + 2 * j * lbo_b, lbo_b);
-                        mma_ss2_elect(TC_Z + (nh ? N1A : 0), a_desc, b_desc, nh ? IDESC1B : IDESC1A, (prod | j) != 0);
-                        if constexpr (prod == 2 && j == K1_STEPS - 1) commit2_elect(&bar[nh ? BAR_G1B_DONE : BAR_G1A_DONE]);
+                        mma_ss2_elect(zcol, a_desc, b_desc, nh ? IDESC1B : IDESC1A, e != 0);
                     });
+                    commit2_elect(&bar[(nh ? BAR_G1B_DONE : BAR_G1A_DONE) + B]);
+                };
+                // GEMM2 K half kh of the tile whose parity is ph: A = z (tensor memory: hi at +0, lo at +8 of every 16-column k-step)
+                auto g2_half = [&](auto KH, uint32_t zcol, uint32_t ph) {
+                    constexpr int kh = decltype(KH)::value, NJA = N1A / 16, nj = kh ? K2_STEPS - NJA : NJA;
+                    mbar_wait_park(&bar[kh ? BAR_A2B_FULL : BAR_A2A_FULL], ph);
+                    tc::fence_after_sync();
+                    static_for<0, 3 * nj>([&](auto I) {
+                        constexpr int i = decltype(I)::value, prod = i / nj, jj = i % nj, j = (kh ? NJA : 0) + jj;
+                        mma_ts2_elect(TC_H, zcol + (prod == 1 ? 8 : 0) + 16 * jj, desc_imm(Smem::W + (prod == 2 ? OFF_W2_LO : OFF_W2_HI) + 2 * j * LBO_W2, LBO_W2), IDESC2,
+                                      (kh | i) != 0);
+                    });
+                    if constexpr (kh == 1) commit2_elect(&bar[BAR_G2_DONE]);
+                };
+                auto mma_tile = [&](auto BSEL, int it) {
+                    constexpr int B = decltype(BSEL)::value;
+                    const uint32_t za = TC_ZR + ((2 * it) % 3) * ZR_COLS, zb = TC_ZR + ((2 * it + 1) % 3) * ZR_COLS;
+                    const uint32_t pza = TC_ZR + ((2 * it + 1) % 3) * ZR_COLS, pzb = TC_ZR + ((2 * it + 2) % 3) * ZR_COLS;   // slots of tile it - 1: (2it-2) % 3, (2it-1) % 3
+                    if (lane == 0) TRACE(0, it, 0);
+                    mbar_wait_park(&bar[BAR_A_FULL + B], (it >> 1) & 1);
+                    tc::fence_after_sync();
+                    if (lane == 0) TRACE(0, it, 1);
+                    g1_half(BSEL, std::integral_constant<int, 0>{}, za);
+                    if (it > 0) g2_half(std::integral_constant<int, 0>{}, pza, (uint32_t)((it - 1) & 1));
+                    g1_half(BSEL, std::integral_constant<int, 1>{}, zb);
                     if (lane == 0) TRACE(0, it, 2);
-                    // GEMM2: A = z (tensor memory: hi at +0, lo at +8 of every 16-column k-step)
-                    constexpr int NJA = N1A / 16;
-                    mbar_wait_park(&bar[BAR_A2A_FULL], ph);
-                    tc::fence_after_sync();
-                    if (lane == 0) TRACE(0, it, 3);
-                    static_for<0, 3 * NJA>([&](auto I) {
-                        constexpr int i = decltype(I)::value, prod = i / NJA, j = i % NJA;
-                        mma_ts2_elect(TC_H, TC_Z + (prod == 1 ? 8 : 0) + 16 * j, desc_imm(Smem::W + (prod == 2 ? OFF_W2_LO : OFF_W2_HI) + 2 * j * LBO_W2, LBO_W2), IDESC2, i != 0);
-                    });
-                    mbar_wait_park(&bar[BAR_A2B_FULL], ph);
-                    tc::fence_after_sync();
-                    if (lane == 0) TRACE(0, it, 4);
-                    static_for<0, 3 * (K2_STEPS - NJA)>([&](auto I) {
-                        constexpr int i = decltype(I)::value, prod = i / (K2_STEPS - NJA), j = NJA + i % (K2_STEPS - NJA);
-                        mma_ts2_elect(TC_H, TC_Z + (prod == 1 ? 8 : 0) + 16 * j, desc_imm(Smem::W + (prod == 2 ? OFF_W2_LO : OFF_W2_HI) + 2 * j * LBO_W2, LBO_W2), IDESC2, true);
-                    });
-                    commit2_elect(&bar[BAR_G2_DONE]);
+                    if (it > 0) g2_half(std::integral_constant<int, 1>{}, pzb, (uint32_t)((it - 1) & 1));
                     if (lane == 0) TRACE(0, it, 5);
                 };
                 int it = 0;
@@ -460,6 +471,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
                 {
                     mma_tile(std::integral_constant<int, 0>{}, it);
                     if (pt + npairs < npt) mma_tile(std::integral_constant<int, 1>{}, it + 1);
+                }
+                // GEMM2 of the last tile
+                const int nt = pair < npt ? (npt - 1 - pair) / npairs + 1 : 0;
+                if (nt > 0)
+                {
+                    g2_half(std::integral_constant<int, 0>{}, TC_ZR + ((2 * (nt - 1)) % 3) * ZR_COLS, (uint32_t)((nt - 1) & 1));
+                    g2_half(std::integral_constant<int, 1>{}, TC_ZR + ((2 * (nt - 1) + 1) % 3) * ZR_COLS, (uint32_t)((nt - 1) & 1));
                 }
             }
         }
@@ -625,23 +643,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
             const uint32_t ph = it & 1;
             const int2 ti = tile_of(p, 2 * pt + (int)rank, ntiles);
             const int rows = ti.y & 0xFFFF;
-            mbar_wait_park(&bar[BAR_G1A_DONE], ph);
+            mbar_wait_park(&bar[BAR_G1A_DONE + (it & 1)], (it >> 1) & 1);
             tc::fence_after_sync();
             if (tid == 0) TRACE(1, it, 0);
-            convert_range(lane_base + TC_Z, pp, N1A / 16);
+            const uint32_t za = lane_base + TC_ZR + ((2 * it) % 3) * ZR_COLS, zb = lane_base + TC_ZR + ((2 * it + 1) % 3) * ZR_COLS;
+            convert_range(za, pp, N1A / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(bar_a2a0);
             if (tid == 0) TRACE(1, it, 1);
 
-            mbar_wait_park(&bar[BAR_G1B_DONE], ph);
+            mbar_wait_park(&bar[BAR_G1B_DONE + (it & 1)], (it >> 1) & 1);
             tc::fence_after_sync();
             // GEMM1 is complete (both N halves; the commit is multicast to both CTAs): the A tile is consumed, this CTA's buffer
             // receives the rows of tile it + 2
             if (tid == 0 && pt + 2 * npairs < npt) produce(it + 2, pt + 2 * npairs);
             if (tid == 0) TRACE(1, it, 2);
-            convert_range(lane_base + TC_Z, N1A / 16 + (pp ^ 1), N1 / 16);
+            convert_range(zb, pp ^ 1, N1B / 16);
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
