@@ -361,6 +361,13 @@ int load_pna(flowgnn_ctx* c, const float* const* w)
         FG_CUDA(cudaMemcpyAsync(g.wpack_tc.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
         FG_CUDA(cudaStreamSynchronize(s));
     }
+    {
+        std::vector<unsigned char> pack(4 * pna_fused_pack_bytes());
+        for (int l = 0; l < 4; l++) pna_fused_pack_layer(wcat.data() + (size_t)l * 320 * 240, pack.data() + (size_t)l * pna_fused_pack_bytes(), bf16_rn, bf16_to_float);
+        FG_TRY(g.wpack_fused.reserve(pack.size()));
+        FG_CUDA(cudaMemcpyAsync(g.wpack_fused.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
+        FG_CUDA(cudaStreamSynchronize(s));
+    }
     FG_TRY(upload(g.w_ref, w[1], (size_t)4 * 80 * 12 * 80, s));
     FG_TRY(upload(g.b, w[2], 320, s));
     FG_TRY(upload(g.m1w, w[3], 40 * 80, s));
@@ -500,7 +507,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.wpack3, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wpack_tc, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
-                   &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.wpack_tc, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
+                   &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.wpack_tc, &ctx->pna.wpack_fused, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
                    &ctx->pna.m3w, &ctx->pna.m3b,
                    &ctx->dgn.emb, &ctx->dgn.wt, &ctx->dgn.wpack_tc, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
                    &ctx->dgn.m2w, &ctx->dgn.m2b,
@@ -525,6 +532,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "gin_tc3")) ctx->opt.gin_tc3 = value;
     else if (!std::strcmp(name, "gin_staged")) ctx->opt.gin_staged = value;
     else if (!std::strcmp(name, "pna_tc")) ctx->opt.pna_tc = value;
+    else if (!std::strcmp(name, "pna_fused")) ctx->opt.pna_fused = value;
     else if (!std::strcmp(name, "gcn_tc")) ctx->opt.gcn_tc = value;
     else if (!std::strcmp(name, "dgn_tc")) ctx->opt.dgn_tc = value;
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
@@ -613,13 +621,13 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     if (b.num_graphs == 0) return 0;
     if (model == MODEL_DGN && !b.has_eigen) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
     if ((model == MODEL_GIN || model == MODEL_GCN) && !b.has_attr) { set_last_error("GIN/GCN need edge_attr"); return FG_ERR_INVALID; }
-    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN) ? (PREP_ROW_DESC | PREP_TILES) : 0;
+    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN || model == MODEL_PNA) ? (PREP_ROW_DESC | PREP_TILES) : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
     int rc = prep_batch(b, flags, s);
     b.has_attr = keep_attr;
     FG_TRY(rc);
-    ctx->last_launches += 3 + (model == MODEL_GIN ? 2 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN: pack_tiles, sort_tile_rows)
+    ctx->last_launches += 3 + ((model == MODEL_GIN || model == MODEL_PNA) ? 2 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN, PNA: pack_tiles, sort_tile_rows)
     ctx->timer.marks = 0;
     ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
     ctx->opt.timer_group = ctx->time_layers == 2;

@@ -102,6 +102,7 @@ struct PnaWeights {
     DevBuf wcat;                // [4][320][240]  k = aggr*80+in, n = scaler*80+out
     DevBuf w_ref;               // [4][80][3][4][80] reference layout (exact path for out-degree-0 nodes)
     DevBuf wpack_tc;            // [4][5][61440] bytes: wcat as bf16 hi | lo K-chunks for pna_gemm_kernel (pna_tc.cu)
+    DevBuf wpack_fused;         // [4][5][61440] bytes: the same with K permuted (16 columns x 4 aggregates per chunk) for pna_fused.cu
     DevBuf b;                   // [4][80]
     DevBuf m1w, m1b, m2w, m2b, m3w, m3b;
     float avg_deg = 0.f;
@@ -142,6 +143,7 @@ struct RunOptions {
     int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
     int gcn_tc = 1;                  // GCN: Linear_l on tcgen05 (gcn_tc.cu: aggregate -> bf16x3 GEMM); 0: the fused FFMA kernel (gcn.cu)
     int dgn_tc = 1;                  // DGN: node transform on tcgen05 (dgn_tc.cu: aggregate -> bf16x3 GEMM -> fp32 rows); 0: FFMA kernel (dgn.cu)
+    int pna_fused = 1;               // PNA: ONE kernel per layer (pna_fused.cu: the aggregation is the A producer inside the GEMM kernel); 0: pna_tc / FFMA
     int pna_tc = 1;                  // PNA: node transform on tcgen05 (pna_tc.cu: aggregate -> bf16x3 GEMM -> exact rows); 0: FFMA kernel (pna.cu)
     int gat_node_offset_bug = 1;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
@@ -163,6 +165,10 @@ void gin_tc3_pack_layer(const float* w1, const float* b1, const float* w2, const
 size_t gin_tc2_pack_bytes();
 void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
                         float (*bf16_to_float)(uint16_t));
+int pna_layer_fused_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+int pna_exact_rows_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+size_t pna_fused_pack_bytes();
+void pna_fused_pack_layer(const float* wcat, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
 int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t pna_tc_pack_bytes();
 void pna_tc_pack_layer(const float* wcat, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));

@@ -238,6 +238,16 @@ int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int 
     for (int l = 0; l < 4; l++)
     {
         if (opt.timer) FG_TRY(opt.timer->mark(s));
+        if (opt.pna_fused && opt.pna_tc)
+        {
+            // one kernel for message passing + node transform, then the few rows that need fp32
+            FG_TRY(b.nonfinite.reserve((size_t)N + 16));
+            FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
+            FG_TRY(pna_layer_fused_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
+            FG_TRY(pna_exact_rows_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
+            nl += 2;
+            continue;
+        }
         if (opt.pna_tc)
         {
             FG_TRY(pna_layer_tc_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));

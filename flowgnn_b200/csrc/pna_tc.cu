@@ -489,14 +489,19 @@ int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const fl
         pna_gemm_kernel<<<std::min(num_tiles, sm_count), NT, Smem::BYTES, s>>>(p);
         FG_CUDA(cudaGetLastError());
     }
-    {
-        const int blocks = (int)std::min<long>(ceil_div<long>(N, 32 * EX_WARPS), (long)sm_count * 8);
-        pna_exact_rows_kernel<<<blocks, EX_WARPS * 32, 0, s>>>(h_in, h_out, b.in_ptr.as<int>(), b.src.as<int>(), b.out_deg.as<int>(),
-                                                               b.nonfinite.as<unsigned char>(), w.wcat.as<float>() + (size_t)layer * KA * NC,
-                                                               w.w_ref.as<float>() + (size_t)layer * D * 12 * D, w.b.as<float>() + (size_t)layer * D,
-                                                               w.avg_deg, (int)N);
-        FG_CUDA(cudaGetLastError());
-    }
+    return pna_exact_rows_launch(b, w, layer, h_in, h_out, sm_count, s);
+}
+
+// rows the tensor paths leave out (out-degree 0, non-finite aggregates), in fp32
+int pna_exact_rows_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
+{
+    const long N = b.total_nodes;
+    const int blocks = (int)std::min<long>(ceil_div<long>(N, 32 * EX_WARPS), (long)sm_count * 8);
+    pna_exact_rows_kernel<<<blocks, EX_WARPS * 32, 0, s>>>(h_in, h_out, b.in_ptr.as<int>(), b.src.as<int>(), b.out_deg.as<int>(),
+                                                           b.nonfinite.as<unsigned char>(), w.wcat.as<float>() + (size_t)layer * KA * NC,
+                                                           w.w_ref.as<float>() + (size_t)layer * D * 12 * D, w.b.as<float>() + (size_t)layer * D,
+                                                           w.avg_deg, (int)N);
+    FG_CUDA(cudaGetLastError());
     return 0;
 }
 
