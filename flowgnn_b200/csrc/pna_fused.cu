@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <type_traits>
 
@@ -83,7 +84,8 @@ static_assert(Smem::BYTES <= 232448, "shared memory budget");
 struct PnaFusedParams {
     const float* h_in; float* h_out;
     const int* in_ptr; const int* src;
-    const int4* row_desc;            // per tile: descriptors ordered by in-degree, row position in .y bits 24..30 (prep.cu)
+    const int4* row_desc;            // sorted: per tile ordered by in-degree, row position in .y bits 24..30; else in node order (prep.cu)
+    int sorted;
     const int2* tiles; const int* tile_count;
     const unsigned char* wpack;      // [5][61440] this layer, K permuted (pna_fused_pack_layer)
     const float* b;                  // [80]
@@ -260,10 +262,10 @@ __global__ void __launch_bounds__(NT, 1) pna_layer_fused_kernel(const __grid_con
             const bool ext = (ti.y >> 30) & 1;
             // slot -> row through the degree-ordered descriptors; lanes 0..15 of a warp take four slots of the lower half (small
             // in-degrees), lanes 16..31 four of the upper half, so that every warp gets the same mix (a chunk waits for the slowest)
-            const int slot = (lane >> 4) * (TM / 2) + warp * 4 + ((lane >> 2) & 3);
+            const int slot = p.sorted ? (lane >> 4) * (TM / 2) + warp * 4 + ((lane >> 2) & 3) : warp * 8 + (lane >> 2);
             const bool live = slot < rows;
             const int4 d = live ? lds_i4(desc_base + slot * 16) : make_int4(0, 0, 0, 0);
-            const int R = live ? ((d.y >> 24) & 0x7F) : slot;
+            const int R = (live && p.sorted) ? ((d.y >> 24) & 0x7F) : slot;
             const int node = start + (live ? R : 0);
             int deg = live ? (int)((unsigned)d.x >> 24) : 0;
             if (deg == 255) deg = __ldg(p.in_ptr + node + 1) - __ldg(p.in_ptr + node);
@@ -551,7 +553,9 @@ int pna_layer_fused_launch(DeviceBatch& b, const PnaWeights& w, int layer, const
     PnaFusedParams p{};
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>();
-    p.row_desc = b.row_desc_sorted.as<int4>();
+    static const int sorted_env = [] { const char* e = std::getenv("FLOWGNN_B200_PNA_SORTED"); return e ? std::atoi(e) : 0; }();
+    p.sorted = sorted_env;
+    p.row_desc = p.sorted ? b.row_desc_sorted.as<int4>() : b.row_desc.as<int4>();
     p.tiles = b.tiles.as<int2>(); p.tile_count = b.tile_count.as<int>();
     p.wpack = w.wpack_fused.as<unsigned char>() + (size_t)layer * pna_fused_pack_bytes();
     p.b = w.b.as<float>() + (size_t)layer * D;

@@ -190,9 +190,15 @@ def test_pna_tensor_core_path_matches_reference(ds, ctx, weights, datasets, gold
     ctx.set_option("pna_tc", 0)
     try:
         ffma = ctx.run("pna", datasets[ds], weights["pna"])
+        ctx.set_option("pna_tc", 1)
+        ctx.set_option("pna_fused", 0)
+        two_kernels = ctx.run("pna", datasets[ds])         # round-1 path: aggregate kernel -> A blocks in HBM -> GEMM kernel
     finally:
         ctx.set_option("pna_tc", 1)
-    tc = ctx.run("pna", datasets[ds])
+        ctx.set_option("pna_fused", 1)
+    tc = ctx.run("pna", datasets[ds])                      # default: ONE kernel per layer (pna_fused.cu)
+    assert_parity(two_kernels, golden[ds]["pna"], what=f"pna aggregate->GEMM/{ds}")
+    assert_parity(tc, two_kernels, tol=1e-4, what=f"pna fused vs aggregate->GEMM/{ds}")
     few = ctx.run("pna", datasets[ds].slice(0, 3))
     some = ctx.run("pna", datasets[ds].slice(0, 47))
     assert_parity(ffma, golden[ds]["pna"], what=f"pna ffma/{ds}")
