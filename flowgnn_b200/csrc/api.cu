@@ -159,24 +159,6 @@ static float bf16_to_float(uint16_t h)
     return x;
 }
 
-// One [n][k] fp32 matrix (reference "[out][in]") -> bf16 hi block followed by bf16 lo block, each zero padded
-// to [np][kp] and laid out as the stationary tcgen05 B operand (tc::b_offset_bytes): w = hi + lo + O(2^-17 |w|).
-static void pack_weight_hi_lo(const float* w, int n, int k, int np, int kp, unsigned char* dst)
-{
-    const size_t block = (size_t)np * kp * 2;
-    std::memset(dst, 0, 2 * block);
-    for (int o = 0; o < n; o++)
-        for (int i = 0; i < k; i++)
-        {
-            const float x = w[(size_t)o * k + i];
-            const uint16_t hi = bf16_rn(x);
-            const uint16_t lo = bf16_rn(x - bf16_to_float(hi));
-            const size_t off = fg::tc::b_offset_bytes(o, i, np);
-            std::memcpy(dst + off, &hi, 2);
-            std::memcpy(dst + block + off, &lo, 2);
-        }
-}
-
 static std::vector<float> pad_rows(const float* b, int layers, int n, int np)
 {
     std::vector<float> out((size_t)layers * np, 0.0f);
@@ -235,18 +217,6 @@ int load_gin(flowgnn_ctx* c, const float* const* w)
     FG_TRY(upload(g.w2t, transpose_pad(w[4], 5, 100, 200, 104), s));
     FG_TRY(upload(g.b2, pad_rows(w[5], 5, 100, 104), s));
     {
-        constexpr size_t kBlock = 208 * 112 * 2;
-        std::vector<unsigned char> pack(5 * 4 * kBlock);
-        for (int l = 0; l < 5; l++)
-        {
-            pack_weight_hi_lo(w[2] + (size_t)l * 200 * 100, 200, 100, 208, 112, pack.data() + (size_t)l * 4 * kBlock);
-            pack_weight_hi_lo(w[4] + (size_t)l * 100 * 200, 100, 200, 112, 208, pack.data() + (size_t)l * 4 * kBlock + 2 * kBlock);
-        }
-        FG_TRY(g.wpack.reserve(pack.size()));
-        FG_CUDA(cudaMemcpyAsync(g.wpack.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
-        FG_CUDA(cudaStreamSynchronize(s));
-    }
-    {
         const size_t per_layer = gin_tc2_pack_bytes();
         std::vector<unsigned char> pack(5 * per_layer);
         for (int l = 0; l < 5; l++)
@@ -256,18 +226,6 @@ int load_gin(flowgnn_ctx* c, const float* const* w)
         FG_CUDA(cudaMemcpyAsync(g.wpack2.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
         FG_CUDA(cudaStreamSynchronize(s));
     }
-    {
-        const size_t per_layer = gin_tc3_pack_bytes();
-        std::vector<unsigned char> pack(5 * per_layer);
-        for (int l = 0; l < 5; l++)
-            gin_tc3_pack_layer(w[2] + (size_t)l * 200 * 100, w[3] + (size_t)l * 200, w[4] + (size_t)l * 100 * 200, w[5] + (size_t)l * 100,
-                               pack.data() + (size_t)l * per_layer, bf16_rn, bf16_to_float);
-        FG_TRY(g.wpack3.reserve(pack.size()));
-        FG_CUDA(cudaMemcpyAsync(g.wpack3.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
-        FG_CUDA(cudaStreamSynchronize(s));
-    }
-    FG_TRY(upload(g.ee_raw, w[1], (size_t)5 * ED_FEATURE_PER_LAYER * 100, s));
-    FG_TRY(upload(g.b2p, pad_rows(w[5], 5, 100, 112), s));
     FG_TRY(upload(g.pred_w, w[6], 100, s));
     FG_TRY(upload(g.pred_b, w[7], 1, s));
     return 0;
@@ -504,7 +462,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaStreamDestroy(ctx->copy_stream);
-    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack, &ctx->gin.wpack2, &ctx->gin.wpack3, &ctx->gin.ee_raw, &ctx->gin.b2p, &ctx->gin.pred_w, &ctx->gin.pred_b,
+    DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack2, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wpack_tc, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
                    &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.wpack_tc, &ctx->pna.wpack_fused, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
@@ -527,9 +485,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     if (!name) { set_last_error("null option name"); return FG_ERR_INVALID; }
     if (!std::strcmp(name, "mp_only")) ctx->opt.mp_only = value;
     else if (!std::strcmp(name, "gin_ffma")) ctx->opt.gin_ffma = value;
-    else if (!std::strcmp(name, "gin_tc1")) ctx->opt.gin_tc1 = value;
     else if (!std::strcmp(name, "gin_tc2")) ctx->opt.gin_tc2 = value;
-    else if (!std::strcmp(name, "gin_tc3")) ctx->opt.gin_tc3 = value;
     else if (!std::strcmp(name, "gin_staged")) ctx->opt.gin_staged = value;
     else if (!std::strcmp(name, "pna_tc")) ctx->opt.pna_tc = value;
     else if (!std::strcmp(name, "pna_fused")) ctx->opt.pna_fused = value;

@@ -520,7 +520,7 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
     // gather (each row read from HBM once, in-edge reads from shared memory) writes x = m + h, and the CTA-pair kernel run
     // on "no in-edges" descriptors applies the node MLP.  Sparse graphs (molecules) keep the single fused launch.
     const bool staged = opt.gin_staged < 0 ? (b.total_edges >= 6 * N) : (opt.gin_staged != 0);
-    const bool split_layer = staged && !opt.mp_only && !opt.gin_ffma && !opt.gin_tc1 && !opt.gin_tc3;
+    const bool split_layer = staged && !opt.mp_only && !opt.gin_ffma;
     auto staged_gather = [&](const float* x_in, float* x_out, int l) -> int {
         FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gin_gather_staged_kernel), (int)sizeof(SgSmem)));
         const int grid = std::max(1, std::min(b.num_graphs, sm_count));
@@ -572,9 +572,7 @@ int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int 
         p.num_nodes = (int)N; p.num_tiles = num_tiles; p.relu_out = (l != 4);
         if (!opt.mp_only && !opt.gin_ffma)
         {
-            if (opt.gin_tc3) FG_TRY(gin_layer_tc3_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
-            else if (opt.gin_tc1) FG_TRY(gin_layer_tc_launch(b, w, l, p.h_in, p.h_out, sm_count, s));
-            else if (l == 4 && !opt.gin_unfused_head)
+            if (l == 4 && !opt.gin_unfused_head)
             {
                 // last layer: the epilogue applies the prediction weights per node, only 4 bytes per node leave the kernel
                 FG_TRY(b.node_dot.reserve(sizeof(float) * (size_t)(N + 1)));

@@ -78,14 +78,8 @@ struct GinWeights {
     DevBuf ee_comb;      // [5][60][100]  ((0+T[a0])+T[5+a1])+T[11+a2]
     DevBuf w1t, b1;      // [5][100][208], [5][208]   k-major, N padded with zeros
     DevBuf w2t, b2;      // [5][200][104], [5][104]
-    // tensor-core path (gin_tc.cu): per layer W1_hi | W1_lo | W2_hi | W2_lo as bf16 in the stationary
-    // shared-memory B layout (tc.cuh), 4 x 46,592 bytes; raw edge-embedding rows; b2 padded to 112
-    DevBuf wpack;        // [5][4][46592] bytes
-    DevBuf ee_raw;       // [5][13][100]
-    DevBuf b2p;          // [5][112]
     // CTA-pair tensor-core path (gin_tc2.cu): per layer and cluster rank, half of every weight block
     DevBuf wpack2;       // [5][2][gin_tc2_pack_bytes() / 2] bytes (weights and biases)
-    DevBuf wpack3;       // the same for gin_tc3.cu (N halves 128 + 96)
     DevBuf pred_w, pred_b;
 };
 struct GcnWeights {
@@ -136,10 +130,8 @@ struct RunOptions {
     int mp_only = 0;                 // GIN: node transform = identity (roofline variant): 1 = the mp_only mode of the layer
                                      // kernel itself (gin_fused.cu), 2 = the stand-alone row-per-warp gather kernel (gin.cu)
     int gin_ffma = 0;                // GIN: node MLP on the FP32 FFMA pipe (on-device fp32 reference) instead of tcgen05
-    int gin_tc1 = 0;                 // GIN: single-CTA tcgen05 kernel (gin_tc.cu) instead of the default
     int gin_tc2 = 0;                 // GIN: the round-1 CTA-pair kernel (gin_tc2.cu: gather through L1 from global memory) instead of gin_fused.cu
     int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
-    int gin_tc3 = 0;                 // GIN: CTA-pair kernel with TMA-staged tile rows and the A operand in tensor memory (gin_tc3.cu)
     int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
     int gcn_tc = 1;                  // GCN: Linear_l on tcgen05 (gcn_tc.cu: aggregate -> bf16x3 GEMM); 0: the fused FFMA kernel (gcn.cu)
     int dgn_tc = 1;                  // DGN: node transform on tcgen05 (dgn_tc.cu: aggregate -> bf16x3 GEMM -> fp32 rows); 0: FFMA kernel (dgn.cu)
@@ -152,16 +144,11 @@ struct RunOptions {
 };
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
-int gin_layer_tc_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
                          const float* head_w = nullptr, float* node_dot = nullptr, const int4* row_desc = nullptr);
 int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
                            const float* head_w = nullptr, float* node_dot = nullptr, bool mlp_only = false, int mp_only = 0);
 int gin_pool_dot_launch(const float* node_dot, const DeviceBatch& b, const float* pred_b, cudaStream_t s);
-int gin_layer_tc3_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
-size_t gin_tc3_pack_bytes();
-void gin_tc3_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
-                        float (*bf16_to_float)(uint16_t));
 size_t gin_tc2_pack_bytes();
 void gin_tc2_pack_layer(const float* w1, const float* b1, const float* w2, const float* b2, unsigned char* dst, uint16_t (*bf16_rn)(float),
                         float (*bf16_to_float)(uint16_t));

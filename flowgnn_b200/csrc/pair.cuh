@@ -1,4 +1,4 @@
-// CTA-pair (tcgen05 cta_group::2) building blocks shared by the GIN layer kernels gin_tc2.cu and gin_tc3.cu:
+// CTA-pair (tcgen05 cta_group::2) building blocks shared by the GIN layer kernels gin_fused.cu and gin_tc2.cu:
 // cluster primitives, remote mbarrier arrivals, parked waits, pair MMA / commit / TMEM allocation wrappers, the
 // bf16 hi/lo split, the z conversion epilogue.  See gin_tc2.cu for the design notes.
 #pragma once

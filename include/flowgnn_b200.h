@@ -126,18 +126,24 @@ const char* flowgnn_b200_last_error(void);
 int flowgnn_b200_create(flowgnn_ctx** ctx, int device);
 int flowgnn_b200_destroy(flowgnn_ctx* ctx);
 
-/* Options: "mp_only" (GIN: node transform = identity; the edge gather-scatter roofline variant),
- * "gin_ffma" (GIN: run the node MLP on the FP32 FFMA pipe instead of the tcgen05 bf16x3 split path; the
- * on-device fp32 reference), "gin_tc1" / "gin_tc3" (GIN: the single-CTA tcgen05 kernel / the CTA-pair kernel with
- * TMA-staged tile rows instead of the default CTA-pair kernel; all three compute the same layer),
- * "gin_staged" (GIN: a layer as two launches -- the shared-memory-staged gather, every feature row read from HBM once, and
- * the node MLP; -1 (default): when the batch averages >= 6 in-edges per node (hep10k kNN graphs), 0 / 1: never / always),
- * "pna_tc" (PNA, default 1: node transform on tcgen05 -- aggregate kernel, bf16x3 GEMM, fp32 rows kernel; 0: the fused
- * FP32 FFMA kernel, kept as the on-device fp32 reference),
- * "gcn_tc" / "dgn_tc" (default 1: the dense layer of GCN / DGN on tcgen05 through the aggregate -> GEMM path of tcgemm.cuh;
- * 0: the fused FFMA kernels; environment FLOWGNN_B200_TC_ALL=0/1 sets both defaults),
- * "gat_node_offset_bug" (default 1), "time_layers" (1: see flowgnn_b200_last_layer_ms; 2 (GIN): ONE interval around all
- * layer launches, which leaves them adjacent in the stream so that programmatic dependent launch can overlap them).
+/* Options:
+ *   "mp_only"      GIN: node transform = identity (the edge gather-scatter roofline variant).  1 = the mp_only
+ *                  mode of the layer kernel itself (gin_fused.cu), 2 = the stand-alone row-per-warp / staged gather kernels
+ *   "gin_ffma"     GIN: node MLP on the FP32 FFMA pipe (the on-device fp32 reference) instead of tcgen05 bf16x3
+ *   "gin_tc2"      GIN: the round-1 CTA-pair kernel (gather from global memory through L1) instead of gin_fused.cu (graph-
+ *                  aligned tiles staged by TMA, shared-memory gather); both add in-edges in CSR order: bit-identical results
+ *   "gin_staged"   GIN: a layer as two launches -- the shared-memory-staged gather and the node MLP; -1 (default): when the
+ *                  batch averages >= 6 in-edges per node (hep10k kNN graphs), 0 / 1: never / always
+ *   "gin_unfused_head"  GIN: store h' of the last layer and run the pooling kernel instead of the head fused in the epilogue
+ *   "pna_fused"    PNA, default 1: ONE kernel per layer (pna_fused.cu: the aggregation is the A producer inside the tcgen05
+ *                  GEMM kernel); 0: "pna_tc" decides
+ *   "pna_tc"       PNA, default 1: aggregate kernel -> bf16x3 GEMM -> fp32 rows kernel; 0: the fused FP32 FFMA kernel, kept
+ *                  as the on-device fp32 reference
+ *   "gcn_tc" / "dgn_tc"  default 1: the dense layer of GCN / DGN on tcgen05 (aggregate -> GEMM, tcgemm.cuh); 0: the fused
+ *                  FFMA kernels; environment FLOWGNN_B200_TC_ALL=0/1 sets both defaults
+ *   "gat_node_offset_bug"  default 1
+ *   "time_layers"  1: see flowgnn_b200_last_layer_ms; 2 (GIN): ONE interval around all layer launches, which leaves them
+ *                  adjacent in the stream so that programmatic dependent launch can overlap them
  * Environment: FLOWGNN_B200_CHUNKS=n overrides the number of chunks the host-pointer entry points cut a batch into
  * (default 3 for >= 16,384 graphs: upload of chunk i+1 overlaps the kernels of chunk i). */
 int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value);

@@ -60,22 +60,6 @@ def test_other_datasets_match_reference(model, ds, ctx, weights, datasets, golde
     assert_parity(got, golden[ds][model], what=f"{model}/{ds}")
 
 
-@pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
-def test_gin_single_cta_kernel_agrees_with_cta_pair_kernel(ds, ctx, weights, datasets, golden):
-    """The default GIN layer kernel runs on CTA pairs (tcgen05 cta_group::2, gin_tc2.cu: A tile in shared memory, row
-    descriptors, biases folded into the GEMMs); the single-CTA kernel (gin_tc.cu, option gin_tc1) is kept as a
-    second implementation.  Both must sit inside the 1e-4 contract and agree with each other."""
-    pair = ctx.run("gin", datasets[ds], weights["gin"])
-    ctx.set_option("gin_tc1", 1)
-    try:
-        single = ctx.run("gin", datasets[ds])
-    finally:
-        ctx.set_option("gin_tc1", 0)
-    assert_parity(pair, golden[ds]["gin"], what=f"gin cta pair/{ds}")
-    assert_parity(single, golden[ds]["gin"], what=f"gin single cta/{ds}")
-    assert_parity(pair, single, tol=5e-5, what=f"gin cta pair vs single cta/{ds}")
-
-
 @pytest.mark.parametrize("ds", ["molhiv", "molpcba", "hep10k"])
 @pytest.mark.parametrize("vn", [False, True])
 def test_gin_fused_kernel_agrees_with_round1_pair_kernel(ds, vn, ctx, weights, datasets, golden):
@@ -117,20 +101,6 @@ def test_gin_tiles_pack_whole_graphs(ctx, weights, datasets):
     finally:
         ctx.set_option("mp_only", 0)
     assert np.array_equal(fused_mp.view(np.int32), side_mp.view(np.int32)), "mp_only: layer kernel vs stand-alone gather kernel"
-
-
-@pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
-def test_gin_tma_staged_kernel_agrees(ds, ctx, weights, datasets, golden):
-    """gin_tc3.cu (option gin_tc3): the CTA-pair kernel with the tile's feature rows staged in shared memory by bulk
-    TMA and the A operand in tensor memory -- an alternative data path for the same math, kept under test."""
-    ctx.set_option("gin_tc3", 1)
-    try:
-        staged = ctx.run("gin", datasets[ds], weights["gin"])
-        few = ctx.run("gin", datasets[ds].slice(0, 11))
-    finally:
-        ctx.set_option("gin_tc3", 0)
-    assert_parity(staged, golden[ds]["gin"], what=f"gin tma-staged/{ds}")
-    assert_parity(few, golden[ds]["gin"][:11], what=f"gin tma-staged/{ds} first 11 graphs")
 
 
 @pytest.mark.parametrize("ds", ["molhiv", "hep10k"])
