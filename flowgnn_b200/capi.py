@@ -23,7 +23,7 @@ MODEL_IDS = {"gin": 0, "ginvn": 0, "gcn": 1, "gat": 2, "pna": 3, "dgn": 4}
 
 #: every symbol include/flowgnn_b200.h declares
 EXPORTED_SYMBOLS = (
-    "GIN_compute_graphs", "GCN_compute_graphs", "GAT_compute_graphs", "PNA_compute_graphs", "DGN_compute_graphs",
+    "GIN_compute_graphs", "GIN_compute_graphs_fixed", "GCN_compute_graphs", "GAT_compute_graphs", "PNA_compute_graphs", "DGN_compute_graphs",
     "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
     "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_compute", "flowgnn_b200_download",
     "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
@@ -226,6 +226,40 @@ class ReferenceCall:
     def run(self) -> np.ndarray:
         _check(self._fn(*self._args), self._symbol)
         return self.out
+
+
+def to_fixed(x, frac_bits: int = 10) -> np.ndarray:
+    """``(WT_TYPE)float`` of the reference's host (GIN/src/host_load.cc:60-97): ap_fixed<16, 16 - frac_bits> bit patterns,
+    floor(x * 2^F) (AP_TRN), low 16 bits (AP_WRAP)."""
+    q = np.floor(np.asarray(x, dtype=np.float64) * float(1 << frac_bits)).astype(np.int64)
+    return (q & 0xFFFF).astype(np.uint16).view(np.int16)
+
+
+def compute_graphs_fixed(model: str, batch: Batch, weights: Weights) -> np.ndarray:
+    """Call ``GIN_compute_graphs_fixed``: the kernel ABI of the FPGA build, int16 ap_fixed<16,6> bit patterns in and out
+    (GIN / GIN-VN only).  ``weights`` are the fp32 arrays of the weight files, cast here as the reference's host casts them.
+    Returns the raw int16 predictions (value = raw / 1024)."""
+    lib = load_library()
+    spec: ModelSpec = get_model(model)
+    if spec.name not in ("gin", "ginvn"):
+        raise FlowGNNError("the ap_fixed entry point exists for GIN / GIN-VN")
+    w = check_weights(spec, weights)
+    G = batch.num_graphs
+    reload_weights = np.zeros(G, dtype=np.int32)
+    if G:
+        reload_weights[0] = 1
+    out = np.zeros(G, dtype=np.int16)
+    nn = np.ascontiguousarray(batch.nums_of_nodes, dtype=np.int32)
+    ne = np.ascontiguousarray(batch.nums_of_edges, dtype=np.int32)
+    i16p = ctypes.POINTER(ctypes.c_int16)
+    fixed = [np.ascontiguousarray(to_fixed(w[n])) for n in spec.weight_names]
+    args = [ctypes.c_int(G), nn.ctypes.data_as(_i32p), ne.ctypes.data_as(_i32p), reload_weights.ctypes.data_as(_i32p),
+            out.ctypes.data_as(i16p), batch.node_feature.ctypes.data_as(_i32p), batch.edge_list.ctypes.data_as(_i32p),
+            batch.edge_attr.ctypes.data_as(_i32p)] + [a.ctypes.data_as(i16p) for a in fixed]
+    fn = lib.GIN_compute_graphs_fixed
+    fn.restype = ctypes.c_int
+    _check(fn(*args), "GIN_compute_graphs_fixed")
+    return out
 
 
 def compute_graphs(model: str, batch: Batch, weights: Weights, reload_weights: Optional[np.ndarray] = None,

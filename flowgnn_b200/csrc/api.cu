@@ -85,6 +85,23 @@ static int upload(DevBuf& dst, const float* p, size_t n, cudaStream_t s)
 
 // edge-embedding rows for the 60 distinct bond-attribute triples, summed exactly as the reference
 // does per edge: ((0 + T[a0]) + T[5 + a1]) + T[11 + a2]   (GIN/src/message_passing.cc:136-142)
+// (WT_TYPE)float of the reference's host (GIN/src/host_load.cc:60-97): ap_fixed<16,I>, AP_TRN (floor) and AP_WRAP (low 16 bits)
+static int16_t to_fixed16(float x, int frac_bits)
+{
+    const double scaled = std::floor(std::ldexp((double)x, frac_bits));
+    if (!(std::fabs(scaled) < 9.0e18)) return 0;                     // inf / NaN: undefined in the reference
+    return (int16_t)(uint16_t)(long long)scaled;
+}
+
+template <typename T>
+static int upload_raw(DevBuf& dst, const std::vector<T>& v, cudaStream_t s)
+{
+    FG_TRY(dst.reserve(v.size() * sizeof(T)));
+    FG_CUDA(cudaMemcpyAsync(dst.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    FG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 static std::vector<float> combine_edge_embedding(const float* ee, int layers, int dim)
 {
     std::vector<float> out((size_t)layers * ED_COMBOS * dim);
@@ -228,6 +245,38 @@ int load_gin(flowgnn_ctx* c, const float* const* w)
     }
     FG_TRY(upload(g.pred_w, w[6], 100, s));
     FG_TRY(upload(g.pred_b, w[7], 1, s));
+    // option "fixed_point": the same weights as ap_fixed<16,6> bit patterns
+    {
+        constexpr int F = 10;
+        std::vector<int16_t> ne((size_t)ND_FEATURE_TOTAL * 100), ee((size_t)5 * ED_COMBOS * 100);
+        for (size_t i = 0; i < ne.size(); i++) ne[i] = to_fixed16(w[0][i], F);
+        for (int l = 0; l < 5; l++)
+            for (int a0 = 0; a0 < 5; a0++)
+                for (int a1 = 0; a1 < 6; a1++)
+                    for (int a2 = 0; a2 < 2; a2++)
+                        for (int d = 0; d < 100; d++)
+                        {
+                            const float* t = w[1] + (size_t)l * ED_FEATURE_PER_LAYER * 100;
+                            const int sum = to_fixed16(t[(0 + a0) * 100 + d], F) + to_fixed16(t[(5 + a1) * 100 + d], F) + to_fixed16(t[(11 + a2) * 100 + d], F);
+                            ee[((size_t)l * ED_COMBOS + a0 * 12 + a1 * 2 + a2) * 100 + d] = (int16_t)sum;
+                        }
+        std::vector<int32_t> w1((size_t)5 * 100 * 200), b1(5 * 200), w2((size_t)5 * 200 * 100), b2(5 * 100), pw(100), pb(1);
+        for (int l = 0; l < 5; l++)
+        {
+            for (int o = 0; o < 200; o++)
+                for (int k = 0; k < 100; k++) w1[((size_t)l * 100 + k) * 200 + o] = (int32_t)to_fixed16(w[2][((size_t)l * 200 + o) * 100 + k], F) << (16 - F);
+            for (int o = 0; o < 100; o++)
+                for (int k = 0; k < 200; k++) w2[((size_t)l * 200 + k) * 100 + o] = (int32_t)to_fixed16(w[4][((size_t)l * 100 + o) * 200 + k], F) << (16 - F);
+            for (int o = 0; o < 200; o++) b1[l * 200 + o] = to_fixed16(w[3][l * 200 + o], F);
+            for (int o = 0; o < 100; o++) b2[l * 100 + o] = to_fixed16(w[5][l * 100 + o], F);
+        }
+        for (int k = 0; k < 100; k++) pw[k] = (int32_t)to_fixed16(w[6][k], F) << (16 - F);
+        pb[0] = to_fixed16(w[7][0], F);
+        FG_TRY(upload_raw(g.fx_ne, ne, s)); FG_TRY(upload_raw(g.fx_ee, ee, s));
+        FG_TRY(upload_raw(g.fx_w1, w1, s)); FG_TRY(upload_raw(g.fx_b1, b1, s));
+        FG_TRY(upload_raw(g.fx_w2, w2, s)); FG_TRY(upload_raw(g.fx_b2, b2, s));
+        FG_TRY(upload_raw(g.fx_pw, pw, s)); FG_TRY(upload_raw(g.fx_pb, pb, s));
+    }
     return 0;
 }
 
@@ -359,6 +408,28 @@ int load_dgn(flowgnn_ctx* c, const float* const* w)
     FG_TRY(upload(g.m1b, w[6], 25, s));
     FG_TRY(upload(g.m2w, w[7], 25, s));
     FG_TRY(upload(g.m2b, w[8], 1, s));
+    // option "fixed_point": the same weights as ap_fixed<16,3> bit patterns (DGN/src/host_load.cc casts with (WT_TYPE)float)
+    {
+        constexpr int F = 13;
+        std::vector<int16_t> emb((size_t)9 * 119 * 100);
+        for (size_t i = 0; i < emb.size(); i++) emb[i] = to_fixed16(w[0][i], F);
+        std::vector<int32_t> fw((size_t)4 * 100 * 200), fb(400), m0w(5000), m0b(50), m1w(1250), m1b(25), m2w(25), m2b(1);
+        for (int l = 0; l < 4; l++)
+            for (int o = 0; o < 100; o++)
+                for (int part = 0; part < 2; part++)
+                    for (int k = 0; k < 100; k++)
+                        fw[(((size_t)l * 100 + k) * 2 + part) * 100 + o] = (int32_t)to_fixed16(w[1][(((size_t)l * 100 + o) * 2 + part) * 100 + k], F) << (16 - F);
+        for (int i = 0; i < 400; i++) fb[i] = to_fixed16(w[2][i], F);
+        for (int o = 0; o < 50; o++) for (int k = 0; k < 100; k++) m0w[k * 50 + o] = (int32_t)to_fixed16(w[3][o * 100 + k], F) << (16 - F);
+        for (int o = 0; o < 50; o++) m0b[o] = to_fixed16(w[4][o], F);
+        for (int o = 0; o < 25; o++) for (int k = 0; k < 50; k++) m1w[k * 25 + o] = (int32_t)to_fixed16(w[5][o * 50 + k], F) << (16 - F);
+        for (int o = 0; o < 25; o++) m1b[o] = to_fixed16(w[6][o], F);
+        for (int k = 0; k < 25; k++) m2w[k] = (int32_t)to_fixed16(w[7][k], F) << (16 - F);
+        m2b[0] = to_fixed16(w[8][0], F);
+        FG_TRY(upload_raw(g.fx_emb, emb, s)); FG_TRY(upload_raw(g.fx_w, fw, s)); FG_TRY(upload_raw(g.fx_b, fb, s));
+        FG_TRY(upload_raw(g.fx_m0w, m0w, s)); FG_TRY(upload_raw(g.fx_m0b, m0b, s)); FG_TRY(upload_raw(g.fx_m1w, m1w, s));
+        FG_TRY(upload_raw(g.fx_m1b, m1b, s)); FG_TRY(upload_raw(g.fx_m2w, m2w, s)); FG_TRY(upload_raw(g.fx_m2b, m2b, s));
+    }
     return 0;
 }
 
@@ -493,6 +564,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "dgn_tc")) ctx->opt.dgn_tc = value;
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
+    else if (!std::strcmp(name, "fixed_point")) ctx->opt.fixed_point = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;
     else { set_last_error(std::string("unknown option ") + name); return FG_ERR_INVALID; }
     return 0;
@@ -577,16 +649,25 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     if (b.num_graphs == 0) return 0;
     if (model == MODEL_DGN && !b.has_eigen) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
     if ((model == MODEL_GIN || model == MODEL_GCN) && !b.has_attr) { set_last_error("GIN/GCN need edge_attr"); return FG_ERR_INVALID; }
-    const int flags = (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN || model == MODEL_PNA) ? (PREP_ROW_DESC | PREP_TILES) : 0;
+    const bool fixed = ctx->opt.fixed_point != 0;
+    if (fixed && model != MODEL_GIN && model != MODEL_DGN)
+    {
+        set_last_error("option fixed_point: only GIN / GIN-VN (ap_fixed<16,6>) and DGN (ap_fixed<16,3>) run in the reference's fixed-point arithmetic");
+        return FG_ERR_INVALID;
+    }
+    const int flags = fixed ? 0 : (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN || model == MODEL_PNA) ? (PREP_ROW_DESC | PREP_TILES) : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
     int rc = prep_batch(b, flags, s);
     b.has_attr = keep_attr;
     FG_TRY(rc);
-    ctx->last_launches += 3 + ((model == MODEL_GIN || model == MODEL_PNA) ? 2 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN, PNA: pack_tiles, sort_tile_rows)
+    ctx->last_launches += 3 + ((flags & PREP_TILES) ? 2 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN, PNA: pack_tiles, sort_tile_rows)
     ctx->timer.marks = 0;
     ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
     ctx->opt.timer_group = ctx->time_layers == 2;
+    if (fixed)
+        return model == MODEL_GIN ? gin_fixed_forward(b, ctx->gin, ctx->sm_count, s, &ctx->last_launches)
+                                  : dgn_fixed_forward(b, ctx->dgn, ctx->sm_count, s, &ctx->last_launches);
     switch (model)
     {
     case MODEL_GIN: FG_TRY(gin_forward(b, ctx->gin, ctx->opt, ctx->sm_count, s, &ctx->last_launches)); break;
@@ -873,6 +954,45 @@ int GIN_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, i
     if (!edge_attr_in && num_graphs > 0) { set_last_error("GIN needs edge_attr_in"); return FG_ERR_INVALID; }
     return run_reference_entry(MODEL_GIN, num_graphs, nums_of_nodes, nums_of_edges, reload_weights, out, node_feature_in, edge_list_in,
                                edge_attr_in, nullptr, w, counts);
+}
+
+// The FPGA build's kernel ABI: FM_TYPE / WT_TYPE = ap_fixed<16,6>, i.e. every weight and result is an int16 bit pattern
+// (value = raw / 1024; GIN/src/dcl.h:58-59, 77-95).  Runs gin_fixed.cu, which reproduces that arithmetic bit for bit.
+int GIN_compute_graphs_fixed(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, int16_t* out,
+                             const int32_t* node_feature_in, const int32_t* edge_list_in, const int32_t* edge_attr_in,
+                             const int16_t* node_embedding_weight_in, const int16_t* edge_embedding_weight_in,
+                             const int16_t* node_mlp_1_weights, const int16_t* node_mlp_1_bias, const int16_t* node_mlp_2_weights,
+                             const int16_t* node_mlp_2_bias, const int16_t* graph_pred_weights_in, const int16_t* graph_pred_bias_in)
+{
+    const int16_t* w16[] = {node_embedding_weight_in, edge_embedding_weight_in, node_mlp_1_weights, node_mlp_1_bias,
+                            node_mlp_2_weights, node_mlp_2_bias, graph_pred_weights_in, graph_pred_bias_in};
+    const size_t counts[] = {173 * 100, 5 * 13 * 100, 5 * 200 * 100, 5 * 200, 5 * 100 * 200, 5 * 100, 100, 1};
+    if (num_graphs < 0) { set_last_error("num_graphs < 0"); return FG_ERR_INVALID; }
+    if (num_graphs == 0) return 0;
+    for (const int16_t* p : w16) if (!p) { set_last_error("null weight argument"); return FG_ERR_INVALID; }
+    if (!reload_weights || !out || !edge_attr_in) { set_last_error("null argument"); return FG_ERR_INVALID; }
+    size_t sets = 0;
+    for (int g = 0; g < num_graphs; g++) sets += reload_weights[g] != 0;
+    // raw / 1024 is exact in fp32, and load_gin's floor(x * 1024) recovers the same bits
+    std::vector<std::vector<float>> wf(8);
+    const float* w[8];
+    for (int i = 0; i < 8; i++)
+    {
+        wf[i].resize(std::max<size_t>(sets, 1) * counts[i]);
+        for (size_t k = 0; k < sets * counts[i]; k++) wf[i][k] = (float)w16[i][k] * (1.0f / 1024.0f);
+        w[i] = wf[i].data();
+    }
+    std::vector<float> outf((size_t)num_graphs);
+    flowgnn_ctx* ctx = nullptr;
+    FG_TRY(default_ctx(&ctx));
+    const int keep = ctx->opt.fixed_point;
+    ctx->opt.fixed_point = 1;
+    const int rc = run_reference_entry(MODEL_GIN, num_graphs, nums_of_nodes, nums_of_edges, reload_weights, outf.data(), node_feature_in,
+                                       edge_list_in, edge_attr_in, nullptr, w, counts);
+    ctx->opt.fixed_point = keep;
+    FG_TRY(rc);
+    for (int g = 0; g < num_graphs; g++) out[g] = (int16_t)lrintf(outf[g] * 1024.0f);
+    return 0;
 }
 
 int GCN_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, float* out,

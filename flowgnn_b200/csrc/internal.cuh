@@ -81,6 +81,13 @@ struct GinWeights {
     // CTA-pair tensor-core path (gin_tc2.cu): per layer and cluster rank, half of every weight block
     DevBuf wpack2;       // [5][2][gin_tc2_pack_bytes() / 2] bytes (weights and biases)
     DevBuf pred_w, pred_b;
+    // option "fixed_point" (gin_fixed.cu): the weights as the reference's host casts them, (WT_TYPE)float = floor(x * 1024) mod 2^16
+    // (GIN/src/host_load.cc:60-97).  Matrices are held k-major as raw << 6 (the mad.hi operand format), the rest raw.
+    DevBuf fx_ne;        // int16 [173][100]
+    DevBuf fx_ee;        // int16 [5][60][100]  sum of the three tables of a bond triple, mod 2^16
+    DevBuf fx_w1, fx_b1; // int32 [5][100][200], [5][200]
+    DevBuf fx_w2, fx_b2; // int32 [5][200][100], [5][100]
+    DevBuf fx_pw, fx_pb; // int32 [100], [1]
 };
 struct GcnWeights {
     DevBuf ne_table, ee_comb;   // as GIN
@@ -108,6 +115,10 @@ struct DgnWeights {
     DevBuf wpack_tc;            // [4][4][28672] bytes: W_l as bf16 hi | lo K-chunks for tcg::gemm_kernel (dgn_tc.cu)
     DevBuf b;                   // [4][104]
     DevBuf m0w, m0b, m1w, m1b, m2w, m2b;
+    // option "fixed_point" (dgn_fixed.cu): ap_fixed<16,3> bit patterns, matrices k-major as raw << 3, biases raw
+    DevBuf fx_emb;              // int16 [9][119][100]
+    DevBuf fx_w, fx_b;          // int32 [4][100 k][2][100 out], [4][100]
+    DevBuf fx_m0w, fx_m0b, fx_m1w, fx_m1b, fx_m2w, fx_m2b;   // int32 [100][50], [50], [50][25], [25], [25], [1]
 };
 struct GatWeights {
     DevBuf proj0;               // [9][64]  layer-0 projection of the raw features: [f][d*4+h]
@@ -138,12 +149,15 @@ struct RunOptions {
     int pna_fused = 1;               // PNA: ONE kernel per layer (pna_fused.cu: the aggregation is the A producer inside the GEMM kernel); 0: pna_tc / FFMA
     int pna_tc = 1;                  // PNA: node transform on tcgen05 (pna_tc.cu: aggregate -> bf16x3 GEMM -> exact rows); 0: FFMA kernel (pna.cu)
     int gat_node_offset_bug = 1;
+    int fixed_point = 0;             // GIN, DGN: the reference's ap_fixed<16,6> / <16,3> arithmetic, bit for bit (gin_fixed.cu, dgn_fixed.cu)
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
     int timer_group = 0;             // time_layers == 2: one interval around ALL layer launches (events between the launches
                                      // would keep them from overlapping through programmatic dependent launch)
 };
 
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
+int dgn_fixed_forward(DeviceBatch& b, const DgnWeights& w, int sm_count, cudaStream_t s, int* launches);
+int gin_fixed_forward(DeviceBatch& b, const GinWeights& w, int sm_count, cudaStream_t s, int* launches);
 int gin_layer_tc2_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,
                          const float* head_w = nullptr, float* node_dot = nullptr, const int4* row_desc = nullptr);
 int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s,

@@ -58,6 +58,22 @@ int GIN_compute_graphs(
     const float* graph_pred_weights_in,      /* [][1][100] */
     const float* graph_pred_bias_in);        /* [][1] */
 
+/* The same entry point with the FPGA build's own scalar type: FM_TYPE = WT_TYPE = ap_fixed<16,6> (GIN/src/dcl.h:58-59), i.e.
+ * every weight and every result is an int16 bit pattern, value = raw / 1024 -- what the reference's host produces with
+ * `(WT_TYPE)float` (GIN/src/host_load.cc:60-97) and reads back from `result` (GIN/src/host.cc:160-166).  The arithmetic
+ * is Vitis' bit for bit: exact wide intermediates, floor to 10 fraction bits on every assignment (AP_TRN), wrap to 16 bits
+ * (AP_WRAP), integer division toward zero in the mean pool.  Also reachable through the float
+ * entry points and Part 2 with flowgnn_b200_set_option("fixed_point", 1): fp32 weights are then cast as the reference's
+ * host casts them and `out` holds raw / 1024. */
+int GIN_compute_graphs_fixed(
+    int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights,
+    int16_t* out,                            /* [num_graphs][1] raw */
+    const int32_t* node_feature_in, const int32_t* edge_list_in, const int32_t* edge_attr_in,
+    const int16_t* node_embedding_weight_in, const int16_t* edge_embedding_weight_in,
+    const int16_t* node_mlp_1_weights, const int16_t* node_mlp_1_bias,
+    const int16_t* node_mlp_2_weights, const int16_t* node_mlp_2_bias,
+    const int16_t* graph_pred_weights_in, const int16_t* graph_pred_bias_in);
+
 /* Replaces GCN_compute_graphs, GCN/src/dcl.h:76-96. */
 int GCN_compute_graphs(
     int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights,
@@ -142,6 +158,8 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx);
  *   "gcn_tc" / "dgn_tc"  default 1: the dense layer of GCN / DGN on tcgen05 (aggregate -> GEMM, tcgemm.cuh); 0: the fused
  *                  FFMA kernels; environment FLOWGNN_B200_TC_ALL=0/1 sets both defaults
  *   "gat_node_offset_bug"  default 1
+ *   "fixed_point"          default 0; 1: GIN / GIN-VN in the reference's ap_fixed<16,6> arithmetic, bit for bit (gin_fixed.cu);
+ *                          other models return FLOWGNN_ERR_INVALID while it is set
  *   "time_layers"  1: see flowgnn_b200_last_layer_ms; 2 (GIN): ONE interval around all layer launches, which leaves them
  *                  adjacent in the stream so that programmatic dependent launch can overlap them
  * Environment: FLOWGNN_B200_CHUNKS=n overrides the number of chunks the host-pointer entry points cut a batch into

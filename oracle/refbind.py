@@ -120,3 +120,60 @@ def run_port(model: str, batch, weights, fast: bool = False, gat_node_offset_bug
     if spec.name == "gat":
         lib.oracle_set_gat_node_offset_bug(ctypes.c_int(1 if gat_node_offset_bug else 0))
     return _call(getattr(lib, "oracle_" + spec.symbol), spec, batch, weights)
+
+
+# ---- bit-accurate ap_fixed flavour -------------------------------------------------------------------
+# oracle/_ref/libflowgnn_ref_<model>_fixed.so = the same unmodified reference sources over oracle/shim_fixed/ (an emulation
+# of Vitis' ap_fixed<16,I>: int16 storage, floor on assignment, wrap on overflow).  Arguments and results are int16 bit
+# patterns, exactly the kernel ABI of the FPGA build (FM_TYPE / WT_TYPE arrays, */src/dcl.h).
+
+FRAC_BITS = {"gin": 10, "ginvn": 10, "dgn": 13}
+_i16p = ctypes.POINTER(ctypes.c_int16)
+
+
+def to_fixed(x: np.ndarray, frac_bits: int) -> np.ndarray:
+    """``(WT_TYPE)float`` of the reference's host (GIN/src/host_load.cc:60-97): floor(x * 2^F), low 16 bits."""
+    q = np.floor(np.asarray(x, dtype=np.float64) * float(1 << frac_bits)).astype(np.int64)
+    return (q & 0xFFFF).astype(np.uint16).view(np.int16)
+
+
+def ref_fixed_library_path(model: str) -> str:
+    return os.path.join(_REF_DIR, f"libflowgnn_ref_{model}_fixed.so")
+
+
+def have_ref_fixed(model: str = "gin") -> bool:
+    return os.path.isfile(ref_fixed_library_path(model))
+
+
+def run_reference_fixed(model: str, batch, weights) -> np.ndarray:
+    """Raw int16 predictions (value = raw / 2^F) of the unmodified reference kernel in emulated ap_fixed arithmetic.
+    ``weights`` are the fp32 arrays of the weight files; they are cast as the reference's host casts them."""
+    from flowgnn_b200.models import get_model
+    spec = get_model(model)
+    F = FRAC_BITS[spec.name]
+    lib = _load(ref_fixed_library_path(spec.name))
+    G = batch.num_graphs
+    out = np.zeros(G, dtype=np.int16)
+    reload_weights = np.zeros(G, dtype=np.int32)
+    if G:
+        reload_weights[0] = 1
+    nn = np.ascontiguousarray(batch.nums_of_nodes, dtype=np.int32)
+    ne = np.ascontiguousarray(batch.nums_of_edges, dtype=np.int32)
+    args = [ctypes.c_int(G), _ptr(nn, _i32p), _ptr(ne, _i32p), _ptr(reload_weights, _i32p), _ptr(out, _i16p),
+            _ptr(batch.node_feature, _i32p)]
+    keep = [nn, ne, reload_weights]
+    if spec.uses_eigen:
+        eig = np.ascontiguousarray(to_fixed(batch.node_eigen, F))
+        keep.append(eig)
+        args.append(_ptr(eig, _i16p))
+    args.append(_ptr(batch.edge_list, _i32p))
+    if spec.uses_edge_attr:
+        args.append(_ptr(batch.edge_attr, _i32p))
+    for name, _ in spec.weights:
+        a = np.ascontiguousarray(to_fixed(weights[name], F))
+        keep.append(a)
+        args.append(_ptr(a, _i16p))
+    fn = getattr(lib, spec.symbol)
+    fn.restype = None
+    fn(*args)
+    return out
