@@ -452,7 +452,7 @@ int status_error(int st)
     if (st & 2) { set_last_error("edge_list holds a node id outside [0, num_of_nodes)"); return FG_ERR_INVALID; }
     if (st & 4) { set_last_error("edge_attr holds a value outside the bond vocabulary {5, 6, 2} (GIN/src/host_load.cc:5-6)"); return FG_ERR_INVALID; }
     if (st & 1) { set_last_error("invalid node / edge count of a graph"); return FG_ERR_LIMIT; }
-    if (st & 8) { set_last_error("GIN: an edge spans more than 32,767 node positions (reference cap: MAX_NODE = 500 nodes per graph)"); return FG_ERR_LIMIT; }
+    if (st & 8) { set_last_error("an edge spans more than 32,767 node positions (GIN, GCN row descriptors; reference cap: MAX_NODE = 500 nodes per graph)"); return FG_ERR_LIMIT; }
     return 0;
 }
 
@@ -561,6 +561,8 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "pna_tc")) ctx->opt.pna_tc = value;
     else if (!std::strcmp(name, "pna_fused")) ctx->opt.pna_fused = value;
     else if (!std::strcmp(name, "gcn_tc")) ctx->opt.gcn_tc = value;
+    else if (!std::strcmp(name, "gcn_fused")) ctx->opt.gcn_fused = value;
+    else if (!std::strcmp(name, "dgn_fused")) ctx->opt.dgn_fused = value;
     else if (!std::strcmp(name, "dgn_tc")) ctx->opt.dgn_tc = value;
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
@@ -655,7 +657,7 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
         set_last_error("option fixed_point: only GIN / GIN-VN (ap_fixed<16,6>) and DGN (ap_fixed<16,3>) run in the reference's fixed-point arithmetic");
         return FG_ERR_INVALID;
     }
-    const int flags = fixed ? 0 : (model == MODEL_GCN) ? PREP_GCN_NORM : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN || model == MODEL_PNA) ? (PREP_ROW_DESC | PREP_TILES) : 0;
+    const int flags = fixed ? 0 : (model == MODEL_GCN) ? (PREP_GCN_NORM | PREP_ROW_DESC) : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN || model == MODEL_PNA) ? (PREP_ROW_DESC | PREP_TILES) : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
     int rc = prep_batch(b, flags, s);

@@ -203,6 +203,12 @@ int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int 
     for (int l = 0; l <= 5; l++)
     {
         if (opt.timer) FG_TRY(opt.timer->mark(s));
+        if (opt.gcn_tc && opt.gcn_fused)
+        {
+            FG_TRY(gcn_step_fused_launch(b, w, l, h[(l + 1) & 1], h[l & 1], sm_count, s));
+            nl++;
+            continue;
+        }
         if (opt.gcn_tc && l < 5)
         {
             FG_TRY(gcn_step_tc_launch(b, w, l, h[(l + 1) & 1], h[l & 1], sm_count, s));

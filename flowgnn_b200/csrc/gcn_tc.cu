@@ -10,6 +10,7 @@
 #include "internal.cuh"
 #include "layers.cuh"
 #include "tcgemm.cuh"
+#include "fused_tc.cuh"
 
 #include <algorithm>
 
@@ -22,6 +23,7 @@ constexpr int NCHUNK = 2;                    // K = 128
 constexpr int NPAD = 112;
 constexpr int G8 = 13;                       // column groups of eight that hold real columns (the last one: 96..99)
 constexpr int AG_WARPS = 8;
+constexpr int KC_COLS = 64;
 
 struct GcnAggParams {
     const float* p_in;
@@ -115,6 +117,146 @@ struct GcnEpi {
     }
 };
 
+// ---- option gcn_fused (default): the same step as ONE launch, the aggregation as the A producer inside the GEMM kernel (fused_tc.cuh) ----
+// message passing over p_{l-1} + self term + BatchNorm_{l-1} (+ relu) of columns c .. c+3: the expressions of gcn_aggregate_kernel
+// above, in the same order (in-edges in CSR order)
+struct GcnRowMath {
+    const float* p_in;
+    const int* in_ptr; const int* src; const uint8_t* code; const float* norm; const int* out_deg;
+    const float* ee_comb; const float* root; const float* bn_mean; const float* bn_sqrt_var; const float* bn_weight; const float* bn_bias;
+
+    // four rows at once: their CSR walks advance together, so a lane keeps up to four neighbour rows in flight (the walk of ONE row
+    // is a chain of dependent loads: position -> source -> row)
+    template <bool RELU>
+    __device__ __forceinline__ void finish4(const int (&v)[4], const bool (&live)[4], int c, float4 (&out)[4]) const
+    {
+        int e[4], end[4];
+        float4 m[4];
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+        {
+            e[p] = live[p] ? __ldg(in_ptr + v[p]) : 0;
+            end[p] = live[p] ? __ldg(in_ptr + v[p] + 1) : 0;
+            m[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        while (true)
+        {
+            int u[4], cd[4];
+            float nr[4];
+            bool any = false;
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (e[p] < end[p]) { u[p] = __ldg(src + e[p]); cd[p] = __ldg(code + e[p]); nr[p] = __ldg(norm + e[p]); any = true; }
+            if (!any) break;
+            float4 pu[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (e[p] < end[p]) pu[p] = ldg_f4(p_in + (size_t)u[p] * D + c);
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (e[p] < end[p])
+                {
+                    const float4 t = ldg_f4(ee_comb + cd[p] * D + c);        // 24 KB table, L1 resident
+                    m[p].x += nr[p] * relu_f(t.x + pu[p].x); m[p].y += nr[p] * relu_f(t.y + pu[p].y);
+                    m[p].z += nr[p] * relu_f(t.z + pu[p].z); m[p].w += nr[p] * relu_f(t.w + pu[p].w);
+                    e[p]++;
+                }
+        }
+        // self term, BatchNorm (inference), relu.  The two divisions of the reference's expression (by deg + 1 and by sqrt(var + eps))
+        // are multiplications by reciprocals here: <= 2 ulp from the IEEE quotient, against a 1e-4 bar
+        const float4 rt = ldg_f4(root + c), mu = ldg_f4(bn_mean + c), sv = ldg_f4(bn_sqrt_var + c);
+        const float4 ga = ldg_f4(bn_weight + c), be = ldg_f4(bn_bias + c);
+        const float4 g = make_float4(__fdividef(ga.x, sv.x), __fdividef(ga.y, sv.y), __fdividef(ga.z, sv.z), __fdividef(ga.w, sv.w));
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+        {
+            out[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!live[p]) continue;
+            const float rdeg = __fdividef(1.0f, (float)(__ldg(out_deg + v[p]) + 1));
+            const float4 pv = ldg_f4(p_in + (size_t)v[p] * D + c);
+            float4 r;
+            r.x = (m[p].x + relu_f(pv.x + rt.x) * rdeg - mu.x) * g.x + be.x;
+            r.y = (m[p].y + relu_f(pv.y + rt.y) * rdeg - mu.y) * g.y + be.y;
+            r.z = (m[p].z + relu_f(pv.z + rt.z) * rdeg - mu.z) * g.z + be.z;
+            r.w = (m[p].w + relu_f(pv.w + rt.w) * rdeg - mu.w) * g.w + be.w;
+            if (RELU) { r.x = relu_f(r.x); r.y = relu_f(r.y); r.z = relu_f(r.z); r.w = relu_f(r.w); }
+            out[p] = r;
+        }
+    }
+};
+
+template <bool FIRST>
+struct GcnFused {
+    static constexpr int NCHUNK = fg::NCHUNK, NPAD = fg::NPAD;
+    static constexpr unsigned ksteps(int c) { return c == 0 ? 0xFu : 0x7u; }      // K = 112: columns 64..111 are three steps of chunk 1
+    GcnRowMath r;
+    const int* feat; const float* ne_table;
+    const float* b; float* p_out;
+
+    __device__ __forceinline__ bool gather4(const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
+    {
+        const int col = KC_COLS * c + 4 * j;
+        if (col >= NPAD) return false;
+#pragma unroll
+        for (int p = 0; p < 4; p++) x[p] = make_float4(0.f, 0.f, 0.f, 0.f);      // K padding and rows past the batch hold zeros
+        if (col >= D) return true;
+        if (FIRST)
+        {
+#pragma unroll
+            for (int p = 0; p < 4; p++)                                             // GCN/src/node_embedding.cc:124-127
+                if (live[p]) x[p] = embed_chunk<D>(feat + (size_t)v[p] * ND_FEATURE, ne_table, concat_table_offsets(), col / 4);
+        }
+        else r.template finish4<true>(v, live, col, x);
+        return true;
+    }
+    // one thread, two tiles ahead: the tile's rows (graphs are contiguous, so nearly every source row lies in the tile's own
+    // row range) and its CSR slice into L2, so that the gather's dependent loads do not wait for HBM
+    __device__ __forceinline__ void prefetch_tile(int v0, int rows) const
+    {
+        if (FIRST) { tcf::prefetch_l2(feat + (size_t)v0 * ND_FEATURE, rows * ND_FEATURE * 4); return; }
+        tcf::prefetch_l2(r.p_in + (size_t)v0 * D, rows * D * 4);
+        tcf::prefetch_l2(r.in_ptr + v0, rows * 4 + 4);
+        tcf::prefetch_l2(r.out_deg + v0, rows * 4);
+        const int e0 = __ldg(r.in_ptr + v0), e1 = __ldg(r.in_ptr + v0 + rows);
+        tcf::prefetch_l2(r.src + e0, (e1 - e0) * 4);
+        tcf::prefetch_l2(r.norm + e0, (e1 - e0) * 4);
+        tcf::prefetch_l2(r.code + e0, e1 - e0);
+    }
+    struct Pre {};
+    __device__ __forceinline__ Pre preload(int, bool, int) const { return Pre{}; }
+    __device__ __forceinline__ bool row_begin(int, bool live) const { return live; }
+    __device__ __forceinline__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre&) const
+    {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            if (d0 + j < D)
+            {
+                const float4 bb = ldg_f4(b + d0 + j);
+                stg_f4_stream(p_out + (size_t)v * D + d0 + j, make_float4(__uint_as_float(acc[j]) + bb.x, __uint_as_float(acc[j + 1]) + bb.y,
+                                                                         __uint_as_float(acc[j + 2]) + bb.z, __uint_as_float(acc[j + 3]) + bb.w));
+            }
+    }
+};
+
+// the last step has no Linear: message passing over p_4, self term, BatchNorm_4, no relu (GCN/src/node_embedding.cc:128-146);
+// a warp per four rows, 25 lanes x 4 columns
+__global__ void __launch_bounds__(256, 3) gcn_final_kernel(GcnRowMath r, float* __restrict__ h_out, long num_nodes)
+{
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long v0 = 4 * warp; v0 < num_nodes; v0 += 4 * nwarps)
+        if (lane < D / 4)
+        {
+            const int v[4] = {(int)v0, (int)v0 + 1, (int)v0 + 2, (int)v0 + 3};
+            const bool live[4] = {true, v0 + 1 < num_nodes, v0 + 2 < num_nodes, v0 + 3 < num_nodes};
+            float4 x[4];
+            r.finish4<false>(v, live, 4 * lane, x);
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (live[p]) stg_f4_stream(h_out + (v0 + p) * D + 4 * lane, x[p]);
+        }
+}
+
 }  // namespace
 
 size_t gcn_tc_pack_bytes() { return (size_t)NCHUNK * tcg::Cfg<NPAD>::B_BLOCK; }
@@ -157,6 +299,52 @@ int gcn_step_tc_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* 
     g.num_nodes = (int)N; g.num_tiles = num_tiles;
     GcnEpi epi{w.b.as<float>() + (size_t)l * 104, p_out};
     tcg::gemm_kernel<NCHUNK, NPAD, GcnEpi><<<std::min(num_tiles, sm_count), tcg::NT, C::BYTES, s>>>(g, epi);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static GcnRowMath gcn_row_math(const DeviceBatch& b, const GcnWeights& w, int l, const float* p_in)
+{
+    GcnRowMath r{};
+    r.p_in = p_in;
+    r.in_ptr = b.in_ptr.as<int>(); r.src = b.src.as<int>(); r.code = b.code.as<uint8_t>(); r.norm = b.edge_w.as<float>(); r.out_deg = b.out_deg.as<int>();
+    if (l > 0)
+    {
+        const size_t k = (size_t)(l - 1);
+        r.ee_comb = w.ee_comb.as<float>() + k * ED_COMBOS * D;
+        r.root = w.root.as<float>() + k * D; r.bn_mean = w.bn_mean.as<float>() + k * D; r.bn_sqrt_var = w.bn_sqrt_var.as<float>() + k * D;
+        r.bn_weight = w.bn_weight.as<float>() + k * D; r.bn_bias = w.bn_bias.as<float>() + k * D;
+    }
+    return r;
+}
+
+// step l = 0..4 as one launch; l = 5: the final message passing + BatchNorm
+int gcn_step_fused_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s)
+{
+    const long N = b.total_nodes;
+    if (l == 5)
+    {
+        gcn_final_kernel<<<(int)std::min<long>(ceil_div<long>(N, 32), (long)sm_count * 8), 256, 0, s>>>(gcn_row_math(b, w, 5, p_in), p_out, N);
+        FG_CUDA(cudaGetLastError());
+        return 0;
+    }
+    using C = tcf::Cfg<GcnFused<true>>;
+    tcf::Args g{};
+    g.wpack = w.wpack_tc.as<unsigned char>() + (size_t)l * gcn_tc_pack_bytes();
+    g.num_nodes = (int)N; g.num_tiles = (int)ceil_div<long>(N, tcf::TM);
+    const int grid = std::min(g.num_tiles, sm_count);
+    if (l == 0)
+    {
+        FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&tcf::fused_kernel<GcnFused<true>>), C::BYTES));
+        GcnFused<true> m{gcn_row_math(b, w, 0, p_in), b.node_feature.as<int>(), w.ne_table.as<float>(), w.b.as<float>(), p_out};
+        tcf::fused_kernel<GcnFused<true>><<<grid, tcf::NT, C::BYTES, s>>>(g, m);
+    }
+    else
+    {
+        FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&tcf::fused_kernel<GcnFused<false>>), C::BYTES));
+        GcnFused<false> m{gcn_row_math(b, w, l, p_in), nullptr, nullptr, w.b.as<float>() + (size_t)l * 104, p_out};
+        tcf::fused_kernel<GcnFused<false>><<<grid, tcf::NT, C::BYTES, s>>>(g, m);
+    }
     FG_CUDA(cudaGetLastError());
     return 0;
 }

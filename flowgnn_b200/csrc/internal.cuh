@@ -145,6 +145,8 @@ struct RunOptions {
     int gin_unfused_head = 0;        // GIN pair kernel: store h' of the last layer and run pool_head_kernel instead of the fused head
     int gin_staged = -1;             // GIN: layer = staged shared-memory gather + node MLP launch (-1: when the average in-degree is >= 6)
     int gcn_tc = 1;                  // GCN: Linear_l on tcgen05 (gcn_tc.cu: aggregate -> bf16x3 GEMM); 0: the fused FFMA kernel (gcn.cu)
+    int gcn_fused = 1;               // GCN: ONE launch per step (fused_tc.cuh: the aggregation is the A producer inside the GEMM kernel); 0: aggregate + GEMM launches
+    int dgn_fused = 1;               // DGN: the same
     int dgn_tc = 1;                  // DGN: node transform on tcgen05 (dgn_tc.cu: aggregate -> bf16x3 GEMM -> fp32 rows); 0: FFMA kernel (dgn.cu)
     int pna_fused = 1;               // PNA: ONE kernel per layer (pna_fused.cu: the aggregation is the A producer inside the GEMM kernel); 0: pna_tc / FFMA
     int pna_tc = 1;                  // PNA: node transform on tcgen05 (pna_tc.cu: aggregate -> bf16x3 GEMM -> exact rows); 0: FFMA kernel (pna.cu)
@@ -173,6 +175,7 @@ void pna_fused_pack_layer(const float* wcat, unsigned char* dst, uint16_t (*bf16
 int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t pna_tc_pack_bytes();
 void pna_tc_pack_layer(const float* wcat, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
+int gcn_step_fused_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s);
 int gcn_step_tc_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s);
 size_t gcn_tc_pack_bytes();
 void gcn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
