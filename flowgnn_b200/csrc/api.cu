@@ -400,6 +400,10 @@ int load_dgn(flowgnn_ctx* c, const float* const* w)
         FG_TRY(g.wpack_tc.reserve(pack.size()));
         FG_CUDA(cudaMemcpyAsync(g.wpack_tc.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
         FG_CUDA(cudaStreamSynchronize(s));
+        for (int l = 0; l < 4; l++) dgn_fused_pack_layer(w[1] + (size_t)l * 100 * 200, pack.data() + (size_t)l * dgn_tc_pack_bytes(), bf16_rn, bf16_to_float);
+        FG_TRY(g.wpack_fused.reserve(pack.size()));
+        FG_CUDA(cudaMemcpyAsync(g.wpack_fused.ptr, pack.data(), pack.size(), cudaMemcpyHostToDevice, s));
+        FG_CUDA(cudaStreamSynchronize(s));
     }
     FG_TRY(upload(g.b, pad_rows(w[2], 4, 100, 104), s));
     FG_TRY(upload(g.m0w, w[3], 50 * 100, s));
@@ -538,7 +542,9 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
                    &ctx->pna.ne_table, &ctx->pna.wcat, &ctx->pna.wpack_tc, &ctx->pna.wpack_fused, &ctx->pna.w_ref, &ctx->pna.b, &ctx->pna.m1w, &ctx->pna.m1b, &ctx->pna.m2w, &ctx->pna.m2b,
                    &ctx->pna.m3w, &ctx->pna.m3b,
-                   &ctx->dgn.emb, &ctx->dgn.wt, &ctx->dgn.wpack_tc, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
+                   &ctx->dgn.emb, &ctx->dgn.wt, &ctx->dgn.wpack_tc, &ctx->dgn.wpack_fused, &ctx->dgn.fx_emb, &ctx->dgn.fx_w, &ctx->dgn.fx_b, &ctx->dgn.fx_m0w, &ctx->dgn.fx_m0b,
+                   &ctx->dgn.fx_m1w, &ctx->dgn.fx_m1b, &ctx->dgn.fx_m2w, &ctx->dgn.fx_m2b, &ctx->gin.fx_ne, &ctx->gin.fx_ee, &ctx->gin.fx_w1, &ctx->gin.fx_b1, &ctx->gin.fx_w2, &ctx->gin.fx_b2,
+                   &ctx->gin.fx_pw, &ctx->gin.fx_pb, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
                    &ctx->dgn.m2w, &ctx->dgn.m2b,
                    &ctx->gat.proj0, &ctx->gat.projt, &ctx->gat.skipt, &ctx->gat.a_src, &ctx->gat.a_tgt, &ctx->gat.pred_w, &ctx->gat.pred_b};
     for (DevBuf* b : w) b->release();

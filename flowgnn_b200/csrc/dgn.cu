@@ -172,6 +172,12 @@ int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int 
     for (int l = 0; l < 4; l++)
     {
         if (opt.timer) FG_TRY(opt.timer->mark(s));
+        if (opt.dgn_tc && opt.dgn_fused)
+        {
+            FG_TRY(dgn_layer_fused_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
+            nl += 2;
+            continue;
+        }
         if (opt.dgn_tc)
         {
             FG_TRY(dgn_layer_tc_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));

@@ -12,6 +12,7 @@
 #include "internal.cuh"
 #include "layers.cuh"
 #include "tcgemm.cuh"
+#include "fused_tc.cuh"
 
 #include <algorithm>
 
@@ -163,6 +164,145 @@ __global__ void __launch_bounds__(EX_WARPS * 32) dgn_exact_rows_kernel(DgnAggPar
     }
 }
 
+// ---- option dgn_fused (default): the layer as ONE launch, the aggregation as the A producer inside the GEMM kernel (fused_tc.cuh) ----
+// K layout: chunk c = [a1 columns 32c .. 32c+31 | a2 columns 32c .. 32c+31], so that one chunk needs 128 bytes of every
+// neighbour row and both halves of a gather half-warp walk the same in-edges: lanes 0-7 accumulate m0 = sum h_u (-> a1),
+// lanes 8-15 m1 = sum h_u eig_w (-> a2).  Chunk 3 holds columns 96..99 only: K steps 0 (a1) and 2 (a2).
+struct DgnFused {
+    static constexpr int NCHUNK = 4, NPAD = fg::NPAD;
+    static constexpr unsigned ksteps(int c) { return c < 3 ? 0xFu : 0x5u; }
+    DgnAggParams p;
+    const float* b; float* h_out;
+
+    struct Rows { int e0[4], end[4]; };
+    __device__ __forceinline__ Rows rows_begin(const int (&v)[4], const bool (&live)[4]) const
+    {
+        Rows r;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            r.e0[q] = live[q] ? __ldg(p.in_ptr + v[q]) : 0;
+            r.end[q] = live[q] ? __ldg(p.in_ptr + v[q] + 1) : 0;
+        }
+        return r;
+    }
+    __device__ __forceinline__ bool gather4(const Rows& rows, const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
+    {
+        const int part = j >> 3, col = 32 * c + 4 * (j & 7);
+        if (c == 3 && (j & 7) >= 4) return false;                  // outside the issued K steps
+#pragma unroll
+        for (int q = 0; q < 4; q++) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);      // K padding and rows past the batch hold zeros
+        if (col >= D) return true;
+        // what the end of the walk needs, requested before it starts
+        float fin0[4], fin1[4];                                      // part 0: out-degree; part 1: A_v = sum |eig_w|, B_v = sum eig_w
+        float4 hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            fin0[q] = fin1[q] = 0.f; hv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!live[q]) continue;
+            if (part) { fin0[q] = __ldg(p.abssum + v[q]); fin1[q] = __ldg(p.wsum + v[q]); hv[q] = ldg_f4(p.h_in + (size_t)v[q] * D + col); }
+            else fin0[q] = (float)__ldg(p.out_deg + v[q]);
+        }
+        int e[4];
+        float4 m[4];
+        int u[4];
+        float w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            e[q] = rows.e0[q];
+            m[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            u[q] = 0; w[q] = 1.0f;
+            if (e[q] < rows.end[q]) { u[q] = __ldg(p.src + e[q]); if (part) w[q] = __ldg(p.eig_w + e[q]); }
+        }
+        // The four rows' CSR walks advance together (in-edges in CSR order: the loop of dgn_aggregate4 above); the source and weight
+        // of each row's NEXT in-edge are requested together with the CURRENT neighbour rows: one memory round trip per step
+        while ((e[0] < rows.end[0]) | (e[1] < rows.end[1]) | (e[2] < rows.end[2]) | (e[3] < rows.end[3]))
+        {
+            float4 hu[4];
+            int un[4];
+            float wn[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                un[q] = 0; wn[q] = 1.0f;
+                if (e[q] < rows.end[q]) hu[q] = ldg_f4(p.h_in + (size_t)u[q] * D + col);
+                if (e[q] + 1 < rows.end[q]) { un[q] = __ldg(p.src + e[q] + 1); if (part) wn[q] = __ldg(p.eig_w + e[q] + 1); }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (e[q] < rows.end[q])
+                {
+                    if (part) { m[q].x += hu[q].x * w[q]; m[q].y += hu[q].y * w[q]; m[q].z += hu[q].z * w[q]; m[q].w += hu[q].w * w[q]; }
+                    else { m[q].x += hu[q].x; m[q].y += hu[q].y; m[q].z += hu[q].z; m[q].w += hu[q].w; }
+                    e[q]++;
+                    u[q] = un[q]; w[q] = wn[q];
+                }
+        }
+        // the reference divides (m0 / deg, (m1 - B h) / A); here one IEEE reciprocal per row and a multiplication per column:
+        // <= 1 ulp from the quotient (the bar is 1e-4), and deg = 0 still gives inf * m0 = +-inf or NaN exactly where m0 / 0 does
+        bool bad[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            float4 a;
+            if (part)
+            {
+                const float abssum = fin0[q] == 0.0f ? 0.0001220703125f : fin0[q];       // ap_fixed_epsilon of <16,3> = 2^-13
+                const float rab = 1.0f / abssum;
+                a = make_float4(fabsf((m[q].x - fin1[q] * hv[q].x) * rab), fabsf((m[q].y - fin1[q] * hv[q].y) * rab),
+                                fabsf((m[q].z - fin1[q] * hv[q].z) * rab), fabsf((m[q].w - fin1[q] * hv[q].w) * rab));
+            }
+            else
+            {
+                const float rdeg = 1.0f / fin0[q];
+                a = make_float4(m[q].x * rdeg, m[q].y * rdeg, m[q].z * rdeg, m[q].w * rdeg);
+            }
+            bad[q] = live[q] && (a.x * 0.0f + a.y * 0.0f) + (a.z * 0.0f + a.w * 0.0f) != 0.0f;     // x * 0 is 0 for finite x and NaN otherwise
+            if (live[q]) x[q] = a;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (bad[q]) p.nonfinite[v[q]] = 1;                       // before this warp's arrival on the stage: the epilogue sees it
+        return true;
+    }
+    __device__ __forceinline__ void prefetch_tile(int v0, int rows) const
+    {
+        tcf::prefetch_l2(p.h_in + (size_t)v0 * D, rows * D * 4);
+        tcf::prefetch_l2(p.in_ptr + v0, rows * 4 + 4);
+        tcf::prefetch_l2(p.out_deg + v0, rows * 4);
+        tcf::prefetch_l2(p.abssum + v0, rows * 4);
+        tcf::prefetch_l2(p.wsum + v0, rows * 4);
+        const int e0 = __ldg(p.in_ptr + v0), e1 = __ldg(p.in_ptr + v0 + rows);
+        tcf::prefetch_l2(p.src + e0, (e1 - e0) * 4);
+        tcf::prefetch_l2(p.eig_w + e0, (e1 - e0) * 4);
+    }
+    // the residual h[v][d0 .. d0+15], requested one accumulator piece ahead
+    struct Pre { float4 h[4]; };
+    __device__ __forceinline__ Pre preload(int v, bool live, int d0) const
+    {
+        Pre r;
+#pragma unroll
+        for (int j = 0; j < 4; j++) r.h[j] = (live && d0 + 4 * j < D) ? ldg_f4(p.h_in + (size_t)v * D + d0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return r;
+    }
+    __device__ __forceinline__ bool row_begin(int v, bool live) const { return live && __ldcg(p.nonfinite + v) == 0; }     // flagged rows: dgn_exact_rows_kernel
+    __device__ __forceinline__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre& pre) const
+    {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            if (d0 + j < D)
+            {
+                const float4 bb = ldg_f4(b + d0 + j);
+                const float4 hv = pre.h[j / 4];
+                stg_f4_stream(h_out + (size_t)v * D + d0 + j,
+                              make_float4(hv.x + relu_f(__uint_as_float(acc[j]) + bb.x), hv.y + relu_f(__uint_as_float(acc[j + 1]) + bb.y),
+                                          hv.z + relu_f(__uint_as_float(acc[j + 2]) + bb.z), hv.w + relu_f(__uint_as_float(acc[j + 3]) + bb.w)));
+            }
+    }
+};
+
 }  // namespace
 
 size_t dgn_tc_pack_bytes() { return (size_t)NCHUNK * tcg::Cfg<NPAD>::B_BLOCK; }
@@ -172,6 +312,41 @@ void dgn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(f
 {
     tcg::pack_weights<NPAD>(w, D, KA, NCHUNK, [](int k) { return (k % KPART) < D ? (k / KPART) * D + (k % KPART) : -1; }, dst, bf16_rn,
                             bf16_to_float);
+}
+
+// W_l for dgn_fused: k' = chunk * 64 + part * 32 + (in % 32), chunk = in / 32
+void dgn_fused_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t))
+{
+    tcg::pack_weights<NPAD>(w, D, KA, NCHUNK, [](int k) { const int col = 32 * (k / 64) + k % 32; return col < D ? ((k % 64) / 32) * D + col : -1; }, dst,
+                            bf16_rn, bf16_to_float);
+}
+
+int dgn_layer_fused_launch(DeviceBatch& b, const DgnWeights& w, int l, const float* h_in, float* h_out, int sm_count, cudaStream_t s)
+{
+    using C = tcf::Cfg<DgnFused>;
+    FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&tcf::fused_kernel<DgnFused>), C::BYTES));
+    const long N = b.total_nodes;
+    FG_TRY(b.nonfinite.reserve((size_t)N + 16));
+    FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
+    DgnAggParams p{};
+    p.h_in = h_in;
+    p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.eig_w = b.edge_w.as<float>(); p.out_deg = b.out_deg.as<int>();
+    p.abssum = b.node_w0.as<float>(); p.wsum = b.node_w1.as<float>();
+    p.apack = nullptr; p.nonfinite = b.nonfinite.as<unsigned char>();
+    p.num_nodes = N;
+    const float* bias = w.b.as<float>() + (size_t)l * DP;
+    tcf::Args g{};
+    g.wpack = w.wpack_fused.as<unsigned char>() + (size_t)l * dgn_tc_pack_bytes();
+    g.num_nodes = (int)N; g.num_tiles = (int)ceil_div<long>(N, tcf::TM);
+    DgnFused m{p, bias, h_out};
+    tcf::fused_kernel<DgnFused><<<std::min(g.num_tiles, sm_count), tcf::NT, C::BYTES, s>>>(g, m);
+    FG_CUDA(cudaGetLastError());
+    {
+        const int blocks = (int)std::min<long>(ceil_div<long>(N, 32 * EX_WARPS), (long)sm_count * 8);
+        dgn_exact_rows_kernel<<<blocks, EX_WARPS * 32, 0, s>>>(p, w.wt.as<float>() + (size_t)l * KA * DP, bias, h_out);
+        FG_CUDA(cudaGetLastError());
+    }
+    return 0;
 }
 
 int dgn_layer_tc_launch(DeviceBatch& b, const DgnWeights& w, int l, const float* h_in, float* h_out, int sm_count, cudaStream_t s)

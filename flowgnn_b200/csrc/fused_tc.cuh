@@ -86,7 +86,8 @@ struct Args {
 
 // Model:  static constexpr int NCHUNK, NPAD;
 //         static constexpr unsigned ksteps(int c)                       bit j set: K = 16 step j of chunk c holds real columns
-//         __device__ bool gather4(const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
+//         struct Rows; __device__ Rows rows_begin(const int (&v)[4], const bool (&live)[4]) const    per-row state shared by the chunks
+//         __device__ bool gather4(const Rows&, const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
 //                                                                       the lane's K slots 4j .. 4j+3 of chunk c for its four rows;
 //                                                                       false: nothing to store (slots outside the issued steps)
 //         __device__ void prefetch_tile(int v0, int rows) const;                       one thread, two tiles ahead: whatever the gather will read -> L2
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
             const int r0 = gw * (TM / GATHER_WARPS) + sub;
             const int v[4] = {tile * TM + r0, tile * TM + r0 + 2, tile * TM + r0 + 4, tile * TM + r0 + 6};
             const bool live[4] = {v[0] < g.num_nodes, v[1] < g.num_nodes, v[2] < g.num_nodes, v[3] < g.num_nodes};
+            const typename Model::Rows rows = m.rows_begin(v, live);     // what every chunk of these rows needs (CSR positions ...): loaded once
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; c++, n++)
             {
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
                 tcg::mbar_wait_park(&bar_empty[s], ((n / C::STAGES) & 1) ^ 1);
                 unsigned char* hi = smem + C::STAGE0 + s * A_BLOCK;
                 float4 x[4];
-                if (m.gather4(v, live, c, j, x))
+                if (m.gather4(rows, v, live, c, j, x))
                 {
 #pragma unroll
                     for (int p = 0; p < 4; p++) put4(hi, r0 + 2 * p, 4 * j, x[p]);

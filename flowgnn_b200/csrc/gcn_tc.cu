@@ -122,65 +122,72 @@ struct GcnEpi {
 // above, in the same order (in-edges in CSR order)
 struct GcnRowMath {
     const float* p_in;
-    const int* in_ptr; const int* src; const uint8_t* code; const float* norm; const int* out_deg;
+    const int* in_ptr; const int* src; const uint8_t* code; const float* norm; const int* out_deg; const int4* row_desc;
     const float* ee_comb; const float* root; const float* bn_mean; const float* bn_sqrt_var; const float* bn_weight; const float* bn_bias;
 
-    // four rows at once: their CSR walks advance together, so a lane keeps up to four neighbour rows in flight (the walk of ONE row
-    // is a chain of dependent loads: position -> source -> row)
+    // Four rows per lane.  Round trip 1: the four rows' descriptors (first four in-edges packed by prep.cu: relative source | bond
+    // code, in-degree), CSR positions and out-degrees.  Then, pair of rows by pair of rows, ONE more round trip: the own rows, every
+    // neighbour row and edge norm at once.  In-edges beyond the fourth (rare in molecules) walk the CSR arrays.
     template <bool RELU>
     __device__ __forceinline__ void finish4(const int (&v)[4], const bool (&live)[4], int c, float4 (&out)[4]) const
     {
-        int e[4], end[4];
-        float4 m[4];
+        int4 d[4];
+        int eb[4], od[4];
 #pragma unroll
         for (int p = 0; p < 4; p++)
         {
-            e[p] = live[p] ? __ldg(in_ptr + v[p]) : 0;
-            end[p] = live[p] ? __ldg(in_ptr + v[p] + 1) : 0;
-            m[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            d[p] = make_int4(0, 0, 0, 0); eb[p] = od[p] = 0;
+            if (live[p]) { d[p] = __ldg(row_desc + v[p]); eb[p] = __ldg(in_ptr + v[p]); od[p] = __ldg(out_deg + v[p]); }
         }
-        while (true)
+#pragma unroll
+        for (int p = 0; p < 4; p++)
         {
-            int u[4], cd[4];
+            const int dq[4] = {d[p].x, d[p].y, d[p].z, d[p].w};
+            const int deg = live[p] ? (int)((unsigned)d[p].x >> 24) : 0;               // capped at 255 by prep.cu
+            float4 pu[4], pv = make_float4(0.f, 0.f, 0.f, 0.f);
             float nr[4];
-            bool any = false;
+            if (live[p]) pv = ldg_f4(p_in + (size_t)v[p] * D + c);
 #pragma unroll
-            for (int p = 0; p < 4; p++)
-                if (e[p] < end[p]) { u[p] = __ldg(src + e[p]); cd[p] = __ldg(code + e[p]); nr[p] = __ldg(norm + e[p]); any = true; }
-            if (!any) break;
-            float4 pu[4];
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-                if (e[p] < end[p]) pu[p] = ldg_f4(p_in + (size_t)u[p] * D + c);
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-                if (e[p] < end[p])
+            for (int q = 0; q < 4; q++)
+                if (q < deg)
                 {
-                    const float4 t = ldg_f4(ee_comb + cd[p] * D + c);        // 24 KB table, L1 resident
-                    m[p].x += nr[p] * relu_f(t.x + pu[p].x); m[p].y += nr[p] * relu_f(t.y + pu[p].y);
-                    m[p].z += nr[p] * relu_f(t.z + pu[p].z); m[p].w += nr[p] * relu_f(t.w + pu[p].w);
-                    e[p]++;
+                    pu[q] = ldg_f4(p_in + (size_t)(v[p] + (dq[q] & 0xFFFF) - 32768) * D + c);
+                    nr[q] = __ldg(norm + eb[p] + q);
                 }
-        }
-        // self term, BatchNorm (inference), relu.  The two divisions of the reference's expression (by deg + 1 and by sqrt(var + eps))
-        // are multiplications by reciprocals here: <= 2 ulp from the IEEE quotient, against a 1e-4 bar
-        const float4 rt = ldg_f4(root + c), mu = ldg_f4(bn_mean + c), sv = ldg_f4(bn_sqrt_var + c);
-        const float4 ga = ldg_f4(bn_weight + c), be = ldg_f4(bn_bias + c);
-        const float4 g = make_float4(__fdividef(ga.x, sv.x), __fdividef(ga.y, sv.y), __fdividef(ga.z, sv.z), __fdividef(ga.w, sv.w));
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int p = 0; p < 4; p++)
-        {
-            out[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!live[p]) continue;
-            const float rdeg = __fdividef(1.0f, (float)(__ldg(out_deg + v[p]) + 1));
-            const float4 pv = ldg_f4(p_in + (size_t)v[p] * D + c);
+            for (int q = 0; q < 4; q++)
+                if (q < deg)
+                {
+                    const float4 t = ldg_f4(ee_comb + ((dq[q] >> 16) & 0xFF) * D + c);        // 24 KB table, L1 resident
+                    m.x += nr[q] * relu_f(t.x + pu[q].x); m.y += nr[q] * relu_f(t.y + pu[q].y);
+                    m.z += nr[q] * relu_f(t.z + pu[q].z); m.w += nr[q] * relu_f(t.w + pu[q].w);
+                }
+            if (deg > 4)
+            {
+                const int end = __ldg(in_ptr + v[p] + 1);
+                for (int e = eb[p] + 4; e < end; e++)
+                {
+                    const int u = __ldg(src + e), cd = __ldg(code + e);
+                    const float n1 = __ldg(norm + e);
+                    const float4 p1 = ldg_f4(p_in + (size_t)u * D + c);
+                    const float4 t = ldg_f4(ee_comb + cd * D + c);
+                    m.x += n1 * relu_f(t.x + p1.x); m.y += n1 * relu_f(t.y + p1.y); m.z += n1 * relu_f(t.z + p1.z); m.w += n1 * relu_f(t.w + p1.w);
+                }
+            }
+            // self term, BatchNorm (inference), relu.  The two divisions of the reference's expression (by deg + 1 and by
+            // sqrt(var + eps)) are multiplications by reciprocals here: <= 2 ulp from the IEEE quotient, against a 1e-4 bar
+            const float4 rt = ldg_f4(root + c), mu = ldg_f4(bn_mean + c), sv = ldg_f4(bn_sqrt_var + c);
+            const float4 ga = ldg_f4(bn_weight + c), be = ldg_f4(bn_bias + c);
+            const float4 g = make_float4(__fdividef(ga.x, sv.x), __fdividef(ga.y, sv.y), __fdividef(ga.z, sv.z), __fdividef(ga.w, sv.w));
+            const float rdeg = __fdividef(1.0f, (float)(od[p] + 1));
             float4 r;
-            r.x = (m[p].x + relu_f(pv.x + rt.x) * rdeg - mu.x) * g.x + be.x;
-            r.y = (m[p].y + relu_f(pv.y + rt.y) * rdeg - mu.y) * g.y + be.y;
-            r.z = (m[p].z + relu_f(pv.z + rt.z) * rdeg - mu.z) * g.z + be.z;
-            r.w = (m[p].w + relu_f(pv.w + rt.w) * rdeg - mu.w) * g.w + be.w;
+            r.x = (m.x + relu_f(pv.x + rt.x) * rdeg - mu.x) * g.x + be.x;
+            r.y = (m.y + relu_f(pv.y + rt.y) * rdeg - mu.y) * g.y + be.y;
+            r.z = (m.z + relu_f(pv.z + rt.z) * rdeg - mu.z) * g.z + be.z;
+            r.w = (m.w + relu_f(pv.w + rt.w) * rdeg - mu.w) * g.w + be.w;
             if (RELU) { r.x = relu_f(r.x); r.y = relu_f(r.y); r.z = relu_f(r.z); r.w = relu_f(r.w); }
-            out[p] = r;
+            out[p] = live[p] ? r : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 };
@@ -193,7 +200,9 @@ struct GcnFused {
     const int* feat; const float* ne_table;
     const float* b; float* p_out;
 
-    __device__ __forceinline__ bool gather4(const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
+    struct Rows {};
+    __device__ __forceinline__ Rows rows_begin(const int (&)[4], const bool (&)[4]) const { return Rows{}; }
+    __device__ __forceinline__ bool gather4(const Rows&, const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
     {
         const int col = KC_COLS * c + 4 * j;
         if (col >= NPAD) return false;
@@ -217,6 +226,7 @@ struct GcnFused {
         tcf::prefetch_l2(r.p_in + (size_t)v0 * D, rows * D * 4);
         tcf::prefetch_l2(r.in_ptr + v0, rows * 4 + 4);
         tcf::prefetch_l2(r.out_deg + v0, rows * 4);
+        tcf::prefetch_l2(r.row_desc + v0, rows * 16);
         const int e0 = __ldg(r.in_ptr + v0), e1 = __ldg(r.in_ptr + v0 + rows);
         tcf::prefetch_l2(r.src + e0, (e1 - e0) * 4);
         tcf::prefetch_l2(r.norm + e0, (e1 - e0) * 4);
@@ -240,7 +250,7 @@ struct GcnFused {
 
 // the last step has no Linear: message passing over p_4, self term, BatchNorm_4, no relu (GCN/src/node_embedding.cc:128-146);
 // a warp per four rows, 25 lanes x 4 columns
-__global__ void __launch_bounds__(256, 3) gcn_final_kernel(GcnRowMath r, float* __restrict__ h_out, long num_nodes)
+__global__ void __launch_bounds__(256, 2) gcn_final_kernel(GcnRowMath r, float* __restrict__ h_out, long num_nodes)
 {
     const int lane = threadIdx.x & 31;
     const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -308,6 +318,7 @@ static GcnRowMath gcn_row_math(const DeviceBatch& b, const GcnWeights& w, int l,
     GcnRowMath r{};
     r.p_in = p_in;
     r.in_ptr = b.in_ptr.as<int>(); r.src = b.src.as<int>(); r.code = b.code.as<uint8_t>(); r.norm = b.edge_w.as<float>(); r.out_deg = b.out_deg.as<int>();
+    r.row_desc = b.row_desc.as<int4>();
     if (l > 0)
     {
         const size_t k = (size_t)(l - 1);

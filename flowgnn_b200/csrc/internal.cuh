@@ -113,6 +113,7 @@ struct DgnWeights {
     DevBuf wt;                  // [4][200][104]  k = part*100+in
     DevBuf w_ref;               // [4][100][200] reference layout (exact path for out-degree-0 nodes)
     DevBuf wpack_tc;            // [4][4][28672] bytes: W_l as bf16 hi | lo K-chunks for tcg::gemm_kernel (dgn_tc.cu)
+    DevBuf wpack_fused;         // the same with K interleaved per 32 columns ([a1 | a2] per chunk) for the fused layer kernel (dgn_tc.cu)
     DevBuf b;                   // [4][104]
     DevBuf m0w, m0b, m1w, m1b, m2w, m2b;
     // option "fixed_point" (dgn_fixed.cu): ap_fixed<16,3> bit patterns, matrices k-major as raw << 3, biases raw
@@ -179,6 +180,8 @@ int gcn_step_fused_launch(DeviceBatch& b, const GcnWeights& w, int l, const floa
 int gcn_step_tc_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s);
 size_t gcn_tc_pack_bytes();
 void gcn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
+int dgn_layer_fused_launch(DeviceBatch& b, const DgnWeights& w, int l, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
+void dgn_fused_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
 int dgn_layer_tc_launch(DeviceBatch& b, const DgnWeights& w, int l, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t dgn_tc_pack_bytes();
 void dgn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
