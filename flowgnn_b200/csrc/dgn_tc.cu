@@ -15,6 +15,7 @@
 #include "fused_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace fg {
 
