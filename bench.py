@@ -52,8 +52,8 @@ WORKLOADS = {
 #: (D, L, attr words A, extra bytes per node X) of SURVEY.md 8(d): B_layer = 8*D*N + E*(8+4A) + X*N
 ALGO = {"gin": (100, 5, 3, 0), "ginvn": (100, 5, 3, 0), "gcn": (100, 5, 3, 0), "gat": (64, 5, 0, 64), "pna": (80, 4, 0, 0),
         "dgn": (100, 4, 0, 0)}
-LAYER_KERNEL = {"gin": "gin_layer_fused_kernel", "ginvn": "gin_layer_fused_kernel", "gcn": "gcn_aggregate_kernel + tcg::gemm_kernel (two launches per step)", "gat": "gat_layer_kernel",
-                "pna": "pna_aggregate_kernel + pna_gemm_kernel + pna_exact_rows_kernel (three launches per layer)", "dgn": "dgn_aggregate_kernel + tcg::gemm_kernel + dgn_exact_rows_kernel (three launches per layer)"}
+LAYER_KERNEL = {"gin": "gin_layer_fused_kernel", "ginvn": "gin_layer_fused_kernel", "gcn": "tcf::fused_kernel<GcnFused> (one launch per step: gather -> tcgen05 GEMM -> bias)", "gat": "gat_layer_kernel",
+                "pna": "pna_layer_fused_kernel (+ pna_exact_rows_kernel for the few non-finite rows)", "dgn": "tcf::fused_kernel<DgnFused> (+ dgn_exact_rows_kernel for the few non-finite rows)"}
 
 
 def metric_name(model: str) -> str:
@@ -534,7 +534,10 @@ def run_b200_arm(args):
     if dense:
         traffic = None
     roofline = {"bound": "hbm", "kernel": layer_kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": lb,
+                "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel, "
+                                  "per launch; a committed constant, NOT measured in this run" if traffic else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": lb,
                 "mean_launch_ms": mean_layer_ms, "share_of_step": mean_layer_ms * ALGO[model][1] * args.steps / ev0.elapsed_time(ev1)}
 
     edge_gather = None

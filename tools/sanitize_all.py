@@ -2,9 +2,10 @@
 `compute-sanitizer --tool memcheck|racecheck|synccheck`, see tools/sanitize.sh).
 
 Covers: scan + both CSR-build kernels (small graphs, a 300-node graph, a 1,500-node graph on the global-memory tables),
-the embedding kernels, the GIN CTA-pair layer kernel (fused head and unfused), the staged gather + node-MLP launches of
-dense graphs, the mp_only variant, GCN / DGN / PNA aggregate -> tcgen05 GEMM -> exact-rows launches, GAT, the pooling /
-head kernels, and the chunked host-pointer entry point (two streams, two device batches)."""
+tile packing and row sorting, the embedding kernels, the GIN fused layer kernel (gin_fused.cu: fused head and unfused), the staged
+gather + node-MLP launches of dense graphs, the mp_only mode, the fused GCN / DGN step kernels (fused_tc.cuh) + gcn_final +
+dgn_exact_rows, the fused PNA layer kernel (pna_fused.cu) + pna_exact_rows, GAT, the pooling / head kernels, the ap_fixed
+kernels of GIN and DGN (option fixed_point), and the chunked host-pointer entry point (two streams, two device batches)."""
 import os
 import sys
 
@@ -48,6 +49,11 @@ with Context(0) as c:
         y = c.run("gin", mol)
         c.set_option(opt, 0 if opt != "gin_staged" else -1)
         print("gin", opt, float(np.abs(y).max()), flush=True)
+    for model in ("gin", "dgn"):
+        c.set_option("fixed_point", 1)
+        y = c.run(model, mixed, load_weights(model, os.path.join(gold, "weights", DIRS[model])))
+        c.set_option("fixed_point", 0)
+        print(model, "fixed_point", float(np.abs(y).max()), flush=True)
 # the chunked host-pointer entry point (>= 8,192 graphs -> 2 chunks on two streams)
 big = mol.tile(8192 + 64)
 call = ReferenceCall("gin", big, w)
