@@ -666,10 +666,9 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     const int flags = fixed ? 0 : (model == MODEL_GCN) ? (PREP_GCN_NORM | PREP_ROW_DESC) : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN || model == MODEL_PNA) ? (PREP_ROW_DESC | PREP_TILES) : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
-    int rc = prep_batch(b, flags, s);
+    int rc = prep_batch(b, flags, s, &ctx->last_launches);
     b.has_attr = keep_attr;
     FG_TRY(rc);
-    ctx->last_launches += 3 + ((flags & PREP_TILES) ? 2 : 0);      // scan_offsets + the two build_csr instantiations (+ GIN, PNA: pack_tiles, sort_tile_rows)
     ctx->timer.marks = 0;
     ctx->opt.timer = ctx->time_layers ? &ctx->timer : nullptr;
     ctx->opt.timer_group = ctx->time_layers == 2;

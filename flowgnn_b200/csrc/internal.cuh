@@ -69,7 +69,7 @@ struct DeviceBatch {
 enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2, PREP_ROW_DESC = 4, PREP_TILES = 8 };
 
 // graph preprocessing: offsets scan + per-graph CSR build (prep.cu)
-int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream);
+int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches = nullptr);
 
 // ---- per-model device weights, repacked once by load_weights (api.cu) ----------------------------
 struct GinWeights {

@@ -25,9 +25,8 @@ constexpr int SCAN_THREADS = 1024;
 // offsets in its serial graph loop, GIN/src/GIN_compute.cc:44,96-97).  One block of 32 warps; every warp owns
 // a contiguous segment of graphs: pass 1 sums it (coalesced, independent loads), the 32 segment totals are
 // scanned, pass 2 re-reads the segment and writes warp-scanned offsets with a running carry.
-__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const int* __restrict__ nn, const int* __restrict__ ne,
-                                                                    int* __restrict__ node_off, int* __restrict__ edge_off,
-                                                                    int num_graphs)
+__device__ __forceinline__ void scan_offsets_body(const int* __restrict__ nn, const int* __restrict__ ne, int* __restrict__ node_off,
+                                                  int* __restrict__ edge_off, int num_graphs)
 {
     __shared__ int2 seg_tot[SCAN_THREADS / 32];
     const unsigned full = 0xffffffffu;
@@ -80,6 +79,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const int* _
         node_off[num_graphs] = carry.x;
         edge_off[num_graphs] = carry.y;
     }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const int* __restrict__ nn, const int* __restrict__ ne,
+                                                                    int* __restrict__ node_off, int* __restrict__ edge_off,
+                                                                    int num_graphs)
+{
+    scan_offsets_body(nn, ne, node_off, edge_off, num_graphs);
 }
 
 // Row descriptor of a node for the GIN tensor-core kernel (gin_tc2.cu): its first four in-edges, each packed as
@@ -353,7 +359,7 @@ constexpr int TILE_ROWS = 128;
 constexpr int PACK_THREADS = 1024;
 
 template <bool WRITE>
-__device__ __forceinline__ int pack_chunk(const int* __restrict__ nn, const int* __restrict__ node_off, int g0, int g1, int2* out)
+__device__ __forceinline__ int pack_chunk(const int* __restrict__ nn, const int* node_off, int g0, int g1, int2* out)
 {
     int count = 0, start = 0, rows = 0;
     for (int g = g0; g < g1; g++)
@@ -379,8 +385,8 @@ __device__ __forceinline__ int pack_chunk(const int* __restrict__ nn, const int*
     return count;
 }
 
-__global__ void __launch_bounds__(PACK_THREADS) pack_tiles_kernel(const int* __restrict__ nn, const int* __restrict__ node_off, int num_graphs,
-                                                                  int2* __restrict__ tiles, int* __restrict__ tile_count)
+__device__ __forceinline__ void pack_tiles_body(const int* __restrict__ nn, const int* node_off, int num_graphs, int2* __restrict__ tiles,
+                                                int* __restrict__ tile_count)
 {
     __shared__ int warp_tot[PACK_THREADS / 32];
     const unsigned full = 0xffffffffu;
@@ -412,6 +418,18 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_tiles_kernel(const int* __r
     }
     __syncthreads();
     pack_chunk<true>(nn, node_off, g0, g1, tiles + warp_tot[wid] + incl - mine);
+}
+
+// offsets scan + tile packing as ONE launch: both are single-block kernels and the second only needs the first's node offsets
+// (every launch of the prep chain costs the chunked host-pointer path ~10 us per chunk)
+static_assert(PACK_THREADS == SCAN_THREADS, "scan_pack_kernel runs both bodies on one block");
+__global__ void __launch_bounds__(PACK_THREADS) scan_pack_kernel(const int* __restrict__ nn, const int* __restrict__ ne, int* node_off,
+                                                                 int* __restrict__ edge_off, int num_graphs, int2* __restrict__ tiles,
+                                                                 int* __restrict__ tile_count)
+{
+    scan_offsets_body(nn, ne, node_off, edge_off, num_graphs);
+    __syncthreads();                       // node_off is complete and visible to the block
+    pack_tiles_body(nn, node_off, num_graphs, tiles, tile_count);
 }
 
 // Row descriptors of every tile re-ordered by in-degree (stable), the row's position inside the tile in bits 24..30 of .y.
@@ -482,7 +500,7 @@ __global__ void __launch_bounds__(256) sort_tile_rows_kernel(const int2* __restr
 
 }  // namespace
 
-int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
+int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches)
 {
     const int G = b.num_graphs;
     if (G <= 0) return 0;
@@ -503,19 +521,20 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
     }
     FG_CUDA(cudaMemsetAsync(b.status.ptr, 0, sizeof(int), stream));
 
-    scan_offsets_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.nums_of_edges.as<int>(), b.node_off.as<int>(),
-                                                         b.edge_off.as<int>(), G);
-    FG_CUDA(cudaGetLastError());
-
+    int nl = 1;
     if (flags & PREP_TILES)
     {
         // upper bound: a tile closes at most once per graph, per 128 rows of a large graph and per packing chunk
         b.max_tiles = (long)G + b.total_nodes / TILE_ROWS + PACK_THREADS + 1;
         FG_TRY(b.tiles.reserve(sizeof(int2) * (size_t)b.max_tiles));
         FG_TRY(b.tile_count.reserve(sizeof(int)));
-        pack_tiles_kernel<<<1, PACK_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.node_off.as<int>(), G, b.tiles.as<int2>(), b.tile_count.as<int>());
-        FG_CUDA(cudaGetLastError());
+        scan_pack_kernel<<<1, PACK_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.nums_of_edges.as<int>(), b.node_off.as<int>(), b.edge_off.as<int>(), G,
+                                                         b.tiles.as<int2>(), b.tile_count.as<int>());
     }
+    else
+        scan_offsets_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.nums_of_edges.as<int>(), b.node_off.as<int>(),
+                                                             b.edge_off.as<int>(), G);
+    FG_CUDA(cudaGetLastError());
 
     CsrParams p;
     p.nn = b.nums_of_nodes.as<int>(); p.ne = b.nums_of_edges.as<int>();
@@ -534,15 +553,22 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream)
     p.num_graphs = G; p.flags = flags; p.has_attr = b.has_attr ? 1 : 0;
     build_csr_small_kernel<<<ceil_div(G, 8), 8 * 32, 0, stream>>>(p);
     FG_CUDA(cudaGetLastError());
-    build_csr_large_kernel<<<std::max(1, std::min(ceil_div(G, 128), 148 * 4)), 4 * 32, 0, stream>>>(p);
-    FG_CUDA(cudaGetLastError());
+    nl++;
+    if (b.max_graph_nodes > CSR_NCAP_SMALL)          // counts are validated on the host (upload_into): nothing else is left for this kernel
+    {
+        build_csr_large_kernel<<<std::max(1, std::min(ceil_div(G, 128), 148 * 4)), 4 * 32, 0, stream>>>(p);
+        FG_CUDA(cudaGetLastError());
+        nl++;
+    }
     if ((flags & PREP_TILES) && (flags & PREP_ROW_DESC))
     {
         FG_TRY(b.row_desc_sorted.reserve(sizeof(int4) * (size_t)(b.total_nodes + 1)));
         sort_tile_rows_kernel<<<(int)std::max<long>(1, std::min<long>(ceil_div<long>(b.max_tiles, 8), 148 * 8)), 256, 0, stream>>>(
             b.tiles.as<int2>(), b.tile_count.as<int>(), b.row_desc.as<int4>(), b.row_desc_sorted.as<int4>());
         FG_CUDA(cudaGetLastError());
+        nl++;
     }
+    if (launches) *launches += nl;
     return 0;
 }
 
