@@ -78,7 +78,7 @@ struct Smem {
     static constexpr int TMEM_PTR = BAR + BAR_COUNT * 8;
     static constexpr int BYTES = TMEM_PTR + 16;
 };
-static_assert(Smem::ROWS % 128 == 0 && Smem::A % 1024 == 0, "alignment of the TMA / UMMA operands");
+static_assert(Smem::ROWS % 1024 == 0 && SLICE_BYTES % 1024 == 0 && Smem::A % 1024 == 0, "alignment of the (swizzled) TMA / UMMA operands");
 static_assert(Smem::BYTES <= 232448, "shared memory budget");
 
 struct PnaFusedParams {
@@ -289,13 +289,15 @@ __global__ void __launch_bounds__(NT, 1) pna_layer_fused_kernel(const __grid_con
                 mbar_wait_park(&bar[BAR_S_FULL + c], it & 1);                          // column slice c of this tile has landed
                 if (!ext)
                 {
-                    const uint32_t sl = rows_base + c * SLICE_BYTES + 16 * q;
-                    const uint32_t own = sl + (uint32_t)R * SLICE_ROW_BYTES;
+                    // the slices land with the 64-byte TMA swizzle: 16-byte unit u of row r sits at unit u ^ ((r >> 1) & 3).  With plain
+                    // 64-byte rows the eight rows of a load instruction fall into two bank groups (4-way conflicts); swizzled, into eight
+                    const uint32_t sl = rows_base + c * SLICE_BYTES;
+                    auto row_addr = [&](int r) { return sl + (uint32_t)r * SLICE_ROW_BYTES + (uint32_t)((q ^ ((r >> 1) & 3)) << 4); };
 #pragma unroll
                     for (int e = 0; e < 4; e++)
-                        if (e < deg) agg_add(a, lds_f4(own + (uint32_t)(rel[e] * SLICE_ROW_BYTES)));
+                        if (e < deg) agg_add(a, lds_f4(row_addr(R + rel[e])));
                     for (int e = 4; e < deg; e++)
-                        agg_add(a, lds_f4(sl + (uint32_t)(__ldg(p.src + eb + e) - start) * SLICE_ROW_BYTES));
+                        agg_add(a, lds_f4(row_addr(__ldg(p.src + eb + e) - start)));
                 }
                 else
                 {
@@ -521,7 +523,7 @@ static int encode_rows_map(CUtensorMap* map, const float* h, long num_nodes)
     const cuuint32_t box[2] = {16, (cuuint32_t)TM};
     const cuuint32_t estride[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(h), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r)); return FG_ERR_STATE; }
     return 0;
 }
