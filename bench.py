@@ -52,7 +52,7 @@ WORKLOADS = {
 #: (D, L, attr words A, extra bytes per node X) of SURVEY.md 8(d): B_layer = 8*D*N + E*(8+4A) + X*N
 ALGO = {"gin": (100, 5, 3, 0), "ginvn": (100, 5, 3, 0), "gcn": (100, 5, 3, 0), "gat": (64, 5, 0, 64), "pna": (80, 4, 0, 0),
         "dgn": (100, 4, 0, 0)}
-LAYER_KERNEL = {"gin": "gin_layer_fused_kernel", "ginvn": "gin_layer_fused_kernel", "gcn": "tcf::fused_kernel<GcnFused> (one launch per step: gather -> tcgen05 GEMM -> bias)", "gat": "gat_layer_kernel",
+LAYER_KERNEL = {"gin": "gin_layer_fused_kernel", "ginvn": "gin_layer_fused_kernel", "gcn": "tcf::fused_kernel<GcnFused> (one launch per step: gather -> tcgen05 GEMM -> bias)", "gat": "tcf::fused_kernel<GatFused> (one launch per layer: attention gather -> ELU -> tcgen05 GEMM [W_proj ; W_skip])",
                 "pna": "pna_layer_fused_kernel (+ pna_exact_rows_kernel for the few non-finite rows)", "dgn": "tcf::fused_kernel<DgnFused> (+ dgn_exact_rows_kernel for the few non-finite rows)"}
 
 

@@ -341,6 +341,12 @@ int load_gat(flowgnn_ctx* c, const float* const* w)
     FG_TRY(upload(g.projt, projt, s));
     FG_TRY(upload(g.skipt, skipt, s));
     FG_TRY(upload(g.proj0, proj0, s));
+    {
+        std::vector<unsigned char> pack(5 * gat_tc_pack_bytes());
+        for (int l = 0; l < 5; l++)
+            gat_tc_pack_layer(projt.data() + (size_t)l * 64 * 64, skipt.data() + (size_t)l * 64 * 64, pack.data() + (size_t)l * gat_tc_pack_bytes(), bf16_rn, bf16_to_float);
+        FG_TRY(upload_raw(g.wpack_tc, pack, s));
+    }
     FG_TRY(upload(g.pred_w, w[4], 16, s));
     FG_TRY(upload(g.pred_b, w[5], 1, s));
     return 0;
@@ -546,7 +552,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
                    &ctx->dgn.fx_m1w, &ctx->dgn.fx_m1b, &ctx->dgn.fx_m2w, &ctx->dgn.fx_m2b, &ctx->gin.fx_ne, &ctx->gin.fx_ee, &ctx->gin.fx_w1, &ctx->gin.fx_b1, &ctx->gin.fx_w2, &ctx->gin.fx_b2,
                    &ctx->gin.fx_pw, &ctx->gin.fx_pb, &ctx->dgn.w_ref, &ctx->dgn.b, &ctx->dgn.m0w, &ctx->dgn.m0b, &ctx->dgn.m1w, &ctx->dgn.m1b,
                    &ctx->dgn.m2w, &ctx->dgn.m2b,
-                   &ctx->gat.proj0, &ctx->gat.projt, &ctx->gat.skipt, &ctx->gat.a_src, &ctx->gat.a_tgt, &ctx->gat.pred_w, &ctx->gat.pred_b};
+                   &ctx->gat.wpack_tc, &ctx->gat.proj0, &ctx->gat.projt, &ctx->gat.skipt, &ctx->gat.a_src, &ctx->gat.a_tgt, &ctx->gat.pred_w, &ctx->gat.pred_b};
     for (DevBuf* b : w) b->release();
     for (int i = 0; i < ctx->timer.created; i++) cudaEventDestroy(ctx->timer.ev[i]);
     cudaEventDestroy(ctx->ev0);
@@ -572,6 +578,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "dgn_tc")) ctx->opt.dgn_tc = value;
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
+    else if (!std::strcmp(name, "gat_tc")) ctx->opt.gat_tc = value;
     else if (!std::strcmp(name, "fixed_point")) ctx->opt.fixed_point = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;
     else { set_last_error(std::string("unknown option ") + name); return FG_ERR_INVALID; }

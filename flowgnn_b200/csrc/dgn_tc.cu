@@ -289,7 +289,10 @@ struct DgnFused {
         return r;
     }
     __device__ __forceinline__ bool row_begin(int v, bool live) const { return live && __ldcg(p.nonfinite + v) == 0; }     // flagged rows: dgn_exact_rows_kernel
-    __device__ __forceinline__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre& pre) const
+    struct RowState {};
+    __device__ __forceinline__ RowState row_state() const { return RowState{}; }
+    __device__ __forceinline__ void row_end(int, const RowState&) const {}
+    __device__ __forceinline__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre& pre, RowState&) const
     {
 #pragma unroll
         for (int j = 0; j < 16; j += 4)

@@ -93,7 +93,9 @@ struct Args {
 //         __device__ void prefetch_tile(int v0, int rows) const;                       one thread, two tiles ahead: whatever the gather will read -> L2
 //         struct Pre;  __device__ Pre preload(int v, bool live, int d0) const;         what the epilogue adds to columns d0 .. d0+15
 //         __device__ bool row_begin(int v, bool live) const;                           after the accumulator is complete; false: skip row
-//         __device__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre&) const;
+//         struct RowState; __device__ RowState row_state() const;
+//         __device__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre&, RowState&) const;
+//         __device__ void row_end(int v, const RowState&) const;
 template <class Model>
 __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
 {
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
             tc::fence_after_sync();
             const bool on = m.row_begin(v, live);
             const uint32_t taddr = tbase + a * C::ACC_COLS + ((uint32_t)(warp * 32) << 16);
+            typename Model::RowState st = m.row_state();                // what a row carries from piece to piece (GAT: its scores)
 #pragma unroll 1
             for (int d0 = 0; d0 < NPAD; d0 += 16)
             {
@@ -187,9 +190,10 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
                 tc::ld16(taddr + d0, acc);
                 typename Model::Pre nxt = m.preload(v, live && d0 + 16 < NPAD, d0 + 16);
                 tc::wait_ld();
-                if (on) m.store(v, d0, acc, pre);
+                if (on) m.store(v, d0, acc, pre, st);
                 pre = nxt;
             }
+            if (on) m.row_end(v, st);
             tc::fence_before_sync();
             tcg::mbar_arrive(&bar_acc_empty[a]);
         }

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(128) gat_embed_kernel(const int* __restrict__ 
                                                         const int* __restrict__ nn, int num_graphs, int feat_bug,
                                                         const float* __restrict__ proj0, const float* __restrict__ a_src,
                                                         const float* __restrict__ a_tgt, float* __restrict__ hproj,
-                                                        float* __restrict__ o_prev, float* __restrict__ S, float* __restrict__ T)
+                                                        float* __restrict__ o_prev, float* __restrict__ S, float* __restrict__ T,
+                                                        const float* __restrict__ skipt0)
 {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -40,6 +41,14 @@ __global__ void __launch_bounds__(128) gat_embed_kernel(const int* __restrict__ 
     float w0[ND_FEATURE], w1[ND_FEATURE];
 #pragma unroll
     for (int f = 0; f < ND_FEATURE; f++) { w0[f] = __ldg(proj0 + f * HF + lane); w1[f] = __ldg(proj0 + f * HF + lane + 32); }
+    // gat_tc: the layer-0 skip projection of the raw features (k = 4 f: dim f, head 0) is written instead of the features themselves
+    float k0[ND_FEATURE], k1[ND_FEATURE];
+#pragma unroll
+    for (int f = 0; f < ND_FEATURE; f++)
+    {
+        k0[f] = skipt0 ? __ldg(skipt0 + 4 * f * HF + lane) : 0.f;
+        k1[f] = skipt0 ? __ldg(skipt0 + 4 * f * HF + lane + 32) : 0.f;
+    }
     const float as0 = __ldg(a_src + lane), as1 = __ldg(a_src + lane + 32);
     const float at0 = __ldg(a_tgt + lane), at1 = __ldg(a_tgt + lane + 32);
     for (int v = 0; v < n; v++)
@@ -62,6 +71,12 @@ __global__ void __launch_bounds__(128) gat_embed_kernel(const int* __restrict__ 
         {
             if (lane == 4 * f) o0 = x[f];
             if (lane + 32 == 4 * f) o1 = x[f];
+        }
+        if (skipt0)
+        {
+            o0 = 0.f; o1 = 0.f;
+#pragma unroll
+            for (int f = 0; f < ND_FEATURE; f++) { o0 = fmaf(x[f], k0[f], o0); o1 = fmaf(x[f], k1[f], o1); }      // k ascending, as TileGemm sums
         }
         op[lane] = o0;
         op[lane + 32] = o1;
@@ -281,9 +296,33 @@ int gat_forward(DeviceBatch& b, const GatWeights& w, const RunOptions& opt, int 
     int nl = 0;
     gat_embed_kernel<<<ceil_div(b.num_graphs, 4), 128, 0, s>>>(b.node_feature.as<int>(), b.node_off.as<int>(), b.nums_of_nodes.as<int>(),
                                                              b.num_graphs, opt.gat_node_offset_bug ? 1 : 0, w.proj0.as<float>(),
-                                                             w.a_src.as<float>(), w.a_tgt.as<float>(), hp[0], o[0], S[0], T[0]);
+                                                             w.a_src.as<float>(), w.a_tgt.as<float>(), hp[0], o[0], S[0], T[0],
+                                                             opt.gat_tc ? w.skipt.as<float>() : nullptr);
     FG_CUDA(cudaGetLastError());
     nl++;
+    if (opt.gat_tc)
+    {
+        // o[] holds skip_l instead of o_{l-1}: the fused kernel of layer l produces hproj, skip and the scores of layer l + 1 (gat_tc.cu)
+        for (int l = 0; l < 4; l++)
+        {
+            if (opt.timer) FG_TRY(opt.timer->mark(s));
+            FG_TRY(gat_layer_tc_launch(b, w, l, hp[l & 1], o[l & 1], S[l & 1], T[l & 1], hp[(l + 1) & 1], o[(l + 1) & 1], S[(l + 1) & 1], T[(l + 1) & 1],
+                                       sm_count, s));
+            nl++;
+        }
+        if (opt.timer) FG_TRY(opt.timer->mark(s));
+        FG_TRY(gat_final_launch(b, hp[0], o[0], S[0], T[0], hp[1], sm_count, s));
+        nl++;
+        if (opt.timer) FG_TRY(opt.timer->mark(s));
+        HeadParams hd{};
+        hd.x = hp[1]; hd.dim = 16; hd.node_off = b.node_off.as<int>(); hd.nn = b.nums_of_nodes.as<int>(); hd.num_graphs = b.num_graphs;
+        hd.w[0] = w.pred_w.as<float>(); hd.b[0] = w.pred_b.as<float>(); hd.dims[0] = 16; hd.dims[1] = 1; hd.num_layers = 1;
+        hd.out = b.out.as<float>();
+        FG_TRY(launch_pool_head(hd, s));
+        nl++;
+        if (launches) *launches += nl;
+        return 0;
+    }
     FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gat_layer_kernel<false>), GatSmem::BYTES));
     FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&gat_layer_kernel<true>), GatSmem::BYTES));
     const int num_tiles = (int)ceil_div<long>(N, TILE_M);

@@ -235,7 +235,10 @@ struct GcnFused {
     struct Pre {};
     __device__ __forceinline__ Pre preload(int, bool, int) const { return Pre{}; }
     __device__ __forceinline__ bool row_begin(int, bool live) const { return live; }
-    __device__ __forceinline__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre&) const
+    struct RowState {};
+    __device__ __forceinline__ RowState row_state() const { return RowState{}; }
+    __device__ __forceinline__ void row_end(int, const RowState&) const {}
+    __device__ __forceinline__ void store(int v, int d0, const uint32_t (&acc)[16], const Pre&, RowState&) const
     {
 #pragma unroll
         for (int j = 0; j < 16; j += 4)

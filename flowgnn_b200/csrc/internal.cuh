@@ -127,6 +127,7 @@ struct GatWeights {
     DevBuf skipt;               // [5][64][64]
     DevBuf a_src, a_tgt;        // [5][64]  index d*4+h
     DevBuf pred_w, pred_b;      // [16], [1]
+    DevBuf wpack_tc;            // [5][32768] bytes: [W_proj_l ; W_skip_l] as one [128 x 64] bf16 hi | lo block per layer (gat_tc.cu; layer 0 unused)
 };
 
 // Optional per-layer device timing: one event before each layer launch and one after the last.
@@ -151,6 +152,7 @@ struct RunOptions {
     int dgn_tc = 1;                  // DGN: node transform on tcgen05 (dgn_tc.cu: aggregate -> bf16x3 GEMM -> fp32 rows); 0: FFMA kernel (dgn.cu)
     int pna_fused = 1;               // PNA: ONE kernel per layer (pna_fused.cu: the aggregation is the A producer inside the GEMM kernel); 0: pna_tc / FFMA
     int pna_tc = 1;                  // PNA: node transform on tcgen05 (pna_tc.cu: aggregate -> bf16x3 GEMM -> exact rows); 0: FFMA kernel (pna.cu)
+    int gat_tc = 1;                  // GAT: the two dense maps of a layer as ONE tcgen05 GEMM inside a fused gather kernel (gat_tc.cu); 0: the FP32 kernel (gat.cu)
     int gat_node_offset_bug = 1;
     int fixed_point = 0;             // GIN, DGN: the reference's ap_fixed<16,6> / <16,3> arithmetic, bit for bit (gin_fixed.cu, dgn_fixed.cu)
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
@@ -185,6 +187,11 @@ void dgn_fused_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn
 int dgn_layer_tc_launch(DeviceBatch& b, const DgnWeights& w, int l, const float* h_in, float* h_out, int sm_count, cudaStream_t s);
 size_t dgn_tc_pack_bytes();
 void dgn_tc_pack_layer(const float* w, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
+size_t gat_tc_pack_bytes();
+void gat_tc_pack_layer(const float* projt, const float* skipt, unsigned char* dst, uint16_t (*bf16_rn)(float), float (*bf16_to_float)(uint16_t));
+int gat_layer_tc_launch(const DeviceBatch& b, const GatWeights& w, int l, const float* hproj, const float* skip, const float* S, const float* T,
+                        float* hproj_out, float* skip_out, float* S_out, float* T_out, int sm_count, cudaStream_t s);
+int gat_final_launch(const DeviceBatch& b, const float* hproj, const float* skip, const float* S, const float* T, float* emb, int sm_count, cudaStream_t s);
 int gcn_forward(DeviceBatch& b, const GcnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);

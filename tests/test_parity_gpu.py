@@ -50,6 +50,28 @@ def test_full_molhiv_matches_reference(model, ctx, weights, datasets, golden):
     assert_parity(got, golden["molhiv"][model], what=f"{model}/molhiv")
 
 
+@pytest.mark.parametrize("ds", ["molhiv", "molpcba"])
+def test_gat_tensor_core_path_matches_reference(ds, ctx, weights, datasets, golden):
+    """GAT's default path (gat_tc.cu: attention gather -> ELU -> ONE tcgen05 GEMM [W_proj ; W_skip] per layer, exp once per (edge, head))
+    and the FP32 kernel (option gat_tc = 0) against the reference outputs and against each other; batches ending inside a tile."""
+    ctx.set_option("gat_node_offset_bug", 1)
+    b = datasets[ds]
+    try:
+        ctx.set_option("gat_tc", 0)
+        ffma = ctx.run("gat", b, weights["gat"])
+        ctx.set_option("gat_tc", 1)
+        tc = ctx.run("gat", b)
+        few = ctx.run("gat", b.slice(0, 3))
+        some = ctx.run("gat", b.slice(0, 47))
+    finally:
+        ctx.set_option("gat_tc", 1)
+    assert_parity(ffma, golden[ds]["gat"], what=f"gat fp32/{ds}")
+    assert_parity(tc, golden[ds]["gat"], what=f"gat tcgen05/{ds}")
+    assert_parity(few, golden[ds]["gat"][:3], what=f"gat tcgen05/{ds} first 3 graphs")
+    assert_parity(some, golden[ds]["gat"][:47], what=f"gat tcgen05/{ds} first 47 graphs")
+    assert_parity(tc, ffma, tol=2e-5, what=f"gat tcgen05 vs fp32/{ds}")
+
+
 # Measured max scaled errors of the default kernels against the reference outputs (tools/margins_probe.py, profiles/r2w_parity_margins.txt),
 # pinned at about twice the measurement: the contract is 1e-4, a regression that eats the margin should fail here first.
 PINNED_MARGIN = {
