@@ -200,6 +200,8 @@ struct flowgnn_ctx {
     static constexpr int PIPE = 2;      // measured: a third buffer lets the uploads run ahead but slows the kernels more than it saves
     DeviceBatch pipe[PIPE];
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;                 // the input embedding runs here, next to the CSR / tile build (RunOptions::aux)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t up_done[PIPE] = {}, buf_free[PIPE] = {};
     float* h_out = nullptr; size_t h_out_cap = 0;      // pinned staging of the predictions
     int* h_status = nullptr;                           // pinned, one word per chunk
@@ -515,6 +517,9 @@ int flowgnn_b200_create(flowgnn_ctx** out, int device)
     if (const char* e = std::getenv("FLOWGNN_B200_TC_ALL")) c->opt.gcn_tc = c->opt.dgn_tc = std::atoi(e) != 0;
     FG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    FG_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    FG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    FG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < flowgnn_ctx::PIPE; i++)
     {
         FG_CUDA(cudaEventCreateWithFlags(&c->up_done[i], cudaEventDisableTiming));
@@ -543,6 +548,9 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     DevBuf* w[] = {&ctx->gin.ne_table, &ctx->gin.ne_table4, &ctx->pna.ne_table4, &ctx->gin.ee_comb, &ctx->gin.w1t, &ctx->gin.b1, &ctx->gin.w2t, &ctx->gin.b2, &ctx->gin.wpack2, &ctx->gin.pred_w, &ctx->gin.pred_b,
                    &ctx->gcn.ne_table, &ctx->gcn.ee_comb, &ctx->gcn.wpack_tc, &ctx->gcn.wt, &ctx->gcn.b, &ctx->gcn.root, &ctx->gcn.bn_mean, &ctx->gcn.bn_sqrt_var,
                    &ctx->gcn.bn_weight, &ctx->gcn.bn_bias, &ctx->gcn.pred_w, &ctx->gcn.pred_b,
@@ -579,6 +587,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "gin_unfused_head")) ctx->opt.gin_unfused_head = value;
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
     else if (!std::strcmp(name, "gat_tc")) ctx->opt.gat_tc = value;
+    else if (!std::strcmp(name, "embed_overlap")) ctx->opt.embed_overlap = value;
     else if (!std::strcmp(name, "fixed_point")) ctx->opt.fixed_point = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;
     else { set_last_error(std::string("unknown option ") + name); return FG_ERR_INVALID; }
@@ -673,6 +682,9 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     const int flags = fixed ? 0 : (model == MODEL_GCN) ? (PREP_GCN_NORM | PREP_ROW_DESC) : (model == MODEL_DGN) ? PREP_DGN_EIG : (model == MODEL_GIN || model == MODEL_PNA) ? (PREP_ROW_DESC | PREP_TILES) : 0;
     const bool keep_attr = b.has_attr;
     if (model != MODEL_GIN && model != MODEL_GCN) b.has_attr = false;     // GAT/PNA/DGN kernels take no edge_attr
+    ctx->opt.aux = ctx->opt.embed_overlap ? ctx->aux_stream : nullptr;
+    ctx->opt.ev_fork = ctx->ev_fork; ctx->opt.ev_join = ctx->ev_join;
+    if (ctx->opt.aux) FG_CUDA(cudaEventRecord(ctx->ev_fork, s));
     int rc = prep_batch(b, flags, s, &ctx->last_launches);
     b.has_attr = keep_attr;
     FG_TRY(rc);

@@ -162,8 +162,10 @@ int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int 
         for (int f = 0; f < ND_FEATURE; f++) eo.off[f] = f * 119;      // nine separate [119][100] tables
         const long items = N * Q;
         const int blocks = (int)std::min<long>(ceil_div<long>(items, 256), (long)sm_count * 16);
-        embed_table_kernel<D><<<blocks, 256, 0, s>>>(b.node_feature.as<int>(), w.emb.as<float>(), eo, h[0], N);
+        const cudaStream_t es = embed_stream(opt, s);      // overlaps the CSR / tile build (api.cu::compute_on)
+        embed_table_kernel<D><<<blocks, 256, 0, es>>>(b.node_feature.as<int>(), w.emb.as<float>(), eo, h[0], N);
         FG_CUDA(cudaGetLastError());
+        FG_TRY(embed_join(opt, es, s));
         nl++;
     }
     FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&dgn_layer_kernel), DgnSmem::BYTES));

@@ -155,11 +155,30 @@ struct RunOptions {
     int gat_tc = 1;                  // GAT: the two dense maps of a layer as ONE tcgen05 GEMM inside a fused gather kernel (gat_tc.cu); 0: the FP32 kernel (gat.cu)
     int gat_node_offset_bug = 1;
     int fixed_point = 0;             // GIN, DGN: the reference's ap_fixed<16,6> / <16,3> arithmetic, bit for bit (gin_fixed.cu, dgn_fixed.cu)
+    // The input embedding needs only node_feature, the CSR / tile build only the edge lists: the embedding kernel runs on `aux`
+    // between `ev_fork` (recorded on the compute stream before the build is launched) and `ev_join` (awaited before layer 0)
+    int embed_overlap = 1;           // GIN, PNA, DGN: the embedding launch on a second stream, concurrent with the CSR / tile build
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     LayerTimer* timer = nullptr;     // set while option "time_layers" is on
     int timer_group = 0;             // time_layers == 2: one interval around ALL layer launches (events between the launches
                                      // would keep them from overlapping through programmatic dependent launch)
 };
 
+// stream for the embedding launch (aux after ev_fork, or the compute stream itself) / make the compute stream wait for it
+inline cudaStream_t embed_stream(const RunOptions& opt, cudaStream_t s)
+{
+    if (!opt.aux) return s;
+    if (cudaStreamWaitEvent(opt.aux, opt.ev_fork, 0) != cudaSuccess) return s;
+    return opt.aux;
+}
+inline int embed_join(const RunOptions& opt, cudaStream_t es, cudaStream_t s)
+{
+    if (es == s) return 0;
+    FG_CUDA(cudaEventRecord(opt.ev_join, es));
+    FG_CUDA(cudaStreamWaitEvent(s, opt.ev_join, 0));
+    return 0;
+}
 int gin_forward(DeviceBatch& b, const GinWeights& w, const RunOptions& opt, int sm_count, cudaStream_t s, int* launches);
 int dgn_fixed_forward(DeviceBatch& b, const DgnWeights& w, int sm_count, cudaStream_t s, int* launches);
 int gin_fixed_forward(DeviceBatch& b, const GinWeights& w, int sm_count, cudaStream_t s, int* launches);
