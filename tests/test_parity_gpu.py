@@ -223,26 +223,28 @@ def test_pna_tensor_core_path_matches_reference(ds, ctx, weights, datasets, gold
 @pytest.mark.parametrize("model", ["gcn", "dgn"])
 @pytest.mark.parametrize("ds", ["molhiv", "molpcba", "hep10k"])
 def test_gcn_dgn_tensor_core_paths_match_reference(model, ds, ctx, weights, datasets, golden):
-    """Options gcn_tc / dgn_tc (default 1; gcn_tc.cu, dgn_tc.cu on tcgemm.cuh; 0 selects the fused FFMA kernels, kept as the
-    on-device fp32 reference): the aggregate kernel writes bf16 hi/lo A blocks, the
-    dense layer runs on tcgen05 (3 products), DGN's non-finite rows (out-degree 0) are evaluated in fp32.  Both settings
-    must sit inside the 1e-4 contract (non-finite values positionally) and agree with each other, also on batches that
-    end inside a 128-row tile."""
-    opt = model + "_tc"
+    """Three implementations of the GCN step / DGN layer: the default ONE-launch kernel (fused_tc.cuh: the aggregation is the A
+    producer inside the tcgen05 GEMM kernel), round 1's aggregate -> HBM -> GEMM launches (option <model>_fused = 0, tcgemm.cuh)
+    and the fused FFMA kernel (option <model>_tc = 0, the on-device fp32 reference).  DGN's non-finite rows (out-degree 0) are
+    evaluated in fp32 by all of them.  Every setting must sit inside the 1e-4 contract (non-finite values positionally) and they
+    must agree with each other, also on batches that end inside a 128-row tile."""
     out = {}
     try:
-        for mode in (0, 1):
-            ctx.set_option(opt, mode)
-            out[mode] = ctx.run(model, datasets[ds], weights[model])
+        for name, tc, fused in (("ffma", 0, 1), ("two_launch", 1, 0), ("fused", 1, 1)):
+            ctx.set_option(model + "_tc", tc)
+            ctx.set_option(model + "_fused", fused)
+            out[name] = ctx.run(model, datasets[ds], weights[model])
         few = ctx.run(model, datasets[ds].slice(0, 3))
         some = ctx.run(model, datasets[ds].slice(0, 47))
     finally:
-        ctx.set_option(opt, int(__import__("os").environ.get("FLOWGNN_B200_TC_ALL", DEFAULT_TC)))
-    assert_parity(out[0], golden[ds][model], what=f"{model} ffma/{ds}")
-    assert_parity(out[1], golden[ds][model], what=f"{model} tcgen05/{ds}")
-    assert_parity(few, golden[ds][model][:3], what=f"{model} tcgen05/{ds} first 3 graphs")
-    assert_parity(some, golden[ds][model][:47], what=f"{model} tcgen05/{ds} first 47 graphs")
-    assert_parity(out[1], out[0], tol=1e-4, what=f"{model} tcgen05 vs ffma/{ds}")
+        ctx.set_option(model + "_tc", int(__import__("os").environ.get("FLOWGNN_B200_TC_ALL", DEFAULT_TC)))
+        ctx.set_option(model + "_fused", 1)
+    for name, y in out.items():
+        assert_parity(y, golden[ds][model], what=f"{model} {name}/{ds}")
+    assert_parity(few, golden[ds][model][:3], what=f"{model} fused/{ds} first 3 graphs")
+    assert_parity(some, golden[ds][model][:47], what=f"{model} fused/{ds} first 47 graphs")
+    assert_parity(out["fused"], out["ffma"], tol=5e-5, what=f"{model} fused vs ffma/{ds}")
+    assert_parity(out["fused"], out["two_launch"], tol=5e-5, what=f"{model} fused vs two launches/{ds}")
 
 
 def test_gat_hep10k_is_the_prediction_bias(ctx, weights, datasets, golden):
