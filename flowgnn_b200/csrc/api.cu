@@ -14,6 +14,7 @@
 
 #include "../../include/flowgnn_b200.h"
 #include "internal.cuh"
+#include "layers.cuh"
 #include "tc.cuh"
 
 namespace fg {
@@ -674,6 +675,15 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     if (model == MODEL_DGN && !b.has_eigen) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
     if ((model == MODEL_GIN || model == MODEL_GCN) && !b.has_attr) { set_last_error("GIN/GCN need edge_attr"); return FG_ERR_INVALID; }
     const bool fixed = ctx->opt.fixed_point != 0;
+    if (b.total_nodes == 0 && !fixed)
+    {
+        // every graph is empty: the mean pool is 0 / 0, and the reference's fp32 flavour carries that NaN through every head
+        FG_TRY(b.status.reserve(sizeof(int)));
+        FG_CUDA(cudaMemsetAsync(b.status.ptr, 0, sizeof(int), s));
+        FG_TRY(fill_outputs(b.out.as<float>(), std::nanf(""), b.num_graphs, s));
+        ctx->last_launches += 1;
+        return 0;
+    }
     if (fixed && model != MODEL_GIN && model != MODEL_DGN)
     {
         set_last_error("option fixed_point: only GIN / GIN-VN (ap_fixed<16,6>) and DGN (ap_fixed<16,3>) run in the reference's fixed-point arithmetic");

@@ -79,6 +79,21 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) pool_head_kernel(HeadParams p
 
 }  // namespace
 
+namespace {
+__global__ void fill_kernel(float* __restrict__ out, float value, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = value;
+}
+}  // namespace
+
+int fill_outputs(float* out, float value, int n, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    fill_kernel<<<std::min(ceil_div(n, 256), 1024), 256, 0, stream>>>(out, value, n);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_pool_head(const HeadParams& p, cudaStream_t stream)
 {
     if (p.num_graphs <= 0) return 0;

@@ -330,6 +330,7 @@ int dgn_layer_fused_launch(DeviceBatch& b, const DgnWeights& w, int l, const flo
     using C = tcf::Cfg<DgnFused>;
     FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&tcf::fused_kernel<DgnFused>), C::BYTES));
     const long N = b.total_nodes;
+    if (N == 0) return 0;
     FG_TRY(b.nonfinite.reserve((size_t)N + 16));
     FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
     DgnAggParams p{};

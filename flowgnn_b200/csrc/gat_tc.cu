@@ -216,6 +216,7 @@ int gat_layer_tc_launch(const DeviceBatch& b, const GatWeights& w, int l, const 
     using C = tcf::Cfg<GatFused>;
     FG_TRY(opt_in_smem(reinterpret_cast<const void*>(&tcf::fused_kernel<GatFused>), C::BYTES));
     const long N = b.total_nodes;
+    if (N == 0) return 0;
     tcf::Args g{};
     g.wpack = w.wpack_tc.as<unsigned char>() + (size_t)(l + 1) * gat_tc_pack_bytes();
     g.num_nodes = (int)N; g.num_tiles = (int)ceil_div<long>(N, tcf::TM);
@@ -229,6 +230,7 @@ int gat_layer_tc_launch(const DeviceBatch& b, const GatWeights& w, int l, const 
 int gat_final_launch(const DeviceBatch& b, const float* hproj, const float* skip, const float* S, const float* T, float* emb, int sm_count, cudaStream_t s)
 {
     const long N = b.total_nodes;
+    if (N == 0) return 0;
     gat_final_kernel<<<(int)std::min<long>(ceil_div<long>(N, 64), (long)sm_count * 8), 256, 0, s>>>(
         GatAttend{hproj, S, T, b.in_ptr.as<int>(), b.src.as<int>()}, skip, emb, (int)N);
     FG_CUDA(cudaGetLastError());

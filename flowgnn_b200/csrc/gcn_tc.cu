@@ -336,6 +336,7 @@ static GcnRowMath gcn_row_math(const DeviceBatch& b, const GcnWeights& w, int l,
 int gcn_step_fused_launch(DeviceBatch& b, const GcnWeights& w, int l, const float* p_in, float* p_out, int sm_count, cudaStream_t s)
 {
     const long N = b.total_nodes;
+    if (N == 0) return 0;                        // a batch of empty graphs: nothing to launch (grid 0 is an invalid configuration)
     if (l == 5)
     {
         gcn_final_kernel<<<(int)std::min<long>(ceil_div<long>(N, 32), (long)sm_count * 8), 256, 0, s>>>(gcn_row_math(b, w, 5, p_in), p_out, N);

@@ -258,5 +258,6 @@ struct HeadParams {
 };
 
 int launch_pool_head(const HeadParams& p, cudaStream_t stream);
+int fill_outputs(float* out, float value, int n, cudaStream_t stream);
 
 }  // namespace fg

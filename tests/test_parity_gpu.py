@@ -360,6 +360,17 @@ def test_edge_cases_empty_batch_and_edgeless_graph(ctx, weights):
         got = ctx.run(model, b, weights[model])
         ctx.set_option("gat_node_offset_bug", 1)
         assert_parity(got, want, what=f"{model} edgeless/directed")
+    # graphs without nodes (the mean pool divides by zero: the reference's fp32 flavour gives NaN), alone and among ordinary graphs
+    z = Batch(np.array([0, 0]), np.array([0, 0]), np.zeros((0, 9), np.int32), np.zeros((0, 2), np.int32), np.zeros((0, 3), np.int32), np.zeros((0, 4), np.float32))
+    from flowgnn_b200.dataset import concat
+    mixed = concat([z, b, z])
+    for model in ("gin", "gcn", "gat", "pna", "dgn"):
+        ctx.set_option("gat_node_offset_bug", 0)
+        got0 = ctx.run(model, z, weights[model])
+        got = ctx.run(model, mixed, weights[model])
+        ctx.set_option("gat_node_offset_bug", 1)
+        assert_parity(got0, refbind.run_port(model, z, weights[model], gat_node_offset_bug=False), what=f"{model} empty graphs")
+        assert_parity(got, refbind.run_port(model, mixed, weights[model], gat_node_offset_bug=False), what=f"{model} empty graphs among others")
 
 
 @pytest.mark.parametrize("model", ["gin", "gcn", "gat", "pna", "dgn"])
