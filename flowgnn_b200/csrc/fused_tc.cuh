@@ -79,6 +79,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p, int bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
 }
 
+// lanes that share a row in the gather: 16 (4 K slots per lane, four rows per lane; default) or 8 (Model::LPR = 8: 8 K slots, two rows)
+template <class Model, class = void> struct LanesPerRow { static constexpr int value = 16; };
+template <class Model> struct LanesPerRow<Model, decltype((void)Model::LPR)> { static constexpr int value = Model::LPR; };
+template <class Model> constexpr int lanes_per_row() { return LanesPerRow<Model>::value; }
+
 struct Args {
     const unsigned char* wpack;      // [NCHUNK][Cfg<NPAD>::B_BLOCK] this step
     int num_nodes; int num_tiles;
@@ -201,7 +206,6 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
     else
     {
         const int gw = warp - FIRST_GATHER_WARP;
-        const int sub = lane >> 4, j = lane & 15;
         uint32_t n = 0;
         if (gw == 0 && lane == 0 && (int)(blockIdx.x + gridDim.x) < g.num_tiles)
             m.prefetch_tile((blockIdx.x + gridDim.x) * TM, min(TM, g.num_nodes - (int)(blockIdx.x + gridDim.x) * TM));
@@ -209,6 +213,36 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
         {
             const int ahead = tile + 2 * gridDim.x;
             if (gw == 0 && lane == 0 && ahead < g.num_tiles) m.prefetch_tile(ahead * TM, min(TM, g.num_nodes - ahead * TM));
+            if constexpr (lanes_per_row<Model>() == 8)
+            {
+                // eight lanes per row, 8 K slots per lane (one 16-byte unit of the swizzled row), two rows per lane: the per-row work
+                // (indices, predicates, attention weights) is amortised over twice the columns
+                const int sub = lane >> 3, j = lane & 7;
+                const int r0 = gw * (TM / GATHER_WARPS) + sub;
+                const int v[2] = {tile * TM + r0, tile * TM + r0 + 4};
+                const bool live[2] = {v[0] < g.num_nodes, v[1] < g.num_nodes};
+                const typename Model::Rows rows = m.rows_begin(v, live);
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; c++, n++)
+                {
+                    const uint32_t s = n % C::STAGES;
+                    tcg::mbar_wait_park(&bar_empty[s], ((n / C::STAGES) & 1) ^ 1);
+                    unsigned char* hi = smem + C::STAGE0 + s * A_BLOCK;
+                    float4 x[2][2];
+                    if (m.gather2(rows, v, live, c, j, x))
+                    {
+#pragma unroll
+                        for (int p = 0; p < 2; p++) { put4(hi, r0 + 4 * p, 8 * j, x[p][0]); put4(hi, r0 + 4 * p, 8 * j + 4, x[p][1]); }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tcg::mbar_arrive(&bar_full[s]);
+                }
+                continue;
+            }
+            else
+            {
+            const int sub = lane >> 4, j = lane & 15;
             // the warp's eight rows: lane (sub, j) owns rows r0, r0 + 2, r0 + 4, r0 + 6, walked together
             const int r0 = gw * (TM / GATHER_WARPS) + sub;
             const int v[4] = {tile * TM + r0, tile * TM + r0 + 2, tile * TM + r0 + 4, tile * TM + r0 + 6};
@@ -229,6 +263,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tcg::mbar_arrive(&bar_full[s]);
+            }
             }
         }
     }
