@@ -190,6 +190,90 @@ struct GcnRowMath {
             out[p] = live[p] ? r : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
+
+    // Eight lanes per row (fused_tc.cuh, LPR = 8): two rows per lane, eight columns c .. c+7 per row (n8 = how many of them are real:
+    // 8, or 4 for the row's last piece 96..99).  The rows' CSR walks advance together; the (source, code, norm) of a row's NEXT in-edge
+    // are requested together with its CURRENT neighbour row.  The per-edge work that does not depend on the column -- indices,
+    // predicates, addresses -- is amortised over eight columns instead of four.
+    template <bool RELU>
+    __device__ __forceinline__ void finish2x8(const int (&v)[2], const bool (&live)[2], int c, bool two, float4 (&out)[2][2]) const
+    {
+        int e[2], end[2], u[2], cd[2];
+        float nr[2];
+        float4 m[2][2], pv[2][2];
+        float degp1[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            e[q] = live[q] ? __ldg(in_ptr + v[q]) : 0;
+            end[q] = live[q] ? __ldg(in_ptr + v[q] + 1) : 0;
+            degp1[q] = live[q] ? (float)(__ldg(out_deg + v[q]) + 1) : 1.0f;
+            m[q][0] = m[q][1] = pv[q][0] = pv[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live[q]) { pv[q][0] = ldg_f4(p_in + (size_t)v[q] * D + c); if (two) pv[q][1] = ldg_f4(p_in + (size_t)v[q] * D + c + 4); }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            u[q] = 0; cd[q] = 0; nr[q] = 0.f;
+            if (e[q] < end[q]) { u[q] = __ldg(src + e[q]); cd[q] = __ldg(code + e[q]); nr[q] = __ldg(norm + e[q]); }
+        }
+        while ((e[0] < end[0]) | (e[1] < end[1]))
+        {
+            float4 pu[2][2];
+            int un[2], cn[2];
+            float nn[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                un[q] = 0; cn[q] = 0; nn[q] = 0.f;
+                if (e[q] < end[q])
+                {
+                    pu[q][0] = ldg_f4(p_in + (size_t)u[q] * D + c);
+                    if (two) pu[q][1] = ldg_f4(p_in + (size_t)u[q] * D + c + 4);
+                    if (e[q] + 1 < end[q]) { un[q] = __ldg(src + e[q] + 1); cn[q] = __ldg(code + e[q] + 1); nn[q] = __ldg(norm + e[q] + 1); }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                if (e[q] < end[q])
+                {
+                    const float4 t0 = ldg_f4(ee_comb + cd[q] * D + c);           // 24 KB table, L1 resident
+                    m[q][0].x += nr[q] * relu_f(t0.x + pu[q][0].x); m[q][0].y += nr[q] * relu_f(t0.y + pu[q][0].y);
+                    m[q][0].z += nr[q] * relu_f(t0.z + pu[q][0].z); m[q][0].w += nr[q] * relu_f(t0.w + pu[q][0].w);
+                    if (two)
+                    {
+                        const float4 t1 = ldg_f4(ee_comb + cd[q] * D + c + 4);
+                        m[q][1].x += nr[q] * relu_f(t1.x + pu[q][1].x); m[q][1].y += nr[q] * relu_f(t1.y + pu[q][1].y);
+                        m[q][1].z += nr[q] * relu_f(t1.z + pu[q][1].z); m[q][1].w += nr[q] * relu_f(t1.w + pu[q][1].w);
+                    }
+                    e[q]++;
+                    u[q] = un[q]; cd[q] = cn[q]; nr[q] = nn[q];
+                }
+        }
+        // self term, BatchNorm (inference), relu.  The two divisions of the reference's expression (by deg + 1 and by sqrt(var + eps))
+        // are multiplications by reciprocals here: <= 2 ulp from the IEEE quotient, against a 1e-4 bar
+        const float rdeg[2] = {__fdividef(1.0f, degp1[0]), __fdividef(1.0f, degp1[1])};
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+        {
+            if (i == 1 && !two) { out[0][1] = out[1][1] = make_float4(0.f, 0.f, 0.f, 0.f); break; }
+            const int ci = c + 4 * i;
+            const float4 rt = ldg_f4(root + ci), mu = ldg_f4(bn_mean + ci), sv = ldg_f4(bn_sqrt_var + ci);
+            const float4 ga = ldg_f4(bn_weight + ci), be = ldg_f4(bn_bias + ci);
+            const float4 g = make_float4(__fdividef(ga.x, sv.x), __fdividef(ga.y, sv.y), __fdividef(ga.z, sv.z), __fdividef(ga.w, sv.w));
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+            {
+                float4 r;
+                r.x = (m[q][i].x + relu_f(pv[q][i].x + rt.x) * rdeg[q] - mu.x) * g.x + be.x;
+                r.y = (m[q][i].y + relu_f(pv[q][i].y + rt.y) * rdeg[q] - mu.y) * g.y + be.y;
+                r.z = (m[q][i].z + relu_f(pv[q][i].z + rt.z) * rdeg[q] - mu.z) * g.z + be.z;
+                r.w = (m[q][i].w + relu_f(pv[q][i].w + rt.w) * rdeg[q] - mu.w) * g.w + be.w;
+                if (RELU) { r.x = relu_f(r.x); r.y = relu_f(r.y); r.z = relu_f(r.z); r.w = relu_f(r.w); }
+                out[q][i] = live[q] ? r : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
 };
 
 template <bool FIRST>
@@ -200,7 +284,30 @@ struct GcnFused {
     const int* feat; const float* ne_table;
     const float* b; float* p_out;
 
+    static constexpr int LPR = FIRST ? 16 : 8;          // the embedding step is nine table lookups per piece: more lanes, fewer pieces per lane
     struct Rows {};
+    __device__ __forceinline__ Rows rows_begin(const int (&)[2], const bool (&)[2]) const { return Rows{}; }
+    __device__ __forceinline__ bool gather2(const Rows&, const int (&v)[2], const bool (&live)[2], int c, int j, float4 (&x)[2][2]) const
+    {
+        const int col = KC_COLS * c + 8 * j;
+        if (col >= NPAD) return false;
+#pragma unroll
+        for (int q = 0; q < 2; q++) x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);      // K padding and rows past the batch hold zeros
+        if (col >= D) return true;
+        const bool two = col + 4 < D;                                                        // the row's last piece holds columns 96..99 only
+        if (FIRST)
+        {
+#pragma unroll
+            for (int q = 0; q < 2; q++)                                                      // GCN/src/node_embedding.cc:124-127
+                if (live[q])
+                {
+                    x[q][0] = embed_chunk<D>(feat + (size_t)v[q] * ND_FEATURE, ne_table, concat_table_offsets(), col / 4);
+                    if (two) x[q][1] = embed_chunk<D>(feat + (size_t)v[q] * ND_FEATURE, ne_table, concat_table_offsets(), col / 4 + 1);
+                }
+        }
+        else r.template finish2x8<true>(v, live, col, two, x);
+        return true;
+    }
     __device__ __forceinline__ Rows rows_begin(const int (&)[4], const bool (&)[4]) const { return Rows{}; }
     __device__ __forceinline__ bool gather4(const Rows&, const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
     {
