@@ -167,104 +167,116 @@ __global__ void __launch_bounds__(EX_WARPS * 32) dgn_exact_rows_kernel(DgnAggPar
 
 // ---- option dgn_fused (default): the layer as ONE launch, the aggregation as the A producer inside the GEMM kernel (fused_tc.cuh) ----
 // K layout: chunk c = [a1 columns 32c .. 32c+31 | a2 columns 32c .. 32c+31], so that one chunk needs 128 bytes of every
-// neighbour row and both halves of a gather half-warp walk the same in-edges: lanes 0-7 accumulate m0 = sum h_u (-> a1),
-// lanes 8-15 m1 = sum h_u eig_w (-> a2).  Chunk 3 holds columns 96..99 only: K steps 0 (a1) and 2 (a2).
+// neighbour row and both halves of a lane group walk the same in-edges.  Chunk 3 holds columns 96..99 only: K steps 0 (a1) and 2 (a2).
 struct DgnFused {
     static constexpr int NCHUNK = 4, NPAD = fg::NPAD;
     static constexpr unsigned ksteps(int c) { return c < 3 ? 0xFu : 0x5u; }
     DgnAggParams p;
     const float* b; float* h_out;
 
-    struct Rows { int e0[4], end[4]; };
-    __device__ __forceinline__ Rows rows_begin(const int (&v)[4], const bool (&live)[4]) const
+    // Eight lanes per row (fused_tc.cuh, LPR = 8): lanes 0-3 of a group accumulate m0 = sum h_u (-> a1) for columns 32c + 8j .. + 7,
+    // lanes 4-7 m1 = sum h_u eig_w (-> a2) for the same columns, over the SAME in-edge walk; two rows per lane.
+    static constexpr int LPR = 8;
+    struct Rows { int e0[2], end[2]; };
+    __device__ __forceinline__ Rows rows_begin(const int (&v)[2], const bool (&live)[2]) const
     {
         Rows r;
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 2; q++)
         {
             r.e0[q] = live[q] ? __ldg(p.in_ptr + v[q]) : 0;
             r.end[q] = live[q] ? __ldg(p.in_ptr + v[q] + 1) : 0;
         }
         return r;
     }
-    __device__ __forceinline__ bool gather4(const Rows& rows, const int (&v)[4], const bool (&live)[4], int c, int j, float4 (&x)[4]) const
+    __device__ __forceinline__ bool gather2(const Rows& rows, const int (&v)[2], const bool (&live)[2], int c, int j, float4 (&x)[2][2]) const
     {
-        const int part = j >> 3, col = 32 * c + 4 * (j & 7);
-        if (c == 3 && (j & 7) >= 4) return false;                  // outside the issued K steps
+        const int part = j >> 2, col = 32 * c + 8 * (j & 3);
+        if (c == 3 && (j & 3) >= 2) return false;                  // outside the issued K steps
 #pragma unroll
-        for (int q = 0; q < 4; q++) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);      // K padding and rows past the batch hold zeros
+        for (int q = 0; q < 2; q++) x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);      // K padding and rows past the batch hold zeros
         if (col >= D) return true;
+        const bool two = col + 4 < D;                               // the row's last piece holds columns 96..99 only
         // what the end of the walk needs, requested before it starts
-        float fin0[4], fin1[4];                                      // part 0: out-degree; part 1: A_v = sum |eig_w|, B_v = sum eig_w
-        float4 hv[4];
+        float fin0[2], fin1[2];                                      // part 0: out-degree; part 1: A_v = sum |eig_w|, B_v = sum eig_w
+        float4 hv[2][2];
+        int e[2], u[2];
+        float w[2];
+        float4 m[2][2];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 2; q++)
         {
-            fin0[q] = fin1[q] = 0.f; hv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fin0[q] = fin1[q] = 0.f;
+            hv[q][0] = hv[q][1] = m[q][0] = m[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            e[q] = rows.e0[q]; u[q] = 0; w[q] = 1.0f;
             if (!live[q]) continue;
-            if (part) { fin0[q] = __ldg(p.abssum + v[q]); fin1[q] = __ldg(p.wsum + v[q]); hv[q] = ldg_f4(p.h_in + (size_t)v[q] * D + col); }
+            if (part)
+            {
+                fin0[q] = __ldg(p.abssum + v[q]); fin1[q] = __ldg(p.wsum + v[q]);
+                hv[q][0] = ldg_f4(p.h_in + (size_t)v[q] * D + col);
+                if (two) hv[q][1] = ldg_f4(p.h_in + (size_t)v[q] * D + col + 4);
+            }
             else fin0[q] = (float)__ldg(p.out_deg + v[q]);
-        }
-        int e[4];
-        float4 m[4];
-        int u[4];
-        float w[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-        {
-            e[q] = rows.e0[q];
-            m[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            u[q] = 0; w[q] = 1.0f;
             if (e[q] < rows.end[q]) { u[q] = __ldg(p.src + e[q]); if (part) w[q] = __ldg(p.eig_w + e[q]); }
         }
-        // The four rows' CSR walks advance together (in-edges in CSR order: the loop of dgn_aggregate4 above); the source and weight
-        // of each row's NEXT in-edge are requested together with the CURRENT neighbour rows: one memory round trip per step
-        while ((e[0] < rows.end[0]) | (e[1] < rows.end[1]) | (e[2] < rows.end[2]) | (e[3] < rows.end[3]))
+        // the rows' CSR walks advance together (in-edges in CSR order: the loop of dgn_aggregate4 above); the source and weight of each
+        // row's NEXT in-edge are requested together with the CURRENT neighbour row
+        while ((e[0] < rows.end[0]) | (e[1] < rows.end[1]))
         {
-            float4 hu[4];
-            int un[4];
-            float wn[4];
+            float4 hu[2][2];
+            int un[2];
+            float wn[2];
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < 2; q++)
             {
                 un[q] = 0; wn[q] = 1.0f;
-                if (e[q] < rows.end[q]) hu[q] = ldg_f4(p.h_in + (size_t)u[q] * D + col);
-                if (e[q] + 1 < rows.end[q]) { un[q] = __ldg(p.src + e[q] + 1); if (part) wn[q] = __ldg(p.eig_w + e[q] + 1); }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++)
                 if (e[q] < rows.end[q])
                 {
-                    if (part) { m[q].x += hu[q].x * w[q]; m[q].y += hu[q].y * w[q]; m[q].z += hu[q].z * w[q]; m[q].w += hu[q].w * w[q]; }
-                    else { m[q].x += hu[q].x; m[q].y += hu[q].y; m[q].z += hu[q].z; m[q].w += hu[q].w; }
+                    hu[q][0] = ldg_f4(p.h_in + (size_t)u[q] * D + col);
+                    if (two) hu[q][1] = ldg_f4(p.h_in + (size_t)u[q] * D + col + 4);
+                    if (e[q] + 1 < rows.end[q]) { un[q] = __ldg(p.src + e[q] + 1); if (part) wn[q] = __ldg(p.eig_w + e[q] + 1); }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                if (e[q] < rows.end[q])
+                {
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+                    {
+                        if (i == 1 && !two) break;
+                        if (part) { m[q][i].x += hu[q][i].x * w[q]; m[q][i].y += hu[q][i].y * w[q]; m[q][i].z += hu[q][i].z * w[q]; m[q][i].w += hu[q][i].w * w[q]; }
+                        else { m[q][i].x += hu[q][i].x; m[q][i].y += hu[q][i].y; m[q][i].z += hu[q][i].z; m[q][i].w += hu[q][i].w; }
+                    }
                     e[q]++;
                     u[q] = un[q]; w[q] = wn[q];
                 }
         }
         // the reference divides (m0 / deg, (m1 - B h) / A); here one IEEE reciprocal per row and a multiplication per column:
         // <= 1 ulp from the quotient (the bar is 1e-4), and deg = 0 still gives inf * m0 = +-inf or NaN exactly where m0 / 0 does
-        bool bad[4];
+        bool bad[2];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 2; q++)
         {
-            float4 a;
-            if (part)
+            const float r = 1.0f / (part ? (fin0[q] == 0.0f ? 0.0001220703125f : fin0[q]) : fin0[q]);      // ap_fixed_epsilon of <16,3> = 2^-13
+            float probe = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
             {
-                const float abssum = fin0[q] == 0.0f ? 0.0001220703125f : fin0[q];       // ap_fixed_epsilon of <16,3> = 2^-13
-                const float rab = 1.0f / abssum;
-                a = make_float4(fabsf((m[q].x - fin1[q] * hv[q].x) * rab), fabsf((m[q].y - fin1[q] * hv[q].y) * rab),
-                                fabsf((m[q].z - fin1[q] * hv[q].z) * rab), fabsf((m[q].w - fin1[q] * hv[q].w) * rab));
+                if (i == 1 && !two) break;
+                float4 a;
+                if (part)
+                    a = make_float4(fabsf((m[q][i].x - fin1[q] * hv[q][i].x) * r), fabsf((m[q][i].y - fin1[q] * hv[q][i].y) * r),
+                                    fabsf((m[q][i].z - fin1[q] * hv[q][i].z) * r), fabsf((m[q][i].w - fin1[q] * hv[q][i].w) * r));
+                else
+                    a = make_float4(m[q][i].x * r, m[q][i].y * r, m[q][i].z * r, m[q][i].w * r);
+                probe += (a.x * 0.0f + a.y * 0.0f) + (a.z * 0.0f + a.w * 0.0f);        // x * 0 is 0 for finite x and NaN otherwise
+                if (live[q]) x[q][i] = a;
             }
-            else
-            {
-                const float rdeg = 1.0f / fin0[q];
-                a = make_float4(m[q].x * rdeg, m[q].y * rdeg, m[q].z * rdeg, m[q].w * rdeg);
-            }
-            bad[q] = live[q] && (a.x * 0.0f + a.y * 0.0f) + (a.z * 0.0f + a.w * 0.0f) != 0.0f;     // x * 0 is 0 for finite x and NaN otherwise
-            if (live[q]) x[q] = a;
+            bad[q] = live[q] && probe != 0.0f;
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < 2; q++)
             if (bad[q]) p.nonfinite[v[q]] = 1;                       // before this warp's arrival on the stage: the epilogue sees it
         return true;
     }
