@@ -213,7 +213,34 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
         {
             const int ahead = tile + 2 * gridDim.x;
             if (gw == 0 && lane == 0 && ahead < g.num_tiles) m.prefetch_tile(ahead * TM, min(TM, g.num_nodes - ahead * TM));
-            if constexpr (lanes_per_row<Model>() == 8)
+            if constexpr (lanes_per_row<Model>() == 4)
+            {
+                // four lanes per row, 16 K slots per lane (two 16-byte units of the swizzled row), one row per lane group: a warp walks its
+                // eight rows together
+                const int j = lane & 3;
+                const int r0 = gw * (TM / GATHER_WARPS) + (lane >> 2);
+                const int v = tile * TM + r0;
+                const bool live = v < g.num_nodes;
+                const typename Model::Rows rows = m.rows_begin(v, live);
+#pragma unroll 1
+                for (int c = 0; c < NCHUNK; c++, n++)
+                {
+                    const uint32_t s = n % C::STAGES;
+                    tcg::mbar_wait_park(&bar_empty[s], ((n / C::STAGES) & 1) ^ 1);
+                    unsigned char* hi = smem + C::STAGE0 + s * A_BLOCK;
+                    float4 x[4];
+                    if (m.gather1(rows, v, live, c, j, x))
+                    {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) put4(hi, r0, 16 * j + 4 * i, x[i]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) tcg::mbar_arrive(&bar_full[s]);
+                }
+                continue;
+            }
+            else if constexpr (lanes_per_row<Model>() == 8)
             {
                 // eight lanes per row, 8 K slots per lane (one 16-byte unit of the swizzled row), two rows per lane: the per-row work
                 // (indices, predicates, attention weights) is amortised over twice the columns

@@ -10,7 +10,7 @@
 //                                  GEMM [W_proj_{l+1} ; W_skip_{l+1}]; epilogue: hproj_{l+1}, skip_{l+1}, and the scores
 //                                  S_{l+1}, T_{l+1} = <hproj_{l+1} per head, a_src / a_tgt> accumulated over the accumulator pieces
 //   gat_final_kernel               l = 4: emb = (sum_h msg + sum_h skip_4) / 4   (finalize.cc:46-112), then the shared pool + head
-// exp(leaky(S_v + T_u)) is evaluated ONCE per (edge, head): lane j < 4 of the 8 lanes that share a row evaluates head j and the four
+// exp(leaky(S_v + T_u)) is evaluated ONCE per (edge, head): lane j of the 4 lanes that share a row evaluates head j and the four
 // weights travel by shuffle (the FP32 kernel evaluates all four in each of its 16 column threads).
 #include "internal.cuh"
 #include "layers.cuh"
@@ -25,100 +25,61 @@ namespace {
 constexpr int HF = 64;               // heads * dims, index d * 4 + h
 constexpr int NH = 4;
 
-// Eight lanes share a row: lane j holds dims 2j and 2j + 1 (eight consecutive floats of the [dim][head] row), lanes 0..3 of the
-// group also evaluate the attention weight of head j.  Two rows per lane (a warp covers 4 + 4 rows).
+// Four lanes share a row: lane j holds dims 4j .. 4j + 3 (sixteen consecutive floats of the [dim][head] row) and evaluates the
+// attention weight of head j.  One row per lane group: a warp walks its eight rows together.
 struct GatAttend {
     const float* hproj; const float* S; const float* T;
     const int* in_ptr; const int* src;
 
-    struct Rows { int e0[2], end[2]; };
-    __device__ __forceinline__ Rows rows_begin(const int (&v)[2], const bool (&live)[2]) const
+    struct Rows { int e0, end; };
+    __device__ __forceinline__ Rows rows_begin(int v, bool live) const
     {
         Rows r;
-#pragma unroll
-        for (int q = 0; q < 2; q++)
-        {
-            r.e0[q] = live[q] ? __ldg(in_ptr + v[q]) : 0;
-            r.end[q] = live[q] ? __ldg(in_ptr + v[q] + 1) : 0;
-        }
+        r.e0 = live ? __ldg(in_ptr + v) : 0;
+        r.end = live ? __ldg(in_ptr + v + 1) : 0;
         return r;
     }
 
-    // msg[q][i] = (sum_u w_u hproj_u) / (sum_u w_u) for dim 2j + i (four heads) of the lane's two rows; u = v first, then the
-    // in-edges in CSR order.  The eight lanes of a row execute this together (the weights are exchanged with shuffles inside the group).
-    __device__ __forceinline__ void attend2(const Rows& rows, const int (&v)[2], const bool (&live)[2], int j, float4 (&msg)[2][2]) const
+    // msg[i] = (sum_u w_u hproj_u) / (sum_u w_u) for dim 4j + i (four heads); u = v first, then the in-edges in CSR order.  The four
+    // lanes of a row execute this together (the weights are exchanged with shuffles inside the group).
+    __device__ __forceinline__ void attend1(const Rows& rows, int v, bool live, int j, float4 (&msg)[4]) const
     {
-        const int base = threadIdx.x & 24, hsel = j & 3;
-        const unsigned group_mask = 0xFFu << base;
-        float sv[2];
-        float4 num[2][2], den[2];
-        int e[2];
+        const int base = threadIdx.x & 28;
+        const unsigned group_mask = 0xFu << base;
+        const float sv = live ? __ldg(S + (size_t)v * NH + j) : 0.f;
+        float4 num[4], den = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 2; q++)
+        for (int i = 0; i < 4; i++) num[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = rows.e0 - 1;                                        // position e0 - 1 stands for the self loop
+        int u = v;
+        while (live && e < rows.end)                                // the four lanes of a row agree on this
         {
-            sv[q] = live[q] ? __ldg(S + (size_t)v[q] * NH + hsel) : 0.f;
-            num[q][0] = num[q][1] = den[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            e[q] = rows.e0[q] - 1;                                  // position e0 - 1 stands for the self loop
-        }
-        // the source of the NEXT step is requested together with the current rows
-        int u[2];
+            // the source of the NEXT step is requested together with the current row
+            const float tu = __ldg(T + (size_t)u * NH + j);
+            float4 hu[4];
 #pragma unroll
-        for (int q = 0; q < 2; q++) u[q] = v[q];
-        while (true)
-        {
-            const bool act0 = live[0] && e[0] < rows.end[0], act1 = live[1] && e[1] < rows.end[1];
-            if (!(act0 | act1)) break;                              // the eight lanes of a row agree on this
-            const bool act[2] = {act0, act1};
-            float tu[2];
-            float4 hu[2][2];
-            int un[2];
+            for (int i = 0; i < 4; i++) hu[i] = ldg_f4(hproj + (size_t)u * HF + 16 * j + 4 * i);
+            int un = v;
+            if (e + 1 < rows.end) un = __ldg(src + e + 1);
+            float sc = sv + tu;
+            sc = (sc < 0.f) ? sc * 0.2f : sc;                       // leaky relu, slope 0.2 (message_passing.cc:126-127)
+            const float w = __expf(sc);
+            const float w0 = __shfl_sync(group_mask, w, base + 0), w1 = __shfl_sync(group_mask, w, base + 1);
+            const float w2 = __shfl_sync(group_mask, w, base + 2), w3 = __shfl_sync(group_mask, w, base + 3);
+            den.x += w0; den.y += w1; den.z += w2; den.w += w3;
 #pragma unroll
-            for (int q = 0; q < 2; q++)
+            for (int i = 0; i < 4; i++)
             {
-                un[q] = v[q];
-                if (act[q])
-                {
-                    tu[q] = __ldg(T + (size_t)u[q] * NH + hsel);
-                    hu[q][0] = ldg_f4(hproj + (size_t)u[q] * HF + 8 * j);
-                    hu[q][1] = ldg_f4(hproj + (size_t)u[q] * HF + 8 * j + 4);
-                    if (e[q] + 1 < rows.end[q]) un[q] = __ldg(src + e[q] + 1);
-                }
+                num[i].x += w0 * hu[i].x; num[i].y += w1 * hu[i].y; num[i].z += w2 * hu[i].z; num[i].w += w3 * hu[i].w;
             }
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-            {
-                float w = 0.f;
-                if (act[q])
-                {
-                    float sc = sv[q] + tu[q];
-                    sc = (sc < 0.f) ? sc * 0.2f : sc;               // leaky relu, slope 0.2 (message_passing.cc:126-127)
-                    w = __expf(sc);
-                }
-                // within a group every lane has the same act[q]; the other three groups of the warp may be elsewhere in their walks
-                const float w0 = __shfl_sync(group_mask, w, base + 0), w1 = __shfl_sync(group_mask, w, base + 1);
-                const float w2 = __shfl_sync(group_mask, w, base + 2), w3 = __shfl_sync(group_mask, w, base + 3);
-                if (act[q])
-                {
-                    den[q].x += w0; den[q].y += w1; den[q].z += w2; den[q].w += w3;
-#pragma unroll
-                    for (int i = 0; i < 2; i++)
-                    {
-                        num[q][i].x += w0 * hu[q][i].x; num[q][i].y += w1 * hu[q][i].y; num[q][i].z += w2 * hu[q][i].z; num[q][i].w += w3 * hu[q][i].w;
-                    }
-                    e[q]++;
-                    u[q] = un[q];
-                }
-            }
+            e++;
+            u = un;
         }
+        // one IEEE reciprocal per head instead of a division per element: <= 1 ulp from the quotient
+        const float4 rd = make_float4(1.0f / den.x, 1.0f / den.y, 1.0f / den.z, 1.0f / den.w);
 #pragma unroll
-        for (int q = 0; q < 2; q++)
-        {
-            // one IEEE reciprocal per head instead of a division per element: <= 1 ulp from the quotient
-            const float4 rd = make_float4(1.0f / den[q].x, 1.0f / den[q].y, 1.0f / den[q].z, 1.0f / den[q].w);
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-                msg[q][i] = live[q] ? make_float4(num[q][i].x * rd.x, num[q][i].y * rd.y, num[q][i].z * rd.z, num[q][i].w * rd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < 4; i++)
+            msg[i] = live ? make_float4(num[i].x * rd.x, num[i].y * rd.y, num[i].z * rd.z, num[i].w * rd.w) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 };
 
@@ -132,23 +93,21 @@ struct GatFused {
     float* hproj_out; float* skip_out; float* S_out; float* T_out;        // layer l + 1
     const float* a_src; const float* a_tgt;                               // [64] of layer l + 1, index d * 4 + h
 
-    static constexpr int LPR = 8;                                          // lanes per row (fused_tc.cuh): 8 K slots per lane, two rows per lane
+    static constexpr int LPR = 4;                                          // lanes per row (fused_tc.cuh): 16 K slots per lane, one row per lane group
     using Rows = GatAttend::Rows;
-    __device__ __forceinline__ Rows rows_begin(const int (&v)[2], const bool (&live)[2]) const { return at.rows_begin(v, live); }
-    __device__ __forceinline__ bool gather2(const Rows& rows, const int (&v)[2], const bool (&live)[2], int, int j, float4 (&x)[2][2]) const
+    __device__ __forceinline__ Rows rows_begin(int v, bool live) const { return at.rows_begin(v, live); }
+    __device__ __forceinline__ bool gather1(const Rows& rows, int v, bool live, int, int j, float4 (&x)[4]) const
     {
-        float4 msg[2][2];
-        at.attend2(rows, v, live, j, msg);
+        float4 msg[4];
+        at.attend1(rows, v, live, j, msg);
 #pragma unroll
-        for (int q = 0; q < 2; q++)
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-            {
-                x[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!live[q]) continue;
-                const float4 sk = ldg_f4(skip + (size_t)v[q] * HF + 8 * j + 4 * i);
-                x[q][i] = make_float4(elu_f(msg[q][i].x + sk.x), elu_f(msg[q][i].y + sk.y), elu_f(msg[q][i].z + sk.z), elu_f(msg[q][i].w + sk.w));      // node_embedding.cc:176-195
-            }
+        for (int i = 0; i < 4; i++)
+        {
+            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!live) continue;
+            const float4 sk = ldg_f4(skip + (size_t)v * HF + 16 * j + 4 * i);
+            x[i] = make_float4(elu_f(msg[i].x + sk.x), elu_f(msg[i].y + sk.y), elu_f(msg[i].z + sk.z), elu_f(msg[i].w + sk.w));      // node_embedding.cc:176-195
+        }
         return true;
     }
     __device__ __forceinline__ void prefetch_tile(int v0, int rows) const
@@ -192,34 +151,32 @@ struct GatFused {
     }
 };
 
-// last layer: emb[v][d] = (sum_h msg[d][h] + sum_h skip_4[d][h]) / 4 (finalize.cc:46-112); eight lanes per row, eight rows per warp
+// last layer: emb[v][d] = (sum_h msg[d][h] + sum_h skip_4[d][h]) / 4 (finalize.cc:46-112); four lanes per row, eight rows per warp
 __global__ void __launch_bounds__(256) gat_final_kernel(GatAttend at, const float* __restrict__ skip, float* __restrict__ emb, int num_nodes)
 {
-    const int lane = threadIdx.x & 31, sub = lane >> 3, j = lane & 7;
+    const int lane = threadIdx.x & 31, sub = lane >> 2, j = lane & 3;
     const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
     for (long v0 = 8 * warp; v0 < num_nodes; v0 += 8 * nwarps)
     {
-        const int v[2] = {(int)v0 + sub, (int)v0 + 4 + sub};
-        const bool live[2] = {v[0] < num_nodes, v[1] < num_nodes};
+        const int v = (int)v0 + sub;
+        const bool live = v < num_nodes;
         const GatAttend::Rows rows = at.rows_begin(v, live);
-        float4 msg[2][2];
-        at.attend2(rows, v, live, j, msg);
+        float4 msg[4];
+        at.attend1(rows, v, live, j, msg);
+        if (live)
+        {
+            float of[4];
 #pragma unroll
-        for (int q = 0; q < 2; q++)
-            if (live[q])
+            for (int i = 0; i < 4; i++)
             {
-                float of[2];
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-                {
-                    const float4 sk = ldg_f4(skip + (size_t)v[q] * HF + 8 * j + 4 * i);
-                    float o = 0.f;
-                    o += msg[q][i].x; o += msg[q][i].y; o += msg[q][i].z; o += msg[q][i].w;
-                    o += sk.x; o += sk.y; o += sk.z; o += sk.w;
-                    of[i] = o / 4.0f;
-                }
-                *reinterpret_cast<float2*>(emb + (size_t)v[q] * 16 + 2 * j) = make_float2(of[0], of[1]);
+                const float4 sk = ldg_f4(skip + (size_t)v * HF + 16 * j + 4 * i);
+                float o = 0.f;
+                o += msg[i].x; o += msg[i].y; o += msg[i].z; o += msg[i].w;
+                o += sk.x; o += sk.y; o += sk.z; o += sk.w;
+                of[i] = o / 4.0f;
             }
+            *reinterpret_cast<float4*>(emb + (size_t)v * 16 + 4 * j) = make_float4(of[0], of[1], of[2], of[3]);
+        }
     }
 }
 

@@ -11,8 +11,8 @@ timeout 120 python tools/fixed_probe.py 2>&1 | tail -1 > gpurun_out/${tag}_fixed
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 200 --csv --log-file gpurun_out/${tag}_launches_gin_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras --no-pageable > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gin_layer_fused -s 8 -c 1 -f -o gpurun_out/${tag}_ncu_gin_layer_fused python tools/gin_probe.py 41127 1 fused > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pna_layer_fused -s 1 -c 1 -f -o gpurun_out/${tag}_ncu_pna_layer_fused python tools/model_probe.py pna 100000 1 > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:gat_layer -s 3 -c 1 -f -o gpurun_out/${tag}_ncu_gat python tools/model_probe.py gat 41127 1 > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 5 -c 1 -f -o gpurun_out/${tag}_ncu_gcn python tools/model_probe.py gcn 41127 1 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_ncu_gat python tools/model_probe.py gat 41127 1 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 6 -c 1 -f -o gpurun_out/${tag}_ncu_gcn python tools/model_probe.py gcn 41127 1 > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_ncu_dgn python tools/model_probe.py dgn 41127 1 > /dev/null 2>&1
 for m in gat gcn dgn pna; do timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches_${m}.csv python tools/model_probe.py $m $( [ $m = pna ] && echo 100000 || echo 41127 ) 1 > /dev/null 2>&1; done
 bash tools/sanitize.sh ${tag}
