@@ -174,110 +174,80 @@ struct DgnFused {
     DgnAggParams p;
     const float* b; float* h_out;
 
-    // Eight lanes per row (fused_tc.cuh, LPR = 8): lanes 0-3 of a group accumulate m0 = sum h_u (-> a1) for columns 32c + 8j .. + 7,
-    // lanes 4-7 m1 = sum h_u eig_w (-> a2) for the same columns, over the SAME in-edge walk; two rows per lane.
-    static constexpr int LPR = 8;
-    struct Rows { int e0[2], end[2]; };
-    __device__ __forceinline__ Rows rows_begin(const int (&v)[2], const bool (&live)[2]) const
+    // Four lanes per row (fused_tc.cuh, LPR = 4): lanes 0-1 of a group accumulate m0 = sum h_u (-> a1) for columns 32c + 16j .. + 15,
+    // lanes 2-3 m1 = sum h_u eig_w (-> a2) for the same columns, over the SAME in-edge walk; a warp walks its eight rows together.
+    static constexpr int LPR = 4;
+    struct Rows { int e0, end; };
+    __device__ __forceinline__ Rows rows_begin(int v, bool live) const
     {
         Rows r;
-#pragma unroll
-        for (int q = 0; q < 2; q++)
-        {
-            r.e0[q] = live[q] ? __ldg(p.in_ptr + v[q]) : 0;
-            r.end[q] = live[q] ? __ldg(p.in_ptr + v[q] + 1) : 0;
-        }
+        r.e0 = live ? __ldg(p.in_ptr + v) : 0;
+        r.end = live ? __ldg(p.in_ptr + v + 1) : 0;
         return r;
     }
-    __device__ __forceinline__ bool gather2(const Rows& rows, const int (&v)[2], const bool (&live)[2], int c, int j, float4 (&x)[2][2]) const
+    __device__ __forceinline__ bool gather1(const Rows& rows, int v, bool live, int c, int j, float4 (&x)[4]) const
     {
-        const int part = j >> 2, col = 32 * c + 8 * (j & 3);
-        if (c == 3 && (j & 3) >= 2) return false;                  // outside the issued K steps
+        const int part = j >> 1, col = 32 * c + 16 * (j & 1);
+        if (c == 3 && (j & 1)) return false;                       // chunk 3: columns 96..111 only (K steps 0 and 2)
 #pragma unroll
-        for (int q = 0; q < 2; q++) x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);      // K padding and rows past the batch hold zeros
-        if (col >= D) return true;
-        const bool two = col + 4 < D;                               // the row's last piece holds columns 96..99 only
+        for (int i = 0; i < 4; i++) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);      // K padding and rows past the batch hold zeros
+        if (!live) return true;
+        const int np = (col + 16 <= D) ? 4 : (D - col) / 4;         // real float4 pieces of this lane: 4, or 1 for columns 96..99
         // what the end of the walk needs, requested before it starts
-        float fin0[2], fin1[2];                                      // part 0: out-degree; part 1: A_v = sum |eig_w|, B_v = sum eig_w
-        float4 hv[2][2];
-        int e[2], u[2];
-        float w[2];
-        float4 m[2][2];
+        float fin0, fin1 = 0.f;                                      // part 0: out-degree; part 1: A_v = sum |eig_w|, B_v = sum eig_w
+        float4 hv[4], m[4];
 #pragma unroll
-        for (int q = 0; q < 2; q++)
+        for (int i = 0; i < 4; i++) hv[i] = m[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (part)
         {
-            fin0[q] = fin1[q] = 0.f;
-            hv[q][0] = hv[q][1] = m[q][0] = m[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            e[q] = rows.e0[q]; u[q] = 0; w[q] = 1.0f;
-            if (!live[q]) continue;
-            if (part)
-            {
-                fin0[q] = __ldg(p.abssum + v[q]); fin1[q] = __ldg(p.wsum + v[q]);
-                hv[q][0] = ldg_f4(p.h_in + (size_t)v[q] * D + col);
-                if (two) hv[q][1] = ldg_f4(p.h_in + (size_t)v[q] * D + col + 4);
-            }
-            else fin0[q] = (float)__ldg(p.out_deg + v[q]);
-            if (e[q] < rows.end[q]) { u[q] = __ldg(p.src + e[q]); if (part) w[q] = __ldg(p.eig_w + e[q]); }
+            fin0 = __ldg(p.abssum + v); fin1 = __ldg(p.wsum + v);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < np) hv[i] = ldg_f4(p.h_in + (size_t)v * D + col + 4 * i);
         }
-        // the rows' CSR walks advance together (in-edges in CSR order: the loop of dgn_aggregate4 above); the source and weight of each
-        // row's NEXT in-edge are requested together with the CURRENT neighbour row
-        while ((e[0] < rows.end[0]) | (e[1] < rows.end[1]))
+        else fin0 = (float)__ldg(p.out_deg + v);
+        int e = rows.e0, u = 0;
+        float w = 1.0f;
+        if (e < rows.end) { u = __ldg(p.src + e); if (part) w = __ldg(p.eig_w + e); }
+        // in-edges in CSR order (the loop of dgn_aggregate4 above); the source and weight of the NEXT in-edge are requested together
+        // with the CURRENT neighbour row
+        while (e < rows.end)
         {
-            float4 hu[2][2];
-            int un[2];
-            float wn[2];
+            float4 hu[4];
 #pragma unroll
-            for (int q = 0; q < 2; q++)
-            {
-                un[q] = 0; wn[q] = 1.0f;
-                if (e[q] < rows.end[q])
+            for (int i = 0; i < 4; i++)
+                if (i < np) hu[i] = ldg_f4(p.h_in + (size_t)u * D + col + 4 * i);
+            int un = 0;
+            float wn = 1.0f;
+            if (e + 1 < rows.end) { un = __ldg(p.src + e + 1); if (part) wn = __ldg(p.eig_w + e + 1); }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (i < np)
                 {
-                    hu[q][0] = ldg_f4(p.h_in + (size_t)u[q] * D + col);
-                    if (two) hu[q][1] = ldg_f4(p.h_in + (size_t)u[q] * D + col + 4);
-                    if (e[q] + 1 < rows.end[q]) { un[q] = __ldg(p.src + e[q] + 1); if (part) wn[q] = __ldg(p.eig_w + e[q] + 1); }
+                    if (part) { m[i].x += hu[i].x * w; m[i].y += hu[i].y * w; m[i].z += hu[i].z * w; m[i].w += hu[i].w * w; }
+                    else { m[i].x += hu[i].x; m[i].y += hu[i].y; m[i].z += hu[i].z; m[i].w += hu[i].w; }
                 }
-            }
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-                if (e[q] < rows.end[q])
-                {
-#pragma unroll
-                    for (int i = 0; i < 2; i++)
-                    {
-                        if (i == 1 && !two) break;
-                        if (part) { m[q][i].x += hu[q][i].x * w[q]; m[q][i].y += hu[q][i].y * w[q]; m[q][i].z += hu[q][i].z * w[q]; m[q][i].w += hu[q][i].w * w[q]; }
-                        else { m[q][i].x += hu[q][i].x; m[q][i].y += hu[q][i].y; m[q][i].z += hu[q][i].z; m[q][i].w += hu[q][i].w; }
-                    }
-                    e[q]++;
-                    u[q] = un[q]; w[q] = wn[q];
-                }
+            e++;
+            u = un; w = wn;
         }
         // the reference divides (m0 / deg, (m1 - B h) / A); here one IEEE reciprocal per row and a multiplication per column:
         // <= 1 ulp from the quotient (the bar is 1e-4), and deg = 0 still gives inf * m0 = +-inf or NaN exactly where m0 / 0 does
-        bool bad[2];
+        const float r = 1.0f / (part ? (fin0 == 0.0f ? 0.0001220703125f : fin0) : fin0);      // ap_fixed_epsilon of <16,3> = 2^-13
+        float probe = 0.f;
 #pragma unroll
-        for (int q = 0; q < 2; q++)
-        {
-            const float r = 1.0f / (part ? (fin0[q] == 0.0f ? 0.0001220703125f : fin0[q]) : fin0[q]);      // ap_fixed_epsilon of <16,3> = 2^-13
-            float probe = 0.f;
-#pragma unroll
-            for (int i = 0; i < 2; i++)
+        for (int i = 0; i < 4; i++)
+            if (i < np)
             {
-                if (i == 1 && !two) break;
                 float4 a;
                 if (part)
-                    a = make_float4(fabsf((m[q][i].x - fin1[q] * hv[q][i].x) * r), fabsf((m[q][i].y - fin1[q] * hv[q][i].y) * r),
-                                    fabsf((m[q][i].z - fin1[q] * hv[q][i].z) * r), fabsf((m[q][i].w - fin1[q] * hv[q][i].w) * r));
+                    a = make_float4(fabsf((m[i].x - fin1 * hv[i].x) * r), fabsf((m[i].y - fin1 * hv[i].y) * r), fabsf((m[i].z - fin1 * hv[i].z) * r),
+                                    fabsf((m[i].w - fin1 * hv[i].w) * r));
                 else
-                    a = make_float4(m[q][i].x * r, m[q][i].y * r, m[q][i].z * r, m[q][i].w * r);
+                    a = make_float4(m[i].x * r, m[i].y * r, m[i].z * r, m[i].w * r);
                 probe += (a.x * 0.0f + a.y * 0.0f) + (a.z * 0.0f + a.w * 0.0f);        // x * 0 is 0 for finite x and NaN otherwise
-                if (live[q]) x[q][i] = a;
+                x[i] = a;
             }
-            bad[q] = live[q] && probe != 0.0f;
-        }
-#pragma unroll
-        for (int q = 0; q < 2; q++)
-            if (bad[q]) p.nonfinite[v[q]] = 1;                       // before this warp's arrival on the stage: the epilogue sees it
+        if (probe != 0.0f) p.nonfinite[v] = 1;                      // before this warp's arrival on the stage: the epilogue sees it
         return true;
     }
     __device__ __forceinline__ void prefetch_tile(int v0, int rows) const
