@@ -177,6 +177,7 @@ struct DgnFused {
     // Four lanes per row (fused_tc.cuh, LPR = 4): lanes 0-1 of a group accumulate m0 = sum h_u (-> a1) for columns 32c + 16j .. + 15,
     // lanes 2-3 m1 = sum h_u eig_w (-> a2) for the same columns, over the SAME in-edge walk; a warp walks its eight rows together.
     static constexpr int LPR = 4;
+    static __device__ __forceinline__ int kslot(int j, int i) { return 16 * j + 4 * i; }
     struct Rows { int e0, end; };
     __device__ __forceinline__ Rows rows_begin(int v, bool live) const
     {

@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
             if (gw == 0 && lane == 0 && ahead < g.num_tiles) m.prefetch_tile(ahead * TM, min(TM, g.num_nodes - ahead * TM));
             if constexpr (lanes_per_row<Model>() == 4)
             {
-                // four lanes per row, 16 K slots per lane (two 16-byte units of the swizzled row), one row per lane group: a warp walks its
-                // eight rows together
+                // four lanes per row, 16 K slots per lane as four pieces of four (which four is the model's choice, Model::kslot), one row
+                // per lane group: a warp walks its eight rows together
                 const int j = lane & 3;
                 const int r0 = gw * (TM / GATHER_WARPS) + (lane >> 2);
                 const int v = tile * TM + r0;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(NT, 1) fused_kernel(Args g, Model m)
                     if (m.gather1(rows, v, live, c, j, x))
                     {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) put4(hi, r0, 16 * j + 4 * i, x[i]);
+                        for (int i = 0; i < 4; i++) put4(hi, r0, m.kslot(j, i), x[i]);
                     }
                     fence_proxy_async();
                     __syncwarp();

@@ -25,8 +25,8 @@ namespace {
 constexpr int HF = 64;               // heads * dims, index d * 4 + h
 constexpr int NH = 4;
 
-// Four lanes share a row: lane j holds dims 4j .. 4j + 3 (sixteen consecutive floats of the [dim][head] row) and evaluates the
-// attention weight of head j.  One row per lane group: a warp walks its eight rows together.
+// Four lanes share a row: lane j holds dims j, 4 + j, 8 + j, 12 + j (its i-th load is the 16 bytes at 64 i + 16 j of the [dim][head]
+// row, so the four lanes of a row read 64 contiguous bytes per instruction: full sectors) and evaluates the attention weight of head j.  One row per lane group: a warp walks its eight rows together.
 struct GatAttend {
     const float* hproj; const float* S; const float* T;
     const int* in_ptr; const int* src;
@@ -40,7 +40,7 @@ struct GatAttend {
         return r;
     }
 
-    // msg[i] = (sum_u w_u hproj_u) / (sum_u w_u) for dim 4j + i (four heads); u = v first, then the in-edges in CSR order.  The four
+    // msg[i] = (sum_u w_u hproj_u) / (sum_u w_u) for dim 4i + j (four heads); u = v first, then the in-edges in CSR order.  The four
     // lanes of a row execute this together (the weights are exchanged with shuffles inside the group).
     __device__ __forceinline__ void attend1(const Rows& rows, int v, bool live, int j, float4 (&msg)[4]) const
     {
@@ -58,7 +58,7 @@ struct GatAttend {
             const float tu = __ldg(T + (size_t)u * NH + j);
             float4 hu[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) hu[i] = ldg_f4(hproj + (size_t)u * HF + 16 * j + 4 * i);
+            for (int i = 0; i < 4; i++) hu[i] = ldg_f4(hproj + (size_t)u * HF + 16 * i + 4 * j);
             int un = v;
             if (e + 1 < rows.end) un = __ldg(src + e + 1);
             float sc = sv + tu;
@@ -96,6 +96,7 @@ struct GatFused {
     static constexpr int LPR = 4;                                          // lanes per row (fused_tc.cuh): 16 K slots per lane, one row per lane group
     using Rows = GatAttend::Rows;
     __device__ __forceinline__ Rows rows_begin(int v, bool live) const { return at.rows_begin(v, live); }
+    static __device__ __forceinline__ int kslot(int j, int i) { return 16 * i + 4 * j; }      // piece i of lane j: dim 4i + j, heads 0..3
     __device__ __forceinline__ bool gather1(const Rows& rows, int v, bool live, int, int j, float4 (&x)[4]) const
     {
         float4 msg[4];
@@ -105,7 +106,7 @@ struct GatFused {
         {
             x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!live) continue;
-            const float4 sk = ldg_f4(skip + (size_t)v * HF + 16 * j + 4 * i);
+            const float4 sk = ldg_f4(skip + (size_t)v * HF + 16 * i + 4 * j);
             x[i] = make_float4(elu_f(msg[i].x + sk.x), elu_f(msg[i].y + sk.y), elu_f(msg[i].z + sk.z), elu_f(msg[i].w + sk.w));      // node_embedding.cc:176-195
         }
         return true;
@@ -169,13 +170,14 @@ __global__ void __launch_bounds__(256) gat_final_kernel(GatAttend at, const floa
 #pragma unroll
             for (int i = 0; i < 4; i++)
             {
-                const float4 sk = ldg_f4(skip + (size_t)v * HF + 16 * j + 4 * i);
+                const float4 sk = ldg_f4(skip + (size_t)v * HF + 16 * i + 4 * j);
                 float o = 0.f;
                 o += msg[i].x; o += msg[i].y; o += msg[i].z; o += msg[i].w;
                 o += sk.x; o += sk.y; o += sk.z; o += sk.w;
                 of[i] = o / 4.0f;
             }
-            *reinterpret_cast<float4*>(emb + (size_t)v * 16 + 4 * j) = make_float4(of[0], of[1], of[2], of[3]);
+            #pragma unroll
+            for (int i = 0; i < 4; i++) emb[(size_t)v * 16 + 4 * i + j] = of[i];
         }
     }
 }
