@@ -278,7 +278,8 @@ def measure_resident(ctx, model, steps, warmup, stream, barrier, grouped):
 
 
 def run_extra_configs(args, rank, world, local, dev, barrier, max_over_ranks, sum_over_ranks, hbm_peak):
-    """BASELINE configs C4 and C5 inside the same JSON line (the driver only runs `bench.py --gpus N`):
+    """BASELINE configs C3, C4 and C5 inside the same JSON line (the driver only runs `bench.py --gpus N`):
+      gat_molhiv           GAT (5 layers, 4 heads) on molhiv-shaped graphs, 41,127 per GPU (weak);
       pna_molpcba_sharded  ONE batch of 437,929 molpcba-shaped graphs cut by graph index over the N ranks
                            (flowgnn_b200.sharding.shard_of -- strong scaling; NCCL only tallies);
       ginvn_hep10k         GIN-VN on hep10k-shaped graphs, 40,000 per GPU (weak), plus a batch-size sweep.
@@ -302,6 +303,24 @@ def run_extra_configs(args, rank, world, local, dev, barrier, max_over_ranks, su
         finally:
             ctx.close()
         return ms, layer_ms, launches, y
+
+    # ---- C3: GAT on molhiv-shaped graphs, weak scaling -------------------------------------------------------
+    model = "gat"
+    batch = make_workload(model, WORKLOADS[model][1], seed_offset=rank, base_graphs=4096)
+    ms, layer_ms, launches, y = one(model, batch, False)
+    ms = max_over_ranks(ms)
+    done = sum_over_ranks(float(batch.num_graphs))
+    lb = layer_bytes(model, batch.total_nodes, batch.total_edges)
+    mean_layer = max_over_ranks(float(np.mean(layer_ms[:-1])))                  # the four fused layer launches (the fifth interval is the final gather)
+    out["gat_molhiv"] = {
+        "metric": metric_name(model), "value": done * steps / (ms * 1e-3), "unit": "graphs/s", "scaling": "weak",
+        "workload": f"GAT forward (5 layers, 4 heads x 16), {batch.num_graphs} synthetic molhiv-shaped graphs per GPU per step",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "gpu_launches": int(launches),
+        "finite_outputs": sum_over_ranks(float(np.isfinite(y).sum())),
+        "roofline": {"bound": "hbm", "kernel": LAYER_KERNEL[model], "achieved": lb / (mean_layer * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": lb / (mean_layer * 1e-3) / 1e9 / hbm_peak, "mean_layer_ms": mean_layer, "algorithmic_bytes_per_layer": lb},
+    }
+    del batch
 
     # ---- C4: PNA, one molpcba-sized batch sharded by graph index ------------------------------------------
     model = "pna"
