@@ -53,6 +53,9 @@ void DevBuf::release()
 
 void DeviceBatch::release()
 {
+    if (h_pack) { cudaFreeHost(h_pack); h_pack = nullptr; h_pack_cap = 0; }
+    if (h_pack_done) { cudaEventDestroy(h_pack_done); h_pack_done = nullptr; }
+    for (DevBuf* b : {&node_off_perm, &edge_off_perm, &tiles_perm, &node_off_in, &edge_off_in, &node_map}) b->release();
     DevBuf* all[] = {&nums_of_nodes, &nums_of_edges, &node_feature, &edge_list, &edge_attr, &node_eigen, &node_off, &edge_off,
                      &in_ptr, &src, &code, &edge_w, &out_deg, &node_w0, &node_w1, &row_desc, &row_desc_sorted, &row_desc0, &sort_tmp, &big_tab, &status, &tiles, &tile_count, &node_dot, &apack, &nonfinite,
                      &act[0], &act[1], &act[2], &act[3], &score[0], &score[1], &score[2], &score[3], &out};
@@ -589,6 +592,7 @@ int flowgnn_b200_set_option(flowgnn_ctx* ctx, const char* name, int value)
     else if (!std::strcmp(name, "gat_node_offset_bug")) ctx->opt.gat_node_offset_bug = value;
     else if (!std::strcmp(name, "gat_tc")) ctx->opt.gat_tc = value;
     else if (!std::strcmp(name, "embed_overlap")) ctx->opt.embed_overlap = value;
+    else if (!std::strcmp(name, "pack_graphs")) ctx->opt.pack_graphs = value;
     else if (!std::strcmp(name, "fixed_point")) ctx->opt.fixed_point = value;
     else if (!std::strcmp(name, "time_layers")) ctx->time_layers = value;
     else { set_last_error(std::string("unknown option ") + name); return FG_ERR_INVALID; }
@@ -624,6 +628,8 @@ int flowgnn_b200_load_weights(flowgnn_ctx* ctx, int model, const float* const* w
 }  // extern "C"
 
 namespace {
+
+void pack_graphs(const int32_t* nn, const int32_t* ne, int G, std::vector<int32_t>& node_off, std::vector<int32_t>& edge_off, std::vector<int32_t>& tiles);
 
 int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_nodes, int64_t total_edges, const int32_t* nums_of_nodes,
                 const int32_t* nums_of_edges, const int32_t* node_feature, const int32_t* edge_list, const int32_t* edge_attr,
@@ -665,7 +671,127 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
     if (edge_attr) FG_TRY(copy_in(b.edge_attr, edge_attr, sizeof(int) * 3 * (size_t)total_edges, s));
     if (node_eigen) FG_TRY(copy_in(b.node_eigen, node_eigen, sizeof(float) * 4 * (size_t)total_nodes, s));
     FG_TRY(b.out.reserve(sizeof(float) * (size_t)(num_graphs + 1)));
+    // re-ordered graph offsets + tile list for the models with graph-aligned tiles (used by prep.cu when option pack_graphs is on).
+    // They travel from a pinned staging block owned by the batch, so that the copies stay asynchronous (the chunked entry points
+    // overlap this upload with the previous chunk's kernels).
+    b.has_perm = false;
+    if (num_graphs > 0 && total_nodes > 0)
+    {
+        static thread_local std::vector<int32_t> po, pe, pt;
+        pack_graphs(nums_of_nodes, nums_of_edges, num_graphs, po, pe, pt);
+        b.tiles_perm_count = (long)pt.size() / 2;
+        pt.push_back((int32_t)b.tiles_perm_count);          // the count rides behind the list
+        const size_t words = po.size() + pe.size() + pt.size();
+        if (!b.h_pack_done) FG_CUDA(cudaEventCreateWithFlags(&b.h_pack_done, cudaEventDisableTiming));
+        else FG_CUDA(cudaEventSynchronize(b.h_pack_done));   // the previous upload of this batch has left the staging block
+        if (words > b.h_pack_cap)
+        {
+            if (b.h_pack) cudaFreeHost(b.h_pack);
+            b.h_pack = nullptr; b.h_pack_cap = 0;
+            FG_CUDA(cudaMallocHost(&b.h_pack, sizeof(int32_t) * (words + words / 4)));
+            b.h_pack_cap = words + words / 4;
+        }
+        int32_t* h = b.h_pack;
+        std::memcpy(h, po.data(), sizeof(int32_t) * po.size());
+        std::memcpy(h + po.size(), pe.data(), sizeof(int32_t) * pe.size());
+        std::memcpy(h + po.size() + pe.size(), pt.data(), sizeof(int32_t) * pt.size());
+        FG_TRY(copy_in(b.node_off_perm, h, sizeof(int32_t) * po.size(), s));
+        FG_TRY(copy_in(b.edge_off_perm, h + po.size(), sizeof(int32_t) * pe.size(), s));
+        FG_TRY(copy_in(b.tiles_perm, h + po.size() + pe.size(), sizeof(int32_t) * pt.size(), s));
+        FG_CUDA(cudaEventRecord(b.h_pack_done, s));
+        b.has_perm = true;
+    }
     return 0;
+}
+
+// Tile packing.  The GIN and PNA layer kernels work on tiles of whole graphs, at most 128 rows each (prep.cu).  Closing a tile whenever
+// the next graph does not fit fills the tiles of a molecule batch to ~89 %; re-ordering the graphs inside windows of 256 by best-fit
+// decreasing fills them to ~98 %, i.e. 9 % fewer tiles for every layer launch.  The order only decides WHERE a graph's rows live in
+// HBM (node_off_perm / edge_off_perm, indexed by the caller's graph number): inputs are read and predictions written in caller order.
+// O(G) on the host, hidden behind the upload it precedes.
+void pack_graphs(const int32_t* nn, const int32_t* ne, int G, std::vector<int32_t>& node_off, std::vector<int32_t>& edge_off, std::vector<int32_t>& tiles)
+{
+    constexpr int W = 256, T = 128;
+    node_off.assign((size_t)G + 1, 0);
+    edge_off.assign((size_t)G + 1, 0);
+    tiles.clear();
+    tiles.reserve((size_t)G / 4 + 16);
+    int32_t pos = 0, epos = 0;
+    int order[W], bin_of[W], bin_count[W + 1];
+    static thread_local std::vector<int> by_cap[T + 1];     // bins with exactly c free rows
+    for (int w0 = 0; w0 < G; w0 += W)
+    {
+        const int m = std::min(W, G - w0);
+        // graphs above a tile first, in caller order, as runs of "external" tiles (bit 30); then the others by size, largest first
+        int cnt[T + 2] = {0};
+        for (int i = 0; i < m; i++)
+        {
+            const int n = nn[w0 + i];
+            if (n > T)
+            {
+                node_off[w0 + i] = pos; edge_off[w0 + i] = epos;
+                for (int r = 0; r < n; r += T) { tiles.push_back(pos + r); tiles.push_back(std::min(T, n - r) | (1 << 30)); }
+                pos += n; epos += ne[w0 + i];
+            }
+            else cnt[T - n]++;                              // bucket 0 = size 128 ... bucket 128 = size 0
+        }
+        int start[T + 2];
+        start[0] = 0;
+        for (int c = 0; c <= T; c++) start[c + 1] = start[c] + cnt[c];
+        const int small = start[T + 1];
+        for (int i = 0; i < m; i++) { const int n = nn[w0 + i]; if (n <= T) order[start[T - n]++] = i; }
+        // best fit: the fullest bin that still takes the graph
+        uint64_t mask[3] = {0, 0, 0};                       // capacities 0..128 with a bin
+        int bins = 0;
+        for (int k = 0; k < small; k++)
+        {
+            const int i = order[k], n = nn[w0 + i];
+            int c = -1;
+            if (n > 0)
+                for (int word = n >> 6, bit = n & 63; word < 3; word++, bit = 0)
+                {
+                    const uint64_t mm = mask[word] & (~0ull << bit);
+                    if (mm) { c = word * 64 + __builtin_ctzll(mm); break; }
+                }
+            int b;
+            if (n == 0) b = bins ? 0 : -1;                   // an empty graph takes no rows: anywhere
+            else if (c >= 0)
+            {
+                b = by_cap[c].back(); by_cap[c].pop_back();
+                if (by_cap[c].empty()) mask[c >> 6] &= ~(1ull << (c & 63));
+            }
+            else { b = bins++; c = T; }
+            if (n > 0)
+            {
+                const int rest = c - n;
+                by_cap[rest].push_back(b);
+                mask[rest >> 6] |= 1ull << (rest & 63);
+            }
+            bin_of[k] = b;
+        }
+        for (int c = 0; c <= T; c++) by_cap[c].clear();
+        // lay the bins out one after the other (stable inside a bin)
+        int bstart[W + 2], fill[W + 1], members[W];
+        for (int q = 0; q <= bins; q++) bin_count[q] = 0;
+        for (int k = 0; k < small; k++) if (bin_of[k] >= 0) bin_count[bin_of[k]]++;
+        bstart[0] = 0;
+        for (int q = 0; q < bins; q++) { bstart[q + 1] = bstart[q] + bin_count[q]; fill[q] = bstart[q]; }
+        for (int k = 0; k < small; k++) if (bin_of[k] >= 0) members[fill[bin_of[k]]++] = k;
+        for (int q = 0; q < bins; q++)
+        {
+            const int first = pos;
+            for (int idx = bstart[q]; idx < bstart[q + 1]; idx++)
+            {
+                const int g = w0 + order[members[idx]];
+                node_off[g] = pos; edge_off[g] = epos;
+                pos += nn[g]; epos += ne[g];
+            }
+            if (pos > first) { tiles.push_back(first); tiles.push_back(pos - first); }
+        }
+        for (int k = 0; k < small; k++)
+            if (bin_of[k] < 0) { const int g = w0 + order[k]; node_off[g] = pos; edge_off[g] = epos; epos += ne[g]; }      // empty graphs of a window without bins
+    }
+    node_off[G] = pos; edge_off[G] = epos;
 }
 
 // load_graph + the full forward of `model` on a resident batch, all on stream `s`
@@ -695,7 +821,10 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     ctx->opt.aux = ctx->opt.embed_overlap ? ctx->aux_stream : nullptr;
     ctx->opt.ev_fork = ctx->ev_fork; ctx->opt.ev_join = ctx->ev_join;
     if (ctx->opt.aux) FG_CUDA(cudaEventRecord(ctx->ev_fork, s));
-    int rc = prep_batch(b, flags, s, &ctx->last_launches);
+    // graphs re-ordered for tile packing: not for dense batches, whose GIN layers go through the staged gather (it walks graphs in caller order)
+    const bool dense = (ctx->opt.gin_staged < 0) ? (b.total_edges >= 6 * b.total_nodes) : (ctx->opt.gin_staged != 0);
+    const bool use_perm = ctx->opt.pack_graphs && !(model == MODEL_GIN && dense);
+    int rc = prep_batch(b, flags, s, &ctx->last_launches, use_perm);
     b.has_attr = keep_attr;
     FG_TRY(rc);
     ctx->timer.marks = 0;

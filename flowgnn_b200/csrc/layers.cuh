@@ -187,7 +187,7 @@ constexpr int EMB4_B = 119, EMB4_C = EMB4_B + 48, EMB4_E = EMB4_C + 120;
 
 template <int DIM>
 __global__ void __launch_bounds__(256) embed4_kernel(const int* __restrict__ feat, const float* __restrict__ table9, const float* __restrict__ table4,
-                                                     float* __restrict__ h, long num_nodes)
+                                                     float* __restrict__ h, long num_nodes, const int* __restrict__ node_map = nullptr)
 {
     constexpr int Q = DIM / 4;
     const unsigned full = 0xffffffffu;
@@ -202,7 +202,13 @@ __global__ void __launch_bounds__(256) embed4_kernel(const int* __restrict__ fea
     per += per & 1;
     const long v_end = min(num_nodes, (warp + 1) * per);
     long v = warp * per;
-    auto load_feat = [&](long vv) { const long node = vv + (lane >> 4); return (fl < ND_FEATURE && node < v_end) ? __ldg(feat + node * ND_FEATURE + fl) : 0; };
+    // node_map (graphs re-ordered for tile packing, prep.cu): row v of h is the caller's node node_map[v]
+    auto load_feat = [&](long vv) {
+        const long node = vv + (lane >> 4);
+        if (!(fl < ND_FEATURE && node < v_end)) return 0;
+        const long src = node_map ? (long)__ldg(node_map + node) : node;
+        return __ldg(feat + src * ND_FEATURE + fl);
+    };
     int f_next = v < v_end ? load_feat(v) : 0;
     for (; v < v_end; v += 2)
     {
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(256) embed4_kernel(const int* __restrict__ fea
                     s[i] = make_float4(((a.x + bb.x) + c.x) + e.x, ((a.y + bb.y) + c.y) + e.y, ((a.z + bb.z) + c.z) + e.z, ((a.w + bb.w) + c.w) + e.w);
                 }
                 else
-                    s[i] = embed_chunk<DIM>(feat + (v + i) * ND_FEATURE, table9, concat_table_offsets(), lane);
+                    s[i] = embed_chunk<DIM>(feat + (node_map ? (long)__ldg(node_map + v + i) : v + i) * ND_FEATURE, table9, concat_table_offsets(), lane);
             }
         }
 #pragma unroll

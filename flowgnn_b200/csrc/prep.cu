@@ -106,7 +106,10 @@ constexpr int CSR_NCAP_SMALL = 128;
 // tables (12 KB per warp, 16 warps per SM); each kernel skips the graphs of the other.
 
 struct CsrParams {
-    const int* nn; const int* ne; const int* node_off; const int* edge_off;
+    const int* nn; const int* ne; const int* node_off; const int* edge_off;      // where the graph's rows / in-edges are WRITTEN
+    const int* node_in_off; const int* edge_in_off;                                // where its inputs are READ (caller order); the same arrays
+                                                                                   // unless the graphs are re-ordered for tile packing (api.cu)
+    int* node_map;                   // [N] caller-order node index of every (re-ordered) row, or nullptr
     const int* edge_list; const int* edge_attr; const float* node_eigen;
     int* in_ptr; int* src; uint8_t* code; float* edge_w; int* out_deg; float* node_w0; float* node_w1; int4* row_desc;
     int* sort_tmp; int* status;
@@ -145,14 +148,17 @@ __device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int n
     const int lane = threadIdx.x & 31;
     const int n = p.nn[g], e = p.ne[g];
     const int nb = p.node_off[g], eb = p.edge_off[g];
-    if (g == p.num_graphs - 1 && lane == 0) p.in_ptr[nb + n] = eb + e;
+    const int nb_in = p.node_in_off[g], eb_in = p.edge_in_off[g];
+    if (nb + n == p.total_nodes && n > 0 && lane == 0) p.in_ptr[nb + n] = eb + e;      // the graph that ends the (possibly re-ordered) batch
+    if (p.node_map)
+        for (int i = lane; i < n; i += 32) p.node_map[nb + i] = nb_in + i;
     if (n > ncap || n < 0 || e < 0)
     {
         if (lane == 0) atomicOr(p.status, 1);
         neutralise_graph(p, nb, n, eb, e);
         return;
     }
-    const int2* edges = reinterpret_cast<const int2*>(p.edge_list) + eb;
+    const int2* edges = reinterpret_cast<const int2*>(p.edge_list) + eb_in;
     const unsigned full = 0xffffffffu;
 
     for (int i = lane; i < n; i += 32) { pu[i] = 0; pv[i] = 0; }
@@ -232,7 +238,7 @@ __device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int n
             p.src[pos] = nb + uv.x;
             if (p.has_attr)
             {
-                const int* a = p.edge_attr + 3 * (size_t)(eb + i);
+                const int* a = p.edge_attr + 3 * (size_t)(eb_in + i);
                 const int a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
                 // bond features outside the vocabulary {5, 6, 2} (GIN/src/host_load.cc:5-6) would alias another triple
                 // or index past the combined table: reject the batch (code 0 keeps the layer kernels in bounds)
@@ -249,7 +255,7 @@ __device__ __forceinline__ void build_graph_csr(const CsrParams& p, int g, int n
             }
             else if (p.flags & PREP_DGN_EIG)
             {
-                const float* eig = p.node_eigen + 4 * (size_t)nb;
+                const float* eig = p.node_eigen + 4 * (size_t)nb_in;
                 p.edge_w[pos] = __fsub_rn(__ldg(eig + 4 * uv.x + 1), __ldg(eig + 4 * uv.y + 1));
             }
             __syncwarp(mask);
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(256) sort_tile_rows_kernel(const int2* __restr
 
 }  // namespace
 
-int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches)
+int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bool use_perm)
 {
     const int G = b.num_graphs;
     if (G <= 0) return 0;
@@ -521,8 +527,31 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches)
     }
     FG_CUDA(cudaMemsetAsync(b.status.ptr, 0, sizeof(int), stream));
 
+    // Re-ordered graphs (api.cu::pack_graphs, computed on the host at upload): the rows of graph g are written at node_off_perm[g],
+    // its inputs are still read at the caller's offsets; the tile list came with the upload.  Everything downstream uses node_off.
+    const bool perm = use_perm && b.has_perm && (flags & PREP_TILES);
+    b.perm_active = perm;
     int nl = 1;
-    if (flags & PREP_TILES)
+    if (perm)
+    {
+        FG_TRY(b.node_off_in.reserve(sizeof(int) * (size_t)(G + 1)));
+        FG_TRY(b.edge_off_in.reserve(sizeof(int) * (size_t)(G + 1)));
+    }
+    int* scan_node = perm ? b.node_off_in.as<int>() : b.node_off.as<int>();
+    int* scan_edge = perm ? b.edge_off_in.as<int>() : b.edge_off.as<int>();
+    if (perm)
+    {
+        FG_CUDA(cudaMemcpyAsync(b.node_off.ptr, b.node_off_perm.ptr, sizeof(int) * (size_t)(G + 1), cudaMemcpyDeviceToDevice, stream));
+        FG_CUDA(cudaMemcpyAsync(b.edge_off.ptr, b.edge_off_perm.ptr, sizeof(int) * (size_t)(G + 1), cudaMemcpyDeviceToDevice, stream));
+        b.max_tiles = b.tiles_perm_count;
+        FG_TRY(b.tiles.reserve(sizeof(int2) * (size_t)std::max<long>(b.max_tiles, 1)));
+        FG_TRY(b.tile_count.reserve(sizeof(int)));
+        FG_CUDA(cudaMemcpyAsync(b.tiles.ptr, b.tiles_perm.ptr, sizeof(int2) * (size_t)b.max_tiles + sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        FG_CUDA(cudaMemcpyAsync(b.tile_count.ptr, b.tiles_perm.as<char>() + sizeof(int2) * (size_t)b.max_tiles, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        FG_TRY(b.node_map.reserve(sizeof(int) * (size_t)(b.total_nodes + 1)));
+        scan_offsets_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.nums_of_edges.as<int>(), scan_node, scan_edge, G);
+    }
+    else if (flags & PREP_TILES)
     {
         // upper bound: a tile closes at most once per graph, per 128 rows of a large graph and per packing chunk
         b.max_tiles = (long)G + b.total_nodes / TILE_ROWS + PACK_THREADS + 1;
@@ -539,6 +568,8 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches)
     CsrParams p;
     p.nn = b.nums_of_nodes.as<int>(); p.ne = b.nums_of_edges.as<int>();
     p.node_off = b.node_off.as<int>(); p.edge_off = b.edge_off.as<int>();
+    p.node_in_off = scan_node; p.edge_in_off = scan_edge;
+    p.node_map = perm ? b.node_map.as<int>() : nullptr;
     p.edge_list = b.edge_list.as<int>(); p.edge_attr = b.edge_attr.as<int>(); p.node_eigen = b.node_eigen.as<float>();
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>(); p.edge_w = b.edge_w.as<float>();
     p.out_deg = b.out_deg.as<int>(); p.node_w0 = b.node_w0.as<float>(); p.node_w1 = b.node_w1.as<float>();
