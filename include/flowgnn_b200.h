@@ -159,6 +159,8 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx);
  *                  FFMA kernels; environment FLOWGNN_B200_TC_ALL=0/1 sets both defaults
  *   "gcn_fused", "dgn_fused"  default 1: GCN step / DGN layer as ONE launch (fused_tc.cuh: the aggregation is the A producer inside the
  *                          tcgen05 GEMM kernel); 0: round 1's aggregate + GEMM launches (needs "gcn_tc" / "dgn_tc" = 1)
+ *   "pack_graphs"  default 1: GIN / PNA store the graphs' rows in an order (windows of 256, best fit) that fills the 128-row tiles of the
+ *                  layer kernels to ~98 %; inputs are read and `out` is written in the caller's order either way
  *   "gat_tc"       default 1: GAT's two dense maps per layer as ONE tcgen05 GEMM inside a fused gather kernel (gat_tc.cu); 0: the FP32 kernel
  *   "embed_overlap" default 1: GIN / PNA / DGN run the input embedding on a second stream, concurrent with the CSR / tile build
  *   "gat_node_offset_bug"  default 1
