@@ -72,6 +72,29 @@ def test_gat_tensor_core_path_matches_reference(ds, ctx, weights, datasets, gold
     assert_parity(tc, ffma, tol=2e-5, what=f"gat tcgen05 vs fp32/{ds}")
 
 
+@pytest.mark.parametrize("model", ["gin", "pna"])
+def test_tile_packing_does_not_change_a_bit(model, ctx, weights, datasets):
+    """Option pack_graphs (default 1): the graphs' rows are stored in an order that fills the 128-row tiles (best fit inside windows of 256
+    graphs, computed on the host at upload).  A row's result does not depend on which rows share its tile, so the predictions must be
+    BIT-identical with and without it -- on molecules, and on a batch that mixes empty graphs, single atoms, graphs of exactly 128 and
+    129 nodes and graphs above the shared-memory tables."""
+    from flowgnn_b200.dataset import Batch, concat
+    rng = np.random.default_rng(3)
+    z = Batch(np.array([0]), np.array([0]), np.zeros((0, 9), np.int32), np.zeros((0, 2), np.int32), np.zeros((0, 3), np.int32), np.zeros((0, 4), np.float32))
+    mol = datasets["molhiv"]
+    mixed = concat([mol.slice(0, 300), z, _chain_graph(128, rng, True), _chain_graph(129, rng, True), mol.slice(300, 310), _chain_graph(1100, rng, True), z,
+                    _chain_graph(1, rng, True), mol.slice(310, 700)])
+    for b in (mol, mixed):
+        try:
+            ctx.set_option("pack_graphs", 0)
+            plain = ctx.run(model, b, weights[model])
+            ctx.set_option("pack_graphs", 1)
+            packed = ctx.run(model, b)
+        finally:
+            ctx.set_option("pack_graphs", 1)
+        assert np.array_equal(plain.view(np.int32), packed.view(np.int32))
+
+
 # Measured max scaled errors of the default kernels against the reference outputs (tools/margins_probe.py, profiles/r2w_parity_margins.txt),
 # pinned at about twice the measurement: the contract is 1e-4, a regression that eats the margin should fail here first.
 PINNED_MARGIN = {
