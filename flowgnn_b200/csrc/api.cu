@@ -629,7 +629,8 @@ int flowgnn_b200_load_weights(flowgnn_ctx* ctx, int model, const float* const* w
 
 namespace {
 
-void pack_graphs(const int32_t* nn, const int32_t* ne, int G, std::vector<int32_t>& node_off, std::vector<int32_t>& edge_off, std::vector<int32_t>& tiles);
+void pack_graphs(const int32_t* nn, const int32_t* ne, int G, std::vector<int32_t>& node_off, std::vector<int32_t>& edge_off, std::vector<int32_t>& tiles,
+                 std::vector<int32_t>& node_in, std::vector<int32_t>& edge_in);
 
 int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_nodes, int64_t total_edges, const int32_t* nums_of_nodes,
                 const int32_t* nums_of_edges, const int32_t* node_feature, const int32_t* edge_list, const int32_t* edge_attr,
@@ -677,11 +678,11 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
     b.has_perm = false;
     if (num_graphs > 0 && total_nodes > 0)
     {
-        static thread_local std::vector<int32_t> po, pe, pt;
-        pack_graphs(nums_of_nodes, nums_of_edges, num_graphs, po, pe, pt);
+        static thread_local std::vector<int32_t> po, pe, pt, pin, pie;
+        pack_graphs(nums_of_nodes, nums_of_edges, num_graphs, po, pe, pt, pin, pie);
         b.tiles_perm_count = (long)pt.size() / 2;
         pt.push_back((int32_t)b.tiles_perm_count);          // the count rides behind the list
-        const size_t words = po.size() + pe.size() + pt.size();
+        const size_t words = po.size() + pe.size() + pt.size() + pin.size() + pie.size();
         if (!b.h_pack_done) FG_CUDA(cudaEventCreateWithFlags(&b.h_pack_done, cudaEventDisableTiming));
         else FG_CUDA(cudaEventSynchronize(b.h_pack_done));   // the previous upload of this batch has left the staging block
         if (words > b.h_pack_cap)
@@ -698,6 +699,11 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
         FG_TRY(copy_in(b.node_off_perm, h, sizeof(int32_t) * po.size(), s));
         FG_TRY(copy_in(b.edge_off_perm, h + po.size(), sizeof(int32_t) * pe.size(), s));
         FG_TRY(copy_in(b.tiles_perm, h + po.size() + pe.size(), sizeof(int32_t) * pt.size(), s));
+        int32_t* h2 = h + po.size() + pe.size() + pt.size();
+        std::memcpy(h2, pin.data(), sizeof(int32_t) * pin.size());
+        std::memcpy(h2 + pin.size(), pie.data(), sizeof(int32_t) * pie.size());
+        FG_TRY(copy_in(b.node_off_in, h2, sizeof(int32_t) * pin.size(), s));
+        FG_TRY(copy_in(b.edge_off_in, h2 + pin.size(), sizeof(int32_t) * pie.size(), s));
         FG_CUDA(cudaEventRecord(b.h_pack_done, s));
         b.has_perm = true;
     }
@@ -709,8 +715,16 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
 // decreasing fills them to ~98 %, i.e. 9 % fewer tiles for every layer launch.  The order only decides WHERE a graph's rows live in
 // HBM (node_off_perm / edge_off_perm, indexed by the caller's graph number): inputs are read and predictions written in caller order.
 // O(G) on the host, hidden behind the upload it precedes.
-void pack_graphs(const int32_t* nn, const int32_t* ne, int G, std::vector<int32_t>& node_off, std::vector<int32_t>& edge_off, std::vector<int32_t>& tiles)
+void pack_graphs(const int32_t* nn, const int32_t* ne, int G, std::vector<int32_t>& node_off, std::vector<int32_t>& edge_off, std::vector<int32_t>& tiles,
+                 std::vector<int32_t>& node_in, std::vector<int32_t>& edge_in)
 {
+    // caller-order offsets (what scan_offsets_kernel computes on the device when the graphs are not re-ordered)
+    node_in.resize((size_t)G + 1); edge_in.resize((size_t)G + 1);
+    {
+        int32_t a = 0, c = 0;
+        for (int g = 0; g < G; g++) { node_in[g] = a; edge_in[g] = c; a += nn[g]; c += ne[g]; }
+        node_in[G] = a; edge_in[G] = c;
+    }
     constexpr int W = 256, T = 128;
     node_off.assign((size_t)G + 1, 0);
     edge_off.assign((size_t)G + 1, 0);

@@ -80,6 +80,7 @@ enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2, PREP_ROW_DESC = 4, PREP_TI
 
 // graph preprocessing: offsets scan + per-graph CSR build (prep.cu)
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches = nullptr, bool use_perm = false);
+int node_map_launch(DeviceBatch& b, cudaStream_t stream);
 
 // ---- per-model device weights, repacked once by load_weights (api.cu) ----------------------------
 struct GinWeights {

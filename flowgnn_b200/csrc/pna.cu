@@ -228,8 +228,8 @@ int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int 
     int nl = 0;
     {
         const int blocks = (int)std::min<long>(ceil_div<long>(N, 8), (long)sm_count * 8);      // 8 warps per block, a warp per node
-        // overlaps the CSR / tile build (api.cu::compute_on) -- unless the graphs are re-ordered: the row -> caller-node map is the build's output
-        const cudaStream_t es = b.perm_active ? s : embed_stream(opt, s);
+        const cudaStream_t es = embed_stream(opt, s);      // overlaps the CSR / tile build (api.cu::compute_on)
+        if (b.perm_active) { FG_TRY(node_map_launch(b, es)); nl++; }      // re-ordered graphs: row -> caller-order node
         embed4_kernel<D><<<blocks, 256, 0, es>>>(b.node_feature.as<int>(), w.ne_table.as<float>(), w.ne_table4.as<float>(), h[0], N,
                                                  b.perm_active ? b.node_map.as<int>() : nullptr);
         FG_CUDA(cudaGetLastError());

@@ -532,11 +532,6 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bo
     const bool perm = use_perm && b.has_perm && (flags & PREP_TILES);
     b.perm_active = perm;
     int nl = 1;
-    if (perm)
-    {
-        FG_TRY(b.node_off_in.reserve(sizeof(int) * (size_t)(G + 1)));
-        FG_TRY(b.edge_off_in.reserve(sizeof(int) * (size_t)(G + 1)));
-    }
     int* scan_node = perm ? b.node_off_in.as<int>() : b.node_off.as<int>();
     int* scan_edge = perm ? b.edge_off_in.as<int>() : b.edge_off.as<int>();
     if (perm)
@@ -546,10 +541,9 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bo
         b.max_tiles = b.tiles_perm_count;
         FG_TRY(b.tiles.reserve(sizeof(int2) * (size_t)std::max<long>(b.max_tiles, 1)));
         FG_TRY(b.tile_count.reserve(sizeof(int)));
-        FG_CUDA(cudaMemcpyAsync(b.tiles.ptr, b.tiles_perm.ptr, sizeof(int2) * (size_t)b.max_tiles + sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        if (b.max_tiles) FG_CUDA(cudaMemcpyAsync(b.tiles.ptr, b.tiles_perm.ptr, sizeof(int2) * (size_t)b.max_tiles, cudaMemcpyDeviceToDevice, stream));
         FG_CUDA(cudaMemcpyAsync(b.tile_count.ptr, b.tiles_perm.as<char>() + sizeof(int2) * (size_t)b.max_tiles, sizeof(int), cudaMemcpyDeviceToDevice, stream));
-        FG_TRY(b.node_map.reserve(sizeof(int) * (size_t)(b.total_nodes + 1)));
-        scan_offsets_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.nums_of_nodes.as<int>(), b.nums_of_edges.as<int>(), scan_node, scan_edge, G);
+        nl = 0;                                             // the caller-order offsets came with the upload too: no scan launch
     }
     else if (flags & PREP_TILES)
     {
@@ -569,7 +563,7 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bo
     p.nn = b.nums_of_nodes.as<int>(); p.ne = b.nums_of_edges.as<int>();
     p.node_off = b.node_off.as<int>(); p.edge_off = b.edge_off.as<int>();
     p.node_in_off = scan_node; p.edge_in_off = scan_edge;
-    p.node_map = perm ? b.node_map.as<int>() : nullptr;
+    p.node_map = nullptr;                                   // written by node_map_launch (on the embedding's stream)
     p.edge_list = b.edge_list.as<int>(); p.edge_attr = b.edge_attr.as<int>(); p.node_eigen = b.node_eigen.as<float>();
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>(); p.edge_w = b.edge_w.as<float>();
     p.out_deg = b.out_deg.as<int>(); p.node_w0 = b.node_w0.as<float>(); p.node_w1 = b.node_w1.as<float>();
@@ -600,6 +594,31 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bo
         nl++;
     }
     if (launches) *launches += nl;
+    return 0;
+}
+
+namespace {
+// row -> caller-order node index of a re-ordered batch: a warp per graph
+__global__ void __launch_bounds__(256) node_map_kernel(const int* __restrict__ nn, const int* __restrict__ node_off, const int* __restrict__ node_in_off,
+                                                       int* __restrict__ node_map, int num_graphs)
+{
+    const int lane = threadIdx.x & 31;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < num_graphs; g += (gridDim.x * blockDim.x) >> 5)
+    {
+        const int n = __ldg(nn + g), nb = __ldg(node_off + g), nb_in = __ldg(node_in_off + g);
+        for (int i = lane; i < n; i += 32) node_map[nb + i] = nb_in + i;
+    }
+}
+}  // namespace
+
+// For the embedding kernels of a re-ordered batch.  Reads only what came with the upload (node_off_perm, node_off_in), so it can run on
+// the embedding's stream next to the CSR build.
+int node_map_launch(DeviceBatch& b, cudaStream_t stream)
+{
+    FG_TRY(b.node_map.reserve(sizeof(int) * (size_t)(b.total_nodes + 1)));
+    node_map_kernel<<<std::max(1, std::min(ceil_div(b.num_graphs, 8), 148 * 8)), 256, 0, stream>>>(b.nums_of_nodes.as<int>(), b.node_off_perm.as<int>(),
+                                                                                                  b.node_off_in.as<int>(), b.node_map.as<int>(), b.num_graphs);
+    FG_CUDA(cudaGetLastError());
     return 0;
 }
 
