@@ -315,7 +315,9 @@ __global__ void __launch_bounds__(NT, 1) pna_layer_fused_kernel(const __grid_con
                     // mean = S / n;  std = sqrt(relu(Q / n - mean^2))  (PNA/src/node_embedding.cc:123-150), statement by statement
                     mean[j] = div_n(a.s[j]);
                     const float var = relu_f(__fsub_rn(div_n(a.q[j]), __fmul_rn(mean[j], mean[j])));
-                    sd[j] = var == 0.f ? 0.f : __fsqrt_rn(var);
+                    float sq;
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(var));      // <= 1 ulp from the IEEE root; the value goes through a bf16 split anyway
+                    sd[j] = var == 0.f ? 0.f : sq;
                     finite_probe = fmaf(a.s[j], 0.f, fmaf(a.q[j], 0.f, finite_probe));
                 }
                 // the stage's A block must be free (the MMAs of chunk g - 2 have read it)
