@@ -152,6 +152,13 @@ __host__ __device__ constexpr uint64_t desc_imm(uint32_t off, uint32_t lbo)
 {
     return (uint64_t)(((SMEM_BASE + off) >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
+// A chunks use the 128-byte-swizzle K-major layout (row = 128 contiguous bytes, 16-byte unit u of row r at u ^ (r % 8); 8-row groups
+// 1,024 bytes apart, a K = 16 step advances the start address by 32 bytes): the eight rows of a gather warp's store then fall into
+// eight different bank groups, where the no-swizzle layout (8-byte pieces at a 2,048-byte stride) cost a 2-way conflict per store
+__host__ __device__ constexpr uint64_t desc_imm_sw128(uint32_t off)
+{
+    return (uint64_t)(((SMEM_BASE + off) >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 template <int I, int N, typename F>
 __device__ __forceinline__ void static_for(F&& f)
 {
@@ -323,11 +330,12 @@ __global__ void __launch_bounds__(NT, 1) pna_layer_fused_kernel(const __grid_con
                 // the stage's A block must be free (the MMAs of chunk g - 2 have read it)
                 if (g >= 2) mbar_wait_park(&bar[BAR_A_EMPTY + s], ((g >> 1) - 1) & 1);
                 // aggregator_t order (PNA/src/dcl.h:29-35): mean, min, max, std; kk = aggregate * 16 + 4 q + j inside the chunk
-                const uint32_t a_row = smem_u32(smem + Smem::A + s * A_BLOCK) + (uint32_t)(live ? R : slot) * 16 + (q & 1) * 8;
+                const uint32_t arow = (uint32_t)(live ? R : slot);
+                const uint32_t a_row = smem_u32(smem + Smem::A + s * A_BLOCK) + arow * 128 + (q & 1) * 8;
                 auto put = [&](int ag, const float (&x)[4]) {
                     uint32_t h0 = 0, l0 = 0, h1 = 0, l1 = 0;
                     if (live) { split2(x[0], x[1], h0, l0); split2(x[2], x[3], h1, l1); }
-                    const uint32_t dst = a_row + (uint32_t)(2 * ag + (q >> 1)) * LBO_A;
+                    const uint32_t dst = a_row + ((((uint32_t)(2 * ag + (q >> 1))) ^ (arow & 7)) << 4);
                     sts_v2(dst, h0, h1);
                     sts_v2(dst + A_HALF, l0, l1);
                 };
@@ -411,8 +419,8 @@ __global__ void __launch_bounds__(NT, 1) pna_layer_fused_kernel(const __grid_con
                     tc::fence_after_sync();
                     static_for<0, KH / 16>([&](auto JJ) {
                         constexpr int jj = decltype(JJ)::value, j = h * (KH / 16) + jj;                  // k-step inside the A chunk
-                        constexpr uint64_t a_hi = desc_imm(Smem::A + S * A_BLOCK + 2 * j * LBO_A, LBO_A);
-                        constexpr uint64_t a_lo = desc_imm(Smem::A + S * A_BLOCK + A_HALF + 2 * j * LBO_A, LBO_A);
+                        constexpr uint64_t a_hi = desc_imm_sw128(Smem::A + S * A_BLOCK + 32 * j);
+                        constexpr uint64_t a_lo = desc_imm_sw128(Smem::A + S * A_BLOCK + A_HALF + 32 * j);
                         constexpr uint64_t b_hi = desc_imm(Smem::W + ws * W_BLOCK + 2 * jj * LBO_B, LBO_B);
                         constexpr uint64_t b_lo = desc_imm(Smem::W + ws * W_BLOCK + W_HALF + 2 * jj * LBO_B, LBO_B);
                         mma_ss_elect(d_tmem, a_hi, b_hi, IDESC, !(first && j == 0));
