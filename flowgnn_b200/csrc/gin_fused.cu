@@ -123,7 +123,10 @@ __device__ __forceinline__ unsigned long long gtime()
 __device__ __forceinline__ int2 tile_of(const GinFusedParams& p, int t, int ntiles)
 {
     int2 v = make_int2(0, 0);
-    if (t < ntiles) asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p.tiles + t));
+    if (t >= ntiles) return v;
+    // no tile list: the node MLP alone (second launch of a dense-graph layer) needs no graph alignment -- plain 128-row tiles, all full
+    if (!p.tiles) return make_int2(t * TM, min(TM, p.num_nodes - t * TM));
+    asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p.tiles + t));
     return v;
 }
 
@@ -381,7 +384,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) gin_layer_fus
 #ifdef FG_TC2_TRACE
     if (p.trace && tid == 0) p.trace[2048 + blockIdx.x] = gtime();             // per-CTA loop start / end (tools/trace_fused.py)
 #endif
-    const int ntiles = __ldg(p.tile_count);
+    const int ntiles = p.tiles ? __ldg(p.tile_count) : (p.num_nodes + TM - 1) / TM;
     if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[7] = (unsigned long long)ntiles;
     const int npt = (ntiles + 1) >> 1;                       // pair tiles
     // producer (one thread): the tile's feature rows + row descriptors -> buffer s (two bulk copies onto one barrier), its
@@ -768,7 +771,7 @@ int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer,
     p.h_in = h_in; p.h_out = h_out;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.code = b.code.as<uint8_t>();
     p.row_desc = mlp_only ? nullptr : b.row_desc_sorted.as<int4>();      // nullptr: every row without in-edges = the node MLP alone (dense graphs, gin.cu)
-    p.tiles = b.tiles.as<int2>(); p.tile_count = b.tile_count.as<int>();
+    p.tiles = mlp_only ? nullptr : b.tiles.as<int2>(); p.tile_count = b.tile_count.as<int>();
     p.ee_comb = w.ee_comb.as<float>() + (size_t)layer * ED_COMBOS * D;
     p.wpack = w.wpack2.as<unsigned char>() + (size_t)layer * 2 * W_BYTES;
     p.num_nodes = (int)b.total_nodes;
@@ -776,7 +779,8 @@ int gin_layer_fused_launch(const DeviceBatch& b, const GinWeights& w, int layer,
     p.mp_only = mp_only;
     p.head_w = head_w; p.node_dot = node_dot;
     p.trace = gin_tc2_trace_buffer;
-    const int pairs = (int)std::max<long>(1, std::min<long>((b.max_tiles + 1) / 2, sm_count / 2));
+    const long tiles_bound = mlp_only ? (b.total_nodes + TM - 1) / TM : b.max_tiles;
+    const int pairs = (int)std::max<long>(1, std::min<long>((tiles_bound + 1) / 2, sm_count / 2));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = Smem::BYTES; cfg.stream = s;
     cudaLaunchAttribute attr[1];
