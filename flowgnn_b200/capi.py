@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
     "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_compute", "flowgnn_b200_download",
     "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
-    "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host",
+    "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host", "flowgnn_b200_narrow_words",
 )
 
 
@@ -63,6 +63,8 @@ def load_library() -> ctypes.CDLL:
         lib.flowgnn_b200_last_layer_ms.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
         lib.flowgnn_b200_pin_host.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
         lib.flowgnn_b200_unpin_host.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_narrow_words.restype = ctypes.c_uint32
+        lib.flowgnn_b200_narrow_words.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -93,6 +95,15 @@ def pin_host(a: np.ndarray) -> None:
 
 def unpin_host(a: np.ndarray) -> None:
     _check(load_library().flowgnn_b200_unpin_host(a.ctypes.data), "unpin_host")
+
+
+def narrow_words(src: np.ndarray, width: int, threads: int = 1):
+    """The host-side step of the narrowed upload (option ``host_stage``): int32 words -> u8 / u16 with ``threads`` host threads.
+    Returns (narrowed array, OR of all source words).  No GPU is touched."""
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    dst = np.zeros(src.size, dtype=np.uint8 if width == 1 else np.uint16)
+    seen = load_library().flowgnn_b200_narrow_words(src.ctypes.data, src.size, int(width), dst.ctypes.data, int(threads))
+    return dst, int(seen)
 
 
 class Context:

@@ -36,6 +36,7 @@ struct DeviceBatch {
     DevBuf edge_list;                      // int32 [E][2], graph-local ids
     DevBuf edge_attr;                      // int32 [E][3]
     DevBuf node_eigen;                     // float [N][4]
+    DevBuf packed_in;                      // host-pointer entry points: one chunk's narrowed inputs (host_stage.h), widened by unpack_inputs_kernel
 
     // load_graph outputs: CSR by DESTINATION over global node ids, in-edges ordered (source, list order)
     DevBuf node_off, edge_off;             // int32 [G+1] first row / in-edge position of every graph (exclusive prefix sums in the order the rows are stored)
@@ -81,6 +82,8 @@ enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2, PREP_ROW_DESC = 4, PREP_TI
 // graph preprocessing: offsets scan + per-graph CSR build (prep.cu)
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches = nullptr, bool use_perm = false);
 int node_map_launch(DeviceBatch& b, cudaStream_t stream);
+int unpack_inputs_launch(const uint8_t* block, size_t off_edge, size_t off_attr, int32_t* feat, size_t n_feat, int32_t* edges, size_t n_edge,
+                         int32_t* attr, size_t n_attr, cudaStream_t stream);
 
 // ---- per-model device weights, repacked once by load_weights (api.cu) ----------------------------
 struct GinWeights {
@@ -169,6 +172,9 @@ struct RunOptions {
     // The input embedding needs only node_feature, the CSR / tile build only the edge lists: the embedding kernel runs on `aux`
     // between `ev_fork` (recorded on the compute stream before the build is launched) and `ev_join` (awaited before layer 0)
     int pack_graphs = 1;             // GIN, PNA: graphs re-ordered inside windows of 256 so that whole graphs fill the 128-row tiles (api.cu::pack_graphs)
+    int host_stage = -1;             // host-pointer entry points: inputs narrowed to u8 / u16 by a host thread pool into pinned memory (host_stage.h);
+                                     // mask of arrays (1 node_feature, 2 edge_list, 4 edge_attr), 0 off, -1: all when the caller's arrays are
+                                     // pageable, or page-locked with >= 8 host threads to spare for this GPU
     int embed_overlap = 1;           // GIN, PNA, DGN: the embedding launch on a second stream, concurrent with the CSR / tile build
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -622,4 +622,57 @@ int node_map_launch(DeviceBatch& b, cudaStream_t stream)
     return 0;
 }
 
+namespace {
+// Widen the narrowed inputs of the host-pointer entry points (host_stage.h) into the int32 arrays of the caller layout:
+// a thread takes four source values (one 4-byte / 8-byte load) and stores one int4, so a warp reads 128 / 256 contiguous
+// bytes and writes 512.  The three regions of the block start at multiples of 16 bytes and are padded to them.
+__global__ void __launch_bounds__(256) unpack_inputs_kernel(const uint8_t* __restrict__ block, size_t off_edge, size_t off_attr,
+                                                            int32_t* __restrict__ feat, size_t n_feat, int32_t* __restrict__ edges, size_t n_edge,
+                                                            int32_t* __restrict__ attr, size_t n_attr)
+{
+    const size_t ga = (n_feat + 3) / 4, gb = (n_edge + 3) / 4, gc = (n_attr + 3) / 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ga + gb + gc; g += stride)
+    {
+        int4 v;
+        int32_t* dst;
+        size_t left;
+        if (g >= ga && g < ga + gb)
+        {
+            const size_t k = g - ga;
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(block + off_edge) + k);
+            v = make_int4((int)(w.x & 0xFFFFu), (int)(w.x >> 16), (int)(w.y & 0xFFFFu), (int)(w.y >> 16));
+            dst = edges + 4 * k; left = n_edge - 4 * k;
+        }
+        else
+        {
+            const bool a = g < ga;
+            const size_t k = a ? g : g - ga - gb;
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(block + (a ? 0 : off_attr)) + k);
+            v = make_int4((int)(w & 0xFFu), (int)((w >> 8) & 0xFFu), (int)((w >> 16) & 0xFFu), (int)(w >> 24));
+            dst = (a ? feat : attr) + 4 * k; left = (a ? n_feat : n_attr) - 4 * k;
+        }
+        if (left >= 4) *reinterpret_cast<int4*>(dst) = v;
+        else
+        {
+            dst[0] = v.x;
+            if (left > 1) dst[1] = v.y;
+            if (left > 2) dst[2] = v.z;
+        }
+    }
+}
+}  // namespace
+
+// counts of 0 skip a region (that array was uploaded unchanged because it holds values outside the narrow range)
+int unpack_inputs_launch(const uint8_t* block, size_t off_edge, size_t off_attr, int32_t* feat, size_t n_feat, int32_t* edges, size_t n_edge,
+                         int32_t* attr, size_t n_attr, cudaStream_t stream)
+{
+    const size_t groups = (n_feat + 3) / 4 + (n_edge + 3) / 4 + (n_attr + 3) / 4;
+    if (!groups) return 0;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((groups + 255) / 256, 148 * 8));
+    unpack_inputs_kernel<<<blocks, 256, 0, stream>>>(block, off_edge, off_attr, feat, n_feat, edges, n_edge, attr, n_attr);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace fg

@@ -159,6 +159,12 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx);
  *                  FFMA kernels; environment FLOWGNN_B200_TC_ALL=0/1 sets both defaults
  *   "gcn_fused", "dgn_fused"  default 1: GCN step / DGN layer as ONE launch (fused_tc.cuh: the aggregation is the A producer inside the
  *                          tcgen05 GEMM kernel); 0: round 1's aggregate + GEMM launches (needs "gcn_tc" / "dgn_tc" = 1)
+ *   "host_stage"   default -1 (automatic): the Part-1 entry points narrow node_feature / edge_attr to one byte and edge_list to two bytes
+ *                  per value with a pool of host threads (FLOWGNN_B200_HOST_THREADS, default min(12, 3/4 of the usable cores /
+ *                  LOCAL_WORLD_SIZE)) into pinned memory, copy 9 B per node + 7 B per edge instead of 36 + 20, and widen them on the device;
+ *                  the caller's arrays may be pageable.  Value = mask of the arrays to narrow (1 node_feature, 2 edge_list, 4 edge_attr),
+ *                  0 = off; automatic = all three for pageable arrays, and for page-locked ones when 8 threads are available.  An array
+ *                  holding a value that does not fit is uploaded unchanged.  Results are bit-identical.  (FLOWGNN_B200_HOST_STAGE overrides.)
  *   "pack_graphs"  default 1: GIN / PNA store the graphs' rows in an order (windows of 256, best fit) that fills the 128-row tiles of the
  *                  layer kernels to ~98 %; inputs are read and `out` is written in the caller's order either way
  *   "gat_tc"       default 1: GAT's two dense maps per layer as ONE tcgen05 GEMM inside a fused gather kernel (gat_tc.cu); 0: the FP32 kernel
@@ -210,6 +216,13 @@ int flowgnn_b200_synchronize(flowgnn_ctx* ctx);
  * of chunk i+1 with the kernels of chunk i.  Pageable buffers work too, the copies are then staged by the driver. */
 int flowgnn_b200_pin_host(void* ptr, size_t bytes);
 int flowgnn_b200_unpin_host(void* ptr);
+
+/* The host-side step of the narrowed upload of the Part-1 entry points (option "host_stage"): dst[i] = the low `width` bytes
+ * (1 or 2) of src[i], computed by `threads` host threads (>= 1; the caller is one of them).  Returns the OR of all source
+ * words: bits above the narrow width mean a value did not fit, and the entry points then upload that array unchanged.
+ * Exported for tests and for callers that want to measure their host; no GPU is touched.  width outside {1, 2}: returns
+ * 0xFFFFFFFF and writes nothing. */
+uint32_t flowgnn_b200_narrow_words(const int32_t* src, size_t n, int width, void* dst, int threads);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,147 @@
+"""Narrowed upload of the host-pointer entry points (flowgnn_b200/csrc/host_stage.h, option ``host_stage``).
+
+The reference's kernel ABI passes int32 words for nine atom features per node, two graph-local node ids and three bond attributes
+per edge (GIN/src/dcl.h:61-67).  The entry points narrow them to u8 / u16 with a pool of host threads, copy the narrow block and
+widen it on the device.  CPU: the host-side step.  GPU: predictions are bit-identical with the step on and off, for pageable and
+page-locked callers, any thread count, and inputs that do not fit (those arrays travel unchanged)."""
+import os
+
+import numpy as np
+import pytest
+
+from flowgnn_b200 import capi
+
+
+def _lib():
+    if not os.path.isfile(capi.LIB_PATH):
+        pytest.skip("libflowgnn_b200.so not built (run __graft_entry__.build())")
+    return capi.load_library()
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+@pytest.mark.parametrize("width", [1, 2])
+@pytest.mark.parametrize("n", [0, 1, 5, 65536, 65537, 1_000_003])
+def test_narrow_words_matches_numpy(threads, width, n):
+    _lib()
+    rng = np.random.default_rng(n + width)
+    src = rng.integers(0, 256 if width == 1 else 65536, size=n, dtype=np.int32)
+    got, seen = capi.narrow_words(src, width, threads)
+    assert np.array_equal(got, src.astype(np.uint8 if width == 1 else np.uint16))
+    assert seen == (int(np.bitwise_or.reduce(src)) if n else 0)
+    assert seen & ~((1 << (8 * width)) - 1) == 0
+
+
+@pytest.mark.parametrize("bad", [-1, 256, 70000, np.iinfo(np.int32).min])
+def test_narrow_words_reports_values_that_do_not_fit(bad):
+    _lib()
+    src = np.zeros(200_000, dtype=np.int32)
+    src[123_456] = bad
+    for width in (1, 2):
+        _, seen = capi.narrow_words(src, width, 4)
+        fits = 0 <= bad < (1 << (8 * width))
+        assert (seen & ~((1 << (8 * width)) - 1) == 0) == fits
+
+
+def test_narrow_words_rejects_other_widths():
+    _lib()
+    assert capi.narrow_words(np.zeros(4, np.int32), 4, 1)[1] == 0xFFFFFFFF
+
+
+# ---- GPU --------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def ctx():
+    from flowgnn_b200.capi import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _run_entry(model, batch, w, stage, threads=None, chunks=None):
+    env = {"FLOWGNN_B200_HOST_STAGE": stage, "FLOWGNN_B200_HOST_THREADS": threads, "FLOWGNN_B200_CHUNKS": chunks}
+    old = {k: os.environ.get(k) for k in env}
+    try:
+        for k, v in env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        return capi.ReferenceCall(model, batch, w).run().copy()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["gin", "ginvn", "gcn", "gat", "pna", "dgn"])
+def test_narrowed_upload_is_bit_identical(model, weights, datasets):
+    from flowgnn_b200.dataset import synthetic_molecules
+    b = datasets["molhiv"].slice(0, 1500) if model != "dgn" else synthetic_molecules(1500, "molhiv", seed=5, with_eigen=True)
+    if model == "ginvn":
+        b = datasets["hep10k"].slice(0, 200)
+    want = _run_entry(model, b, weights[model], stage=0)
+    assert np.isfinite(want).sum() > 0.9 * want.size
+    # FLOWGNN_B200_HOST_STAGE is a mask of the arrays to narrow: 1 node_feature, 2 edge_list, 4 edge_attr
+    for threads, mask in ((1, 7), (5, 7), (3, 5), (2, 2), (4, 1)):
+        got = _run_entry(model, b, weights[model], stage=mask, threads=threads)
+        assert np.array_equal(got.view(np.int32), want.view(np.int32)), (model, threads, mask)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [1, 2, 3, 5])
+def test_narrowed_upload_chunked_large_batch(chunks, ctx, weights, datasets):
+    """A batch large enough for the chunked pipeline (two pinned blocks and two device batches alternate), every chunk count;
+    default mode = pageable numpy arrays -> narrowed; against the device-resident one-shot path."""
+    b = datasets["molpcba"].tile(20000)
+    want = ctx.run("gin", b, weights["gin"])
+    got = _run_entry("gin", b, weights["gin"], stage=None, chunks=chunks)
+    again = _run_entry("gin", b, weights["gin"], stage=5, chunks=chunks)
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    assert np.array_equal(again.view(np.int32), want.view(np.int32))
+
+
+@pytest.mark.gpu
+def test_narrowed_upload_with_pinned_caller_memory(weights, datasets):
+    b = datasets["molhiv"].slice(0, 2000)
+    want = _run_entry("gin", b, weights["gin"], stage=0)
+    arrays = [b.node_feature, b.edge_list, b.edge_attr]
+    for a in arrays:
+        capi.pin_host(a)
+    try:
+        for stage in (0, 7, 5, None):
+            got = _run_entry("gin", b, weights["gin"], stage=stage)
+            assert np.array_equal(got.view(np.int32), want.view(np.int32)), stage
+    finally:
+        for a in arrays:
+            capi.unpin_host(a)
+
+
+@pytest.mark.gpu
+def test_inputs_that_do_not_fit_travel_unchanged(weights, datasets):
+    """Out-of-vocabulary node features (the embedding's fallback path) and ids that are not node ids: the array with such a value is
+    uploaded as int32, so the device sees exactly what the caller passed -- same predictions, same error."""
+    import copy
+    b = copy.deepcopy(datasets["molhiv"].slice(0, 800))
+    b.node_feature[17, 3] = 300            # does not fit a byte; out of vocabulary either way
+    b.node_feature[400, 0] = -2
+    want = _run_entry("gin", b, weights["gin"], stage=0)
+    got = _run_entry("gin", b, weights["gin"], stage=7, threads=3)
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    # an edge id beyond 16 bits is an invalid edge: rejected with the same error on both paths
+    b2 = copy.deepcopy(datasets["molhiv"].slice(0, 800))
+    b2.edge_list[1000, 1] = 70000
+    for stage in (0, 7):
+        with pytest.raises(capi.FlowGNNError, match="node id"):
+            _run_entry("gin", b2, weights["gin"], stage=stage)
+    # ... and so is one that fits 16 bits but is not a node of its graph (caught on the device after the widening)
+    b3 = copy.deepcopy(datasets["molhiv"].slice(0, 800))
+    b3.edge_list[1000, 1] = 600
+    for stage in (0, 7):
+        with pytest.raises(capi.FlowGNNError, match="node id"):
+            _run_entry("gin", b3, weights["gin"], stage=stage)
+    # the entry point still works afterwards
+    b4 = datasets["molhiv"].slice(0, 800)
+    assert np.array_equal(_run_entry("gin", b4, weights["gin"], stage=7).view(np.int32), _run_entry("gin", b4, weights["gin"], stage=0).view(np.int32))

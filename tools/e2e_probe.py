@@ -1,38 +1,68 @@
-"""End-to-end time of the host-pointer entry point (pinned caller buffers) for a few chunk counts (env FLOWGNN_B200_CHUNKS).
-    python tools/e2e_probe.py [model=gin] [reps=30]"""
+"""End-to-end time of the host-pointer entry point for chunk counts (FLOWGNN_B200_CHUNKS), the narrowed upload on / off
+(FLOWGNN_B200_HOST_STAGE), host thread counts (FLOWGNN_B200_HOST_THREADS) and pageable / page-locked caller arrays.
+    python tools/e2e_probe.py [model=gin] [reps=20]"""
 import os
-import subprocess
 import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-if len(sys.argv) > 3 and sys.argv[3] == "child":
-    import numpy as np
-    import bench
-    from flowgnn_b200.capi import ReferenceCall, pin_host
-    from flowgnn_b200.weights import load_weights
-    model, reps = sys.argv[1], int(sys.argv[2])
-    d = {"gin": "GIN", "ginvn": "GIN", "gcn": "GCN", "gat": "GAT", "pna": "PNA", "dgn": "DGN"}[model]
-    w = load_weights(model, os.path.join(ROOT, "tests", "golden", "weights", d))
-    b = bench.make_workload(model, bench.WORKLOADS[model][1], base_graphs=4096)
-    for a in (b.node_feature, b.edge_list, b.edge_attr, b.node_eigen):
-        if a is not None:
-            pin_host(a)
-    call = ReferenceCall(model, b, w)
-    for _ in range(5):
+import numpy as np
+import bench
+from flowgnn_b200.capi import ReferenceCall, pin_host
+from flowgnn_b200.weights import load_weights
+
+model = sys.argv[1] if len(sys.argv) > 1 else "gin"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+d = {"gin": "GIN", "ginvn": "GIN", "gcn": "GCN", "gat": "GAT", "pna": "PNA", "dgn": "DGN"}[model]
+w = load_weights(model, os.path.join(ROOT, "tests", "golden", "weights", d))
+b = bench.make_workload(model, bench.WORKLOADS[model][1], base_graphs=4096)
+call = ReferenceCall(model, b, w)
+
+
+def measure(tag, **env):
+    for k in ("FLOWGNN_B200_CHUNKS", "FLOWGNN_B200_HOST_STAGE", "FLOWGNN_B200_HOST_THREADS", "FLOWGNN_B200_GRADE"):
+        os.environ.pop(k, None)
+    for k, v in env.items():
+        os.environ["FLOWGNN_B200_" + k] = str(v)
+    for _ in range(3):
         call.run()
     ts = []
     for _ in range(reps):
         t = time.perf_counter(); call.run(); ts.append(time.perf_counter() - t)
     ms = float(np.median(ts)) * 1e3
-    print(f"chunks={os.environ.get('FLOWGNN_B200_CHUNKS', 'default')}: {ms:.3f} ms per call = {b.num_graphs / ms / 1e3:.2f} M graphs/s (min {min(ts) * 1e3:.3f} ms)", flush=True)
-else:
-    model = sys.argv[1] if len(sys.argv) > 1 else "gin"
-    reps = sys.argv[2] if len(sys.argv) > 2 else "30"
-    for c in ("", "1", "2", "3", "4", "5", "6", "8"):
-        env = dict(os.environ)
-        if c:
-            env["FLOWGNN_B200_CHUNKS"] = c
-        subprocess.run([sys.executable, __file__, model, reps, "child"], env=env)
+    print(f"{tag:10s} {str(env):60s} {ms:7.3f} ms = {b.num_graphs / ms / 1e3:6.2f} M graphs/s (min {min(ts) * 1e3:.3f} ms)", flush=True)
+
+
+if len(sys.argv) > 3 and sys.argv[3] == "trace":
+    for a in (b.node_feature, b.edge_list, b.edge_attr, b.node_eigen):
+        if a is not None:
+            pin_host(a)
+    for env in ({}, {"HOST_STAGE": 7}, {"GRADE": "1,2,4"}, {"GRADE": "1,3,6"}, {"GRADE": "1,2,3,4"}, {"GRADE": "1,2,4,6"}, {"GRADE": "1,2,4", "HOST_STAGE": 7},
+                {"GRADE": "1,3,6", "HOST_STAGE": 7}, {"GRADE": "2,3,4"}, {"GRADE": "1,2,2,2"}, {"HOST_THREADS": 8}, {"HOST_THREADS": 16}):
+        measure("pinned", **env)
+        if len(env) == 0 or env.get("GRADE") == "1,2,4":
+            os.environ["FLOWGNN_B200_E2E_TRACE"] = "1"
+            call.run()
+            del os.environ["FLOWGNN_B200_E2E_TRACE"]
+    sys.exit(0)
+measure("pageable")
+measure("pageable", HOST_STAGE=0)
+for t in (6, 8, 12):
+    measure("pageable", HOST_STAGE=7, HOST_THREADS=t)
+for c in (2, 3, 4, 5, 6, 8):
+    measure("pageable", HOST_STAGE=7, CHUNKS=c)
+for a in (b.node_feature, b.edge_list, b.edge_attr, b.node_eigen):
+    if a is not None:
+        pin_host(a)
+measure("pinned")
+measure("pinned", HOST_STAGE=0)
+for m in (7, 5, 4, 1, 6, 3):
+    measure("pinned", HOST_STAGE=m)
+for m in (5, 4, 1):
+    for c in (2, 4, 5, 6):
+        measure("pinned", HOST_STAGE=m, CHUNKS=c)
+for m in (7, 5):
+    for t in (4, 6, 12):
+        measure("pinned", HOST_STAGE=m, HOST_THREADS=t)
