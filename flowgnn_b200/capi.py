@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
     "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_compute", "flowgnn_b200_download",
     "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
-    "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host", "flowgnn_b200_narrow_words",
+    "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host", "flowgnn_b200_narrow_words", "flowgnn_b200_last_transfer_bytes",
 )
 
 
@@ -63,6 +63,8 @@ def load_library() -> ctypes.CDLL:
         lib.flowgnn_b200_last_layer_ms.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
         lib.flowgnn_b200_pin_host.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
         lib.flowgnn_b200_unpin_host.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_last_transfer_bytes.restype = None
+        lib.flowgnn_b200_last_transfer_bytes.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
         lib.flowgnn_b200_narrow_words.restype = ctypes.c_uint32
         lib.flowgnn_b200_narrow_words.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         _lib = lib
@@ -95,6 +97,13 @@ def pin_host(a: np.ndarray) -> None:
 
 def unpin_host(a: np.ndarray) -> None:
     _check(load_library().flowgnn_b200_unpin_host(a.ctypes.data), "unpin_host")
+
+
+def last_transfer_bytes():
+    """(host -> device, device -> host) bytes of this thread's last ``<MODEL>_compute_graphs`` call."""
+    h2d, d2h = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    load_library().flowgnn_b200_last_transfer_bytes(ctypes.byref(h2d), ctypes.byref(d2h))
+    return int(h2d.value), int(d2h.value)
 
 
 def narrow_words(src: np.ndarray, width: int, threads: int = 1):

@@ -468,10 +468,14 @@ int check_ctx(flowgnn_ctx* ctx)
     return 0;
 }
 
+// bytes the calling thread's last host-pointer entry-point call moved over PCIe (flowgnn_b200_last_transfer_bytes)
+thread_local uint64_t g_h2d_bytes = 0, g_d2h_bytes = 0;
+
 int copy_in(DevBuf& dst, const void* src, size_t bytes, cudaStream_t s)
 {
     FG_TRY(dst.reserve(bytes));
     if (bytes) FG_CUDA(cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, s));
+    g_h2d_bytes += bytes;
     return 0;
 }
 
@@ -735,6 +739,7 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
         narrow_ok[2] = staged->ok[2] && edge_attr && plan.n_attr == n_attr;
         FG_TRY(b.packed_in.reserve(plan.bytes));
         if (plan.bytes) FG_CUDA(cudaMemcpyAsync(b.packed_in.ptr, staged->h, plan.bytes, cudaMemcpyHostToDevice, s));
+        g_h2d_bytes += plan.bytes;
         if (staged->done) FG_CUDA(cudaEventRecord(staged->done, s));
     }
     if (write_after) FG_CUDA(cudaStreamWaitEvent(s, write_after, 0));
@@ -1031,6 +1036,12 @@ int flowgnn_b200_unpin_host(void* ptr)
     return 0;
 }
 
+void flowgnn_b200_last_transfer_bytes(uint64_t* h2d, uint64_t* d2h)
+{
+    if (h2d) *h2d = g_h2d_bytes;
+    if (d2h) *d2h = g_d2h_bytes;
+}
+
 uint32_t flowgnn_b200_narrow_words(const int32_t* src, size_t n, int width, void* dst, int threads)
 {
     if ((width != 1 && width != 2) || (n && (!src || !dst))) return 0xFFFFFFFFu;
@@ -1115,6 +1126,7 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
     if (!nn || !ne || !reload || !out || !feat || !edges) { set_last_error("null argument"); return FG_ERR_INVALID; }
     flowgnn_ctx* ctx = nullptr;
     FG_TRY(default_ctx(&ctx));
+    g_h2d_bytes = 0; g_d2h_bytes = 0;
     const int nw = kNumWeights[model];
     long set = -1;
     int64_t node_base = 0, edge_base = 0;
@@ -1292,6 +1304,7 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             {
                 FG_CUDA(cudaMemcpyAsync(ctx->h_out + (c0 - g), db.out.ptr, sizeof(float) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, ctx->stream));
                 FG_CUDA(cudaMemcpyAsync(ctx->h_status + ci, db.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                g_d2h_bytes += sizeof(float) * (size_t)(c1 - c0) + sizeof(int);
             }
             else ctx->h_status[ci] = 0;
             FG_CUDA(cudaEventRecord(ctx->buf_free[ci % P], ctx->stream));

@@ -224,6 +224,10 @@ int flowgnn_b200_unpin_host(void* ptr);
  * 0xFFFFFFFF and writes nothing. */
 uint32_t flowgnn_b200_narrow_words(const int32_t* src, size_t n, int width, void* dst, int threads);
 
+/* Bytes the calling thread's last <MODEL>_compute_graphs call copied host -> device and device -> host (batch inputs, offsets and
+ * tile lists, predictions and status words; weights are uploaded only when their contents change and are not counted). */
+void flowgnn_b200_last_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
+
 #ifdef __cplusplus
 }
 #endif
