@@ -138,6 +138,8 @@ void NarrowRun::start(HostPool& pool, const Chunk* chunks, int n, uint8_t* block
             if (!chunks[c].src[a]) continue;
             for (size_t i0 = 0; i0 < counts[a]; i0 += SLICE) { jobs_.push_back({c, a, i0, std::min(SLICE, counts[a] - i0)}); jobs++; }
         }
+        if (chunks[c].eig)
+            for (size_t i0 = 0; i0 < chunks[c].plan.n_eig; i0 += SLICE) { jobs_.push_back({c, 3, i0, std::min(SLICE, chunks[c].plan.n_eig - i0)}); jobs++; }
         remaining_[c].store(jobs, std::memory_order_relaxed);
     }
     active_ = true;
@@ -146,6 +148,12 @@ void NarrowRun::start(HostPool& pool, const Chunk* chunks, int n, uint8_t* block
         if (job.array < 0) { first_(job.chunk); remaining_[job.chunk].fetch_sub(1, std::memory_order_release); return; }
         const Chunk& ch = chunks_[job.chunk];
         uint8_t* base = block_ + ch.base;
+        if (job.array == 3)
+        {
+            std::memcpy(base + ch.plan.off_eig + 4 * job.i0, ch.eig + job.i0, 4 * job.len);
+            remaining_[job.chunk].fetch_sub(1, std::memory_order_release);
+            return;
+        }
         uint32_t seen;
         if (job.array == 0) seen = narrow_u8(ch.src[0] + job.i0, base + ch.plan.off_feat + job.i0, job.len);
         else if (job.array == 1) seen = narrow_u16(ch.src[1] + job.i0, reinterpret_cast<uint16_t*>(base + ch.plan.off_edge) + job.i0, job.len);

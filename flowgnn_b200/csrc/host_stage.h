@@ -50,19 +50,21 @@ uint32_t narrow_u8(const int32_t* src, uint8_t* dst, size_t n);
 uint32_t narrow_u16(const int32_t* src, uint16_t* dst, size_t n);
 
 // One chunk's narrowed inputs inside a pinned block: [feat u8 x 9N | pad16][edge u16 x 2E | pad16][attr u8 x 3E | pad16]
-// (element counts are 0 for arrays that are not narrowed)
+// [node_eigen f32 x 4N] (element counts are 0 for arrays that do not go through the block)
 struct NarrowPlan {
     size_t n_feat = 0, n_edge = 0, n_attr = 0;             // element counts (9N, 2E, 3E or 0)
-    size_t off_feat = 0, off_edge = 0, off_attr = 0, bytes = 0;
+    size_t n_eig = 0;                                      // DGN node_eigen floats (4N or 0): copied as they are, so that a pageable array is read by the pool
+    size_t off_feat = 0, off_edge = 0, off_attr = 0, off_eig = 0, bytes = 0;
     static size_t pad16(size_t b) { return (b + 15) & ~size_t(15); }
-    // which[a]: array a (feat / edge_list / edge_attr) is narrowed; the others take no room
-    void layout(size_t nodes, size_t edges, const bool which[3])
+    // which[a]: array a (feat / edge_list / edge_attr / node_eigen) goes through the block; the others take no room
+    void layout(size_t nodes, size_t edges, const bool which[4])
     {
-        n_feat = which[0] ? 9 * nodes : 0; n_edge = which[1] ? 2 * edges : 0; n_attr = which[2] ? 3 * edges : 0;
+        n_feat = which[0] ? 9 * nodes : 0; n_edge = which[1] ? 2 * edges : 0; n_attr = which[2] ? 3 * edges : 0; n_eig = which[3] ? 4 * nodes : 0;
         off_feat = 0;
         off_edge = pad16(n_feat);
         off_attr = off_edge + pad16(2 * n_edge);
-        bytes = off_attr + pad16(n_attr);
+        off_eig = off_attr + pad16(n_attr);
+        bytes = off_eig + pad16(4 * n_eig);
     }
 };
 
@@ -75,6 +77,7 @@ public:
         NarrowPlan plan;
         size_t base = 0;                                    // byte offset of the chunk's block inside the run's pinned block
         const int32_t* src[3] = {nullptr, nullptr, nullptr}; // feat / edge_list / edge_attr of this chunk (nullptr: not narrowed)
+        const float* eig = nullptr;                         // node_eigen of this chunk (nullptr: not staged)
     };
     // total bytes of the pinned block for these chunks (fills Chunk::base)
     static size_t layout(Chunk* chunks, int n);

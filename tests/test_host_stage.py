@@ -104,6 +104,19 @@ def test_narrowed_upload_chunked_large_batch(chunks, ctx, weights, datasets):
 
 
 @pytest.mark.gpu
+def test_large_inputs_are_cut_into_more_chunks(ctx, weights, datasets):
+    """Above ~200 MB of caller bytes the entry point cuts weight-3 chunks of about 100 MB (up to 16 chunks): PNA on a 300 MB batch,
+    pageable arrays, against the device-resident one-shot run."""
+    b = datasets["molpcba"].tile(200000)
+    assert b.node_feature.nbytes + b.edge_list.nbytes > 250e6
+    want = ctx.run("pna", b, weights["pna"])
+    got = _run_entry("pna", b, weights["pna"], stage=None)
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    h2d, d2h = capi.last_transfer_bytes()
+    assert h2d < 0.4 * (b.node_feature.nbytes + b.edge_list.nbytes) and d2h >= 4 * b.num_graphs
+
+
+@pytest.mark.gpu
 def test_narrowed_upload_with_pinned_caller_memory(weights, datasets):
     b = datasets["molhiv"].slice(0, 2000)
     want = _run_entry("gin", b, weights["gin"], stage=0)
