@@ -25,7 +25,7 @@ MODEL_IDS = {"gin": 0, "ginvn": 0, "gcn": 1, "gat": 2, "pna": 3, "dgn": 4}
 EXPORTED_SYMBOLS = (
     "GIN_compute_graphs", "GIN_compute_graphs_fixed", "GCN_compute_graphs", "GAT_compute_graphs", "PNA_compute_graphs", "DGN_compute_graphs",
     "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
-    "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_compute", "flowgnn_b200_download",
+    "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_upload_batch_packed", "flowgnn_b200_compute", "flowgnn_b200_download",
     "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
     "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host", "flowgnn_b200_narrow_words", "flowgnn_b200_last_transfer_bytes",
 )
@@ -56,6 +56,7 @@ def load_library() -> ctypes.CDLL:
         lib.flowgnn_b200_upload_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_void_p]
+        lib.flowgnn_b200_upload_batch_packed.argtypes = lib.flowgnn_b200_upload_batch.argtypes
         lib.flowgnn_b200_compute.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p]
         lib.flowgnn_b200_download.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.flowgnn_b200_last_launch_count.argtypes = [ctypes.c_void_p]
@@ -161,6 +162,17 @@ class Context:
         _check(self._lib.flowgnn_b200_upload_batch(self._h, int(num_graphs), int(total_nodes), int(total_edges),
                                                    _addr(nums_of_nodes), _addr(nums_of_edges), _addr(node_feature),
                                                    _addr(edge_list), _addr(edge_attr), _addr(node_eigen)), "upload_batch")
+        self._num_graphs = int(num_graphs)
+
+    def upload_packed_arrays(self, num_graphs, total_nodes, total_edges, nums_of_nodes, nums_of_edges, node_feature_u8, edge_list_u16,
+                             edge_attr_u8=None, node_eigen=None) -> None:
+        """``flowgnn_b200_upload_batch_packed``: the big arrays in the narrow layout of the packed dataset files (uint8 / uint16 / uint8)."""
+        for a, dt in ((node_feature_u8, np.uint8), (edge_list_u16, np.uint16), (edge_attr_u8, np.uint8)):
+            if isinstance(a, np.ndarray) and a.dtype != dt:
+                raise FlowGNNError(f"packed upload wants {np.dtype(dt).name}, got {a.dtype}")
+        _check(self._lib.flowgnn_b200_upload_batch_packed(self._h, int(num_graphs), int(total_nodes), int(total_edges),
+                                                          _addr(nums_of_nodes), _addr(nums_of_edges), _addr(node_feature_u8),
+                                                          _addr(edge_list_u16), _addr(edge_attr_u8), _addr(node_eigen)), "upload_batch_packed")
         self._num_graphs = int(num_graphs)
 
     def compute(self, model: str, timed: bool = True) -> float:

@@ -214,6 +214,8 @@ struct flowgnn_ctx {
     cudaStream_t aux_stream = nullptr;                 // the input embedding runs here, next to the CSR / tile build (RunOptions::aux)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t up_done[PIPE] = {}, buf_free[PIPE] = {};
+    cudaStream_t d2h_stream = nullptr;                 // predictions of chunk i leave on their own stream: behind a long upload the small
+    cudaEvent_t fwd_done[PIPE] = {};                   // download took 0.25-0.35 ms to be served, and chunk i+1's kernels were queued behind it
     float* h_out = nullptr; size_t h_out_cap = 0;      // pinned staging of the predictions
     // narrowed uploads (host_stage.h): thread pool, the pinned block of the call in flight, its narrowing run
     std::unique_ptr<HostPool> pool;
@@ -539,12 +541,14 @@ int flowgnn_b200_create(flowgnn_ctx** out, int device)
     FG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     FG_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    FG_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     FG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     FG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < flowgnn_ctx::PIPE; i++)
     {
         FG_CUDA(cudaEventCreateWithFlags(&c->up_done[i], cudaEventDisableTiming));
         FG_CUDA(cudaEventCreateWithFlags(&c->buf_free[i], cudaEventDisableTiming));
+        FG_CUDA(cudaEventCreateWithFlags(&c->fwd_done[i], cudaEventDisableTiming));
     }
     FG_CUDA(cudaMallocHost(&c->h_status, sizeof(int) * 64));
     FG_CUDA(cudaEventCreate(&c->ev0));
@@ -565,6 +569,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
         ctx->pipe[i].release();
         cudaEventDestroy(ctx->up_done[i]);
         cudaEventDestroy(ctx->buf_free[i]);
+        cudaEventDestroy(ctx->fwd_done[i]);
     }
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -572,6 +577,7 @@ int flowgnn_b200_destroy(flowgnn_ctx* ctx)
     if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
     if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);
     cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -657,6 +663,7 @@ void pack_graphs(const int32_t* nn, const int32_t* ne, int G, std::vector<int32_
 // chunk after chunk as each one completes (NarrowRun::wait_chunk) while the pool is already working on the next ones.
 struct StagedChunk {
     const uint8_t* h = nullptr;            // the chunk's narrowed block in pinned memory
+    const void* part[3] = {nullptr, nullptr, nullptr};   // or, h == nullptr: the caller's own narrow arrays (flowgnn_b200_upload_batch_packed)
     NarrowPlan plan;
     bool ok[3] = {false, false, false};    // feat / edge_list / edge_attr were narrowed and every value fits
     cudaEvent_t done = nullptr;            // recorded behind the copy of the block
@@ -694,7 +701,8 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
         set_last_error("batch too large for 32-bit node/edge positions; split it");
         return FG_ERR_LIMIT;
     }
-    if (num_graphs > 0 && (!nums_of_nodes || !nums_of_edges || (total_nodes && !node_feature) || (total_edges && !edge_list)))
+    const bool own_narrow = staged && !staged->h;        // the caller's arrays are narrow already: there are no int32 ones
+    if (num_graphs > 0 && (!nums_of_nodes || !nums_of_edges || (total_nodes && !node_feature && !own_narrow) || (total_edges && !edge_list && !own_narrow)))
     {
         set_last_error("null batch array");
         return FG_ERR_INVALID;
@@ -739,8 +747,21 @@ int upload_into(DeviceBatch& b, cudaStream_t s, int num_graphs, int64_t total_no
         narrow_ok[2] = staged->ok[2] && edge_attr && plan.n_attr == n_attr;
         const size_t blob = plan.off_eig;                   // (node_eigen, if it rides in the block, goes straight to its own buffer below)
         FG_TRY(b.packed_in.reserve(blob));
-        if (blob) FG_CUDA(cudaMemcpyAsync(b.packed_in.ptr, staged->h, blob, cudaMemcpyHostToDevice, s));
-        g_h2d_bytes += blob;
+        if (staged->h)
+        {
+            if (blob) FG_CUDA(cudaMemcpyAsync(b.packed_in.ptr, staged->h, blob, cudaMemcpyHostToDevice, s));
+            g_h2d_bytes += blob;
+        }
+        else
+        {
+            const size_t off[3] = {plan.off_feat, plan.off_edge, plan.off_attr}, len[3] = {plan.n_feat, 2 * plan.n_edge, plan.n_attr};
+            for (int a = 0; a < 3; a++)
+                if (len[a] && staged->part[a])
+                {
+                    FG_CUDA(cudaMemcpyAsync(b.packed_in.as<uint8_t>() + off[a], staged->part[a], len[a], cudaMemcpyHostToDevice, s));
+                    g_h2d_bytes += len[a];
+                }
+        }
         if (staged->done) FG_CUDA(cudaEventRecord(staged->done, s));
     }
     if (write_after) FG_CUDA(cudaStreamWaitEvent(s, write_after, 0));
@@ -971,6 +992,27 @@ int flowgnn_b200_upload_batch(flowgnn_ctx* ctx, int num_graphs, int64_t total_no
     ctx->batch_ready = false;
     FG_TRY(upload_into(ctx->batch, ctx->stream, num_graphs, total_nodes, total_edges, nums_of_nodes, nums_of_edges, node_feature, edge_list,
                        edge_attr, node_eigen));
+    ctx->batch_ready = true;
+    return 0;
+}
+
+int flowgnn_b200_upload_batch_packed(flowgnn_ctx* ctx, int num_graphs, int64_t total_nodes, int64_t total_edges,
+                                     const int32_t* nums_of_nodes, const int32_t* nums_of_edges, const uint8_t* node_feature,
+                                     const uint16_t* edge_list, const uint8_t* edge_attr, const float* node_eigen)
+{
+    FG_TRY(check_ctx(ctx));
+    DeviceGuard guard(ctx->device);
+    ctx->batch_ready = false;
+    if ((total_nodes > 0 && !node_feature) || (total_edges > 0 && !edge_list)) { set_last_error("null batch array"); return FG_ERR_INVALID; }
+    StagedChunk sc;
+    const bool which[4] = {true, true, edge_attr != nullptr, false};
+    sc.plan.layout((size_t)std::max<int64_t>(total_nodes, 0), (size_t)std::max<int64_t>(total_edges, 0), which);
+    sc.part[0] = node_feature; sc.part[1] = edge_list; sc.part[2] = edge_attr;
+    sc.ok[0] = sc.ok[1] = true; sc.ok[2] = edge_attr != nullptr;
+    // upload_into only tests the third int32 pointer for "the model's batch has edge attributes": hand it a non-null token
+    const int32_t* attr_token = edge_attr ? reinterpret_cast<const int32_t*>(edge_attr) : nullptr;
+    FG_TRY(upload_into(ctx->batch, ctx->stream, num_graphs, total_nodes, total_edges, nums_of_nodes, nums_of_edges, nullptr, nullptr, attr_token,
+                       node_eigen, &sc));
     ctx->batch_ready = true;
     return 0;
 }
@@ -1296,7 +1338,7 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             {
                 if (c->pool) c->narrow.finish(*c->pool);
                 if (!armed) return;
-                cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream);
+                cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->d2h_stream);
             }
         } drain{ctx};
         auto ensure_weights = [&]() -> int {
@@ -1318,14 +1360,16 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             FG_TRY(compute_on(ctx, db, ctx->stream, model));
             trace.d("compute ends " + std::to_string(ci), ctx->stream);
             trace.h("compute issued " + std::to_string(ci));
+            FG_CUDA(cudaEventRecord(ctx->fwd_done[ci % P], ctx->stream));
+            FG_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->fwd_done[ci % P], 0));
             if (c1 > c0)
             {
-                FG_CUDA(cudaMemcpyAsync(ctx->h_out + (c0 - g), db.out.ptr, sizeof(float) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, ctx->stream));
-                FG_CUDA(cudaMemcpyAsync(ctx->h_status + ci, db.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(cudaMemcpyAsync(ctx->h_out + (c0 - g), db.out.ptr, sizeof(float) * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                FG_CUDA(cudaMemcpyAsync(ctx->h_status + ci, db.status.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->d2h_stream));
                 g_d2h_bytes += sizeof(float) * (size_t)(c1 - c0) + sizeof(int);
             }
             else ctx->h_status[ci] = 0;
-            FG_CUDA(cudaEventRecord(ctx->buf_free[ci % P], ctx->stream));
+            FG_CUDA(cudaEventRecord(ctx->buf_free[ci % P], ctx->d2h_stream));     // the batch is free once its predictions have left
             return 0;
         };
         if (staged)
@@ -1356,6 +1400,7 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
                 if (ci + P < nchunks) FG_TRY(issue_upload(ci + P));                     // reuses this chunk's buffer once it is free
             }
         }
+        FG_CUDA(cudaStreamSynchronize(ctx->d2h_stream));                  // (behind the last chunk's kernels)
         FG_CUDA(cudaStreamSynchronize(ctx->stream));
         trace.h("synchronised");
         trace.dump();

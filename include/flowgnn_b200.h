@@ -190,6 +190,14 @@ int flowgnn_b200_upload_batch(
     const int32_t* node_feature, const int32_t* edge_list,
     const int32_t* edge_attr /* may be NULL */, const float* node_eigen /* may be NULL */);
 
+/* The same batch with the big arrays in the narrow layout of the packed dataset files (flowgnn_b200/dataset.py::save_packed):
+ * node_feature as uint8 [N][9], edge_list as uint16 [E][2] (graph-local ids), edge_attr as uint8 [E][3] (or NULL), 9 B per node +
+ * 7 B per edge over PCIe instead of the reference ABI's 36 + 20 (GIN/src/dcl.h:61-67).  Widened on the device into the int32
+ * arrays the kernels read; everything else as flowgnn_b200_upload_batch.  A dataset whose values do not fit uses that call. */
+int flowgnn_b200_upload_batch_packed(flowgnn_ctx* ctx, int num_graphs, int64_t total_nodes, int64_t total_edges,
+                                     const int32_t* nums_of_nodes, const int32_t* nums_of_edges, const uint8_t* node_feature,
+                                     const uint16_t* edge_list, const uint8_t* edge_attr, const float* node_eigen);
+
 /* Run graph preprocessing (load_graph) + the full forward of `model` on the resident batch.
  * `elapsed_ms` (may be NULL) receives the device time between CUDA events around exactly that work;
  * passing it makes the call synchronous. */

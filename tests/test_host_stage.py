@@ -158,3 +158,22 @@ def test_inputs_that_do_not_fit_travel_unchanged(weights, datasets):
     # the entry point still works afterwards
     b4 = datasets["molhiv"].slice(0, 800)
     assert np.array_equal(_run_entry("gin", b4, weights["gin"], stage=7).view(np.int32), _run_entry("gin", b4, weights["gin"], stage=0).view(np.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["gin", "gat", "pna", "dgn"])
+def test_packed_upload_is_bit_identical(model, ctx, weights, datasets):
+    """Part 2: flowgnn_b200_upload_batch_packed takes the narrow arrays of the packed dataset files; same predictions as the int32 upload."""
+    from flowgnn_b200.dataset import synthetic_molecules
+    from flowgnn_b200.models import get_model
+    b = datasets["molpcba"].slice(0, 3001) if model != "dgn" else synthetic_molecules(3001, "molhiv", seed=7, with_eigen=True)
+    spec = get_model(model)
+    want = ctx.run(model, b, weights[model])
+    ctx.upload_packed_arrays(b.num_graphs, b.total_nodes, b.total_edges, b.nums_of_nodes, b.nums_of_edges, b.node_feature.astype(np.uint8),
+                             b.edge_list.astype(np.uint16), b.edge_attr.astype(np.uint8) if spec.uses_edge_attr else None,
+                             b.node_eigen if spec.uses_eigen else None)
+    ctx.compute(model)
+    got = ctx.download()
+    assert np.array_equal(got.view(np.int32), want.view(np.int32)), model
+    with pytest.raises(capi.FlowGNNError):
+        ctx.upload_packed_arrays(b.num_graphs, b.total_nodes, b.total_edges, b.nums_of_nodes, b.nums_of_edges, None, None)
