@@ -2,6 +2,9 @@
 #include "host_stage.h"
 
 #include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <cstdlib>
@@ -85,8 +88,10 @@ void HostPool::finish()
     njobs_ = 0; next_ = 0;
 }
 
-// The loops are written so that gcc vectorises them (mask + pack); the OR keeps the range check off the critical path.
-uint32_t narrow_u8(const int32_t* __restrict src, uint8_t* __restrict dst, size_t n)
+// Portable loops (gcc vectorises them: mask + pack) and, on x86-64 with AVX2, explicit versions with non-temporal stores: the
+// narrow block is written once and read next by the DMA engine, so it need not be read into the cache first (a sixth less memory
+// traffic where the narrowing is what bounds the call, e.g. 785 MB of hep10k inputs per step).
+static uint32_t narrow_u8_plain(const int32_t* __restrict src, uint8_t* __restrict dst, size_t n)
 {
     uint32_t seen = 0;
     for (size_t i = 0; i < n; i++)
@@ -98,7 +103,7 @@ uint32_t narrow_u8(const int32_t* __restrict src, uint8_t* __restrict dst, size_
     return seen;
 }
 
-uint32_t narrow_u16(const int32_t* __restrict src, uint16_t* __restrict dst, size_t n)
+static uint32_t narrow_u16_plain(const int32_t* __restrict src, uint16_t* __restrict dst, size_t n)
 {
     uint32_t seen = 0;
     for (size_t i = 0; i < n; i++)
@@ -108,6 +113,81 @@ uint32_t narrow_u16(const int32_t* __restrict src, uint16_t* __restrict dst, siz
         dst[i] = (uint16_t)v;
     }
     return seen;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define FG_HAVE_AVX2_PATH 1
+__attribute__((target("avx2"))) static uint32_t or_lanes(__m256i v)
+{
+    alignas(32) uint32_t w[8];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(w), v);
+    return w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7];
+}
+
+__attribute__((target("avx2"))) static uint32_t narrow_u8_avx2(const int32_t* src, uint8_t* dst, size_t n)
+{
+    size_t i = 0;
+    uint32_t seen = 0;
+    for (; i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31); i++) { const uint32_t v = (uint32_t)src[i]; seen |= v; dst[i] = (uint8_t)v; }
+    __m256i acc = _mm256_setzero_si256();
+    const __m256i mask = _mm256_set1_epi32(0xFF), order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    for (; i + 32 <= n; i += 32)
+    {
+        __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)), b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 8));
+        __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 16)), d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 24));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(a, b), _mm256_or_si256(c, d)));
+        // per 128-bit half: a0-3 b0-3 | a4-7 b4-7, then a0-3 b0-3 c0-3 d0-3 | a4-7 b4-7 c4-7 d4-7; the dword permute restores the order
+        const __m256i ab = _mm256_packus_epi32(_mm256_and_si256(a, mask), _mm256_and_si256(b, mask));
+        const __m256i cd = _mm256_packus_epi32(_mm256_and_si256(c, mask), _mm256_and_si256(d, mask));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_permutevar8x32_epi32(_mm256_packus_epi16(ab, cd), order));
+    }
+    _mm_sfence();
+    seen |= or_lanes(acc);
+    for (; i < n; i++) { const uint32_t v = (uint32_t)src[i]; seen |= v; dst[i] = (uint8_t)v; }
+    return seen;
+}
+
+__attribute__((target("avx2"))) static uint32_t narrow_u16_avx2(const int32_t* src, uint16_t* dst, size_t n)
+{
+    size_t i = 0;
+    uint32_t seen = 0;
+    for (; i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31); i++) { const uint32_t v = (uint32_t)src[i]; seen |= v; dst[i] = (uint16_t)v; }
+    __m256i acc = _mm256_setzero_si256();
+    const __m256i mask = _mm256_set1_epi32(0xFFFF);
+    for (; i + 16 <= n; i += 16)
+    {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)), b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 8));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(a, b));
+        const __m256i ab = _mm256_packus_epi32(_mm256_and_si256(a, mask), _mm256_and_si256(b, mask));      // a0-3 b0-3 | a4-7 b4-7
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_permute4x64_epi64(ab, 0xD8));
+    }
+    _mm_sfence();
+    seen |= or_lanes(acc);
+    for (; i < n; i++) { const uint32_t v = (uint32_t)src[i]; seen |= v; dst[i] = (uint16_t)v; }
+    return seen;
+}
+
+static bool have_avx2()
+{
+    static const bool yes = __builtin_cpu_supports("avx2") && !std::getenv("FLOWGNN_B200_NO_AVX2");
+    return yes;
+}
+#endif
+
+uint32_t narrow_u8(const int32_t* src, uint8_t* dst, size_t n)
+{
+#ifdef FG_HAVE_AVX2_PATH
+    if (have_avx2()) return narrow_u8_avx2(src, dst, n);
+#endif
+    return narrow_u8_plain(src, dst, n);
+}
+
+uint32_t narrow_u16(const int32_t* src, uint16_t* dst, size_t n)
+{
+#ifdef FG_HAVE_AVX2_PATH
+    if (have_avx2()) return narrow_u16_avx2(src, dst, n);
+#endif
+    return narrow_u16_plain(src, dst, n);
 }
 
 size_t NarrowRun::layout(Chunk* chunks, int n)

@@ -3,7 +3,7 @@
 cd tools/hs_probe
 g++ -O3 -std=c++17 -pthread narrow_probe.cc ../../flowgnn_b200/csrc/host_stage.cc -o /tmp/narrow_probe && g++ -O2 -pthread bw_probe.cc -o /tmp/bw_probe
 nproc; lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket"
-for t in 1 2 4 8 16; do /tmp/narrow_probe $t | sort -k2 -n | head -1; done
+for t in 1 2 4 8 12 16; do /tmp/narrow_probe $t; FLOWGNN_B200_NO_AVX2=1 /tmp/narrow_probe $t; done
 for t in 1 4 8 16; do /tmp/bw_probe $t; done
 python - <<'PY'
 import torch, time
