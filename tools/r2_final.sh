@@ -15,5 +15,9 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:fuse
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 6 -c 1 -f -o gpurun_out/${tag}_ncu_gcn python tools/model_probe.py gcn 41127 1 > /dev/null 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_ncu_dgn python tools/model_probe.py dgn 41127 1 > /dev/null 2>&1
 for m in gat gcn dgn pna; do timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${tag}_launches_${m}.csv python tools/model_probe.py $m $( [ $m = pna ] && echo 100000 || echo 41127 ) 1 > /dev/null 2>&1; done
+timeout 200 python tools/e2e_probe.py gin 20 > gpurun_out/${tag}_e2e_probe.txt 2>&1
+timeout 100 python tools/e2e_probe.py gin 10 trace > gpurun_out/${tag}_e2e_trace.txt 2>&1
+for m in dgn pna ginvn; do timeout 100 python tools/e2e_probe.py $m 5 2>&1 | head -3 >> gpurun_out/${tag}_e2e_probe.txt; done
+bash tools/hs_probe/run.sh > gpurun_out/${tag}_host_probe.txt 2>&1
 bash tools/sanitize.sh ${tag}
 ls -la gpurun_out/ | grep ${tag}

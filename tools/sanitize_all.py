@@ -59,4 +59,16 @@ big = mol.tile(8192 + 64)
 call = ReferenceCall("gin", big, w)
 y = call.run()
 print("entry point", y.shape, float(np.abs(y).max()), flush=True)
+# the same with the plain int32 copies, and Part 2's packed upload (unpack_inputs_kernel on odd sizes)
+os.environ["FLOWGNN_B200_HOST_STAGE"] = "0"
+y0 = call.run().copy()
+del os.environ["FLOWGNN_B200_HOST_STAGE"]
+assert np.array_equal(y0.view(np.int32), call.run().view(np.int32))
+with Context(0) as c:
+    c.load_weights("gin", w)
+    odd = mol.slice(0, 77)
+    c.upload_packed_arrays(odd.num_graphs, odd.total_nodes, odd.total_edges, odd.nums_of_nodes, odd.nums_of_edges, odd.node_feature.astype(np.uint8),
+                           odd.edge_list.astype(np.uint16), odd.edge_attr.astype(np.uint8))
+    c.compute("gin")
+    print("packed upload", float(np.abs(c.download()).max()), flush=True)
 print("sanitize workload done", flush=True)
