@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
     "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_upload_batch_packed", "flowgnn_b200_compute", "flowgnn_b200_download",
     "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
-    "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host", "flowgnn_b200_narrow_words", "flowgnn_b200_last_transfer_bytes",
+    "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host", "flowgnn_b200_narrow_words", "flowgnn_b200_last_transfer_bytes", "flowgnn_b200_compute_graphs_packed",
 )
 
 
@@ -257,6 +257,43 @@ class ReferenceCall:
 
     def run(self) -> np.ndarray:
         _check(self._fn(*self._args), self._symbol)
+        return self.out
+
+
+class PackedCall:
+    """A prepared call of ``flowgnn_b200_compute_graphs_packed``: the host-pointer pipeline of the entry points for a caller whose
+    dataset is in the packed layout (uint8 features, uint16 edge ids, uint8 bond attributes).  Arrays may be numpy arrays or views of
+    pinned torch tensors; ``run()`` is the bare C call."""
+
+    def __init__(self, model: str, batch: Batch, weights: Weights, node_feature_u8=None, edge_list_u16=None, edge_attr_u8=None):
+        lib = load_library()
+        spec: ModelSpec = get_model(model)
+        w = check_weights(spec, weights)
+        arrs = [w[n] for n in spec.weight_names]
+        self._wptrs = (_f32p * len(arrs))(*[a.ctypes.data_as(_f32p) for a in arrs])
+        nf = batch.node_feature.astype(np.uint8) if node_feature_u8 is None else node_feature_u8
+        el = batch.edge_list.astype(np.uint16) if edge_list_u16 is None else edge_list_u16
+        ea = None
+        if spec.uses_edge_attr:
+            ea = batch.edge_attr.astype(np.uint8) if edge_attr_u8 is None else edge_attr_u8
+        for a, dt in ((nf, np.uint8), (el, np.uint16), (ea, np.uint8)):
+            if a is not None and a.dtype != dt:
+                raise FlowGNNError(f"packed call wants {np.dtype(dt).name}, got {a.dtype}")
+        eg = batch.node_eigen if spec.uses_eigen else None
+        if spec.uses_eigen and eg is None:
+            raise FlowGNNError("DGN needs node_eigen")
+        self.out = np.zeros(batch.num_graphs, dtype=np.float32)
+        nn = np.ascontiguousarray(batch.nums_of_nodes, dtype=np.int32)
+        ne = np.ascontiguousarray(batch.nums_of_edges, dtype=np.int32)
+        self._keep = (nn, ne, nf, el, ea, eg, arrs, batch)
+        self._args = [ctypes.c_int(MODEL_IDS[spec.name]), ctypes.c_int(batch.num_graphs), ctypes.c_void_p(_addr(nn)), ctypes.c_void_p(_addr(ne)),
+                      ctypes.c_void_p(_addr(self.out)), ctypes.c_void_p(_addr(nf)), ctypes.c_void_p(_addr(el)), ctypes.c_void_p(_addr(ea)),
+                      ctypes.c_void_p(_addr(eg)), self._wptrs, ctypes.c_int(len(arrs))]
+        self._fn = lib.flowgnn_b200_compute_graphs_packed
+        self._fn.restype = ctypes.c_int
+
+    def run(self) -> np.ndarray:
+        _check(self._fn(*self._args), "flowgnn_b200_compute_graphs_packed")
         return self.out
 
 

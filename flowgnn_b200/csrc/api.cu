@@ -1166,13 +1166,25 @@ uint64_t hash_weights(const float* const* w, const size_t* counts, int n, size_t
 
 // Walk the batch as runs of graphs that share a weight set (reload_weights[g] != 0 starts the next
 // set; GIN/src/GIN_compute.cc:49-63) and run each through the extended interface.
+// the big arrays in the narrow layout of the packed dataset files instead of the reference ABI's int32 words (flowgnn_b200_compute_graphs_packed)
+struct PackedInputs { const uint8_t* feat; const uint16_t* edges; const uint8_t* attr; };
+
 int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne, const int* reload, float* out,
                         const int32_t* feat, const int32_t* edges, const int32_t* attr, const float* eig,
-                        const float* const* weights, const size_t* counts)
+                        const float* const* weights, const size_t* counts, const PackedInputs* packed = nullptr)
 {
     if (num_graphs < 0) { set_last_error("num_graphs < 0"); return FG_ERR_INVALID; }
     if (num_graphs == 0) return 0;
-    if (!nn || !ne || !reload || !out || !feat || !edges) { set_last_error("null argument"); return FG_ERR_INVALID; }
+    std::vector<int> one_set;
+    if (packed)
+    {
+        if (!packed->feat || !packed->edges) { set_last_error("null argument"); return FG_ERR_INVALID; }
+        if (!reload) { one_set.assign((size_t)num_graphs, 0); one_set[0] = 1; reload = one_set.data(); }
+        // upload_into only asks whether the int32 attribute pointer is null ("this model's batch has edge attributes")
+        attr = packed->attr ? reinterpret_cast<const int32_t*>(packed->attr) : nullptr;
+    }
+    else if (!feat || !edges) { set_last_error("null argument"); return FG_ERR_INVALID; }
+    if (!nn || !ne || !reload || !out) { set_last_error("null argument"); return FG_ERR_INVALID; }
     flowgnn_ctx* ctx = nullptr;
     FG_TRY(default_ctx(&ctx));
     g_h2d_bytes = 0; g_d2h_bytes = 0;
@@ -1264,13 +1276,14 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         if (stage_mask != 0)
         {
             cudaPointerAttributes at;
-            pinned = cudaPointerGetAttributes(&at, feat) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+            pinned = cudaPointerGetAttributes(&at, packed ? static_cast<const void*>(packed->feat) : feat) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
             (void)cudaGetLastError();
         }
         if (stage_mask < 0) stage_mask = !pinned || HostPool::default_threads() >= 8 ? 7 : 0;
         stage_mask &= 7;
+        if (packed) stage_mask = 7;                          // nothing to narrow: the pool only computes the chunks' tile packing
         // DGN's node_eigen keeps its format; a pageable array goes through the block too, so that the pool reads it instead of the driver
-        const bool stage_eig = stage_mask != 0 && eig && !pinned;
+        const bool stage_eig = stage_mask != 0 && eig && !pinned && !packed;
         const bool staged = stage_mask != 0;
         constexpr int P = flowgnn_ctx::PIPE;
         auto chunk_feat = [&](int ci) { return gat_bug ? feat : feat + ND_FEATURE * cnode[ci]; };
@@ -1281,6 +1294,7 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             for (int ci = 0; ci < nchunks; ci++)
             {
                 nchunk[ci].plan.layout((size_t)(cnode[ci + 1] - cnode[ci]), (size_t)(cedge[ci + 1] - cedge[ci]), which);
+                if (packed) continue;                        // no slices to narrow
                 nchunk[ci].src[0] = which[0] ? chunk_feat(ci) : nullptr;
                 nchunk[ci].src[1] = which[1] ? edges + 2 * cedge[ci] : nullptr;
                 nchunk[ci].src[2] = which[2] ? attr + 3 * cedge[ci] : nullptr;
@@ -1320,10 +1334,19 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
                 sc.h = ctx->stage_h + ctx->narrow.chunk(ci).base;
                 sc.plan = ctx->narrow.chunk(ci).plan;
                 sc.done = ctx->stage_done;
+                if (packed)
+                {
+                    sc.h = nullptr; sc.done = nullptr;
+                    sc.part[0] = packed->feat + (gat_bug ? 0 : ND_FEATURE * cnode[ci]);
+                    sc.part[1] = packed->edges + 2 * cedge[ci];
+                    sc.part[2] = packed->attr ? packed->attr + 3 * cedge[ci] : nullptr;
+                    sc.ok[0] = sc.ok[1] = true; sc.ok[2] = packed->attr != nullptr;
+                }
             }
             else if (free_ev) { FG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, free_ev, 0)); free_ev = nullptr; }
-            FG_TRY(upload_into(db, ctx->copy_stream, c1 - c0, cnode[ci + 1] - cnode[ci], cedge[ci + 1] - cedge[ci], nn + c0, ne + c0, chunk_feat(ci),
-                               edges + 2 * cedge[ci], attr ? attr + 3 * cedge[ci] : nullptr, eig ? eig + 4 * cnode[ci] : nullptr,
+            FG_TRY(upload_into(db, ctx->copy_stream, c1 - c0, cnode[ci + 1] - cnode[ci], cedge[ci + 1] - cedge[ci], nn + c0, ne + c0,
+                               packed ? nullptr : chunk_feat(ci), packed ? nullptr : edges + 2 * cedge[ci],
+                               packed ? attr : attr ? attr + 3 * cedge[ci] : nullptr, eig ? eig + 4 * cnode[ci] : nullptr,
                                staged ? &sc : nullptr, free_ev, staged ? &ctx->packed[ci] : nullptr));
             FG_CUDA(cudaEventRecord(ctx->up_done[ci % P], ctx->copy_stream));
             trace.h("upload issued " + std::to_string(ci));
@@ -1419,6 +1442,30 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
 }  // namespace
 
 extern "C" {
+
+// The host-pointer pipeline of the entry points below (chunks alternating between two device batches, uploads overlapping kernels,
+// one weight set) for a caller that keeps its dataset in the packed layout: uint8 node features, uint16 graph-local edge ids, uint8 bond
+// attributes (NULL for GAT / PNA / DGN), fp32 node_eigen (DGN, else NULL).  `weights`: the model's arrays in the order of its
+// <MODEL>_compute_graphs argument list.
+int flowgnn_b200_compute_graphs_packed(int model, int num_graphs, const int32_t* nums_of_nodes, const int32_t* nums_of_edges, float* out,
+                                       const uint8_t* node_feature, const uint16_t* edge_list, const uint8_t* edge_attr, const float* node_eigen,
+                                       const float* const* weights, int num_weights)
+{
+    static const size_t counts[NUM_MODELS][11] = {
+        {173 * 100, 5 * 13 * 100, 5 * 200 * 100, 5 * 200, 5 * 100 * 200, 5 * 100, 100, 1},
+        {173 * 100, 5 * 13 * 100, 5 * 100 * 100, 500, 500, 500, 500, 500, 500, 100, 1},
+        {5 * 64, 5 * 64, 5 * 4096, 5 * 4096, 16, 1},
+        {173 * 80, 4 * 80 * 12 * 80, 320, 40 * 80, 40, 20 * 40, 20, 20, 1, 1},
+        {9 * 119 * 100, 4 * 100 * 200, 400, 5000, 50, 1250, 25, 25, 1}};
+    if (model < 0 || model >= NUM_MODELS) { set_last_error("unknown model id"); return FG_ERR_INVALID; }
+    if (!weights || num_weights != kNumWeights[model]) { set_last_error("expected " + std::to_string(kNumWeights[model]) + " weight arrays"); return FG_ERR_INVALID; }
+    for (int i = 0; i < num_weights; i++) if (!weights[i]) { set_last_error("null weight argument"); return FG_ERR_INVALID; }
+    if ((model == MODEL_GIN || model == MODEL_GCN) && !edge_attr && num_graphs > 0) { set_last_error("GIN / GCN need edge_attr"); return FG_ERR_INVALID; }
+    if (model == MODEL_DGN && !node_eigen && num_graphs > 0) { set_last_error("DGN needs node_eigen"); return FG_ERR_INVALID; }
+    const PackedInputs in{node_feature, edge_list, (model == MODEL_GIN || model == MODEL_GCN) ? edge_attr : nullptr};
+    return run_reference_entry(model, num_graphs, nums_of_nodes, nums_of_edges, nullptr, out, nullptr, nullptr, nullptr,
+                               model == MODEL_DGN ? node_eigen : nullptr, weights, counts[model], &in);
+}
 
 int GIN_compute_graphs(int num_graphs, int* nums_of_nodes, int* nums_of_edges, int* reload_weights, float* out,
                        const int32_t* node_feature_in, const int32_t* edge_list_in, const int32_t* edge_attr_in,

@@ -232,6 +232,16 @@ int flowgnn_b200_unpin_host(void* ptr);
  * 0xFFFFFFFF and writes nothing. */
 uint32_t flowgnn_b200_narrow_words(const int32_t* src, size_t n, int width, void* dst, int threads);
 
+/* <MODEL>_compute_graphs for a caller that keeps its dataset in the packed layout (flowgnn_b200/dataset.py::save_packed): uint8
+ * node features [N][9], uint16 graph-local edge ids [E][2], uint8 bond attributes [E][3] (GIN / GCN; NULL otherwise), fp32
+ * node_eigen [N][4] (DGN; NULL otherwise).  Same pipeline as the entry points of Part 1 -- chunks of whole graphs alternate between
+ * two device batches, the upload of chunk i+1 overlaps the kernels of chunk i, predictions are written to `out` before the call
+ * returns -- with 9 B per node + 7 B per edge crossing PCIe and no host-side narrowing.  model: enum flowgnn_model; weights: the
+ * model's arrays in the order of its <MODEL>_compute_graphs argument list (one weight set). */
+int flowgnn_b200_compute_graphs_packed(int model, int num_graphs, const int32_t* nums_of_nodes, const int32_t* nums_of_edges, float* out,
+                                       const uint8_t* node_feature, const uint16_t* edge_list, const uint8_t* edge_attr,
+                                       const float* node_eigen, const float* const* weights, int num_weights);
+
 /* Bytes the calling thread's last <MODEL>_compute_graphs call copied host -> device and device -> host (batch inputs, offsets and
  * tile lists, predictions and status words; weights are uploaded only when their contents change and are not counted). */
 void flowgnn_b200_last_transfer_bytes(uint64_t* h2d, uint64_t* d2h);

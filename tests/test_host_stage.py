@@ -177,3 +177,21 @@ def test_packed_upload_is_bit_identical(model, ctx, weights, datasets):
     assert np.array_equal(got.view(np.int32), want.view(np.int32)), model
     with pytest.raises(capi.FlowGNNError):
         ctx.upload_packed_arrays(b.num_graphs, b.total_nodes, b.total_edges, b.nums_of_nodes, b.nums_of_edges, None, None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["gin", "gcn", "gat", "pna", "dgn"])
+def test_packed_entry_point_is_bit_identical(model, ctx, weights, datasets):
+    """flowgnn_b200_compute_graphs_packed: the chunked host-pointer pipeline fed with the narrow dataset layout (large enough for
+    several chunks; GAT with the reference's node-offset quirk reads features from the start of the caller's buffer)."""
+    from flowgnn_b200.dataset import synthetic_molecules
+    b = datasets["molpcba"].tile(20000) if model != "dgn" else synthetic_molecules(2500, "molhiv", seed=3, with_eigen=True).tile(20000)
+    ctx.set_option("gat_node_offset_bug", 1)
+    want = ctx.run(model, b, weights[model])
+    call = capi.PackedCall(model, b, weights[model])
+    got = call.run().copy()
+    assert np.array_equal(got.view(np.int32), want.view(np.int32)), model
+    assert np.array_equal(call.run().view(np.int32), want.view(np.int32)), model
+    h2d, _ = capi.last_transfer_bytes()
+    assert h2d < 0.45 * (b.node_feature.nbytes + b.edge_list.nbytes + (b.edge_attr.nbytes if model in ("gin", "gcn") else 0)
+                         + (b.node_eigen.nbytes if model == "dgn" else 0)) + 4e6
