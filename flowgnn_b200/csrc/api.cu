@@ -1189,6 +1189,14 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
     FG_TRY(default_ctx(&ctx));
     g_h2d_bytes = 0; g_d2h_bytes = 0;
     const int nw = kNumWeights[model];
+    // the counts drive every offset, on the host (chunk extents, the narrowing slices, the tile packing) and on the device: check them
+    // before anything reads through them
+    for (int k = 0; k < num_graphs; k++)
+        if (nn[k] < 0 || ne[k] < 0)
+        {
+            set_last_error("negative entry in nums_of_nodes / nums_of_edges (graph " + std::to_string(k) + ")");
+            return FG_ERR_INVALID;
+        }
     long set = -1;
     int64_t node_base = 0, edge_base = 0;
     int g = 0;
