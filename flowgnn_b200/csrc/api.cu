@@ -1213,25 +1213,50 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         // the first chunk is small so that the kernels start early, and the weight hash runs while it is in flight.
         // the reference's GAT reads node features from the START of the batch buffer for every graph.
         const bool gat_bug = (model == MODEL_GAT) && ctx->opt.gat_node_offset_bug;
+        // Narrowed uploads (host_stage.h).  Option / FLOWGNN_B200_HOST_STAGE: 0 off, else a mask of the arrays to narrow (1 node_feature,
+        // 2 edge_list, 4 edge_attr).  Automatic: everything when the caller's arrays are pageable (the plain copy would be staged by the
+        // driver, one thread, synchronously: 4.0 M graphs/s on the 41k-graph GIN batch, narrowed 15 M); for page-locked arrays everything
+        // when 8 host threads are free for this GPU (measured on a 16-core B200 box: 2.64 ms per call against 2.87-3.3 ms for the plain
+        // copies; narrowing only node_feature + edge_attr: 2.8-3.0 ms), else the plain copies.
+        int stage_mask = ctx->opt.host_stage;
+        if (const char* e = std::getenv("FLOWGNN_B200_HOST_STAGE")) stage_mask = std::atoi(e);
+        bool pinned = false;
+        if (stage_mask != 0)
+        {
+            cudaPointerAttributes at;
+            pinned = cudaPointerGetAttributes(&at, packed ? static_cast<const void*>(packed->feat) : feat) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+            (void)cudaGetLastError();
+        }
+        if (stage_mask < 0) stage_mask = !pinned || HostPool::default_threads() >= 8 ? 7 : 0;
+        stage_mask &= 7;
+        if (packed) stage_mask = 7;                          // nothing to narrow: the pool only computes the chunks' tile packing
+        // DGN's node_eigen keeps its format; a pageable array goes through the block too, so that the pool reads it instead of the driver
+        const bool stage_eig = stage_mask != 0 && eig && !pinned && !packed;
+        const bool staged = stage_mask != 0;
         const int run_graphs = g1 - g;
         int nchunks = 1;
         int bounds[17];
         for (int i = 0; i <= 16; i++) bounds[i] = g1;
         bounds[0] = g;
         {
-            // graded schedule: chunk i gets weight min(i + 1, 3) (a small first chunk starts the kernels early);
+            // graded schedule (a small first chunk starts the kernels early): weights 1, 2, 3, 3, ... for the plain copies (the upload is the
+            // longer stage: 3.87 / 3.18 / 3.11 / 3.19 / 3.54 ms for 1 / 2 / 3 / 4 / 6 chunks of the 41k-graph batch), 1, 3, 6, 6, ... for the
+            // narrowed upload (the kernels are: 2.60 ms with 1 : 2 : 3, 2.44-2.50 ms with 1 : 3 : 6; 1 : 2 : 4 2.52, four chunks 2.68);
             // FLOWGNN_B200_GRADE="1,2,4" overrides the weights (and the chunk count) for measurements
-            int want = run_graphs >= 16384 ? 3 : run_graphs >= 8192 ? 2 : 1;     // measured on B200: 3.87 / 3.18 / 3.11 / 3.19 / 3.54 ms for 1 / 2 / 3 / 4 / 6 chunks of the 41k-graph batch
+            int want = run_graphs >= 16384 ? 3 : run_graphs >= 8192 ? 2 : 1;
+            const int wmax = staged ? 6 : 3;
             // large inputs (PNA on 437,929 graphs: 945 MB; GIN-VN on 40,000 hep10k graphs: 785 MB): weight-3 chunks of about 100 MB of caller
             // bytes, so that the first chunk (what nothing overlaps) and the last chunk's kernels (what nothing follows) stay small
             {
                 const int64_t run_bytes = (int64_t)sizeof(int) * (ND_FEATURE * n_run + (attr ? 5 : 2) * e_run) + (eig ? 16 * n_run : 0);
-                const int64_t total_w = (run_bytes + (32 << 20) - 1) / (32 << 20);
-                if (want == 3 && total_w > 6) want = (int)std::min<int64_t>(16, 2 + (total_w - 3 + 2) / 3);
+                const int64_t unit = (96 << 20) / wmax;                      // caller bytes per unit of weight
+                const int64_t total_w = (run_bytes + unit - 1) / unit;
+                const int64_t head = staged ? 4 : 3;                          // weight of the two graded chunks in front
+                if (want == 3 && total_w > head + wmax) want = (int)std::min<int64_t>(16, 2 + (total_w - head + wmax - 1) / wmax);
             }
             if (const char* e = std::getenv("FLOWGNN_B200_CHUNKS")) want = std::max(1, std::min(16, std::atoi(e)));
             int weight[16];
-            for (int i = 0; i < 16; i++) weight[i] = std::min(i + 1, 3);
+            for (int i = 0; i < 16; i++) weight[i] = staged ? (i == 0 ? 1 : i == 1 ? 3 : 6) : std::min(i + 1, 3);
             if (const char* e = std::getenv("FLOWGNN_B200_GRADE"))
             {
                 int k = 0;
@@ -1273,26 +1298,6 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             for (int k = bounds[ci]; k < bounds[ci + 1]; k++) { n_c += nn[k]; e_c += ne[k]; }
             cnode[ci + 1] = cnode[ci] + n_c; cedge[ci + 1] = cedge[ci] + e_c;
         }
-        // Narrowed uploads (host_stage.h).  Option / FLOWGNN_B200_HOST_STAGE: 0 off, else a mask of the arrays to narrow (1 node_feature,
-        // 2 edge_list, 4 edge_attr).  Automatic: everything when the caller's arrays are pageable (the plain copy would be staged by the
-        // driver, one thread, synchronously: 4.0 M graphs/s on the 41k-graph GIN batch, narrowed 15 M); for page-locked arrays everything
-        // when 8 host threads are free for this GPU (measured on a 16-core B200 box: 2.64 ms per call against 2.87-3.3 ms for the plain
-        // copies; narrowing only node_feature + edge_attr: 2.8-3.0 ms), else the plain copies.
-        int stage_mask = ctx->opt.host_stage;
-        if (const char* e = std::getenv("FLOWGNN_B200_HOST_STAGE")) stage_mask = std::atoi(e);
-        bool pinned = false;
-        if (stage_mask != 0)
-        {
-            cudaPointerAttributes at;
-            pinned = cudaPointerGetAttributes(&at, packed ? static_cast<const void*>(packed->feat) : feat) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
-            (void)cudaGetLastError();
-        }
-        if (stage_mask < 0) stage_mask = !pinned || HostPool::default_threads() >= 8 ? 7 : 0;
-        stage_mask &= 7;
-        if (packed) stage_mask = 7;                          // nothing to narrow: the pool only computes the chunks' tile packing
-        // DGN's node_eigen keeps its format; a pageable array goes through the block too, so that the pool reads it instead of the driver
-        const bool stage_eig = stage_mask != 0 && eig && !pinned && !packed;
-        const bool staged = stage_mask != 0;
         constexpr int P = flowgnn_ctx::PIPE;
         auto chunk_feat = [&](int ci) { return gat_bug ? feat : feat + ND_FEATURE * cnode[ci]; };
         NarrowRun::Chunk nchunk[NarrowRun::MAX_CHUNKS];

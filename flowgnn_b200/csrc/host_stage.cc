@@ -7,6 +7,7 @@
 #endif
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 
@@ -25,6 +26,7 @@ int HostPool::default_threads()
 
 HostPool::HostPool(int threads)
 {
+    if (const char* e = std::getenv("FLOWGNN_B200_HOST_SPIN_US")) spin_us_ = std::max(0, std::min(100000, std::atoi(e)));
     for (int i = 1; i < threads; i++) workers_.emplace_back([this] { worker(); });
 }
 
@@ -38,11 +40,28 @@ HostPool::~HostPool()
     for (std::thread& t : workers_) t.join();
 }
 
+// An idle worker polls for work for spin_us_ before it sleeps on the condition variable: calls that follow each other within a few
+// milliseconds (a host streaming batches) find the pool awake -- a wake-up through the kernel costs 50-100 us per call and most of the
+// run-to-run jitter -- and a host that stops calling has the threads asleep 2 ms later.
 void HostPool::worker()
 {
     std::unique_lock<std::mutex> lock(mu_);
     for (;;)
     {
+        if (!(stop_ || next_.load(std::memory_order_relaxed) < njobs_.load(std::memory_order_relaxed)) && spin_us_ > 0)
+        {
+            lock.unlock();
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int k = 0;; k++)
+            {
+                if (stop_.load(std::memory_order_relaxed) || next_.load(std::memory_order_relaxed) < njobs_.load(std::memory_order_relaxed)) break;
+#if defined(__x86_64__)
+                _mm_pause();
+#endif
+                if ((k & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) break;
+            }
+            lock.lock();
+        }
         cv_.wait(lock, [this] { return stop_ || next_ < njobs_; });
         if (stop_) return;
         const int j = next_++;

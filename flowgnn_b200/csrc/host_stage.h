@@ -41,8 +41,10 @@ private:
     std::mutex mu_;
     std::condition_variable cv_, cv_done_;
     std::function<void(int)> fn_;
-    int njobs_ = 0, next_ = 0, pending_ = 0;
-    bool stop_ = false;
+    std::atomic<int> njobs_{0}, next_{0};                  // written under mu_; read without it by workers in their spin phase
+    int pending_ = 0;
+    int spin_us_ = 2000;                                   // FLOWGNN_B200_HOST_SPIN_US: how long an idle worker polls before it sleeps
+    std::atomic<bool> stop_{false};
 };
 
 // dst[i] = (narrow)src[i]; returns the OR of all source words (bits outside the narrow type = value out of range)
