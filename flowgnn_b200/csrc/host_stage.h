@@ -43,7 +43,7 @@ private:
     std::function<void(int)> fn_;
     std::atomic<int> njobs_{0}, next_{0};                  // written under mu_; read without it by workers in their spin phase
     int pending_ = 0;
-    int spin_us_ = 2000;                                   // FLOWGNN_B200_HOST_SPIN_US: how long an idle worker polls before it sleeps
+    int spin_us_ = 0;                                      // FLOWGNN_B200_HOST_SPIN_US: how long an idle worker polls before it sleeps
     std::atomic<bool> stop_{false};
 };
 
