@@ -565,7 +565,7 @@ def run_b200_arm(args):
     # buffers, no host threads involved -- what a loader that keeps its dataset packed pays, and what scales with the number of GPUs
     # when the int32 words of the reference ABI saturate the host's memory system
     e2e_packed = None
-    if not args.no_pageable and int(batch.node_feature.max(initial=0)) < 256 and int(batch.edge_list.max(initial=0)) < 65536:
+    if not args.no_packed and int(batch.node_feature.max(initial=0)) < 256 and int(batch.edge_list.max(initial=0)) < 65536:
         packed = {"nf": pinned_copy(batch.node_feature.astype(np.uint8)), "el": pinned_copy(batch.edge_list.astype(np.uint16)),
                   "ea": pinned_copy(batch.edge_attr.astype(np.uint8)) if spec.uses_edge_attr else (None, None)}
         from flowgnn_b200.capi import PackedCall
@@ -711,6 +711,7 @@ def main():
     ap.add_argument("--base-graphs", type=int, default=0, help="generate this many distinct graphs and tile them")
     ap.add_argument("--cpu-graphs-per-core", type=int, default=256, help="reference arm: graphs per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-packed", action="store_true", help="skip the packed-layout end-to-end arm (e2e_packed)")
     ap.add_argument("--no-extras", action="store_true", help="skip the C4 (PNA sharded) / C5 (GIN-VN hep10k) lines")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-caller end-to-end line")
     args = ap.parse_args()

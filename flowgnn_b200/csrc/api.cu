@@ -1215,9 +1215,10 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         const bool gat_bug = (model == MODEL_GAT) && ctx->opt.gat_node_offset_bug;
         // Narrowed uploads (host_stage.h).  Option / FLOWGNN_B200_HOST_STAGE: 0 off, else a mask of the arrays to narrow (1 node_feature,
         // 2 edge_list, 4 edge_attr).  Automatic: everything when the caller's arrays are pageable (the plain copy would be staged by the
-        // driver, one thread, synchronously: 4.0 M graphs/s on the 41k-graph GIN batch, narrowed 15 M); for page-locked arrays everything
-        // when 8 host threads are free for this GPU (measured on a 16-core B200 box: 2.64 ms per call against 2.87-3.3 ms for the plain
-        // copies; narrowing only node_feature + edge_attr: 2.8-3.0 ms), else the plain copies.
+        // driver, one thread, synchronously: 4.0 M graphs/s on the 41k-graph GIN batch, narrowed 16 M); for page-locked arrays everything
+        // when 8 host threads are free for this GPU, node_feature + edge_attr (4 bytes -> 1) with 6 or 7, else the plain copies.  Measured
+        // on a 16-core B200 box, ms per call of the 41k-graph batch (profiles/r2k_e2e_probe.txt): plain copies 2.90; everything narrowed
+        // 2.46 / 2.49 / 2.91 / 3.26 with 12 / 8 / 6 / 4 threads; node_feature + edge_attr only 2.55 / 2.57 / 2.55 / 3.06.
         int stage_mask = ctx->opt.host_stage;
         if (const char* e = std::getenv("FLOWGNN_B200_HOST_STAGE")) stage_mask = std::atoi(e);
         bool pinned = false;
@@ -1227,7 +1228,11 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
             pinned = cudaPointerGetAttributes(&at, packed ? static_cast<const void*>(packed->feat) : feat) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
             (void)cudaGetLastError();
         }
-        if (stage_mask < 0) stage_mask = !pinned || HostPool::default_threads() >= 8 ? 7 : 0;
+        if (stage_mask < 0)
+        {
+            const int threads = HostPool::default_threads();
+            stage_mask = !pinned || threads >= 8 ? 7 : threads >= 6 ? 5 : 0;
+        }
         stage_mask &= 7;
         if (packed) stage_mask = 7;                          // nothing to narrow: the pool only computes the chunks' tile packing
         // DGN's node_eigen keeps its format; a pageable array goes through the block too, so that the pool reads it instead of the driver
