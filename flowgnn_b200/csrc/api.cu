@@ -1218,7 +1218,9 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         // driver, one thread, synchronously: 4.0 M graphs/s on the 41k-graph GIN batch, narrowed 16 M); for page-locked arrays everything
         // when 8 host threads are free for this GPU, node_feature + edge_attr (4 bytes -> 1) with 6 or 7, else the plain copies.  Measured
         // on a 16-core B200 box, ms per call of the 41k-graph batch (profiles/r2k_e2e_probe.txt): plain copies 2.90; everything narrowed
-        // 2.46 / 2.49 / 2.91 / 3.26 with 12 / 8 / 6 / 4 threads; node_feature + edge_attr only 2.55 / 2.57 / 2.55 / 3.06.
+        // 2.46 / 2.49 / 2.91 / 3.26 with 12 / 8 / 6 / 4 threads; node_feature + edge_attr only 2.55 / 2.57 / 2.55 / 3.06.  Two ranks on a
+        // 24-core box (9 threads each, profiles/r2k_e2e_scale_2gpu.txt): plain 2.96, features + attributes 2.93, everything 3.10 -- the
+        // pools of several ranks compete for the host's memory system, so edge_list is narrowed only by a rank that is alone.
         int stage_mask = ctx->opt.host_stage;
         if (const char* e = std::getenv("FLOWGNN_B200_HOST_STAGE")) stage_mask = std::atoi(e);
         bool pinned = false;
@@ -1231,7 +1233,8 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         if (stage_mask < 0)
         {
             const int threads = HostPool::default_threads();
-            stage_mask = !pinned || threads >= 8 ? 7 : threads >= 6 ? 5 : 0;
+            const bool alone = HostPool::local_ranks() == 1;     // several ranks' pools share the host's memory system
+            stage_mask = !pinned || (alone && threads >= 8) ? 7 : threads >= 6 ? 5 : 0;
         }
         stage_mask &= 7;
         if (packed) stage_mask = 7;                          // nothing to narrow: the pool only computes the chunks' tile packing

@@ -13,14 +13,19 @@
 
 namespace fg {
 
+int HostPool::local_ranks()
+{
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) return std::max(1, std::atoi(e));
+    return 1;
+}
+
 int HostPool::default_threads()
 {
     if (const char* e = std::getenv("FLOWGNN_B200_HOST_THREADS")) return std::max(1, std::min(64, std::atoi(e)));
     int cores = (int)std::thread::hardware_concurrency();
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
-    int ranks = 1;                                          // one process per GPU (torchrun): share the cores
-    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, std::atoi(e));
+    const int ranks = local_ranks();                        // one process per GPU (torchrun): share the cores
     return std::max(1, std::min(12, cores * 3 / 4 / ranks));
 }
 

@@ -32,6 +32,7 @@ public:
     void start(int njobs, std::function<void(int)> fn);   // returns at once; workers begin
     bool run_one();                                        // the caller takes ONE job if there is one left
     void finish();                                         // the caller takes jobs too, then waits for the last one
+    static int local_ranks();                              // LOCAL_WORLD_SIZE (one process per GPU under torchrun), else 1
     static int default_threads();                          // FLOWGNN_B200_HOST_THREADS, else min(12, 3/4 of the usable cores / ranks on this node)
 
 private:
