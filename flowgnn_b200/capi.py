@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "GIN_compute_graphs", "GIN_compute_graphs_fixed", "GCN_compute_graphs", "GAT_compute_graphs", "PNA_compute_graphs", "DGN_compute_graphs",
     "flowgnn_b200_last_error", "flowgnn_b200_create", "flowgnn_b200_destroy", "flowgnn_b200_set_option",
     "flowgnn_b200_load_weights", "flowgnn_b200_upload_batch", "flowgnn_b200_upload_batch_packed", "flowgnn_b200_compute", "flowgnn_b200_download",
-    "flowgnn_b200_last_launch_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
+    "flowgnn_b200_last_launch_count", "flowgnn_b200_tile_count", "flowgnn_b200_last_layer_ms", "flowgnn_b200_stream", "flowgnn_b200_synchronize",
     "flowgnn_b200_pin_host", "flowgnn_b200_unpin_host", "flowgnn_b200_narrow_words", "flowgnn_b200_last_transfer_bytes", "flowgnn_b200_compute_graphs_packed",
 )
 
@@ -60,6 +60,8 @@ def load_library() -> ctypes.CDLL:
         lib.flowgnn_b200_compute.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p]
         lib.flowgnn_b200_download.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         lib.flowgnn_b200_last_launch_count.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_tile_count.argtypes = [ctypes.c_void_p]
+        lib.flowgnn_b200_tile_count.restype = ctypes.c_long
         lib.flowgnn_b200_synchronize.argtypes = [ctypes.c_void_p]
         lib.flowgnn_b200_last_layer_ms.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
         lib.flowgnn_b200_pin_host.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
@@ -186,6 +188,11 @@ class Context:
             out = np.empty(self._num_graphs, dtype=np.float32)
         _check(self._lib.flowgnn_b200_download(self._h, _addr(out), self._num_graphs), "download")
         return out
+
+    @property
+    def tile_count(self) -> int:
+        """128-row tiles of whole graphs the uploaded batch was packed into (0: not packed on the host)."""
+        return int(self._lib.flowgnn_b200_tile_count(self._h))
 
     def synchronize(self) -> None:
         _check(self._lib.flowgnn_b200_synchronize(self._h), "synchronize")

@@ -1052,6 +1052,7 @@ int flowgnn_b200_download(flowgnn_ctx* ctx, float* out, int num_graphs)
 }
 
 int flowgnn_b200_last_launch_count(flowgnn_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+long flowgnn_b200_tile_count(flowgnn_ctx* ctx) { return ctx && ctx->batch_ready && ctx->batch.has_perm ? ctx->batch.tiles_perm_count : 0; }
 
 int flowgnn_b200_last_layer_ms(flowgnn_ctx* ctx, float* out, int max_layers)
 {

@@ -209,6 +209,10 @@ int flowgnn_b200_download(flowgnn_ctx* ctx, float* out, int num_graphs);
 /* Kernels launched by the last flowgnn_b200_compute. */
 int flowgnn_b200_last_launch_count(flowgnn_ctx* ctx);
 
+/* Number of 128-row tiles of whole graphs the uploaded batch was packed into (GIN / PNA layer launches work on these; a tile
+ * issues 128 rows of tensor-core work whatever its fill).  0 if the batch was not packed on the host. */
+long flowgnn_b200_tile_count(flowgnn_ctx* ctx);
+
 /* With option "time_layers" = 1, flowgnn_b200_compute brackets every per-layer kernel launch with CUDA
  * events; this returns the device time of each layer launch of the last compute (count written). */
 int flowgnn_b200_last_layer_ms(flowgnn_ctx* ctx, float* out, int max_layers);
