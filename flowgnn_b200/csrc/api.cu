@@ -940,9 +940,9 @@ int compute_on(flowgnn_ctx* ctx, DeviceBatch& b, cudaStream_t s, int model)
     {
         // every graph is empty: the mean pool is 0 / 0, and the reference's fp32 flavour carries that NaN through every head
         FG_TRY(b.status.reserve(sizeof(int)));
-        FG_CUDA(cudaMemsetAsync(b.status.ptr, 0, sizeof(int), s));
+        FG_TRY(zero_bytes_launch(b.status.ptr, sizeof(int), s));
         FG_TRY(fill_outputs(b.out.as<float>(), std::nanf(""), b.num_graphs, s));
-        ctx->last_launches += 1;
+        ctx->last_launches += 2;
         return 0;
     }
     if (fixed && model != MODEL_GIN && model != MODEL_DGN)

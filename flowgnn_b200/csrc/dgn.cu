@@ -177,13 +177,13 @@ int dgn_forward(DeviceBatch& b, const DgnWeights& w, const RunOptions& opt, int 
         if (opt.dgn_tc && opt.dgn_fused)
         {
             FG_TRY(dgn_layer_fused_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
-            nl += 2;
+            nl += 3;                                   // zero the flags, the fused layer, the exact rows
             continue;
         }
         if (opt.dgn_tc)
         {
             FG_TRY(dgn_layer_tc_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
-            nl += 3;
+            nl += 4;
             continue;
         }
         DgnLayerParams p{};

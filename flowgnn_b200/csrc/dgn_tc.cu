@@ -315,7 +315,7 @@ int dgn_layer_fused_launch(DeviceBatch& b, const DgnWeights& w, int l, const flo
     const long N = b.total_nodes;
     if (N == 0) return 0;
     FG_TRY(b.nonfinite.reserve((size_t)N + 16));
-    FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
+    FG_TRY(zero_bytes_launch(b.nonfinite.ptr, (size_t)N, s));
     DgnAggParams p{};
     p.h_in = h_in;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.eig_w = b.edge_w.as<float>(); p.out_deg = b.out_deg.as<int>();
@@ -345,7 +345,7 @@ int dgn_layer_tc_launch(DeviceBatch& b, const DgnWeights& w, int l, const float*
     const int num_tiles = (int)ceil_div<long>(N, tcg::TM);
     FG_TRY(b.apack.reserve((size_t)num_tiles * NCHUNK * tcg::A_BLOCK));
     FG_TRY(b.nonfinite.reserve((size_t)N + 16));
-    FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
+    FG_TRY(zero_bytes_launch(b.nonfinite.ptr, (size_t)N, s));
     DgnAggParams p{};
     p.h_in = h_in;
     p.in_ptr = b.in_ptr.as<int>(); p.src = b.src.as<int>(); p.eig_w = b.edge_w.as<float>(); p.out_deg = b.out_deg.as<int>();

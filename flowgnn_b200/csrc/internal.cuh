@@ -82,6 +82,7 @@ enum PrepFlags { PREP_GCN_NORM = 1, PREP_DGN_EIG = 2, PREP_ROW_DESC = 4, PREP_TI
 // graph preprocessing: offsets scan + per-graph CSR build (prep.cu)
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches = nullptr, bool use_perm = false);
 int node_map_launch(DeviceBatch& b, cudaStream_t stream);
+int zero_bytes_launch(void* p, size_t bytes, cudaStream_t stream);   // a kernel, not a copy-engine memset (prep.cu)
 int unpack_inputs_launch(const uint8_t* block, size_t off_edge, size_t off_attr, int32_t* feat, size_t n_feat, int32_t* edges, size_t n_edge,
                          int32_t* attr, size_t n_attr, cudaStream_t stream);
 

@@ -246,16 +246,16 @@ int pna_forward(DeviceBatch& b, const PnaWeights& w, const RunOptions& opt, int 
         {
             // one kernel for message passing + node transform, then the few rows that need fp32
             FG_TRY(b.nonfinite.reserve((size_t)N + 16));
-            FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
+            FG_TRY(zero_bytes_launch(b.nonfinite.ptr, (size_t)N, s));
             FG_TRY(pna_layer_fused_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
             FG_TRY(pna_exact_rows_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
-            nl += 2;
+            nl += 3;                                   // zero the flags, the fused layer, the exact rows
             continue;
         }
         if (opt.pna_tc)
         {
             FG_TRY(pna_layer_tc_launch(b, w, l, h[l & 1], h[(l + 1) & 1], sm_count, s));
-            nl += 3;
+            nl += 4;
             continue;
         }
         PnaLayerParams p{};

@@ -469,7 +469,7 @@ int pna_layer_tc_launch(DeviceBatch& b, const PnaWeights& w, int layer, const fl
     const int num_tiles = (int)ceil_div<long>(N, TM);
     FG_TRY(b.apack.reserve((size_t)num_tiles * NCHUNK * A_BLOCK));
     FG_TRY(b.nonfinite.reserve((size_t)N + 16));
-    FG_CUDA(cudaMemsetAsync(b.nonfinite.ptr, 0, (size_t)N, s));
+    FG_TRY(zero_bytes_launch(b.nonfinite.ptr, (size_t)N, s));
     {
         const int blocks = (int)std::min<long>(ceil_div<long>(ceil_div<long>(N, 32) * Q2, AG_WARPS), (long)sm_count * 8);
         pna_aggregate_kernel<<<blocks, AG_WARPS * 32, 0, s>>>(h_in, b.in_ptr.as<int>(), b.src.as<int>(), b.apack.as<unsigned char>(),

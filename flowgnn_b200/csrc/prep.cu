@@ -506,6 +506,39 @@ __global__ void __launch_bounds__(256) sort_tile_rows_kernel(const int2* __restr
 
 }  // namespace
 
+// Small fills and device-to-device copies as KERNELS.  cudaMemsetAsync / cudaMemcpyAsync(D2D) are served by the copy engines, where
+// they queue behind whatever upload is in flight: in the chunked entry points every such call inside a forward waited 0.25-0.35 ms
+// for the next chunk's host-to-device copy (DGN: one memset per layer, +1 ms per chunk).
+namespace {
+__global__ void __launch_bounds__(256) zero_bytes_kernel(uint4* __restrict__ p, size_t n16)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+struct CopySeg { int* dst; const int* src; long n; };
+__global__ void __launch_bounds__(256) copy_segments_kernel(CopySeg a, CopySeg b, CopySeg c, CopySeg d, int* zero_word)
+{
+    const long stride = (long)gridDim.x * blockDim.x, t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long i = t; i < a.n; i += stride) a.dst[i] = __ldg(a.src + i);
+    for (long i = t; i < b.n; i += stride) b.dst[i] = __ldg(b.src + i);
+    for (long i = t; i < c.n; i += stride) c.dst[i] = __ldg(c.src + i);
+    for (long i = t; i < d.n; i += stride) d.dst[i] = __ldg(d.src + i);
+    if (t == 0 && zero_word) *zero_word = 0;
+}
+}  // namespace
+
+// zero [p, p + bytes): p from cudaMalloc (256-byte aligned), the buffer padded to a multiple of 16 bytes (DevBuf::reserve rounds to 256)
+int zero_bytes_launch(void* p, size_t bytes, cudaStream_t stream)
+{
+    const size_t n16 = (bytes + 15) / 16;
+    if (!n16) return 0;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n16 + 255) / 256, 148 * 4));
+    zero_bytes_kernel<<<blocks, 256, 0, stream>>>(static_cast<uint4*>(p), n16);
+    FG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
 int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bool use_perm)
 {
     const int G = b.num_graphs;
@@ -525,8 +558,6 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bo
         FG_TRY(b.node_w0.reserve(sizeof(float) * (size_t)(b.total_nodes + 1)));
         FG_TRY(b.node_w1.reserve(sizeof(float) * (size_t)(b.total_nodes + 1)));
     }
-    FG_CUDA(cudaMemsetAsync(b.status.ptr, 0, sizeof(int), stream));
-
     // Re-ordered graphs (api.cu::pack_graphs, computed on the host at upload): the rows of graph g are written at node_off_perm[g],
     // its inputs are still read at the caller's offsets; the tile list came with the upload.  Everything downstream uses node_off.
     const bool perm = use_perm && b.has_perm && (flags & PREP_TILES);
@@ -534,16 +565,18 @@ int prep_batch(DeviceBatch& b, int flags, cudaStream_t stream, int* launches, bo
     int nl = 1;
     int* scan_node = perm ? b.node_off_in.as<int>() : b.node_off.as<int>();
     int* scan_edge = perm ? b.edge_off_in.as<int>() : b.edge_off.as<int>();
+    if (!perm) { FG_TRY(zero_bytes_launch(b.status.ptr, sizeof(int), stream)); nl++; }
     if (perm)
     {
-        FG_CUDA(cudaMemcpyAsync(b.node_off.ptr, b.node_off_perm.ptr, sizeof(int) * (size_t)(G + 1), cudaMemcpyDeviceToDevice, stream));
-        FG_CUDA(cudaMemcpyAsync(b.edge_off.ptr, b.edge_off_perm.ptr, sizeof(int) * (size_t)(G + 1), cudaMemcpyDeviceToDevice, stream));
         b.max_tiles = b.tiles_perm_count;
         FG_TRY(b.tiles.reserve(sizeof(int2) * (size_t)std::max<long>(b.max_tiles, 1)));
         FG_TRY(b.tile_count.reserve(sizeof(int)));
-        if (b.max_tiles) FG_CUDA(cudaMemcpyAsync(b.tiles.ptr, b.tiles_perm.ptr, sizeof(int2) * (size_t)b.max_tiles, cudaMemcpyDeviceToDevice, stream));
-        FG_CUDA(cudaMemcpyAsync(b.tile_count.ptr, b.tiles_perm.as<char>() + sizeof(int2) * (size_t)b.max_tiles, sizeof(int), cudaMemcpyDeviceToDevice, stream));
-        nl = 0;                                             // the caller-order offsets came with the upload too: no scan launch
+        // adopt what came with the upload (one launch, not four copy-engine copies and a memset) and clear the status word
+        const CopySeg sa{b.node_off.as<int>(), b.node_off_perm.as<int>(), (long)G + 1}, sb{b.edge_off.as<int>(), b.edge_off_perm.as<int>(), (long)G + 1};
+        const CopySeg sc{b.tiles.as<int>(), b.tiles_perm.as<int>(), 2 * b.max_tiles}, sd{b.tile_count.as<int>(), b.tiles_perm.as<int>() + 2 * b.max_tiles, 1};
+        copy_segments_kernel<<<(int)std::max<long>(1, std::min<long>(((long)G + 256) / 256, 148 * 2)), 256, 0, stream>>>(sa, sb, sc, sd, b.status.as<int>());
+        FG_CUDA(cudaGetLastError());
+        nl = 1;                                             // (the caller-order offsets came with the upload too: no scan launch)
     }
     else if (flags & PREP_TILES)
     {

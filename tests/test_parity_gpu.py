@@ -180,9 +180,10 @@ def test_gin_staged_gather_layers_agree_with_fused_layers(ds, vn, ctx, weights, 
             ctx.set_option("gin_staged", mode)
             out[mode] = ctx.run("gin", b, weights["gin"])
             launches = ctx.last_launch_count
-            # scan + pack_tiles (one launch), build_csr_small (+ build_csr_large if a graph has more than 128 nodes), sort_tile_rows,
-            # embed, 5 layers (each preceded by the staged gather on dense batches), pool
-            base = 10 + int(b.nums_of_nodes.max() > 128)
+            # status clear + scan + pack_tiles (or, re-ordered batches: adopt the uploaded offsets / tiles + node_map), build_csr_small
+            # (+ build_csr_large if a graph has more than 128 nodes), sort_tile_rows, embed, 5 layers (each preceded by the staged
+            # gather on dense batches), pool
+            base = 11 + int(b.nums_of_nodes.max() > 128)
             assert launches == base + (5 if mode == 1 or (mode == -1 and ds == "hep10k") else 0), (mode, launches)
     finally:
         ctx.set_option("gin_staged", -1)
@@ -576,7 +577,7 @@ def test_full_size_synthetic_batch_properties(ctx, weights):
     assert np.array_equal(y.view(np.int32), ctx.run("gin", b).view(np.int32))
     ids = np.random.default_rng(5).choice(2048, 48, replace=False)
     assert_parity(y[ids], refbind.run_port("gin", base.select(ids), weights["gin"]), what="gin synthetic sample")
-    assert ctx.last_launch_count == 10 + int(b.nums_of_nodes.max() > 128)      # scan + pack_tiles, build_csr (1 or 2), sort_tile_rows, embed, 5 layers, pool
+    assert ctx.last_launch_count == 11 + int(b.nums_of_nodes.max() > 128)      # adopt offsets / tiles, node_map, build_csr (1 or 2), sort_tile_rows, embed, 5 layers, pool
 
 
 FULL_SIZE = {"gcn": ("molhiv", 41127), "gat": ("molhiv", 41127), "dgn": ("molhiv", 41127), "pna": ("molpcba", 437929),
