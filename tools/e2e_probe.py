@@ -1,6 +1,6 @@
 """End-to-end time of the host-pointer entry point for chunk counts (FLOWGNN_B200_CHUNKS), the narrowed upload on / off
 (FLOWGNN_B200_HOST_STAGE), host thread counts (FLOWGNN_B200_HOST_THREADS) and pageable / page-locked caller arrays.
-    python tools/e2e_probe.py [model=gin] [reps=20]"""
+    python tools/e2e_probe.py [model=gin] [reps=20] [trace ['{"HOST_STAGE": 0}' ...]]   (trace: pinned arrays, timeline of one call per setting)"""
 import os
 import sys
 import time
@@ -39,10 +39,12 @@ if len(sys.argv) > 3 and sys.argv[3] == "trace":
     for a in (b.node_feature, b.edge_list, b.edge_attr, b.node_eigen):
         if a is not None:
             pin_host(a)
-    for env in ({}, {"HOST_STAGE": 7}, {"GRADE": "1,2,4"}, {"GRADE": "1,3,6"}, {"GRADE": "1,2,3,4"}, {"GRADE": "1,2,4,6"}, {"GRADE": "1,2,4", "HOST_STAGE": 7},
-                {"GRADE": "1,3,6", "HOST_STAGE": 7}, {"GRADE": "2,3,4"}, {"GRADE": "1,2,2,2"}, {"HOST_THREADS": 8}, {"HOST_THREADS": 16}):
+    import json
+    envs = [json.loads(a) for a in sys.argv[4:]] or [{}, {"HOST_STAGE": 7}, {"GRADE": "1,2,4"}, {"GRADE": "1,3,6"}, {"GRADE": "1,2,3,4"}, {"HOST_STAGE": 0},
+                                                      {"HOST_STAGE": 5}, {"HOST_THREADS": 8}, {"HOST_THREADS": 16}]
+    for env in envs:
         measure("pinned", **env)
-        if len(env) == 0 or env.get("GRADE") == "1,2,4":
+        if len(sys.argv) > 4 or len(env) == 0 or env.get("GRADE") == "1,2,4":
             os.environ["FLOWGNN_B200_E2E_TRACE"] = "1"
             call.run()
             del os.environ["FLOWGNN_B200_E2E_TRACE"]
