@@ -37,7 +37,6 @@ public:
 
 private:
     void worker();
-    bool take(int& j);
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_, cv_done_;
