@@ -47,6 +47,23 @@ def test_narrow_words_rejects_other_widths():
     assert capi.narrow_words(np.zeros(4, np.int32), 4, 1)[1] == 0xFFFFFFFF
 
 
+def test_narrow_run_probe_binary(tmp_path):
+    """tools/hs_probe/narrow_probe.cc drives NarrowRun (all chunks' slices queued at once, the caller helping until its chunk is complete)
+    over the bench batch's sizes and checks every narrowed value; built here with the host compiler, with and without the AVX2 path."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "narrow_probe")
+    subprocess.run([cxx, "-O2", "-std=c++17", "-pthread", os.path.join(root, "tools", "hs_probe", "narrow_probe.cc"),
+                    os.path.join(root, "flowgnn_b200", "csrc", "host_stage.cc"), "-o", exe], check=True)
+    for env in ({}, {"FLOWGNN_B200_NO_AVX2": "1"}):
+        r = subprocess.run([exe, "3"], capture_output=True, text=True, env={**os.environ, **env}, timeout=120)
+        assert r.returncode == 0 and "GB/s" in r.stdout, r.stdout + r.stderr
+
+
 # ---- GPU --------------------------------------------------------------------------------------------------------------
 
 @pytest.fixture(scope="module")
