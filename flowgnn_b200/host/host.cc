@@ -19,8 +19,12 @@
 //                    predictions land in disjoint slices of out[G].  NCCL is used for ONE thing: the throughput tally
 //                    (all-reduce SUM of the graphs done, MAX of the device time) -- there is no collective on the data path
 //   <dataset>.fgb    the packed single-file dataset (flowgnn_b200/dataset.py::save_packed) instead of 3-4 tiny files per graph
+//   --layout packed  keep the batch in the narrow layout after loading (uint8 features, uint16 edge ids, uint8 bond attributes) and call
+//                    flowgnn_b200_compute_graphs_packed instead of <MODEL>_compute_graphs: 9 B per node + 7 B per edge cross PCIe and
+//                    nothing is narrowed inside the timed call (default: int32, the reference's ABI)
 //
 //   host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir | file.fgb> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE] [--gpus N]
+//             [--layout int32|packed]
 #include <cuda_runtime.h>
 #include <nccl.h>
 
@@ -442,15 +446,39 @@ int run_model(const std::string& model, Graphs& g, Weights& w, std::vector<float
                               a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
 }
 
+// the batch in the narrow layout of the packed dataset files (values are checked: a dataset that does not fit keeps the int32 ABI)
+struct NarrowGraphs {
+    std::vector<uint8_t> feat, attr;
+    std::vector<uint16_t> edges;
+    bool from(const Graphs& g)
+    {
+        feat.resize(g.feat.size()); edges.resize(g.edges.size()); attr.resize(g.attr.size());
+        for (size_t i = 0; i < g.feat.size(); i++) { if (g.feat[i] < 0 || g.feat[i] > 255) return false; feat[i] = (uint8_t)g.feat[i]; }
+        for (size_t i = 0; i < g.edges.size(); i++) { if (g.edges[i] < 0 || g.edges[i] > 65535) return false; edges[i] = (uint16_t)g.edges[i]; }
+        for (size_t i = 0; i < g.attr.size(); i++) { if (g.attr[i] < 0 || g.attr[i] > 255) return false; attr[i] = (uint8_t)g.attr[i]; }
+        return true;
+    }
+};
+
+int run_model_packed(const std::string& model, Graphs& g, const NarrowGraphs& n, Weights& w, std::vector<float>& out)
+{
+    std::vector<const float*> a;
+    for (auto& v : w.arrays) a.push_back(v.data());
+    const int id = (model == "gin" || model == "ginvn") ? FLOWGNN_GIN : model == "gcn" ? FLOWGNN_GCN : model == "gat" ? FLOWGNN_GAT : model == "pna" ? FLOWGNN_PNA : FLOWGNN_DGN;
+    const bool with_attr = id == FLOWGNN_GIN || id == FLOWGNN_GCN;
+    return flowgnn_b200_compute_graphs_packed(id, (int)g.nn.size(), g.nn.data(), g.ne.data(), out.data(), n.feat.data(), n.edges.data(),
+                                              with_attr ? n.attr.data() : nullptr, id == FLOWGNN_DGN ? g.eig.data() : nullptr, a.data(), (int)a.size());
+}
+
 }  // namespace
 
 int main(int argc, char** argv)
 {
     if (argc < 4)
-        die("usage: host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir | file.fgb> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE] [--gpus N]");
+        die("usage: host_b200 <gin|ginvn|gcn|gat|pna|dgn> <dataset_dir | file.fgb> <weights_dir> [--graphs N] [--first G] [--trials T] [--out FILE] [--gpus N] [--layout int32|packed]");
     const std::string model = argv[1], root = argv[2], wdir = argv[3];
     int count = -1, first = 1, trials = 25, gpus = 0;            // NUM_TRIALS = 25, GIN/src/host.h:8
-    std::string out_path = "B200_output.txt";
+    std::string out_path = "B200_output.txt", layout = "int32";
     for (int i = 4; i + 1 < argc; i += 2)
     {
         const std::string k = argv[i];
@@ -459,6 +487,7 @@ int main(int argc, char** argv)
         else if (k == "--trials") trials = std::atoi(argv[i + 1]);
         else if (k == "--out") out_path = argv[i + 1];
         else if (k == "--gpus") gpus = std::atoi(argv[i + 1]);
+        else if (k == "--layout") layout = argv[i + 1];
         else die("unknown option " + k);
     }
     const bool packed = root.size() > 4 && root.compare(root.size() - 4, 4, ".fgb") == 0;
@@ -490,18 +519,26 @@ int main(int argc, char** argv)
         std::printf("******* %s written *******\n", out_path.c_str());
         return 0;
     }
+    if (layout != "int32" && layout != "packed") die("--layout wants int32 or packed");
+    NarrowGraphs narrow;
+    bool use_packed = layout == "packed";
+    if (use_packed && !narrow.from(g))
+    {
+        std::printf("a value does not fit the packed layout: keeping the int32 ABI\n");
+        use_packed = false;
+    }
     double best_ms = 1e30, sum_ms = 0;
     for (int t = 0; t < std::max(trials, 1); t++)
     {
         const auto t0 = std::chrono::steady_clock::now();
-        const int rc = run_model(model, g, w, out);
+        const int rc = use_packed ? run_model_packed(model, g, narrow, w, out) : run_model(model, g, w, out);
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (rc != 0) die(std::string("kernel entry point failed (") + std::to_string(rc) + "): " + flowgnn_b200_last_error());
         if (t > 0 || trials == 1) { best_ms = std::min(best_ms, ms); sum_ms += ms; }
     }
     const int timed = trials > 1 ? trials - 1 : 1;
-    std::printf("%s: %d graphs, %d trials: mean %.3f ms, best %.3f ms per batch (host buffers in, predictions out) = %.1f us/graph, %.0f graphs/s\n",
-                model.c_str(), count, trials, sum_ms / timed, best_ms, 1e3 * best_ms / count, count / (best_ms * 1e-3));
+    std::printf("%s: %d graphs, %d trials: mean %.3f ms, best %.3f ms per batch (%s host buffers in, predictions out) = %.1f us/graph, %.0f graphs/s\n",
+                model.c_str(), count, trials, sum_ms / timed, best_ms, use_packed ? "packed" : "int32", 1e3 * best_ms / count, count / (best_ms * 1e-3));
 
     FILE* f = std::fopen(out_path.c_str(), "w");
     if (!f) die("cannot write " + out_path);

@@ -50,6 +50,24 @@ def test_host_driver_matches_reference_outputs(model, tmp_path, datasets, golden
     assert_parity(got, golden["molhiv"][model][:b.num_graphs], what=f"host_b200 {model}")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["gin", "gcn", "gat", "pna", "dgn"])
+def test_host_driver_packed_layout_gives_the_same_file(model, tmp_path, datasets):
+    """--layout packed: the host narrows the batch once after loading and calls flowgnn_b200_compute_graphs_packed; the prediction
+    file must be byte-identical to the one written through <MODEL>_compute_graphs."""
+    assert os.path.isfile(HOST), "host_b200 not built"
+    root, b = _write_dataset(tmp_path, datasets)
+    wdir = os.path.join(GOLDEN, "weights", MODEL_WEIGHT_DIR[model])
+    outs = {}
+    for layout in ("int32", "packed"):
+        out = str(tmp_path / f"out_{layout}.txt")
+        r = subprocess.run([HOST, model, root, wdir, "--trials", "2", "--out", out, "--layout", layout], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr + r.stdout
+        assert f"{layout} host buffers in" in r.stdout, r.stdout
+        outs[layout] = open(out, "rb").read()
+    assert outs["int32"] == outs["packed"] and outs["packed"].count(b"\n") == b.num_graphs
+
+
 def _gpu_count():
     import torch
     return torch.cuda.device_count()
