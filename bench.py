@@ -184,6 +184,15 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def bench_config(model, G, N, E, world):
+    """The `config` object of the JSON line -- built by this one function for BOTH arms, so that they are equal key for key."""
+    shape = WORKLOADS[model][0]
+    return {"workload": f"{model.upper()} forward, {G} synthetic {shape}-shaped graphs per GPU per step",
+            "batch": f"sum N = {N}, sum E = {E} on rank 0; trained weights shipped with the reference",
+            "l2": "inputs larger than L2 (activations 2 x %.0f MB per GPU)" % (N * ALGO[model][0] * 4 / 1e6),
+            "parallelism": f"graphs sharded by index over {world} GPU(s), no data-path collective"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -200,14 +209,17 @@ def run_reference_arm(args):
     total = sum(t)
     value = sample.num_graphs * args.steps / total
     shape, full = WORKLOADS[model]
+    # the B200 arm's batch (rank 0), only to name the same configuration: the timed sample above is its first graphs
+    G_full = args.graphs or full
+    whole = make_workload(model, G_full, seed_offset=0, base_graphs=args.base_graphs)
     sample_txt = (f"first {sample.num_graphs} graphs ({per_core} per core) of the synthetic {shape}-shaped workload per step, "
                   f"one process per core, timed around <MODEL>_compute_graphs only")
     line = {
         "impl": "reference", "metric": metric_name(model), "value": value, "unit": "graphs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{model.upper()} forward, {full} synthetic {shape}-shaped graphs per GPU per step",
-                   "reference_sample_graphs_per_step": sample.num_graphs},
+        "config": bench_config(model, G_full, whole.total_nodes, whole.total_edges, int(os.environ.get("WORLD_SIZE", "1"))),
+        "reference_sample_graphs_per_step": sample.num_graphs,
         "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": cores, "kind": ref.kind, "sample": sample_txt},
         "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -693,10 +705,7 @@ def run_b200_arm(args):
             "metric": metric_name(model), "value": value, "unit": "graphs/s", "timer": "CUDA events on the context's stream (device-timed)",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{model.upper()} forward, {G} synthetic {shape}-shaped graphs per GPU per step",
-                       "batch": f"sum N = {N}, sum E = {E} on rank 0; trained weights shipped with the reference",
-                       "l2": "inputs larger than L2 (activations 2 x %.0f MB per GPU)" % (N * ALGO[model][0] * 4 / 1e6),
-                       "parallelism": f"graphs sharded by index over {world} GPU(s), no data-path collective"},
+            "config": bench_config(model, G, N, E, world),
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "caller_input_bytes_per_step": int(caller_bytes),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "host clock around the synchronous C-ABI calls",
