@@ -1239,8 +1239,12 @@ int run_reference_entry(int model, int num_graphs, const int* nn, const int* ne,
         }
         stage_mask &= 7;
         if (packed) stage_mask = 7;                          // nothing to narrow: the pool only computes the chunks' tile packing
-        // DGN's node_eigen keeps its format; a pageable array goes through the block too, so that the pool reads it instead of the driver
-        const bool stage_eig = stage_mask != 0 && eig && !pinned && !packed;
+        // DGN's node_eigen keeps its format; a pageable array can go through the block too, so that the pool reads it instead of the driver
+        // (off unless FLOWGNN_B200_STAGE_EIG=1: measured on the 41k-graph DGN batch from pageable memory, 5.05 ms per call with node_eigen
+        // through the block -- the middle chunk's kernels then take 2.0 ms instead of 1.2 ms, not understood -- against 4.48 ms with the
+        // plain copy of the 16 B per node, which the driver stages)
+        static const bool eig_through_block = [] { const char* e = std::getenv("FLOWGNN_B200_STAGE_EIG"); return e && std::atoi(e) != 0; }();
+        const bool stage_eig = stage_mask != 0 && eig && !pinned && !packed && eig_through_block;
         const bool staged = stage_mask != 0;
         const int run_graphs = g1 - g;
         int nchunks = 1;

@@ -49,6 +49,11 @@ if len(sys.argv) > 3 and sys.argv[3] == "trace":
             call.run()
             del os.environ["FLOWGNN_B200_E2E_TRACE"]
     sys.exit(0)
+if len(sys.argv) > 3 and sys.argv[3] == "pageable-trace":
+    measure("pageable")
+    os.environ["FLOWGNN_B200_E2E_TRACE"] = "1"
+    call.run()
+    sys.exit(0)
 measure("pageable")
 measure("pageable", HOST_STAGE=0)
 for t in (6, 8, 12):
